@@ -107,6 +107,183 @@ typedef struct {
 
 int mb200_gemm(const mb200_gemm_args* args, void* stream);
 
+
+/* -------------------------------------------------------------------------------------------
+ * HBM-bound operators (elementwise.cu). bf16 storage, fp32 math. Row strides (`ld*`) in elements.
+ * ------------------------------------------------------------------------------------------- */
+/* torch.nn.LayerNorm (GPT-J ln_1/ln_f hf:gptj/modeling_gptj.py:401,573; CLIP ln_*; magma/image_prefix.py:106-107).
+ * mean/rstd (fp32 [rows]) may be NULL when no backward is needed. */
+int mb200_layernorm_fwd(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy,
+                        float* mean, float* rstd, int32_t rows, int32_t d, float eps, void* stream);
+/* dx = res + dLN/dx (res may be NULL). */
+int mb200_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const void* gamma,
+                        const float* mean, const float* rstd, const void* res, int64_t ldres, void* dx, int64_t lddx,
+                        int32_t rows, int32_t d, void* stream);
+int mb200_layernorm_param_grad(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
+                               const float* rstd, float* dgamma, float* dbeta, int32_t rows, int32_t d,
+                               int32_t accumulate, void* stream);
+/* rotate_every_two on q,k of a fused [rows][3][H][hd] buffer (hf:gptj/modeling_gptj.py:57-67,190-207). */
+int mb200_rope(void* qkv, int64_t ld, int32_t rows, int32_t S, int32_t H, int32_t hd, int32_t rot, int32_t pos0,
+               int32_t inverse, void* stream);
+/* softmax(scale*s [+ causal mask]) fp32 -> bf16 (GPTJAttention._attn, hf:gptj/modeling_gptj.py:136-147). */
+int mb200_softmax_fwd(const float* s, int64_t lds, int64_t s_bs, void* p, int64_t ldp, int64_t p_bs, int32_t nz,
+                      int32_t Sq, int32_t Sk, float scale, int32_t causal, int32_t koff, void* stream);
+int mb200_softmax_bwd(const float* dp, int64_t lddp, int64_t dp_bs, const void* p, int64_t ldp, int64_t p_bs,
+                      void* ds, int64_t ldds, int64_t ds_bs, int32_t nz, int32_t Sq, int32_t Sk, float scale,
+                      void* stream);
+/* magma/utils.py:334-364 build_labels — int64, bit-exact. captions [B][ldc], labels [B][S], prefix length L. */
+int mb200_build_labels(const int64_t* captions, int64_t ldc, int64_t* labels, int32_t B, int32_t S, int32_t L,
+                       int64_t eos, void* stream);
+/* magma/magma.py:258-267: x[b,:L] = prefix[b]; x[b,L+s] = wte[captions[b,s]]. */
+int mb200_embed_assemble(const int64_t* captions, int64_t ldc, const void* wte, const void* prefix, int32_t L,
+                         void* x, int32_t B, int32_t S, int32_t d, int32_t vocab, void* stream);
+/* word_embedding(ids) (magma/magma.py:205; sampling.py:88-90 input_ids path). */
+int mb200_embed_gather(const int64_t* ids, const void* wte, void* out, int32_t n, int32_t d, int32_t vocab,
+                       void* stream);
+/* ForCausalLMLoss (hf:loss/loss_utils.py:28-67): shifted CE over bf16 logits [B*S][ldv], ignore -100, mean.
+ * row_loss fp32 [B*S], n_valid int32 [1], loss fp32 [1] are device scratch/outputs. When dlogits != NULL it
+ * receives grad_scale * dloss/dlogits (may alias logits). */
+int mb200_cross_entropy(const void* logits, int64_t ldv, const int64_t* labels, int32_t B, int32_t S, int32_t V,
+                        float* row_loss, int32_t* n_valid, float* loss, void* dlogits, float grad_scale,
+                        void* stream);
+int mb200_colsum(const void* x, int64_t ldx, int32_t rows, int32_t cols, float* out, int32_t accumulate,
+                 void* stream);
+/* nn.Dropout (magma/image_prefix.py:104); mask (1 byte/elt) is saved for backward. */
+int mb200_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, void* stream);
+int mb200_dropout_apply(const void* x, const uint8_t* mask, void* y, int64_t n, float p, void* stream);
+/* CLIP conv1 (stride = kernel = P, no bias) as im2col: images [B,3,R,R] -> patches [B*(R/P)^2][ldp]. */
+int mb200_patchify(const void* img, void* patches, int64_t ldp, int32_t B, int32_t R, int32_t P, void* stream);
+/* x[b,0] = cls + pos[0]; x[b,1+p] = pe[b,p] + pos[1+p]  (CLIP VisionTransformer.forward token assembly). */
+int mb200_vit_assemble(void* x, const void* pe, const void* cls, const void* pos, int32_t B, int32_t T, int32_t w,
+                       void* stream);
+/* torch.argmax(logits.float(), -1) (magma/sampling.py:92,97): lowest index wins ties. */
+int mb200_argmax(const void* x, int64_t ldx, int32_t rows, int32_t V, int64_t* out, void* stream);
+int mb200_add(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
+
+/* Fused AdamW over a flat fp32 arena (torch.optim.AdamW(betas=(0.9,0.95)) of train.py:96-101) with global-norm
+ * clipping (gradient_clipping, magma/config.py:126) and refresh of the bf16 compute copy. gnorm_sq: device fp32 [1]
+ * holding sum(grad^2) (mb200_sumsq accumulates into it; zero it first) or NULL for no clipping. */
+int mb200_sumsq(const float* x, int64_t n, float* out, void* stream);
+int mb200_adamw_step(float* master, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                     const float* gnorm_sq, float max_norm, int32_t step, int32_t zero_grad, void* stream);
+int mb200_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int mb200_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Model-level runtime (engine.cu): the whole GPT-J / CLIP-ViT / ImagePrefix forward and backward
+ * scheduled in C++ (one C call per pass instead of ~1000 Python-level op calls).
+ * All weights bf16; trainable-parameter gradients fp32. Pointers not used by a configuration are NULL.
+ * ------------------------------------------------------------------------------------------- */
+enum { MB200_ADAPTER_NONE = 0, MB200_ADAPTER_NORMAL = 1, MB200_ADAPTER_PARALLEL = 2 };
+
+/* Adapter bottleneck (magma/adapters.py:6-39): Linear(d,r) -> ReLU -> Linear(r,d). */
+typedef struct {
+  const void* wd; /* [r, d] */
+  const void* bd; /* [r]    */
+  const void* wu; /* [d, r] */
+  const void* bu; /* [d]    */
+  float* g_wd;    /* fp32 grads, same shapes; NULL => adapter frozen / inference */
+  float* g_bd;
+  float* g_wu;
+  float* g_bu;
+} mb200_adapter;
+
+/* One GPT-J block (hf:gptj/modeling_gptj.py:400-413; fork GPTNeoBlock with jax=True). */
+typedef struct {
+  const void* ln1_g;
+  const void* ln1_b;
+  const void* w_qkv;    /* [3d, d] = cat(q_proj, k_proj, v_proj).weight */
+  const void* w_out;    /* [d, d]  */
+  const void* w_fc_in;  /* [4d, d] */
+  const void* b_fc_in;  /* [4d]    */
+  const void* w_fc_out; /* [d, 4d] */
+  const void* b_fc_out; /* [d]     */
+  mb200_adapter mlp_ad;
+  mb200_adapter attn_ad;
+} mb200_gptj_layer;
+
+typedef struct {
+  int32_t n_layer, d, n_head, rotary_dim;
+  int32_t vocab;           /* logits width V (50258 after resize_token_embeddings, magma/magma.py:50) */
+  int32_t d_ff;            /* 4d */
+  int32_t mlp_adapter;     /* MB200_ADAPTER_* (magma/magma.py:128-149) */
+  int32_t mlp_adapter_r;
+  int32_t attn_adapter;    /* MB200_ADAPTER_* (magma/magma.py:150-169) */
+  int32_t attn_adapter_r;
+  float ln_eps;
+  int32_t _pad;
+  const mb200_gptj_layer* layers; /* host array [n_layer] */
+  const void* lnf_g;
+  const void* lnf_b;
+  const void* w_lm; /* [V, d] */
+  const void* b_lm; /* [V]    */
+} mb200_gptj_model;
+
+/* bytes of caller-provided workspace for a [B,S] pass. training != 0 keeps per-layer activations. */
+size_t mb200_gptj_workspace_bytes(const mb200_gptj_model* m, int32_t B, int32_t S, int32_t S_kv_max,
+                                  int32_t training);
+
+/* GPTJForCausalLM.forward(inputs_embeds=x, labels=labels) as called from magma/magma.py:270-274.
+ *   x      : bf16 [B,S,d] input embeddings
+ *   labels : int64 [B,S] or NULL (no loss)
+ *   logits : bf16 [B*S][ldv] or NULL. With last_only != 0 only the last position of each row is projected
+ *            (logits is then [B][ldv]) — the decode path of magma/sampling.py:92.
+ *   loss   : fp32 [1] device (mean CE) when labels != NULL
+ *   hidden : bf16 [B,S,d] ln_f output or NULL
+ *   kcache/vcache : bf16 [n_layer][B][H][S_kv_max][hd] or NULL; the K/V of this call are written at positions
+ *            [pos0, pos0+S) and attention runs over [0, pos0+S) (use_cache=True, magma/sampling.py:81-90).
+ * training != 0 saves activations in `ws` for mb200_gptj_backward. */
+int mb200_gptj_forward(const mb200_gptj_model* m, const void* x, const int64_t* labels, void* logits, int64_t ldv,
+                       int32_t last_only, float* loss, void* hidden, void* kcache, void* vcache, int32_t S_kv_max,
+                       int32_t pos0, int32_t B, int32_t S, int32_t training, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* Backward of the pass recorded in `ws` (loss.backward() of magma/train_loop.py:18 with the LM frozen:
+ * dgrad through every GEMM, wgrad only for adapters). dx: bf16 [B,S,d] gradient w.r.t. inputs_embeds.
+ * Layers are processed from layer_hi-1 down to layer_lo; the LM-head/CE backward runs when layer_hi == n_layer.
+ * Splitting the range lets the caller overlap the gradient all-reduce of finished layers with the rest.
+ * accumulate != 0 adds into the fp32 gradient buffers (gradient accumulation), else overwrites. */
+int mb200_gptj_backward(const mb200_gptj_model* m, void* dx, float loss_scale, int32_t layer_hi, int32_t layer_lo,
+                        int32_t accumulate, int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream);
+
+/* CLIP VisionTransformer (openai/CLIP model.py; hf:clip/modeling_clip.py:138-219,282-386,647-694). */
+typedef struct {
+  const void *ln1_g, *ln1_b;
+  const void* w_qkv; /* in_proj_weight [3w, w] */
+  const void* b_qkv; /* [3w] */
+  const void* w_out; /* [w, w] */
+  const void* b_out;
+  const void *ln2_g, *ln2_b;
+  const void* w_fc;  /* [mlp, w] */
+  const void* b_fc;
+  const void* w_proj; /* [w, mlp] */
+  const void* b_proj;
+} mb200_vit_layer;
+
+typedef struct {
+  int32_t n_layer, width, n_head, patch, image, mlp, out_dim, _pad;
+  const void* w_conv;  /* [w, 3*P*P] row stride ld_conv (padded to a multiple of 8) */
+  int64_t ld_conv;
+  const void* cls;     /* [w] */
+  const void* pos;     /* [T, w] */
+  const void *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+  const void* proj_t;  /* visual projection stored transposed: [out_dim, w] */
+  const mb200_vit_layer* layers;
+} mb200_vit_model;
+
+size_t mb200_vit_workspace_bytes(const mb200_vit_model* m, int32_t B);
+/* images bf16 [B,3,R,R] -> pooled features bf16 [B, out_dim] (ln_post(x[:,0]) @ proj). Inference only
+ * (the encoder is frozen on the measured path: magma/magma.py:98-100). */
+int mb200_vit_forward(const mb200_vit_model* m, const void* images, void* feats, int32_t B, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* Fused KV-cache attention for one decode step (Sq = 1): q/k/v come from the fused qkv row [B][3][H][hd] (already
+ * rotated); k,v are appended to the cache at position `pos`, then softmax(q K^T / sqrt(hd)) V over [0, pos].
+ * Replaces the torch.cat cache growth + _attn of hf:gptj/modeling_gptj.py:209-214,136-149 per step. */
+int mb200_attn_decode(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, void* out, int64_t ld_out,
+                      int32_t B, int32_t H, int32_t hd, int32_t S_kv_max, int32_t pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

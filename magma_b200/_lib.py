@@ -68,6 +68,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.mb200_last_error.restype = ctypes.c_char_p
         L.mb200_version.restype = ctypes.c_int
+        _setup_signatures(L)
         _lib = L
     return _lib
 
@@ -75,3 +76,86 @@ def lib():
 def check(rc):
     if rc != 0:
         raise MB200Error(f"magma_b200 error {rc}: {lib().mb200_last_error().decode()}")
+
+
+# ---- model-level runtime structs (include/magma_b200.h) ----
+class AdapterC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("wd", "bd", "wu", "bu", "g_wd", "g_bd", "g_wu", "g_bu")]
+
+
+class GptjLayerC(ctypes.Structure):
+    _fields_ = [
+        (n, ctypes.c_void_p)
+        for n in ("ln1_g", "ln1_b", "w_qkv", "w_out", "w_fc_in", "b_fc_in", "w_fc_out", "b_fc_out")
+    ] + [("mlp_ad", AdapterC), ("attn_ad", AdapterC)]
+
+
+class GptjModelC(ctypes.Structure):
+    _fields_ = [
+        ("n_layer", ctypes.c_int32),
+        ("d", ctypes.c_int32),
+        ("n_head", ctypes.c_int32),
+        ("rotary_dim", ctypes.c_int32),
+        ("vocab", ctypes.c_int32),
+        ("d_ff", ctypes.c_int32),
+        ("mlp_adapter", ctypes.c_int32),
+        ("mlp_adapter_r", ctypes.c_int32),
+        ("attn_adapter", ctypes.c_int32),
+        ("attn_adapter_r", ctypes.c_int32),
+        ("ln_eps", ctypes.c_float),
+        ("_pad", ctypes.c_int32),
+        ("layers", ctypes.POINTER(GptjLayerC)),
+        ("lnf_g", ctypes.c_void_p),
+        ("lnf_b", ctypes.c_void_p),
+        ("w_lm", ctypes.c_void_p),
+        ("b_lm", ctypes.c_void_p),
+    ]
+
+
+class VitLayerC(ctypes.Structure):
+    _fields_ = [
+        (n, ctypes.c_void_p)
+        for n in (
+            "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_out", "b_out", "ln2_g", "ln2_b", "w_fc", "b_fc", "w_proj", "b_proj",
+        )
+    ]
+
+
+class VitModelC(ctypes.Structure):
+    _fields_ = [
+        ("n_layer", ctypes.c_int32),
+        ("width", ctypes.c_int32),
+        ("n_head", ctypes.c_int32),
+        ("patch", ctypes.c_int32),
+        ("image", ctypes.c_int32),
+        ("mlp", ctypes.c_int32),
+        ("out_dim", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
+        ("w_conv", ctypes.c_void_p),
+        ("ld_conv", ctypes.c_int64),
+        ("cls", ctypes.c_void_p),
+        ("pos", ctypes.c_void_p),
+        ("ln_pre_g", ctypes.c_void_p),
+        ("ln_pre_b", ctypes.c_void_p),
+        ("ln_post_g", ctypes.c_void_p),
+        ("ln_post_b", ctypes.c_void_p),
+        ("proj_t", ctypes.c_void_p),
+        ("layers", ctypes.POINTER(VitLayerC)),
+    ]
+
+
+def _setup_signatures(L):
+    L.mb200_gptj_workspace_bytes.restype = ctypes.c_size_t
+    L.mb200_vit_workspace_bytes.restype = ctypes.c_size_t
+
+
+EXPORTED_SYMBOLS = [
+    "mb200_version", "mb200_last_error", "mb200_check_device", "mb200_gemm",
+    "mb200_layernorm_fwd", "mb200_layernorm_bwd", "mb200_layernorm_param_grad", "mb200_rope",
+    "mb200_softmax_fwd", "mb200_softmax_bwd", "mb200_build_labels", "mb200_embed_assemble", "mb200_embed_gather",
+    "mb200_cross_entropy", "mb200_colsum", "mb200_dropout_fwd", "mb200_dropout_apply", "mb200_patchify",
+    "mb200_vit_assemble", "mb200_argmax", "mb200_add", "mb200_sumsq", "mb200_adamw_step",
+    "mb200_cast_f32_to_bf16", "mb200_cast_bf16_to_f32",
+    "mb200_gptj_workspace_bytes", "mb200_gptj_forward", "mb200_gptj_backward",
+    "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode",
+]

@@ -1,0 +1,272 @@
+"""Magma — same public API as magma/magma.py (`Magma(config, device)`, `forward`, `embed`, `preprocess_inputs`,
+`generate`, `add_adapters`, `from_checkpoint`), assembled from the re-backed components.
+
+Differences from the reference, all deliberate and documented in DESIGN.md:
+  * the LM is really frozen when `freeze_lm` is set (the reference only sets requires_grad=True on adapters and
+    never False on anything, magma/magma.py:93-96 — SURVEY.md fact 4);
+  * `seq_len` defaults to the LM's max_position_embeddings (2048) like the reference but honours `config.seq_len`
+    and stays a plain attribute (`model.seq_len = 128`);
+  * the word embedding is gathered straight into the fused [B,S,d] input buffer (the reference embeds the full
+    padded caption and slices, magma.py:258-267) — same values;
+  * trainable parameters (adapters, image_prefix.proj/ln) live in one flat fp32 arena with a bf16 compute copy.
+"""
+from copy import deepcopy
+from pathlib import Path
+from typing import List, Literal, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .adapters import Adapter, AdapterWrapper, ParallelAdapter, ParallelAdapterWrapper
+from .arena import ParamArena
+from .config import MultimodalConfig
+from .image_prefix import ImagePrefix
+from .language_model import LMOutput, _LMTrainFn, get_gptj
+from .sampling import generate
+from .utils import build_labels, get_tokenizer, print_main
+
+
+class _EmbedLMFn(torch.autograd.Function):
+    """loss = LM(cat(prefix, wte[captions][:, :S-L]), labels): assembles the input in one gather kernel, runs the
+    fused forward, and routes d(input)[:, :L] back to the image prefix."""
+
+    @staticmethod
+    def forward(ctx, magma, prefix, captions, labels, anchor):
+        lm = magma.lm
+        x = ops.embed_assemble(captions, lm.transformer.wte.weight, prefix.to(torch.bfloat16).contiguous())
+        loss, logits = lm._run_forward(x, labels, training=True)
+        ctx.magma, ctx.generation = magma, lm._generation
+        ctx.shape, ctx.L, ctx.pdtype = x.shape, prefix.shape[1], prefix.dtype
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        lm = ctx.magma.lm
+        if ctx.generation != lm._generation:
+            raise RuntimeError("backward called after another training forward overwrote the saved activations")
+        scale = lm._loss_scale_hint
+        if scale is None:
+            scale = float(dloss)
+        arena = ctx.magma._arena
+        if arena is not None:
+            arena._accumulate_current = arena.grads_live()
+        dx = lm._run_backward(ctx.shape, scale)
+        if arena is not None:
+            arena.publish_grads()
+        dprefix = dx[:, : ctx.L, :].contiguous().to(ctx.pdtype)
+        return None, dprefix, None, None, None
+
+
+class Magma(nn.Module):
+    def __init__(self, config, device=None, init_seed: Optional[int] = 0):
+        super().__init__()
+        if isinstance(config, (str, Path)):
+            config = MultimodalConfig.from_yml(config)
+        else:
+            assert isinstance(config, MultimodalConfig)
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda" if torch.cuda.is_available() else "cpu")
+        if self.device.type != "cuda":
+            raise RuntimeError("magma_b200 has no CPU path: construct Magma on a CUDA (sm_100) device")
+        self.config = config
+        lm_cfg = getattr(config, "_lm_config", None)  # test hook: small architectures
+        self.lm = get_gptj(config=lm_cfg, device=self.device) if lm_cfg is not None else get_gptj(device=self.device)
+        self.seq_len = config.seq_len or self.lm.config.max_position_embeddings
+        self.tokenizer = get_tokenizer("gpt2", sequence_length=self.seq_len)
+        self.image_token = self.tokenizer.cls_token_id
+        self.eos_token = self.tokenizer.eos_token_id
+        n_tok = len(self.tokenizer) if lm_cfg is None else min(len(self.tokenizer), lm_cfg.vocab_size)
+        self.lm.resize_token_embeddings(n_tok)
+        self.lm.config.pad_token_id = self.tokenizer.eos_token_id
+        self.word_embedding = self.lm.transformer.wte
+        self.transformer = self.lm.transformer.h
+        self.mlp_adapter_added, self.attn_adapter_added = False, False
+        self.image_prefix = ImagePrefix(config=config, out_dim=self.lm.config.hidden_size, device=self.device)
+        self.image_prefix_seq_len = self.image_prefix.out_seq_len
+        self.transforms = None
+        try:
+            from .transforms import get_transforms
+
+            self.transforms = get_transforms(config.image_size, config.encoder_name,
+                                             input_resolution=self.image_prefix.enc.input_resolution)
+        except Exception:  # torchvision / PIL preprocessing is host-side and optional
+            self.transforms = None
+
+        if config.adapter_config:
+            mlp_config = deepcopy(config.adapter_config.get("mlp", None))
+            if mlp_config:
+                assert mlp_config.get("adapter_type") is not None
+                self.add_adapters(location="mlp", adapter_type=mlp_config.pop("adapter_type"),
+                                  downsample_factor=mlp_config.pop("downsample_factor", 4), **mlp_config)
+            attn_config = deepcopy(config.adapter_config.get("attention", None))
+            if attn_config:
+                assert attn_config.get("adapter_type") is not None
+                self.add_adapters(location="attention", adapter_type=attn_config.pop("adapter_type"), **attn_config)
+
+        # freezing (intended semantics of magma.py:92-100)
+        if config.freeze_lm:
+            for name, param in self.lm.named_parameters():
+                param.requires_grad = bool(config.adapter_config) and "adapter" in name
+        else:
+            raise NotImplementedError("freeze_lm: false (full LM fine-tuning) is outside the re-backed hot path")
+        for param in self.image_prefix.enc.parameters():
+            param.requires_grad = False
+        self.encoder_trainable_requested = not config.freeze_img_encoder
+        if init_seed is not None:
+            self.lm.init_weights(seed=init_seed)
+            if hasattr(self.image_prefix.enc, "init_weights"):
+                self.image_prefix.enc.init_weights(seed=init_seed + 1)
+        self._arena = None
+        self.finalize()
+
+    # ------------------------------------------------------------------------------------------
+    def finalize(self):
+        """(Re)build the trainable-parameter arena: adapters in reverse layer order (the order their gradients
+        become ready), then the image prefix. Call again after adding/removing trainable parameters."""
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+
+        def order(item):
+            n = item[0]
+            if ".transformer.h." in n:
+                return (0, -int(n.split(".transformer.h.")[1].split(".")[0]))
+            return (1, 0)
+
+        named.sort(key=order)
+        for _, p in named:
+            if p.dtype != torch.float32:
+                p.data = p.data.float()
+        self._arena = ParamArena(named, self.device) if named else None
+        self.lm.invalidate()
+        self.lm.attach_arena(self._arena)
+        self.image_prefix.attach_arena(self._arena)
+        return self
+
+    @property
+    def arena(self):
+        return self._arena
+
+    def add_adapters(self, downsample_factor: int = 4,
+                     adapter_type: Literal["normal", "parallel", "scaled_parallel"] = "normal",
+                     location: Literal["mlp", "attention"] = "mlp", ff_attr: str = "mlp", attn_attr: str = "attn",
+                     **adapter_kwargs):
+        """magma/magma.py:102-174 — in-place rewiring of each block's `.mlp` / `.attn`."""
+        assert adapter_type in ["normal", "parallel", "scaled_parallel"], \
+            "adapter_type must be one of 'normal', 'parallel', or 'scaled_parallel'"
+        assert location in ["mlp", "attention"], "location must be one of 'mlp' or 'attention'"
+        dim = self.lm.config.hidden_size
+
+        def own_params_to_device(mod):
+            for n, p in mod.named_parameters():
+                if n.startswith("adapter"):
+                    p.data = p.data.to(self.device)
+            return mod
+
+        for l in range(len(self.transformer)):
+            if location == "mlp":
+                if self.mlp_adapter_added:
+                    raise ValueError("Adapter layer already added")
+                mlp = getattr(self.transformer[l], ff_attr)
+                if adapter_type in ["parallel", "scaled_parallel"]:
+                    adapter_layer = own_params_to_device(
+                        ParallelAdapter(module=mlp, dim=dim, downsample_factor=downsample_factor,
+                                        scaled=adapter_type == "scaled_parallel", **adapter_kwargs))
+                else:
+                    adpt = own_params_to_device(Adapter(dim=dim, downsample_factor=downsample_factor, **adapter_kwargs))
+                    adapter_layer = nn.Sequential(*[mlp, adpt])
+                setattr(self.transformer[l], ff_attr, adapter_layer)
+            else:
+                if self.attn_adapter_added:
+                    raise ValueError("Adapter layer already added")
+                attn = getattr(self.transformer[l], attn_attr)
+                if adapter_type in ["parallel", "scaled_parallel"]:
+                    adapter_layer = ParallelAdapterWrapper(module=attn, dim=dim, downsample_factor=downsample_factor,
+                                                           scaled="scaled" in adapter_type, **adapter_kwargs)
+                else:
+                    adapter_layer = AdapterWrapper(attn_block=attn, dim=dim, downsample_factor=downsample_factor,
+                                                   **adapter_kwargs)
+                setattr(self.transformer[l], attn_attr, own_params_to_device(adapter_layer))
+        if location == "mlp":
+            self.mlp_adapter_added = True
+        else:
+            self.attn_adapter_added = True
+        self.lm.invalidate()
+
+    def preprocess_inputs(self, input_list: list, embed=True) -> List[torch.Tensor]:
+        """magma/magma.py:176-193."""
+        from .image_input import ImageInput
+
+        for i in range(len(input_list)):
+            inp = input_list[i]
+            if isinstance(inp, str):
+                input_list[i] = self.tokenizer.encode(inp, return_tensors="pt")
+            elif isinstance(inp, ImageInput):
+                input_list[i] = inp.get_transformed_image(transform_fn=self.transforms)
+            else:
+                raise Exception(f"Invalid input type:{type(inp)}")
+        return self.embed(input_list) if embed else input_list
+
+    def embed(self, inputs: List[torch.Tensor]):
+        """magma/magma.py:195-212 (images are forced to half precision there; bf16 here)."""
+        emb_list = []
+        for x in inputs:
+            if x.ndim == 2:
+                emb_list.append(self.word_embedding(x.to(self.device)))
+            elif x.ndim == 4:
+                emb_list.append(self.image_prefix(x.to(self.device).to(torch.bfloat16)))
+            else:
+                raise ValueError(f"Expected 2d or 4d tensor, got {x.ndim}d")
+        return torch.cat(emb_list, dim=1)
+
+    @torch.no_grad()
+    def generate(self, embeddings, max_steps: int = 100, temperature: float = 0.7, top_k: int = 0, top_p: float = 0.9,
+                 decode: bool = True):
+        """magma/magma.py:214-236."""
+        return generate(self, embeddings=embeddings, max_steps=max_steps, temperature=temperature, top_k=top_k,
+                        top_p=top_p, decode=decode)
+
+    def forward(self, images=None, captions=None, output_hidden_states: bool = False, input_embeddings=None):
+        """magma/magma.py:238-276."""
+        assert captions is not None, "Must provide captions in training"
+        assert any([i is not None for i in [images, input_embeddings]]) and not all(
+            [i is not None for i in [images, input_embeddings]]
+        ), "Pass in either images, or input embeddings, not both."
+        assert captions.shape[1] == self.seq_len, (
+            f"in training, captions should be padded to sequence length ({self.seq_len}), "
+            f"but are length {captions.shape[1]}")
+        captions = captions.to(self.device).contiguous()
+        if input_embeddings is None:
+            if self.encoder_trainable_requested and self.training and torch.is_grad_enabled():
+                raise NotImplementedError("freeze_img_encoder: false needs the ViT backward pass (not built yet); "
+                                          "set freeze_img_encoder: true")
+            input_embeddings = self.image_prefix(images)
+        labels = build_labels(input_embeddings, captions, self.eos_token, self.device)
+        trainable = self._arena is not None and torch.is_grad_enabled()
+        if trainable:
+            anchor = self._arena.params[0]
+            loss, logits = _EmbedLMFn.apply(self, input_embeddings, captions, labels, anchor)
+            return LMOutput(loss=loss, logits=logits, past_key_values=None, hidden_states=None)
+        with torch.no_grad():
+            x = ops.embed_assemble(captions, self.lm.transformer.wte.weight,
+                                   input_embeddings.to(torch.bfloat16).contiguous())
+        return self.lm(inputs_embeds=x, labels=labels, output_hidden_states=output_hidden_states)
+
+    @classmethod
+    def from_checkpoint(cls, config_path, checkpoint_path, device="cuda"):
+        """magma/magma.py:278-301. The published checkpoint uses the fork's parameter names; mapping them onto
+        this module's names is the checkpoint-adapter row of the scope table."""
+        import os
+
+        if not os.path.exists(checkpoint_path):
+            raise FileNotFoundError(f"checkpoint {checkpoint_path} does not exist (no network: cannot download)")
+        model = cls(config=config_path, device=device, init_seed=None)
+        sd = torch.load(checkpoint_path, map_location=torch.device("cpu"))
+        if "module" in sd.keys():
+            sd = sd["module"]
+        print_main(f"loading magma checkpoint from: {checkpoint_path}")
+        model.load_state_dict(sd, strict=False)
+        model.finalize()
+        print_main("magma successfully loaded")
+        model.eval()
+        return model

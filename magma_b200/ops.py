@@ -104,3 +104,170 @@ def gemm(
     g.force_bn = force_bn
     check(lib().mb200_gemm(ctypes.byref(g), _stream()))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# HBM-bound operators
+# --------------------------------------------------------------------------------------------
+def _rows(t):
+    """(rows, d, ld) of a [..., d] tensor whose leading dims collapse to a constant row stride."""
+    d = t.shape[-1]
+    if t.dim() == 1:
+        return 1, d, d
+    t2 = t.reshape(-1, d) if t.is_contiguous() else None
+    if t2 is not None:
+        return t2.shape[0], d, d
+    if t.dim() == 2:
+        return t.shape[0], d, t.stride(0)
+    raise ValueError("non-contiguous >2-D tensor: pass a 2-D view with an explicit row stride")
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, save_stats=True, out=None):
+    rows, d, ldx = _rows(x)
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if out is None else out
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    check(lib().mb200_layernorm_fwd(_ptr(x), ctypes.c_int64(ldx), _ptr(gamma), _ptr(beta), _ptr(y),
+                                    ctypes.c_int64(_rows(y)[2]), _ptr(mean), _ptr(rstd), rows, d,
+                                    ctypes.c_float(eps), _stream()))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, res=None):
+    rows, d, ldx = _rows(x)
+    dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().mb200_layernorm_bwd(_ptr(dy), ctypes.c_int64(_rows(dy)[2]), _ptr(x), ctypes.c_int64(ldx), _ptr(gamma),
+                                    _ptr(mean), _ptr(rstd), _ptr(res), ctypes.c_int64(_rows(res)[2] if res is not None else 0),
+                                    _ptr(dx), ctypes.c_int64(d), rows, d, _stream()))
+    return dx
+
+
+def layernorm_param_grad(dy, x, mean, rstd, dgamma, dbeta, accumulate=False):
+    rows, d, ldx = _rows(x)
+    check(lib().mb200_layernorm_param_grad(_ptr(dy), ctypes.c_int64(_rows(dy)[2]), _ptr(x), ctypes.c_int64(ldx),
+                                           _ptr(mean), _ptr(rstd), _ptr(dgamma), _ptr(dbeta), rows, d,
+                                           int(accumulate), _stream()))
+
+
+def rope_(qkv, S, H, hd, rot, pos0=0, inverse=False):
+    """In place on a [rows, 3*H*hd] fused qkv buffer."""
+    rows = qkv.shape[0]
+    check(lib().mb200_rope(_ptr(qkv), ctypes.c_int64(qkv.stride(0)), rows, S, H, hd, rot, pos0, int(inverse), _stream()))
+    return qkv
+
+
+def softmax_fwd(s, scale, causal, koff=0, ldp=None):
+    """s: fp32 [nz, Sq, Sk(ld)] -> bf16 probabilities with the same padded layout."""
+    nz, Sq, Sk = s.shape
+    lds = s.stride(1)
+    p = torch.zeros(nz, Sq, lds, dtype=torch.bfloat16, device=s.device)[..., :Sk]
+    check(lib().mb200_softmax_fwd(_ptr(s), ctypes.c_int64(lds), ctypes.c_int64(s.stride(0)), _ptr(p),
+                                  ctypes.c_int64(p.stride(1)), ctypes.c_int64(p.stride(0)), nz, Sq, Sk,
+                                  ctypes.c_float(scale), int(causal), koff, _stream()))
+    return p
+
+
+def softmax_bwd(dp, p, scale):
+    nz, Sq, Sk = dp.shape
+    ds = torch.zeros(nz, Sq, p.stride(1), dtype=torch.bfloat16, device=dp.device)[..., :Sk]
+    check(lib().mb200_softmax_bwd(_ptr(dp), ctypes.c_int64(dp.stride(1)), ctypes.c_int64(dp.stride(0)), _ptr(p),
+                                  ctypes.c_int64(p.stride(1)), ctypes.c_int64(p.stride(0)), _ptr(ds),
+                                  ctypes.c_int64(ds.stride(1)), ctypes.c_int64(ds.stride(0)), nz, Sq, Sk,
+                                  ctypes.c_float(scale), _stream()))
+    return ds
+
+
+def build_labels(captions, prefix_len, eos_token):
+    """magma/utils.py:334-364 on device; captions int64 [B,S] -> labels int64 [B,S]."""
+    B, S = captions.shape
+    if captions.dtype != torch.int64:
+        raise TypeError("captions must be int64")
+    labels = torch.empty(B, S, dtype=torch.int64, device=captions.device)
+    check(lib().mb200_build_labels(_ptr(captions), ctypes.c_int64(captions.stride(0)), _ptr(labels), B, S,
+                                   int(prefix_len), ctypes.c_int64(int(eos_token)), _stream()))
+    return labels
+
+
+def embed_assemble(captions, wte, prefix, S=None):
+    B, Sc = captions.shape
+    S = Sc if S is None else S
+    L = 0 if prefix is None else prefix.shape[1]
+    V, d = wte.shape
+    x = torch.empty(B, S, d, dtype=torch.bfloat16, device=wte.device)
+    check(lib().mb200_embed_assemble(_ptr(captions), ctypes.c_int64(captions.stride(0)), _ptr(wte), _ptr(prefix), L,
+                                     _ptr(x), B, S, d, V, _stream()))
+    return x
+
+
+def embed_gather(ids, wte):
+    V, d = wte.shape
+    flat = ids.reshape(-1).contiguous()
+    out = torch.empty(*ids.shape, d, dtype=torch.bfloat16, device=wte.device)
+    check(lib().mb200_embed_gather(_ptr(flat), _ptr(wte), _ptr(out), flat.numel(), d, V, _stream()))
+    return out
+
+
+def cross_entropy(logits, labels, V, write_grad=False, grad_scale=1.0):
+    """logits bf16 [B,S,ldv]; returns (loss fp32 [1], dlogits or None)."""
+    B, S = labels.shape
+    ldv = logits.stride(-2)
+    row_loss = torch.empty(B * S, dtype=torch.float32, device=logits.device)
+    n_valid = torch.zeros(4, dtype=torch.int32, device=logits.device)
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    dl = torch.zeros_like(logits) if write_grad else None
+    check(lib().mb200_cross_entropy(_ptr(logits), ctypes.c_int64(ldv), _ptr(labels), B, S, V, _ptr(row_loss),
+                                    _ptr(n_valid), _ptr(loss), _ptr(dl), ctypes.c_float(grad_scale), _stream()))
+    return loss, dl
+
+
+def colsum(x, out=None, accumulate=False):
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    check(lib().mb200_colsum(_ptr(x), ctypes.c_int64(x.stride(0)), rows, cols, _ptr(out), int(accumulate), _stream()))
+    return out
+
+
+def dropout_fwd(x, p, seed):
+    y = torch.empty_like(x)
+    mask = torch.empty(x.numel(), dtype=torch.uint8, device=x.device)
+    check(lib().mb200_dropout_fwd(_ptr(x), _ptr(y), _ptr(mask), ctypes.c_int64(x.numel()), ctypes.c_float(p),
+                                  ctypes.c_uint64(seed), _stream()))
+    return y, mask
+
+
+def dropout_apply(x, mask, p):
+    y = torch.empty_like(x)
+    check(lib().mb200_dropout_apply(_ptr(x), _ptr(mask), _ptr(y), ctypes.c_int64(x.numel()), ctypes.c_float(p), _stream()))
+    return y
+
+
+def argmax(x, V=None):
+    rows = x.shape[0]
+    V = x.shape[1] if V is None else V
+    out = torch.empty(rows, dtype=torch.int64, device=x.device)
+    check(lib().mb200_argmax(_ptr(x), ctypes.c_int64(x.stride(0)), rows, V, _ptr(out), _stream()))
+    return out
+
+
+def add(a, b, c=None):
+    y = torch.empty_like(a)
+    check(lib().mb200_add(_ptr(a), _ptr(b), _ptr(c), _ptr(y), ctypes.c_int64(a.numel()), _stream()))
+    return y
+
+
+def cast_f32_to_bf16(src, dst):
+    check(lib().mb200_cast_f32_to_bf16(_ptr(src), _ptr(dst), ctypes.c_int64(src.numel()), _stream()))
+
+
+def sumsq(x, out):
+    check(lib().mb200_sumsq(_ptr(x), ctypes.c_int64(x.numel()), _ptr(out), _stream()))
+
+
+def adamw_step(master, grad, m1, m2, shadow, lr, beta1, beta2, eps, wd, grad_scale, gnorm_sq, max_norm, step,
+               zero_grad=True):
+    check(lib().mb200_adamw_step(_ptr(master), _ptr(grad), _ptr(m1), _ptr(m2), _ptr(shadow),
+                                 ctypes.c_int64(master.numel()), ctypes.c_float(lr), ctypes.c_float(beta1),
+                                 ctypes.c_float(beta2), ctypes.c_float(eps), ctypes.c_float(wd),
+                                 ctypes.c_float(grad_scale), _ptr(gnorm_sq), ctypes.c_float(max_norm), int(step),
+                                 int(zero_grad), _stream()))

@@ -1,0 +1,97 @@
+"""Sampling / decode loop — drop-in for magma/sampling.py (same function names and arguments).
+
+`generate` keeps the reference's structure (prefill with inputs_embeds, then one token per step through the KV
+cache) but: the cache is a static [layer,B,H,S_max,hd] buffer appended in place by the fused decode-attention
+kernel (no torch.cat growth), the LM head runs on the B last-position rows only, temperature-0 argmax is a device
+kernel with torch.argmax tie-breaking (lowest index), and the all-EOS early-exit check (sampling.py:109) is polled
+every `eos_check_every` steps instead of forcing a host sync per token — emitted tokens are identical because
+rows are truncated at the first all-EOS step afterwards."""
+from typing import List, Union
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+def top_p_filter(logits, threshold: float = 0.9):
+    """magma/sampling.py:7-19 — reproduced including its inverted-nucleus comparison (`cum_probs < 1 - threshold`,
+    shifted right by one). Runs with torch ops: sampling (T > 0) is a later row of the scope table (§8f rank 4)."""
+    sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+    cum_probs = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
+    sorted_indices_to_remove = cum_probs < (1 - threshold)
+    sorted_indices_to_remove[..., 1:] = sorted_indices_to_remove[..., :-1].clone()
+    sorted_indices_to_remove[..., 0] = 0
+    sorted_logits[sorted_indices_to_remove] = float("-inf")
+    return sorted_logits.scatter(1, sorted_indices, sorted_logits)
+
+
+def top_k_filter(logits, k):
+    """magma/sampling.py:22-30."""
+    assert k > 0
+    val, ind = torch.topk(logits, k)
+    probs = torch.full_like(logits, float("-inf"))
+    probs.scatter_(1, ind, val)
+    return probs
+
+
+def remove_tokens_after_eos(tensor, eos_token, image_token):
+    """magma/sampling.py:33-40."""
+    eos_index = (tensor == eos_token).nonzero()
+    if eos_index.any():
+        tensor[eos_index[0]:] = eos_token
+    tensor = tensor.tolist()
+    return [i for i in tensor if (not i == image_token) and (not i == eos_token)]
+
+
+@torch.no_grad()
+def generate(model, embeddings, max_steps: int = 100, temperature: float = 0.7, top_k: int = 0, top_p: float = 0.9,
+             eos_token: int = None, decode: bool = True, eos_check_every: int = 16) -> Union[List[str], torch.Tensor]:
+    """magma/sampling.py:43-121."""
+    eos_token = eos_token or model.eos_token
+    was_training = model.training
+    model.eval()
+    lm = model.lm
+    b, s, _ = embeddings.shape
+    dev = embeddings.device
+    out = torch.full((b, s + max_steps), model.image_token, dtype=torch.long, device=dev)  # :75, preallocated
+    cache = None
+    n_done = max_steps
+    all_eos = torch.zeros(max_steps, dtype=torch.bool, device=dev)
+    for i in range(max_steps):
+        if i == 0:
+            from .language_model import KVCache
+
+            cfg = lm.config
+            cache = KVCache(cfg.num_layers, b, cfg.num_heads, s + max_steps, cfg.hidden_size // cfg.num_heads, dev)
+            logits = lm.decode_logits(embeddings, cache)                       # :81-85 (prefill)
+        else:
+            x = lm.transformer.wte(out[:, s + i - 1: s + i])                    # :88-90 (input_ids path)
+            logits = lm.decode_logits(x, cache)
+        if temperature == 0.0:
+            next_token = ops.argmax(logits.contiguous() if logits.stride(-1) != 1 else logits, logits.shape[-1])  # :97
+        else:
+            lg = logits.float()                                                 # :92
+            if top_k > 0:
+                lg = top_k_filter(lg, k=top_k)
+            if top_p > 0:
+                lg = top_p_filter(lg, threshold=top_p)
+            probs = F.softmax(lg / temperature, dim=-1)
+            next_token = torch.multinomial(probs, num_samples=1).squeeze(1)
+        out[:, s + i] = next_token                                              # :107
+        if eos_token is not None:
+            all_eos[i] = (next_token == eos_token).all()                        # :109, evaluated lazily
+            if (i + 1) % eos_check_every == 0 or i == max_steps - 1:
+                hit = all_eos[: i + 1].nonzero()
+                if hit.numel():
+                    n_done = int(hit[0]) + 1
+                    break
+    out = out[:, : s + n_done]
+    if decode:
+        captions = []
+        for row in out:
+            row = remove_tokens_after_eos(row, eos_token, model.image_token)
+            captions.append(model.tokenizer.decode(row))
+        out = captions
+    model.train(was_training)
+    return out

@@ -1,0 +1,128 @@
+"""Training step — drop-in for magma/train_loop.py (`train_step`, `eval_step`) plus `B200Engine`, the object that
+stands where the DeepSpeed engine stood (train.py:103-111): `engine(images, captions)`, `engine.backward(loss)`,
+`engine.step()`.
+
+Data parallelism is the reference's only strategy. With the LM frozen the only exchange is the
+gradient of the ~0.24 B trainable parameters, which live in one flat fp32 arena: the engine all-reduces contiguous
+arena slices over NCCL on a side stream as soon as the backward pass has finished the layers they belong to
+(backward is issued in layer chunks), so the exchange overlaps the remaining backward; the fused AdamW kernel then
+applies 1/world averaging, global-norm clipping and the bf16 weight refresh in one pass."""
+import torch
+import torch.distributed as dist
+
+from .utils import reduce_losses
+
+
+class B200Engine:
+    def __init__(self, model, config, n_buckets: int = 4, betas=(0.9, 0.95), eps=1e-8):
+        self.module = model
+        self.config = config
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.grad_accum = max(1, int(getattr(config, "gradient_accumulation_steps", 1) or 1))
+        self.micro_step = 0
+        self.global_step = 0
+        self.betas, self.eps = betas, eps
+        self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
+        self._pending = []
+        n = len(model.lm.transformer.h)
+        nb = max(1, min(n_buckets, n))
+        bounds = [round(i * n / nb) for i in range(nb + 1)]
+        self.chunks = [(bounds[i + 1], bounds[i]) for i in reversed(range(nb))]  # (hi, lo), last layers first
+
+    # DeepSpeed-engine surface used by the reference -------------------------------------------------
+    def __call__(self, images, captions):
+        return self.module(images, captions)
+
+    def train(self, mode=True):
+        self.module.train(mode)
+        return self
+
+    def eval(self):
+        self.module.eval()
+        return self
+
+    def _is_boundary(self):
+        return (self.micro_step + 1) % self.grad_accum == 0
+
+    def _allreduce_slice(self, lo, hi):
+        arena = self.module.arena
+        if self.world == 1 or lo is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(arena.grad[lo:hi], op=dist.ReduceOp.SUM)
+
+    def backward(self, loss):
+        """engine.backward (train_loop.py:18): loss/grad_accum scaling, chunked backward with overlapped all-reduce
+        at the accumulation boundary."""
+        lm = self.module.lm
+        arena = self.module.arena
+        lm._loss_scale_hint = 1.0 / self.grad_accum
+        lm._bwd_chunks = self.chunks
+        boundary = self._is_boundary()
+        if boundary and self.world > 1:
+            def after(hi, lo):
+                s = arena.slice_for([f"lm.transformer.h.{l}." for l in range(lo, hi)])
+                self._allreduce_slice(*s)
+            lm._after_chunk = after
+        else:
+            lm._after_chunk = None
+        try:
+            loss.backward()
+        finally:
+            lm._loss_scale_hint = None
+            lm._after_chunk = None
+        if boundary and self.world > 1:
+            self._allreduce_slice(*arena.slice_for(["image_prefix."]))
+
+    def step(self):
+        """engine.step (train_loop.py:19): optimizer step at the accumulation boundary only."""
+        boundary = self._is_boundary()
+        self.micro_step += 1
+        if not boundary:
+            return
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        cfg = self.config
+        lr = cfg.lr_at(self.global_step) if hasattr(cfg, "lr_at") else cfg.lr
+        self.module.arena.adamw_step(lr=lr, betas=self.betas, eps=self.eps,
+                                     weight_decay=float(getattr(cfg, "weight_decay", 0.0) or 0.0),
+                                     grad_scale=1.0 / self.world,
+                                     max_norm=float(getattr(cfg, "gradient_clipping", 0.0) or 0.0))
+        self.global_step += 1
+
+
+def _to_device(images, captions):
+    return images.cuda(non_blocking=True).to(torch.bfloat16), captions.cuda(non_blocking=True)
+
+
+def train_step(config, train_loader, model_engine):
+    """magma/train_loop.py:7-21 (images.half() there; bf16 here)."""
+    losses = []
+    for _ in range(config.gradient_accumulation_steps):
+        images, captions = next(train_loader)
+        images, captions = _to_device(images, captions)
+        if config.run_blind:
+            images = torch.zeros_like(images)
+        outputs = model_engine(images, captions)
+        loss = outputs.loss
+        losses.append(loss.detach())
+        model_engine.backward(loss)
+        model_engine.step()
+    return reduce_losses(torch.mean(torch.stack(losses))).item()
+
+
+def eval_step(config, eval_loader, model_engine):
+    """magma/train_loop.py:48-60."""
+    losses = []
+    with torch.no_grad():
+        for _ in range(config.eval_steps):
+            images, captions = next(eval_loader)
+            images, captions = _to_device(images, captions)
+            if config.run_blind:
+                images = torch.zeros_like(images)
+            outputs = model_engine(images, captions)
+            losses.append(outputs.loss)
+    return reduce_losses(torch.mean(torch.stack(losses))).item()

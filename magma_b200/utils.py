@@ -1,0 +1,95 @@
+"""Host-side helpers mirroring magma/utils.py for the hot path: build_labels (device kernel), tokenizer seam,
+distributed helpers (torch.distributed over NCCL, env contract of utils.py:255-269)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def is_main():
+    return (not dist.is_initialized()) or dist.get_rank() == 0
+
+
+def print_main(*msg):
+    if is_main():
+        print(*msg)
+
+
+def reduce_losses(losses):
+    """magma/utils.py:26-34 — SUM all-reduce / world size."""
+    if dist.is_initialized():
+        losses = losses.detach().clone()
+        dist.all_reduce(losses, dist.ReduceOp.SUM)
+        return losses / dist.get_world_size()
+    return losses
+
+
+def build_labels(input_embeddings, captions, eos_token, device=None):
+    """Drop-in for magma/utils.py:334-364 (same signature). The Python double loop of the reference (one device
+    sync per token) is one integer kernel here; the result is bit-identical."""
+    shape = input_embeddings.shape[:2]
+    assert captions.shape[1] >= shape[1]
+    return ops.build_labels(captions.contiguous(), int(shape[1]), int(eos_token))
+
+
+class IdTokenizer:
+    """Offline stand-in for GPT2TokenizerFast + '<|image|>' (magma/utils.py:43-58): same ids and length
+    (eos=pad=50256, cls=50257, len=50258). Text <-> id conversion needs the GPT-2 vocabulary files, which are not
+    available offline; encode/decode here are byte-level placeholders."""
+
+    cls_token_id = 50257
+    eos_token_id = 50256
+    pad_token_id = 50256
+    padding_side = "right"
+
+    def __init__(self, sequence_length=2048):
+        self.model_max_length = sequence_length
+
+    def __len__(self):
+        return 50258
+
+    def encode(self, text, return_tensors=None, **_):
+        ids = list(text.encode("utf-8"))
+        return torch.tensor([ids], dtype=torch.long) if return_tensors == "pt" else ids
+
+    def decode(self, ids, **_):
+        return bytes(int(i) % 256 for i in ids).decode("utf-8", errors="replace")
+
+
+def get_tokenizer(name="gpt2", sequence_length=2048):
+    """magma/utils.py:43-58. Uses the real GPT-2 tokenizer when its files are cached locally, else IdTokenizer."""
+    if name != "gpt2":
+        raise ValueError(f"Tokenizer {name} not recognized")
+    try:
+        from transformers import GPT2TokenizerFast
+
+        tok = GPT2TokenizerFast.from_pretrained("gpt2", local_files_only=True)
+        tok.pad_token_id = tok.eos_token_id
+        tok.padding_side = "right"
+        tok.model_max_length = sequence_length
+        tok.add_special_tokens({"cls_token": "<|image|>"})
+        return tok
+    except Exception:
+        return IdTokenizer(sequence_length)
+
+
+def init_distributed(backend="nccl"):
+    """One process per GPU; RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment (utils.py:255-269)."""
+    if dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+        return dist.get_rank(), world, local_rank
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    return 0, 1, local_rank
