@@ -55,6 +55,12 @@ int mb200_version(void);
 const char* mb200_last_error(void);
 /* 0 when the current CUDA device is sm_100 (B200), MB200_E_ARCH otherwise. */
 int mb200_check_device(void);
+/* number of kernels this library has launched since load (bench.py reports the delta as gpu_launches). */
+long long mb200_launch_count(void);
+/* optional per-launch CUDA-event timing of the GEMM core (used by bench.py for the roofline numbers):
+ * enable, run, then read {sum of launch durations in ms, algorithmic FLOPs, algorithmic bytes, launches}. */
+int mb200_prof_enable(int on);
+int mb200_prof_read(double* gemm_ms, double* gemm_flops, double* gemm_bytes, long long* gemm_launches);
 
 /* -------------------------------------------------------------------------------------------
  * GEMM core (tcgen05.mma + TMEM accumulators + TMA operand staging, persistent, warp-specialised)

@@ -147,10 +147,12 @@ class VitModelC(ctypes.Structure):
 def _setup_signatures(L):
     L.mb200_gptj_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_vit_workspace_bytes.restype = ctypes.c_size_t
+    L.mb200_launch_count.restype = ctypes.c_longlong
 
 
 EXPORTED_SYMBOLS = [
     "mb200_version", "mb200_last_error", "mb200_check_device", "mb200_gemm",
+    "mb200_launch_count", "mb200_prof_enable", "mb200_prof_read",
     "mb200_layernorm_fwd", "mb200_layernorm_bwd", "mb200_layernorm_param_grad", "mb200_rope",
     "mb200_softmax_fwd", "mb200_softmax_bwd", "mb200_build_labels", "mb200_embed_assemble", "mb200_embed_gather",
     "mb200_cross_entropy", "mb200_colsum", "mb200_dropout_fwd", "mb200_dropout_apply", "mb200_patchify",

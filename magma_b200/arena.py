@@ -6,7 +6,7 @@ gradient exchange is a handful of large NCCL all-reduces over contiguous slices 
 reduce-scatter/all-gather, train.py:103-111), and the optimizer step is one fused kernel over the arena."""
 import torch
 
-from . import ops
+from . import dp, ops
 
 
 class ParamArena:
@@ -15,11 +15,7 @@ class ParamArena:
         (last layer first), so early slices can be all-reduced while the rest of backward runs."""
         self.names = [n for n, _ in named_params]
         self.params = [p for _, p in named_params]
-        self.offsets = []
-        off = 0
-        for p in self.params:
-            self.offsets.append(off)
-            off += (p.numel() + 63) // 64 * 64  # keep every view 256-byte aligned
+        self.offsets, off = dp.arena_layout([p.numel() for p in self.params])
         self.numel = off
         self.master = torch.zeros(off, dtype=torch.float32, device=device)
         self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=device)
@@ -75,15 +71,9 @@ class ParamArena:
         """True when the parameters still hold gradients from an earlier backward (=> accumulate)."""
         return any(p.grad is not None for p in self.params)
 
-    def slice_for(self, first_name_prefixes):
+    def slice_for(self, prefixes):
         """(lo, hi) element range covering every parameter whose name starts with one of the prefixes."""
-        lo, hi = None, None
-        for n, p, o in zip(self.names, self.params, self.offsets):
-            if any(n.startswith(pre) for pre in first_name_prefixes):
-                lo = o if lo is None else min(lo, o)
-                e = o + (p.numel() + 63) // 64 * 64
-                hi = e if hi is None else max(hi, e)
-        return lo, hi
+        return dp.slice_for(self.names, [p.numel() for p in self.params], self.offsets, prefixes)
 
     def adamw_step(self, lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, grad_scale=1.0, max_norm=0.0):
         if self.exp_avg is None:

@@ -50,9 +50,88 @@ int check_arch() {
   return cached;
 }
 
+// ---------------------------------------------------------------------------------------------
+// launch counter + per-GEMM event profiler
+// ---------------------------------------------------------------------------------------------
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launches() { return g_launches; }
+
+static const int kProfMax = 16384;
+struct ProfState {
+  bool enabled = false;
+  int n = 0;
+  cudaEvent_t* ev0 = nullptr;
+  cudaEvent_t* ev1 = nullptr;
+  double* flops = nullptr;
+  double* bytes = nullptr;
+  int created = 0;
+};
+static ProfState g_prof;
+
+GemmProfScope::GemmProfScope(cudaStream_t s, double fl, double by) : on(false), st(s), slot(-1) {
+  if (!g_prof.enabled || g_prof.n >= kProfMax) return;
+  if (!g_prof.ev0) {
+    g_prof.ev0 = new cudaEvent_t[kProfMax];
+    g_prof.ev1 = new cudaEvent_t[kProfMax];
+    g_prof.flops = new double[kProfMax];
+    g_prof.bytes = new double[kProfMax];
+  }
+  slot = g_prof.n++;
+  if (slot >= g_prof.created) {
+    cudaEventCreate(&g_prof.ev0[slot]);
+    cudaEventCreate(&g_prof.ev1[slot]);
+    g_prof.created = slot + 1;
+  }
+  g_prof.flops[slot] = fl;
+  g_prof.bytes[slot] = by;
+  cudaEventRecord(g_prof.ev0[slot], st);
+  on = true;
+}
+GemmProfScope::~GemmProfScope() {
+  if (on) cudaEventRecord(g_prof.ev1[slot], st);
+}
+
+void prof_enable(int on) {
+  g_prof.enabled = on != 0;
+  g_prof.n = 0;
+}
+int prof_read(double* ms, double* flops, double* bytes, long long* n) {
+  double tms = 0, tf = 0, tb = 0;
+  for (int i = 0; i < g_prof.n; ++i) {
+    float e = 0.f;
+    cudaError_t err = cudaEventSynchronize(g_prof.ev1[i]);
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&e, g_prof.ev0[i], g_prof.ev1[i]);
+    if (err != cudaSuccess) return check_cuda(err, "prof_read");
+    tms += e;
+    tf += g_prof.flops[i];
+    tb += g_prof.bytes[i];
+  }
+  *ms = tms;
+  *flops = tf;
+  *bytes = tb;
+  *n = g_prof.n;
+  g_prof.n = 0;
+  return 0;
+}
+
 }  // namespace mb200
 
-namespace mb200 { const char* last_error(); }
+namespace mb200 {
+const char* last_error();
+long long launches();
+void prof_enable(int on);
+int prof_read(double* ms, double* flops, double* bytes, long long* n);
+}
+
+extern "C" long long mb200_launch_count(void) { return mb200::launches(); }
+extern "C" int mb200_prof_enable(int on) {
+  mb200::prof_enable(on);
+  return 0;
+}
+extern "C" int mb200_prof_read(double* gemm_ms, double* gemm_flops, double* gemm_bytes, long long* gemm_launches) {
+  return mb200::prof_read(gemm_ms, gemm_flops, gemm_bytes, gemm_launches);
+}
 
 extern "C" int mb200_version(void) { return MB200_VERSION; }
 extern "C" const char* mb200_last_error(void) { return mb200::last_error(); }

@@ -37,6 +37,16 @@ int check_cuda(cudaError_t e, const char* what);
 int num_sms();
 int check_arch();  // 0 if the current device is sm_100, else MB200_E_ARCH
 
+// launch accounting (mb200_launch_count) and optional per-GEMM CUDA-event timing (mb200_prof_*)
+void count_launch(int n = 1);
+struct GemmProfScope {
+  bool on;
+  cudaStream_t st;
+  int slot;
+  GemmProfScope(cudaStream_t s, double flops, double bytes);
+  ~GemmProfScope();
+};
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

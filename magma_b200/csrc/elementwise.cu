@@ -635,7 +635,11 @@ using namespace mb200;
     int _rc = mb200::check_arch(); \
     if (_rc) return _rc;           \
   } while (0)
-#define MB_LAUNCH_CHECK() MB_CUDA(cudaGetLastError())
+#define MB_LAUNCH_CHECK()           \
+  do {                              \
+    mb200::count_launch();          \
+    MB_CUDA(cudaGetLastError());    \
+  } while (0)
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int mb200_layernorm_fwd(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y,
@@ -748,6 +752,7 @@ extern "C" int mb200_cross_entropy(const void* logits, int64_t ldv, const int64_
   ce_row_kernel<<<B * S, kCeThreads, 0, ST(stream)>>>((const bf16*)logits, ldv, (const long long*)labels, S, V,
                                                       n_valid, row_loss, (bf16*)dlogits, grad_scale);
   ce_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_loss, B * S, n_valid, loss);
+  mb200::count_launch(2);
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -409,6 +409,7 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
       bf16* vc = vcache + (size_t)l * cache_layer;
       const size_t smem = (((size_t)(pos0 + 1) + 31) & ~(size_t)31) * 4 + 32 * 4;
       attn_decode_kernel<<<B * H, kDecThreads, smem, st>>>(a.qkv, 3 * d, kc, vc, a.attn_o, d, H, hd, Smax, pos0);
+      count_launch();
       MB_CUDA(cudaGetLastError());
     } else {
       Mat Q = mat(a.qkv, 3 * d, 0, hd, (long long)S * 3 * d);
@@ -420,7 +421,8 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
         int grid = (int)((tot + 255) / 256);
         if (grid > num_sms() * 8) grid = num_sms() * 8;
         kv_append_kernel<<<grid, 256, 0, st>>>(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0);
-        MB_CUDA(cudaGetLastError());
+        count_launch();
+      MB_CUDA(cudaGetLastError());
         Kk = mat(kc, hd, 0, (long long)Smax * hd, (long long)H * Smax * hd);
         Vv = mat(vc, hd, 1, (long long)Smax * hd, (long long)H * Smax * hd);
       } else {
@@ -767,6 +769,7 @@ extern "C" int mb200_attn_decode(const void* qkv, int64_t ld_qkv, void* kcache, 
   attn_decode_kernel<<<B * H, kDecThreads, smem, (cudaStream_t)stream>>>((const bf16*)qkv, ld_qkv, (bf16*)kcache,
                                                                          (bf16*)vcache, (bf16*)out, ld_out, H, hd,
                                                                          S_kv_max, pos);
+  count_launch();
   MB_CUDA(cudaGetLastError());
   return 0;
 }

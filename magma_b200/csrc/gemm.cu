@@ -436,7 +436,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     attr_set = true;
   }
   int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
-  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(tmA, tmB, kp);
+  {
+    const double nb = (double)kp.total_tiles / ((double)kp.tiles_m * kp.tiles_n);
+    const double flops = 2.0 * kp.M * (double)kp.N * kp.K * nb;
+    const double bytes = nb * (2.0 * ((double)kp.M * kp.K + (double)kp.N * kp.K) + (double)sizeof(OutT) * kp.M * kp.N);
+    GemmProfScope prof(stream, flops, bytes);
+    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(tmA, tmB, kp);
+  }
+  count_launch();
   MB_CUDA(cudaGetLastError());
   return 0;
 }

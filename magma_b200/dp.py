@@ -1,0 +1,61 @@
+"""Data-parallel host logic (pure Python, device-agnostic so it is testable with gloo on CPU).
+
+The reference's only parallelism is DP under DeepSpeed ZeRO-2 (train.py:103-111). Here every rank
+holds the full (frozen) model and a flat fp32 gradient arena for the ~0.24 B trainable parameters; the arena is
+laid out in the order gradients become ready in backward (last GPT-J layer first, image prefix last) and is
+all-reduced slice by slice as backward proceeds."""
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+ALIGN = 64  # elements; keeps every parameter view 256-byte aligned
+
+
+def arena_layout(numels: Sequence[int]) -> Tuple[List[int], int]:
+    """Offsets (in elements) of each parameter in the flat arena and the total padded length."""
+    offs, off = [], 0
+    for n in numels:
+        offs.append(off)
+        off += (n + ALIGN - 1) // ALIGN * ALIGN
+    return offs, off
+
+
+def backward_order_key(name: str):
+    """Sort key: GPT-J layers descending (their gradients are produced first), then everything else."""
+    if ".transformer.h." in name:
+        return (0, -int(name.split(".transformer.h.")[1].split(".")[0]))
+    return (1, 0)
+
+
+def layer_chunks(n_layer: int, n_buckets: int) -> List[Tuple[int, int]]:
+    """[(layer_hi, layer_lo), ...] covering [0, n_layer) from the top down in n_buckets nearly equal chunks."""
+    nb = max(1, min(n_buckets, n_layer))
+    bounds = [round(i * n_layer / nb) for i in range(nb + 1)]
+    return [(bounds[i + 1], bounds[i]) for i in reversed(range(nb))]
+
+
+def slice_for(names: Sequence[str], numels: Sequence[int], offsets: Sequence[int], prefixes: Sequence[str]):
+    """(lo, hi) element range of the arena covering all parameters whose name starts with one of `prefixes`
+    (None, None when there is none)."""
+    lo = hi = None
+    for n, k, o in zip(names, numels, offsets):
+        if any(n.startswith(p) for p in prefixes):
+            e = o + (k + ALIGN - 1) // ALIGN * ALIGN
+            lo = o if lo is None else min(lo, o)
+            hi = e if hi is None else max(hi, e)
+    return lo, hi
+
+
+def allreduce_slice(flat_grad: torch.Tensor, lo, hi, group=None):
+    """SUM all-reduce of one contiguous arena slice (averaging by 1/world is folded into the optimizer kernel)."""
+    if lo is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=group)
+
+
+def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rank `rank` takes samples [lo, hi) of the global batch (rank i takes [8i, 8i+8))."""
+    per = global_batch // world
+    assert per * world == global_batch, "global batch must divide evenly across ranks"
+    return rank * per, (rank + 1) * per

@@ -17,7 +17,7 @@ from typing import List, Literal, Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import dp, ops
 from .adapters import Adapter, AdapterWrapper, ParallelAdapter, ParallelAdapterWrapper
 from .arena import ParamArena
 from .config import MultimodalConfig
@@ -127,13 +127,7 @@ class Magma(nn.Module):
         become ready), then the image prefix. Call again after adding/removing trainable parameters."""
         named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
 
-        def order(item):
-            n = item[0]
-            if ".transformer.h." in n:
-                return (0, -int(n.split(".transformer.h.")[1].split(".")[0]))
-            return (1, 0)
-
-        named.sort(key=order)
+        named.sort(key=lambda item: dp.backward_order_key(item[0]))
         for _, p in named:
             if p.dtype != torch.float32:
                 p.data = p.data.float()

@@ -10,6 +10,7 @@ applies 1/world averaging, global-norm clipping and the bf16 weight refresh in o
 import torch
 import torch.distributed as dist
 
+from . import dp
 from .utils import reduce_losses
 
 
@@ -24,10 +25,7 @@ class B200Engine:
         self.betas, self.eps = betas, eps
         self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
         self._pending = []
-        n = len(model.lm.transformer.h)
-        nb = max(1, min(n_buckets, n))
-        bounds = [round(i * n / nb) for i in range(nb + 1)]
-        self.chunks = [(bounds[i + 1], bounds[i]) for i in reversed(range(nb))]  # (hi, lo), last layers first
+        self.chunks = dp.layer_chunks(len(model.lm.transformer.h), n_buckets)  # (hi, lo), last layers first
 
     # DeepSpeed-engine surface used by the reference -------------------------------------------------
     def __call__(self, images, captions):
@@ -52,7 +50,7 @@ class B200Engine:
         ev.record(torch.cuda.current_stream())
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(arena.grad[lo:hi], op=dist.ReduceOp.SUM)
+            dp.allreduce_slice(arena.grad, lo, hi)
 
     def backward(self, loss):
         """engine.backward (train_loop.py:18): loss/grad_accum scaling, chunked backward with overlapped all-reduce

@@ -31,6 +31,8 @@ def build_labels(input_embeddings, captions, eos_token, device=None):
     sync per token) is one integer kernel here; the result is bit-identical."""
     shape = input_embeddings.shape[:2]
     assert captions.shape[1] >= shape[1]
+    if shape[1] == 0:  # reference quirk (utils.py:352-355): captions[:, :-0] is empty -> labels is [b, 0]
+        return torch.empty(captions.shape[0], 0, dtype=torch.int64, device=captions.device)
     return ops.build_labels(captions.contiguous(), int(shape[1]), int(eos_token))
 
 
@@ -70,6 +72,8 @@ def get_tokenizer(name="gpt2", sequence_length=2048):
         tok.padding_side = "right"
         tok.model_max_length = sequence_length
         tok.add_special_tokens({"cls_token": "<|image|>"})
+        if len(tok) != 50258 or tok.eos_token_id != 50256 or tok.cls_token_id != 50257:
+            raise RuntimeError("incomplete local GPT-2 tokenizer files")
         return tok
     except Exception:
         return IdTokenizer(sequence_length)

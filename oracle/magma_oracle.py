@@ -126,10 +126,10 @@ def build_labels(prefix_len: int, captions: np.ndarray, eos_token: int) -> np.nd
     captions = np.asarray(captions, dtype=np.int64)
     b, s = captions.shape
     assert s >= prefix_len  # utils.py:349
-    labels = np.concatenate(
-        [np.full((b, prefix_len), -100, dtype=np.int64), captions[:, : s - prefix_len] if prefix_len else captions],
-        axis=1,
-    )  # utils.py:352-355  (captions[:, :-L])
+    # utils.py:352-355, literally: cat(-100 * [b, L], captions[:, :-L]). NB for L == 0 the slice `[:, :-0]` is EMPTY,
+    # so the reference returns a [b, 0] tensor; reproduced here because integer paths are bit-exact by contract.
+    labels = np.concatenate([np.full((b, prefix_len), -100, dtype=np.int64), captions[:, : s - prefix_len if prefix_len else 0]],
+                            axis=1)
     for i in range(b):  # utils.py:358-362: everything AFTER the first eos becomes -100 (the eos itself stays)
         hits = np.nonzero(labels[i] == eos_token)[0]
         if hits.size:

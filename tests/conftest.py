@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA (sm_100 / B200) device; run with `-m gpu`")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+def oracle_cfg_from_record(rec):
+    from oracle.magma_oracle import OracleConfig
+
+    lm, vit = rec["lm"], rec["vit"]
+    ac = rec["adapter_config"] or {}
+    return OracleConfig(
+        d=lm["n_embd"], n_layer=lm["n_layer"], n_head=lm["n_head"], rotary_dim=lm["rotary_dim"],
+        vocab=rec["weights"]["lm.lm_head.weight"].shape[0],
+        mlp_adapter=ac.get("mlp"), attn_adapter=ac.get("attention"), image_seq_len=2,
+        enc_out_dim=vit["projection_dim"], use_image_embed_layernorm=True, vit_width=vit["hidden_size"],
+        vit_layers=vit["num_hidden_layers"], vit_heads=vit["num_attention_heads"], vit_patch=vit["patch_size"],
+        vit_image=vit["image_size"], vit_mlp=vit["intermediate_size"], eos_token=rec["eos"], image_token=rec["cls"])

@@ -182,16 +182,26 @@ def group_ops(dev):
     return ok
 
 
-def lm_case(dev, cfg, tag, B=2, S=24):
+def boost_adapters(w, fixed_mask):
+    """The reference init (std 1e-3, adapters.py:28-36) is invisible in bf16; use O(0.05) weights. With
+    fixed_mask the down-projection bias is +-3 so every ReLU is decided far from zero: bf16 and fp32 then agree on
+    the mask and gradients can be compared tightly (a flipped mask entry is an O(1) relative error in that entry)."""
+    import torch
+
+    for k in w:
+        if ".adapter." in k:
+            w[k] = torch.randn_like(w[k]) * (0.05 if k.endswith("weight") else 0.02)
+            if fixed_mask and k.endswith("adapter.0.bias"):
+                w[k] = torch.where(torch.rand_like(w[k]) < 0.5, -3.0, 3.0) + 0.02 * torch.randn_like(w[k])
+    return w
+
+
+def lm_case(dev, cfg, tag, B=2, S=24, fixed_mask=True, gtol=3e-2):
     import torch
     from oracle import magma_oracle as O
 
     ok = True
-    w = O.init_weights(cfg, seed=1, with_vit=False)
-    # make adapters matter: the reference init (std 1e-3) is too small to see in bf16
-    for k in w:
-        if ".adapter." in k:
-            w[k] = torch.randn_like(w[k]) * (0.05 if k.endswith("weight") else 0.02)
+    w = boost_adapters(O.init_weights(cfg, seed=1, with_vit=False), fixed_mask)
     w16 = {k: v.to(torch.bfloat16).float() for k, v in w.items()}  # oracle sees the same bf16-rounded values
     lm = build_lm(cfg, w16, dev)
     torch.manual_seed(3)
@@ -217,9 +227,9 @@ def lm_case(dev, cfg, tag, B=2, S=24):
         if "adapter" in n:
             r, _ = rel(p.grad, params["lm." + n].grad)
             worst = max(worst, r)
-            if r > 4e-2:
+            if r > gtol:
                 print(f"   grad mismatch {n}: rel={r:.3e}")
-    good = worst < 4e-2
+    good = worst < gtol
     ok &= good
     print(f"[{'OK' if good else 'FAIL'}] {tag} adapter grads worst rel_fro={worst:.3e}", flush=True)
     # inference path equals training-path forward
@@ -230,7 +240,10 @@ def lm_case(dev, cfg, tag, B=2, S=24):
 
 
 def group_lm(dev):
-    return lm_case(dev, small_cfg(), "lm[mlp normal f=4]")
+    ok = lm_case(dev, small_cfg(), "lm[mlp normal f=4]")
+    # realistic regime: ReLU decided near zero -> a few mask entries differ between bf16 and fp32
+    ok &= lm_case(dev, small_cfg(), "lm[mlp normal f=4, free relu mask]", fixed_mask=False, gtol=1.2e-1)
+    return ok
 
 
 def group_lm_variants(dev):
@@ -301,10 +314,7 @@ def group_magma(dev):
     ok = True
     cfg = small_cfg()
     S, B = 32, 3
-    w = O.init_weights(cfg, seed=5)
-    for k in w:
-        if ".adapter." in k:
-            w[k] = torch.randn_like(w[k]) * (0.05 if k.endswith("weight") else 0.02)
+    w = boost_adapters(O.init_weights(cfg, seed=5), True)
     w16 = {k: v.to(torch.bfloat16).float() for k, v in w.items()}
     model = build_magma(cfg, w16, dev, S)
     model.eval()
