@@ -137,7 +137,7 @@ def cpu_reference_run(steps, warmup, budget_s, n_threads=None):
             w1[k].grad = None
         loss, _, _ = O.magma_forward(images, captions, w, cfg)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     times = []
     t_start = time.time()
@@ -248,7 +248,7 @@ def run_b200(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = L.mb200_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
-    last_loss = float(loss)
+    last_loss = float(loss.detach())
     ms_step = ms_total / args.steps
     value = B_PER_GPU * world / (ms_step / 1e3)
 
