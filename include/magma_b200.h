@@ -108,7 +108,12 @@ typedef struct {
   const void* res2;   /* bf16 [M,N], row stride ld_res, or NULL */
   int64_t ld_res;
   int32_t force_bn;   /* 0 = auto tile width, else 64/128/256 (testing / tuning) */
-  int32_t _pad;
+  /* fused rotary embedding (rotate_every_two, hf:gptj/modeling_gptj.py:57-67) applied to adjacent column pairs after
+   * the bias: for columns c < rope_ncols with (c % rope_hd) < rope_rot, using (cos, sin) = rope_tab[row % rope_S]
+   * [(c % rope_hd)/2] (fp32 pairs, mb200_rope_table). rope_mode +1 = forward, -1 = inverse; rope_tab NULL = off. */
+  int32_t rope_mode;
+  const void* rope_tab;
+  int32_t rope_S, rope_hd, rope_rot, rope_ncols;
 } mb200_gemm_args;
 
 int mb200_gemm(const mb200_gemm_args* args, void* stream);
@@ -131,6 +136,9 @@ int mb200_layernorm_param_grad(const void* dy, int64_t lddy, const void* x, int6
 /* rotate_every_two on q,k of a fused [rows][3][H][hd] buffer (hf:gptj/modeling_gptj.py:57-67,190-207). */
 int mb200_rope(void* qkv, int64_t ld, int32_t rows, int32_t S, int32_t H, int32_t hd, int32_t rot, int32_t pos0,
                int32_t inverse, void* stream);
+/* (cos, sin) table fp32 [S][rot/2][2] for positions pos0 .. pos0+S-1 (create_sinusoidal_positions,
+ * hf:gptj/modeling_gptj.py:47-50) consumed by the GEMM's fused rotary epilogue. */
+int mb200_rope_table(float* tab, int32_t S, int32_t rot, int32_t pos0, void* stream);
 /* softmax(scale*s [+ causal mask]) fp32 -> bf16 (GPTJAttention._attn, hf:gptj/modeling_gptj.py:136-147). */
 int mb200_softmax_fwd(const float* s, int64_t lds, int64_t s_bs, void* p, int64_t ldp, int64_t p_bs, int32_t nz,
                       int32_t Sq, int32_t Sk, float scale, int32_t causal, int32_t koff, void* stream);

@@ -52,7 +52,12 @@ class GemmArgs(ctypes.Structure):
         ("res2", ctypes.c_void_p),
         ("ld_res", ctypes.c_int64),
         ("force_bn", ctypes.c_int32),
-        ("_pad", ctypes.c_int32),
+        ("rope_mode", ctypes.c_int32),
+        ("rope_tab", ctypes.c_void_p),
+        ("rope_S", ctypes.c_int32),
+        ("rope_hd", ctypes.c_int32),
+        ("rope_rot", ctypes.c_int32),
+        ("rope_ncols", ctypes.c_int32),
     ]
 
 
@@ -153,7 +158,7 @@ def _setup_signatures(L):
 EXPORTED_SYMBOLS = [
     "mb200_version", "mb200_last_error", "mb200_check_device", "mb200_gemm",
     "mb200_launch_count", "mb200_prof_enable", "mb200_prof_read",
-    "mb200_layernorm_fwd", "mb200_layernorm_bwd", "mb200_layernorm_param_grad", "mb200_rope",
+    "mb200_layernorm_fwd", "mb200_layernorm_bwd", "mb200_layernorm_param_grad", "mb200_rope", "mb200_rope_table",
     "mb200_softmax_fwd", "mb200_softmax_bwd", "mb200_build_labels", "mb200_embed_assemble", "mb200_embed_gather",
     "mb200_cross_entropy", "mb200_colsum", "mb200_dropout_fwd", "mb200_dropout_apply", "mb200_patchify",
     "mb200_vit_assemble", "mb200_argmax", "mb200_add", "mb200_sumsq", "mb200_adamw_step",

@@ -221,6 +221,16 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, long long ld, int rows, int 
   }
 }
 
+__global__ void rope_table_kernel(float2* __restrict__ tab, int S, int half, int rot, int pos0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * half) return;
+  const int p = i % half, s = i / half;
+  const float inv_freq = 1.0f / powf(10000.0f, (float)(2 * p) / (float)rot);
+  float sn, cs;
+  sincosf((float)(pos0 + s) * inv_freq, &sn, &cs);
+  tab[i] = make_float2(cs, sn);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Softmax over fp32 scores -> bf16 probabilities. One warp per row. causal: key j visible iff j <= i + koff.
 // (GPTJAttention._attn, modeling_gptj.py:136-147: fp32 scores / sqrt(hd), mask, softmax, cast to value dtype)
@@ -417,16 +427,18 @@ __global__ void ce_reduce_kernel(const float* __restrict__ row_loss, int M, cons
 // ---------------------------------------------------------------------------------------------
 // column sum: out[c] (+)= sum_r x[r, c]   (bias gradients). grid.x covers 64-column strips.
 // ---------------------------------------------------------------------------------------------
+static constexpr int kColsumRows = 64;  // rows per CTA: grid = (col strips of 64) x (row chunks) for parallelism
 __global__ void __launch_bounds__(256)
-colsum_kernel(const bf16* __restrict__ x, long long ldx, int rows, int cols, float* __restrict__ out,
-              int accumulate) {
+colsum_kernel(const bf16* __restrict__ x, long long ldx, int rows, int cols, float* __restrict__ out) {
   __shared__ float part[8][64];
   const int cl = threadIdx.x & 31;        // column pair within the strip
   const int rg = threadIdx.x >> 5;        // row group 0..7
   const int c0 = blockIdx.x * 64 + cl * 2;
+  const int r0 = blockIdx.y * kColsumRows;
+  const int r1 = min(rows, r0 + kColsumRows);
   float a0 = 0.f, a1 = 0.f;
   if (c0 < cols) {
-    for (int r = rg; r < rows; r += 8) {
+    for (int r = r0 + rg; r < r1; r += 8) {
       const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (long long)r * ldx + c0));
       a0 += v.x;
       a1 += v.y;
@@ -440,7 +452,7 @@ colsum_kernel(const bf16* __restrict__ x, long long ldx, int rows, int cols, flo
 #pragma unroll
     for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
     const int c = blockIdx.x * 64 + threadIdx.x;
-    if (c < cols) out[c] = accumulate ? out[c] + s : s;
+    if (c < cols) atomicAdd(out + c, s);  // one atomic per (column, row chunk); out is zeroed first unless accumulating
   }
 }
 
@@ -584,7 +596,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
 }
 
 __global__ void adamw_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m1,
-                             float* __restrict__ m2, bf16* __restrict__ shadow, long long n, float lr, float b1,
+                             float* __restrict__ m2, bf16* __restrict__ shadow, long long n4, float lr, float b1,
                              float b2, float eps, float wd, float grad_scale, const float* __restrict__ gnorm_sq,
                              float max_norm, float bc1, float bc2, int zero_grad) {
   float coef = grad_scale;
@@ -592,19 +604,39 @@ __global__ void adamw_kernel(float* __restrict__ w, float* __restrict__ g, float
     const float nrm = sqrtf(*gnorm_sq) * grad_scale;
     coef *= fminf(1.f, max_norm / (nrm + 1e-6f));
   }
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * coef;
-    float wi = w[i];
-    wi *= (1.f - lr * wd);
-    const float a = b1 * m1[i] + (1.f - b1) * gi;
-    const float v = b2 * m2[i] + (1.f - b2) * gi * gi;
-    m1[i] = a;
-    m2[i] = v;
-    const float denom = sqrtf(v) / sqrtf(bc2) + eps;
-    wi -= (lr / bc1) * (a / denom);
-    w[i] = wi;
-    if (shadow) shadow[i] = __float2bfloat16(wi);
-    if (zero_grad) g[i] = 0.f;
+  const float inv_sqrt_bc2 = rsqrtf(bc2), step = lr / bc1, decay = 1.f - lr * wd;
+  float4* w4 = reinterpret_cast<float4*>(w);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  float4* a4 = reinterpret_cast<float4*>(m1);
+  float4* v4 = reinterpret_cast<float4*>(m2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 wv = w4[i], gv = g4[i], av = a4[i], vv = v4[i];
+    float* wp = &wv.x;
+    float* gp = &gv.x;
+    float* ap = &av.x;
+    float* vp = &vv.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gi = gp[e] * coef;
+      float wi = wp[e] * decay;
+      const float a = b1 * ap[e] + (1.f - b1) * gi;
+      const float v = b2 * vp[e] + (1.f - b2) * gi * gi;
+      ap[e] = a;
+      vp[e] = v;
+      wi -= step * (a / (sqrtf(v) * inv_sqrt_bc2 + eps));
+      wp[e] = wi;
+    }
+    w4[i] = wv;
+    a4[i] = av;
+    v4[i] = vv;
+    if (shadow) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(wv.x, wv.y), h1 = __floats2bfloat162_rn(wv.z, wv.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(shadow)[i] = u;
+    }
+    if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -690,6 +722,15 @@ extern "C" int mb200_rope(void* qkv, int64_t ld, int32_t rows, int32_t S, int32_
   return 0;
 }
 
+extern "C" int mb200_rope_table(float* tab, int32_t S, int32_t rot, int32_t pos0, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(S > 0 && rot > 0 && rot % 2 == 0, MB200_E_SHAPE, "rope_table: bad S=%d rot=%d", S, rot);
+  const int n = S * (rot / 2);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<float2*>(tab), S, rot / 2, rot, pos0);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mb200_softmax_fwd(const float* s, int64_t lds, int64_t s_bs, void* p, int64_t ldp, int64_t p_bs,
                                  int32_t nz, int32_t Sq, int32_t Sk, float scale, int32_t causal, int32_t koff,
                                  void* stream) {
@@ -761,7 +802,9 @@ extern "C" int mb200_colsum(const void* x, int64_t ldx, int32_t rows, int32_t co
                             void* stream) {
   MB_ENTER();
   MB_REQUIRE(cols % 2 == 0 && ldx % 2 == 0, MB200_E_ALIGN, "colsum: cols and ldx must be even");
-  colsum_kernel<<<(cols + 63) / 64, 256, 0, ST(stream)>>>((const bf16*)x, ldx, rows, cols, out, accumulate);
+  if (!accumulate) MB_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), ST(stream)));
+  dim3 grid((cols + 63) / 64, (rows + kColsumRows - 1) / kColsumRows);
+  colsum_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)x, ldx, rows, cols, out);
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -831,7 +874,8 @@ extern "C" int mb200_adamw_step(float* master, float* grad, float* exp_avg, floa
   MB_ENTER();
   MB_REQUIRE(step >= 1, MB200_E_ARG, "adamw: step must be >= 1");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  adamw_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(master, grad, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n, lr,
+  MB_REQUIRE(n % 4 == 0, MB200_E_ALIGN, "adamw: n must be a multiple of 4 (the arena pads every tensor to 64)");
+  adamw_kernel<<<grid_for(n / 4, 256), 256, 0, ST(stream)>>>(master, grad, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n / 4, lr,
                                                          beta1, beta2, eps, weight_decay, grad_scale, gnorm_sq,
                                                          max_norm, bc1, bc2, zero_grad);
   MB_LAUNCH_CHECK();

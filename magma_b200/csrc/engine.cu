@@ -18,6 +18,7 @@ int mb200_layernorm_fwd(const void*, int64_t, const void*, const void*, void*, i
 int mb200_layernorm_bwd(const void*, int64_t, const void*, int64_t, const void*, const float*, const float*,
                         const void*, int64_t, void*, int64_t, int32_t, int32_t, void*);
 int mb200_rope(void*, int64_t, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t, void*);
+int mb200_rope_table(float*, int32_t, int32_t, int32_t, void*);
 int mb200_softmax_fwd(const float*, int64_t, int64_t, void*, int64_t, int64_t, int32_t, int32_t, int32_t, float,
                       int32_t, int32_t, void*);
 int mb200_softmax_bwd(const float*, int64_t, int64_t, const void*, int64_t, int64_t, void*, int64_t, int64_t, int32_t,
@@ -87,6 +88,7 @@ struct GptjPlan {
   bf16* dlogits;  // [M,ldv]
   float* row_loss;
   int* n_valid;
+  float* rope_tab;  // [S][rot/2] (cos, sin) for positions pos0 .. pos0+S-1
   // backward temporaries
   bf16* g0;
   bf16* g1;
@@ -148,6 +150,7 @@ static int make_plan(GptjPlan& P, const mb200_gptj_model* m, int B, int S, int S
   P.lnf_rstd = c.take<float>(M);
   P.row_loss = c.take<float>(M);
   P.n_valid = c.take<int>(4);
+  P.rope_tab = c.take<float>((size_t)S * m->rotary_dim);
   if (training) {
     P.dlogits = c.take<bf16>(M * (size_t)P.ldv);
     P.g0 = c.take<bf16>(M * d);
@@ -193,6 +196,8 @@ struct Epi {
   const void* res2 = nullptr;
   long long ld_res = 0;
   int accumulate = 0;
+  const float* rope_tab = nullptr;
+  int rope_mode = 0, rope_S = 0, rope_hd = 0, rope_rot = 0, rope_ncols = 0;
 };
 
 static int gemm(cudaStream_t st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, int c_f32,
@@ -229,6 +234,12 @@ static int gemm(cudaStream_t st, int M, int N, int K, Mat A, Mat B, void* C, lon
   g.res1 = e.res1;
   g.res2 = e.res2;
   g.ld_res = e.ld_res;
+  g.rope_tab = e.rope_tab;
+  g.rope_mode = e.rope_mode;
+  g.rope_S = e.rope_S;
+  g.rope_hd = e.rope_hd;
+  g.rope_rot = e.rope_rot;
+  g.rope_ncols = e.rope_ncols;
   return gemm_impl(&g, st);
 }
 
@@ -389,6 +400,7 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
   const float scale = 1.0f / sqrtf((float)hd);
   const size_t cache_layer = (size_t)B * H * Smax * hd;
 
+  MB_TRY(mb200_rope_table(P.rope_tab, S, m->rotary_dim, pos0, st));
   const bf16* xin = x;
   if (training) {
     MB_CUDA(cudaMemcpyAsync(P.acts[0].x_in, x, (size_t)M * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
@@ -401,9 +413,17 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
                           : ((l & 1) ? P.x_final : P.acts[0].x_in);
     // ln_1 (one LN feeds both branches of the parallel-residual block)
     MB_TRY(mb200_layernorm_fwd(xin, d, L.ln1_g, L.ln1_b, a.h, d, a.mean, a.rstd, M, d, m->ln_eps, st));
-    // fused q/k/v projection + rotary
-    MB_TRY(gemm(st, M, 3 * d, d, mat(a.h, d), mat(L.w_qkv, d), a.qkv, 3 * d, 0));
-    MB_TRY(mb200_rope(a.qkv, 3 * d, M, S, H, hd, m->rotary_dim, pos0, 0, st));
+    // fused q/k/v projection with the rotary embedding applied in the GEMM epilogue (q and k column ranges)
+    {
+      Epi e;
+      e.rope_tab = P.rope_tab;
+      e.rope_mode = 1;
+      e.rope_S = S;
+      e.rope_hd = hd;
+      e.rope_rot = m->rotary_dim;
+      e.rope_ncols = 2 * d;
+      MB_TRY(gemm(st, M, 3 * d, d, mat(a.h, d), mat(L.w_qkv, d), a.qkv, 3 * d, 0, e));
+    }
     if (kcache && S == 1) {
       bf16* kc = kcache + (size_t)l * cache_layer;
       bf16* vc = vcache + (size_t)l * cache_layer;
@@ -605,13 +625,18 @@ static int gptj_backward(const mb200_gptj_model* m, bf16* dx, float loss_scale, 
       // dS = P * (dP - rowsum(dP * P)) / sqrt(hd)
       MB_TRY(mb200_softmax_bwd(P.scores, P.ldS, (long long)S * P.ldS, a.P, P.ldP, pb0, P.dS, P.ldP, pb0, B * H, S, S,
                                scale, st));
-      // dQ = dS K ; dK = dS^T Q   (on the rotated q, k)
+      // dQ = dS K ; dK = dS^T Q (gradients w.r.t. the rotated q, k) with the inverse rotation fused in the epilogue
+      Epi er;
+      er.rope_tab = P.rope_tab;
+      er.rope_mode = -1;
+      er.rope_S = S;
+      er.rope_hd = hd;
+      er.rope_rot = m->rotary_dim;
+      er.rope_ncols = hd;
       MB_TRY(gemm(st, S, hd, S, mat(P.dS, P.ldP, 0, pb0, pb1), mat(a.qkv + d, 3 * d, 1, qb0, qb1), P.dqkv, 3 * d, 0,
-                  Epi(), H, B, qb0, qb1));
+                  er, H, B, qb0, qb1));
       MB_TRY(gemm(st, S, hd, S, mat(P.dS, P.ldP, 1, pb0, pb1), mat(a.qkv, 3 * d, 1, qb0, qb1), P.dqkv + d, 3 * d, 0,
-                  Epi(), H, B, qb0, qb1));
-      // inverse rotary on dq, dk
-      MB_TRY(mb200_rope(P.dqkv, 3 * d, M, S, H, hd, m->rotary_dim, 0, 1, st));
+                  er, H, B, qb0, qb1));
     }
     {
       Epi e;

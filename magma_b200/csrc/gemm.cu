@@ -24,7 +24,8 @@ static constexpr int BM = 128;       // UMMA M (cta_group::1)
 static constexpr int BK = 64;        // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 static constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
 static constexpr int kThreads = 256; // 8 warps
-static constexpr int kSmemBudget = 200 * 1024;
+static constexpr int kPrefetch = 8;  // L2 prefetch distance in k-blocks
+static constexpr int kSmemBudget = 192 * 1024;  // operand ring; + 34 KB epilogue staging + barriers < 227 KB
 
 template <int BN>
 struct Cfg {
@@ -33,7 +34,9 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers; 128/256/512 — powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiPitch = 64;      // floats per staged row; 16-byte chunks XOR-swizzled by (row & 15)
+  static constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;  // per-warp [32 rows][64 cols] fp32 staging, 4 warps
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmKernelParams {
@@ -50,6 +53,10 @@ struct GemmKernelParams {
   const bf16* res1;
   const bf16* res2;
   long long ld_res;
+  // fused rotary embedding (rotate_every_two) on column pairs: applied when rope_mode != 0
+  const float2* rope_tab;  // [rope_S][rope_rot/2] (cos, sin) of the position of row (row % rope_S)
+  int rope_mode;           // +1 forward, -1 inverse (transpose rotation)
+  int rope_S, rope_hd, rope_rot, rope_ncols;
 };
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, SWIZZLE_128B, version 1)
@@ -75,7 +82,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * C_::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes);
+  float* epi_stage = reinterpret_cast<float*>(smem + kStages * C_::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes + C_::kEpiBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -121,6 +129,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n_blk = r / p.tiles_m;
         const int z0 = z % p.nb0, z1 = z / p.nb0;
         for (int kb = 0; kb < num_kb; ++kb) {
+          // L2 prefetch kPrefetch k-blocks ahead: the smem ring only covers ~3 stages (~1.5k MMA cycles), less
+          // than a loaded DRAM round trip, so weight tiles are pulled into L2 early and the ring sees L2 latency.
+          if (kb + kPrefetch < num_kb) {
+            const int kp = (kb + kPrefetch) * BK;
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i) tma_prefetch_4d(&tmB, n_blk * BN + i * 64, kp, z0, z1);
+            } else {
+              tma_prefetch_4d(&tmB, kp, n_blk * BN, z0, z1);
+            }
+            if constexpr (A_MN) {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i) tma_prefetch_4d(&tmA, m_blk * BM + i * 64, kp, z0, z1);
+            } else {
+              tma_prefetch_4d(&tmA, kp, m_blk * BM, z0, z1);
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], C_::kStageBytes);
           uint8_t* sa = smem_a + stage * C_::kABytes;
@@ -202,154 +227,158 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
       const long long boff = (long long)z0 * p.c_bs0 + (long long)z1 * p.c_bs1;
-      const long long coff = boff + (long long)row * p.ldc;
-      const long long roff = boff + (long long)row * p.ld_res;
+      float* stg = epi_stage + q * (32 * C_::kEpiPitch);
+      const int n_tile_end = min(p.N, (n_blk + 1) * BN);
+      // coalesced phase-2 mapping: 16 lanes x 4 columns cover one 64-column row segment; 2 rows per instruction
+      const int c4 = (lane & 15) * 4;
+      const int rsub = lane >> 4;
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
+      for (int g = 0; g < BN / 64; ++g) {
+        const int n0 = n_blk * BN + g * 64;
         if (n0 >= p.N) break;  // warp-uniform
-        uint32_t rr[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), rr);
-        tmem_ld_wait();
-        float v[32];
+        // ---- phase 1: TMEM -> registers -> per-warp smem staging (thread i owns accumulator row i) ----
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
-        const bool full = (n0 + 32 <= p.N);
-        if (p.bias) {
+        for (int h = 0; h < 2; ++h) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + g * 64 + h * 32), rr);
+          tmem_ld_wait();
+          float* dst = stg + lane * C_::kEpiPitch;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < p.N) v[j] += __bfloat162float(__ldg(p.bias + n0 + j));
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + ((((h * 32 + j) >> 2) ^ (lane & 15)) << 2)) =
+                make_float4(__uint_as_float(rr[j]) * p.alpha, __uint_as_float(rr[j + 1]) * p.alpha,
+                            __uint_as_float(rr[j + 2]) * p.alpha, __uint_as_float(rr[j + 3]) * p.alpha);
         }
-        if (row_ok) {
+        if (n0 + 64 >= n_tile_end) {
+          // last column group of this tile: the accumulator has been fully read -> hand TMEM back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        __syncwarp();
+        // ---- phase 2: fused epilogue in a row-contiguous layout (full 128-byte lines per row) ----
+        const int col = n0 + c4;
+        const int nvalid = p.N - col;  // > 0 columns of this lane's float4 are in range
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias && nvalid > 0) {
+          if (nvalid >= 4) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
+            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            bv[0] = f0.x; bv[1] = f0.y; bv[2] = f1.x; bv[3] = f1.y;
+          } else {
+            for (int e = 0; e < nvalid; ++e) bv[e] = __bfloat162float(p.bias[col + e]);
+          }
+        }
+        int rope_p = -1;  // index of this lane's first rotary pair, or -1
+        if (p.rope_mode != 0 && col < p.rope_ncols) {
+          const int dim = col % p.rope_hd;
+          if (dim < p.rope_rot) rope_p = dim >> 1;
+        }
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int rl = it * 2 + rsub;
+          const int row = m_blk * BM + q * 32 + rl;
+          if (row >= p.M || nvalid <= 0) continue;
+          const float4 sv =
+              *reinterpret_cast<const float4*>(stg + rl * C_::kEpiPitch + ((((c4 >> 2)) ^ (rl & 15)) << 2));
+          float v[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
+          const long long coff = boff + (long long)row * p.ldc + col;
+          const bool full = nvalid >= 4;
+          if (rope_p >= 0) {
+            const float2* tp = p.rope_tab + (long long)(row % p.rope_S) * (p.rope_rot >> 1) + rope_p;
+            const float2 cs0 = __ldg(tp), cs1 = __ldg(tp + 1);
+            const float sg = p.rope_mode > 0 ? 1.f : -1.f;
+            const float a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+            v[0] = a0 * cs0.x - a1 * cs0.y * sg;
+            v[1] = a1 * cs0.x + a0 * cs0.y * sg;
+            v[2] = a2 * cs1.x - a3 * cs1.y * sg;
+            v[3] = a3 * cs1.x + a2 * cs1.y * sg;
+          }
           if (p.aux_out) {
-            bf16* dst = p.aux_out + coff + n0;
+            bf16* dst = p.aux_out + coff;
             if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0);
-                u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2);
-                u.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(dst + j) = u;
-              }
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+              uint2 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(dst) = u;
             } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+              for (int e = 0; e < nvalid; ++e) dst[e] = __float2bfloat16(v[e]);
             }
           }
           if (p.act == MB200_ACT_GELU_NEW) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
+            for (int e = 0; e < 4; ++e) v[e] = gelu_new_f(v[e]);
           } else if (p.act == MB200_ACT_QUICK_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = quick_gelu_f(v[j]);
+            for (int e = 0; e < 4; ++e) v[e] = quick_gelu_f(v[e]);
           } else if (p.act == MB200_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
           }
           if (p.dact) {
-            const bf16* src = p.aux_in + coff + n0;
-            float a[32];
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            const bf16* src = p.aux_in + coff;
             if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u = *reinterpret_cast<const uint4*>(src + j);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __bfloat1622float2(h[e]);
-                  a[j + 2 * e] = f.x;
-                  a[j + 2 * e + 1] = f.y;
-                }
-              }
+              const uint2 u = *reinterpret_cast<const uint2*>(src);
+              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+              a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y;
             } else {
-              for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? __bfloat162float(src[j]) : 0.f;
+              for (int e = 0; e < nvalid; ++e) a[e] = __bfloat162float(src[e]);
             }
             if (p.dact == MB200_DACT_GELU_NEW) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad_f(a[j]);
+              for (int e = 0; e < 4; ++e) v[e] *= gelu_new_grad_f(a[e]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : 0.f;
+              for (int e = 0; e < 4; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
             }
           }
-#pragma unroll 1
+#pragma unroll
           for (int ri = 0; ri < 2; ++ri) {
             const bf16* rp = ri == 0 ? p.res1 : p.res2;
             if (!rp) continue;
-            const bf16* src = rp + roff + n0;
+            const bf16* src = rp + boff + (long long)row * p.ld_res + col;
             if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u = *reinterpret_cast<const uint4*>(src + j);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __bfloat1622float2(h[e]);
-                  v[j + 2 * e] += f.x;
-                  v[j + 2 * e + 1] += f.y;
-                }
-              }
+              const uint2 u = *reinterpret_cast<const uint2*>(src);
+              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+              v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
             } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += __bfloat162float(src[j]);
+              for (int e = 0; e < nvalid; ++e) v[e] += __bfloat162float(src[e]);
             }
           }
           if constexpr (sizeof(OutT) == 4) {
-            float* dst = reinterpret_cast<float*>(p.C) + coff + n0;
+            float* dst = reinterpret_cast<float*>(p.C) + coff;
             if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (p.accumulate) {
-                  float4 old = *reinterpret_cast<const float4*>(dst + j);
-                  o.x += old.x;
-                  o.y += old.y;
-                  o.z += old.z;
-                  o.w += old.w;
-                }
-                *reinterpret_cast<float4*>(dst + j) = o;
+              float4 o = make_float4(v[0], v[1], v[2], v[3]);
+              if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(dst);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
               }
+              *reinterpret_cast<float4*>(dst) = o;
             } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+              for (int e = 0; e < nvalid; ++e) dst[e] = p.accumulate ? dst[e] + v[e] : v[e];
             }
           } else {
-            bf16* dst = reinterpret_cast<bf16*>(p.C) + coff + n0;
+            bf16* dst = reinterpret_cast<bf16*>(p.C) + coff;
             if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0);
-                u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2);
-                u.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(dst + j) = u;
-              }
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+              uint2 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(dst) = u;
             } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+              for (int e = 0; e < nvalid; ++e) dst[e] = __float2bfloat16(v[e]);
             }
           }
         }
+        __syncwarp();  // staging buffer is reused by the next column group
       }
-      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above) -> release it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
 
@@ -457,18 +486,31 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
   return launch_gemm<BN, true, true, OutT>(tmA, tmB, kp, s);
 }
 
-static int pick_bn(int M, int N, int batches) {
+static int pick_bn(int M, int N, int K, int batches) {
   if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  // prefer 256-wide tiles (halves A re-reads, 96 B/clk smem demand) unless they leave the grid short
+  // Model: time ~ waves * (cost of one tile). A 256-wide tile streams A once per 256 columns and runs the tensor
+  // pipe at 96 B/clk of smem demand; narrower tiles re-read A and are smem-bound (128 B/clk at BN=128, more at 64),
+  // so they only win when wide tiles leave most of the 148 SMs idle (few tiles) — e.g. the adapter down-projection
+  // (M=1024, N=1024: 32 tiles at BN=256, 128 at BN=64).
   const int tiles_m = (M + BM - 1) / BM;
-  const long long t256 = (long long)tiles_m * ((N + 255) / 256) * batches;
-  const long long t128 = (long long)tiles_m * ((N + 127) / 128) * batches;
   const int sms = num_sms();
-  if (t256 >= sms) return 256;
-  // few tiles: compare wave efficiency
-  auto eff = [&](long long t) { return (double)t / (double)(((t + sms - 1) / sms) * sms); };
-  return eff(t256) + 1e-9 >= eff(t128) ? 256 : 128;
+  double best = 1e300;
+  int best_bn = 256;
+  const int cands[3] = {256, 128, 64};
+  const double tile_cost[3] = {1.0, 0.75, 0.5};  // relative time of one (BM x BN x K) tile (BN=128 measured: 0.70-0.79)
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && N <= bn / 2) continue;
+    const long long t = (long long)tiles_m * ((N + bn - 1) / bn) * batches;
+    const long long waves = (t + sms - 1) / sms;
+    const double cost = (double)waves * tile_cost[i];
+    if (cost < best - 1e-12) {
+      best = cost;
+      best_bn = bn;
+    }
+  }
+  (void)K;
+  return best_bn;
 }
 
 int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
@@ -489,7 +531,7 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   int rc = check_arch();
   if (rc) return rc;
 
-  int bn = a->force_bn ? a->force_bn : pick_bn(a->M, a->N, a->nb0 * a->nb1);
+  int bn = a->force_bn ? a->force_bn : pick_bn(a->M, a->N, a->K, a->nb0 * a->nb1);
   MB_REQUIRE(bn == 64 || bn == 128 || bn == 256, MB200_E_ARG, "gemm: force_bn must be 64/128/256");
 
   CUtensorMap tmA, tmB;
@@ -520,6 +562,16 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   kp.res1 = reinterpret_cast<const bf16*>(a->res1);
   kp.res2 = reinterpret_cast<const bf16*>(a->res2);
   kp.ld_res = a->ld_res;
+  kp.rope_tab = reinterpret_cast<const float2*>(a->rope_tab);
+  kp.rope_mode = a->rope_tab ? a->rope_mode : 0;
+  kp.rope_S = a->rope_S;
+  kp.rope_hd = a->rope_hd;
+  kp.rope_rot = a->rope_rot;
+  kp.rope_ncols = a->rope_ncols;
+  if (kp.rope_mode != 0)
+    MB_REQUIRE(a->rope_S > 0 && a->rope_hd > 0 && a->rope_rot % 4 == 0 && a->rope_rot <= a->rope_hd &&
+                   a->rope_hd % 4 == 0 && a->rope_ncols % 4 == 0,
+               MB200_E_ARG, "gemm: bad rope epilogue parameters");
 
   const bool amn = a->A.mn_major != 0, bmn = a->B.mn_major != 0;
   const bool f32 = a->c_dtype == MB200_F32;

@@ -52,6 +52,12 @@ def gemm(
     res2=None,
     accumulate=False,
     force_bn=0,
+    rope_tab=None,
+    rope_mode=0,
+    rope_S=0,
+    rope_hd=0,
+    rope_rot=0,
+    rope_ncols=0,
 ):
     """C[..., M, N] = epilogue(alpha * A @ B^T) on the tcgen05 GEMM core.
 
@@ -102,6 +108,9 @@ def gemm(
             ld_res = m[2]
     g.ld_res = ld_res
     g.force_bn = force_bn
+    if rope_tab is not None and rope_mode:
+        g.rope_tab, g.rope_mode = rope_tab.data_ptr(), int(rope_mode)
+        g.rope_S, g.rope_hd, g.rope_rot, g.rope_ncols = int(rope_S), int(rope_hd), int(rope_rot), int(rope_ncols)
     check(lib().mb200_gemm(ctypes.byref(g), _stream()))
     return out
 
@@ -154,6 +163,12 @@ def rope_(qkv, S, H, hd, rot, pos0=0, inverse=False):
     rows = qkv.shape[0]
     check(lib().mb200_rope(_ptr(qkv), ctypes.c_int64(qkv.stride(0)), rows, S, H, hd, rot, pos0, int(inverse), _stream()))
     return qkv
+
+
+def rope_table(S, rot, pos0=0, device=None):
+    tab = torch.empty(S, rot // 2, 2, dtype=torch.float32, device=device or torch.device("cuda"))
+    check(lib().mb200_rope_table(_ptr(tab), S, rot, pos0, _stream()))
+    return tab
 
 
 def softmax_fwd(s, scale, causal, koff=0, ldp=None):

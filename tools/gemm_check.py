@@ -126,6 +126,23 @@ def run_group(g):
         C = ops.gemm(A, B, aux_in=x, dact=ops.DACT_RELU)
         ok &= report("dact relu", C, base * (x.float() > 0).float())
         torch.cuda.synchronize()
+        # fused rotary epilogue == standalone rope kernel on the plain GEMM output (fwd and inverse)
+        Sx, H, hd, rot = 32, 2, 128, 64
+        Mx = 4 * Sx
+        A2, B2 = mk((Mx, 256), False, dev, 0.5), mk((3 * H * hd, 256), False, dev, 0.125)
+        tab = ops.rope_table(Sx, rot, pos0=7, device=dev)
+        for mode in (1, -1):
+            fused = ops.gemm(A2, B2, rope_tab=tab, rope_mode=mode, rope_S=Sx, rope_hd=hd, rope_rot=rot,
+                             rope_ncols=2 * H * hd)
+            plain = ops.gemm(A2, B2, out_dtype=torch.float32)
+            q = plain.view(Mx // Sx, Sx, 3, H, hd).clone()
+            cs = tab[None, :, None, None, :, 0]
+            sn = tab[None, :, None, None, :, 1] * mode
+            x1, x2 = q[:, :, :2, :, 0:rot:2].clone(), q[:, :, :2, :, 1:rot:2].clone()
+            q[:, :, :2, :, 0:rot:2] = x1 * cs - x2 * sn
+            q[:, :, :2, :, 1:rot:2] = x2 * cs + x1 * sn
+            ok &= report(f"fused rope epilogue mode={mode}", fused, q.view(Mx, -1))
+        torch.cuda.synchronize()
     elif g == "batched":
         # attention-style strided batches: qkv [B,S,3,H,hd] -> Q/K/V views [B,H,S,hd]
         Bsz, S, H, hd = 2, 128, 4, 256
