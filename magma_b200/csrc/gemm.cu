@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace mb200 {
 
@@ -24,7 +25,6 @@ static constexpr int BM = 128;       // UMMA M (cta_group::1)
 static constexpr int BK = 64;        // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 static constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
 static constexpr int kThreads = 256; // 8 warps
-static constexpr int kPrefetch = 8;  // L2 prefetch distance in k-blocks
 static constexpr int kSmemBudget = 192 * 1024;  // operand ring; + 34 KB epilogue staging + barriers < 227 KB
 
 template <int BN>
@@ -57,6 +57,7 @@ struct GemmKernelParams {
   const float2* rope_tab;  // [rope_S][rope_rot/2] (cos, sin) of the position of row (row % rope_S)
   int rope_mode;           // +1 forward, -1 inverse (transpose rotation)
   int rope_S, rope_hd, rope_rot, rope_ncols;
+  int epi_kind;  // EK_*: which specialised epilogue handles full float4 column groups (0 = generic only)
 };
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, SWIZZLE_128B, version 1)
@@ -68,6 +69,109 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue phase 2 (row-contiguous): the four epilogue warps run ONE warp per scheduler, so this code is latency-bound
+// unless it is straight-line with high ILP. epi_rows<> is therefore specialised at compile time on what the epilogue
+// does, fully unrolled over the 16 row-pairs of a 32x64 staging block, with pointer bumps instead of per-iteration
+// address arithmetic; the kernel dispatches once per tile on p.epi_kind (host-chosen) to an instantiation.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void bf16x4_to_f32(const uint2& u, float (&f)[4]) {
+  const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y;
+}
+__device__ __forceinline__ uint2 f32x4_to_bf16(const float (&v)[4]) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  return u;
+}
+
+enum { EK_GENERIC = 0, EK_PLAIN, EK_ROPE, EK_GELU, EK_GELU_AUX, EK_QGELU, EK_RELU, EK_DGELU, EK_DRELU, EK_RES1,
+       EK_RES2, EK_ACCUM };
+
+// One 32-row x 64-column staging block, lanes with 4 valid columns only. stg_lane = smem address of this lane's float4
+// in row `rsub` (XOR-swizzled per row inside). Pointers are element pointers at (row0 + rsub, col).
+template <int ACT, int DACT, int NRES, bool AUX, bool ROPE, bool ACCUM, typename OutT>
+__device__ __forceinline__ void epi_rows(const GemmKernelParams& p, uint32_t stg_warp, int c4, int rsub, int nrows,
+                                         const float (&bv)[4], OutT* cptr, bf16* auxo, const bf16* auxi,
+                                         const bf16* r1, const bf16* r2, int row_first, int rope_p) {
+  const long long cstep = 2 * p.ldc, rstep = 2 * p.ld_res;
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int rl = it * 2 + rsub;
+    if (rl < nrows) {
+      const float4 sv = lds128(stg_warp + (uint32_t)(rl * 256 + ((((c4 >> 2)) ^ (rl & 15)) << 4)));
+      float v[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
+      if constexpr (ROPE) {
+        if (rope_p >= 0) {
+          const float2* tp = p.rope_tab + (long long)((row_first + rl) % p.rope_S) * (p.rope_rot >> 1) + rope_p;
+          const float2 cs0 = __ldg(tp), cs1 = __ldg(tp + 1);
+          const float sg = p.rope_mode > 0 ? 1.f : -1.f;
+          const float a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+          v[0] = a0 * cs0.x - a1 * cs0.y * sg;
+          v[1] = a1 * cs0.x + a0 * cs0.y * sg;
+          v[2] = a2 * cs1.x - a3 * cs1.y * sg;
+          v[3] = a3 * cs1.x + a2 * cs1.y * sg;
+        }
+      }
+      if constexpr (AUX) *reinterpret_cast<uint2*>(auxo + it * cstep) = f32x4_to_bf16(v);
+      if constexpr (ACT == MB200_ACT_GELU_NEW) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = gelu_new_f(v[e]);
+      } else if constexpr (ACT == MB200_ACT_QUICK_GELU) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = quick_gelu_f(v[e]);
+      } else if constexpr (ACT == MB200_ACT_RELU) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+      }
+      if constexpr (DACT != 0) {
+        float a[4];
+        bf16x4_to_f32(*reinterpret_cast<const uint2*>(auxi + it * cstep), a);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if constexpr (DACT == MB200_DACT_GELU_NEW) v[e] *= gelu_new_grad_f(a[e]);
+          else v[e] = a[e] > 0.f ? v[e] : 0.f;
+        }
+      }
+      if constexpr (NRES >= 1) {
+        float a[4];
+        bf16x4_to_f32(*reinterpret_cast<const uint2*>(r1 + it * rstep), a);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] += a[e];
+      }
+      if constexpr (NRES >= 2) {
+        float a[4];
+        bf16x4_to_f32(*reinterpret_cast<const uint2*>(r2 + it * rstep), a);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] += a[e];
+      }
+      if constexpr (sizeof(OutT) == 4) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        float* dst = reinterpret_cast<float*>(cptr) + it * cstep;
+        if constexpr (ACCUM) {
+          const float4 old = *reinterpret_cast<const float4*>(dst);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(dst) = o;
+      } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(cptr) + it * cstep) = f32x4_to_bf16(v);
+      }
+    }
+  }
 }
 
 template <int BN, bool A_MN, bool B_MN, typename OutT>
@@ -129,23 +233,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n_blk = r / p.tiles_m;
         const int z0 = z % p.nb0, z1 = z / p.nb0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          // L2 prefetch kPrefetch k-blocks ahead: the smem ring only covers ~3 stages (~1.5k MMA cycles), less
-          // than a loaded DRAM round trip, so weight tiles are pulled into L2 early and the ring sees L2 latency.
-          if (kb + kPrefetch < num_kb) {
-            const int kp = (kb + kPrefetch) * BK;
-            if constexpr (B_MN) {
-#pragma unroll
-              for (int i = 0; i < BN / 64; ++i) tma_prefetch_4d(&tmB, n_blk * BN + i * 64, kp, z0, z1);
-            } else {
-              tma_prefetch_4d(&tmB, kp, n_blk * BN, z0, z1);
-            }
-            if constexpr (A_MN) {
-#pragma unroll
-              for (int i = 0; i < BM / 64; ++i) tma_prefetch_4d(&tmA, m_blk * BM + i * 64, kp, z0, z1);
-            } else {
-              tma_prefetch_4d(&tmA, kp, m_blk * BM, z0, z1);
-            }
-          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], C_::kStageBytes);
           uint8_t* sa = smem_a + stage * C_::kABytes;
@@ -229,6 +316,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       const long long boff = (long long)z0 * p.c_bs0 + (long long)z1 * p.c_bs1;
       float* stg = epi_stage + q * (32 * C_::kEpiPitch);
+      const uint32_t stg_s = smem_u32(stg);
+      const int row0 = m_blk * BM + q * 32;
+      const int nrows = max(0, min(32, p.M - row0));
       const int n_tile_end = min(p.N, (n_blk + 1) * BN);
       // coalesced phase-2 mapping: 16 lanes x 4 columns cover one 64-column row segment; 2 rows per instruction
       const int c4 = (lane & 15) * 4;
@@ -244,12 +334,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t rr[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + g * 64 + h * 32), rr);
           tmem_ld_wait();
-          float* dst = stg + lane * C_::kEpiPitch;
+          const uint32_t drow = stg_s + (uint32_t)(lane * 256);
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + ((((h * 32 + j) >> 2) ^ (lane & 15)) << 2)) =
-                make_float4(__uint_as_float(rr[j]) * p.alpha, __uint_as_float(rr[j + 1]) * p.alpha,
-                            __uint_as_float(rr[j + 2]) * p.alpha, __uint_as_float(rr[j + 3]) * p.alpha);
+            sts128(drow + (uint32_t)(((((h * 32 + j) >> 2) ^ (lane & 15)) << 4)), __uint_as_float(rr[j]) * p.alpha,
+                   __uint_as_float(rr[j + 1]) * p.alpha, __uint_as_float(rr[j + 2]) * p.alpha,
+                   __uint_as_float(rr[j + 3]) * p.alpha);
         }
         if (n0 + 64 >= n_tile_end) {
           // last column group of this tile: the accumulator has been fully read -> hand TMEM back to the MMA warp
@@ -269,7 +359,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
             bv[0] = f0.x; bv[1] = f0.y; bv[2] = f1.x; bv[3] = f1.y;
           } else {
-            for (int e = 0; e < nvalid; ++e) bv[e] = __bfloat162float(p.bias[col + e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nvalid) bv[e] = __bfloat162float(p.bias[col + e]);
           }
         }
         int rope_p = -1;  // index of this lane's first rotary pair, or -1
@@ -277,13 +369,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int dim = col % p.rope_hd;
           if (dim < p.rope_rot) rope_p = dim >> 1;
         }
+        if (p.epi_kind != EK_GENERIC && nvalid >= 4) {
+          OutT* cptr = reinterpret_cast<OutT*>(p.C) + boff + (long long)(row0 + rsub) * p.ldc + col;
+          const long long aoff = boff + (long long)(row0 + rsub) * p.ldc + col;
+          const long long roff = boff + (long long)(row0 + rsub) * p.ld_res + col;
+          bf16* auxo = p.aux_out ? p.aux_out + aoff : nullptr;
+          const bf16* auxi = p.aux_in ? p.aux_in + aoff : nullptr;
+          const bf16* r1 = p.res1 ? p.res1 + roff : nullptr;
+          const bf16* r2 = p.res2 ? p.res2 + roff : nullptr;
+#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM) \
+  epi_rows<ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT>(p, stg_s, c4, rsub, nrows, bv, cptr, auxo, auxi, r1, r2, row0, rope_p)
+          switch (p.epi_kind) {
+            case EK_PLAIN: MB_EPI(0, 0, 0, false, false, false); break;
+            case EK_ROPE: MB_EPI(0, 0, 0, false, true, false); break;
+            case EK_GELU: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, false, false, false); break;
+            case EK_GELU_AUX: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, true, false, false); break;
+            case EK_QGELU: MB_EPI(MB200_ACT_QUICK_GELU, 0, 0, false, false, false); break;
+            case EK_RELU: MB_EPI(MB200_ACT_RELU, 0, 0, false, false, false); break;
+            case EK_DGELU: MB_EPI(0, MB200_DACT_GELU_NEW, 0, false, false, false); break;
+            case EK_DRELU: MB_EPI(0, MB200_DACT_RELU, 0, false, false, false); break;
+            case EK_RES1: MB_EPI(0, 0, 1, false, false, false); break;
+            case EK_RES2: MB_EPI(0, 0, 2, false, false, false); break;
+            case EK_ACCUM: MB_EPI(0, 0, 0, false, false, true); break;
+            default: break;
+          }
+#undef MB_EPI
+          __syncwarp();
+          continue;
+        }
 #pragma unroll 4
         for (int it = 0; it < 16; ++it) {
           const int rl = it * 2 + rsub;
           const int row = m_blk * BM + q * 32 + rl;
           if (row >= p.M || nvalid <= 0) continue;
-          const float4 sv =
-              *reinterpret_cast<const float4*>(stg + rl * C_::kEpiPitch + ((((c4 >> 2)) ^ (rl & 15)) << 2));
+          const float4 sv = lds128(stg_s + (uint32_t)(rl * 256 + ((((c4 >> 2)) ^ (rl & 15)) << 4)));
           float v[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
           const long long coff = boff + (long long)row * p.ldc + col;
           const bool full = nvalid >= 4;
@@ -306,7 +425,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               u.y = *reinterpret_cast<uint32_t*>(&h1);
               *reinterpret_cast<uint2*>(dst) = u;
             } else {
-              for (int e = 0; e < nvalid; ++e) dst[e] = __float2bfloat16(v[e]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < nvalid) dst[e] = __float2bfloat16(v[e]);
             }
           }
           if (p.act == MB200_ACT_GELU_NEW) {
@@ -328,7 +449,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
               a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y;
             } else {
-              for (int e = 0; e < nvalid; ++e) a[e] = __bfloat162float(src[e]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < nvalid) a[e] = __bfloat162float(src[e]);
             }
             if (p.dact == MB200_DACT_GELU_NEW) {
 #pragma unroll
@@ -349,7 +472,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
               v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
             } else {
-              for (int e = 0; e < nvalid; ++e) v[e] += __bfloat162float(src[e]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < nvalid) v[e] += __bfloat162float(src[e]);
             }
           }
           if constexpr (sizeof(OutT) == 4) {
@@ -362,7 +487,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
               *reinterpret_cast<float4*>(dst) = o;
             } else {
-              for (int e = 0; e < nvalid; ++e) dst[e] = p.accumulate ? dst[e] + v[e] : v[e];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < nvalid) dst[e] = p.accumulate ? dst[e] + v[e] : v[e];
             }
           } else {
             bf16* dst = reinterpret_cast<bf16*>(p.C) + coff;
@@ -373,7 +500,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               u.y = *reinterpret_cast<uint32_t*>(&h1);
               *reinterpret_cast<uint2*>(dst) = u;
             } else {
-              for (int e = 0; e < nvalid; ++e) dst[e] = __float2bfloat16(v[e]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < nvalid) dst[e] = __float2bfloat16(v[e]);
             }
           }
         }
@@ -562,6 +691,27 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   kp.res1 = reinterpret_cast<const bf16*>(a->res1);
   kp.res2 = reinterpret_cast<const bf16*>(a->res2);
   kp.ld_res = a->ld_res;
+  {
+    // pick the specialised epilogue when the request matches one exactly (bias and alpha are free in all of them)
+    const bool rope = a->rope_tab && a->rope_mode != 0;
+    const int nres = (a->res1 ? 1 : 0) + (a->res2 ? 1 : 0);
+    const bool aux = a->aux_out != nullptr;
+    int k = EK_GENERIC;
+    if (!rope && !a->act && !a->dact && nres == 0 && !aux) k = a->accumulate ? EK_ACCUM : EK_PLAIN;
+    else if (rope && !a->act && !a->dact && nres == 0 && !aux && !a->accumulate) k = EK_ROPE;
+    else if (!rope && !a->dact && nres == 0 && !a->accumulate) {
+      if (a->act == MB200_ACT_GELU_NEW) k = aux ? EK_GELU_AUX : EK_GELU;
+      else if (a->act == MB200_ACT_QUICK_GELU && !aux) k = EK_QGELU;
+      else if (a->act == MB200_ACT_RELU && !aux) k = EK_RELU;
+    } else if (!rope && !a->act && nres == 0 && !aux && !a->accumulate) {
+      if (a->dact == MB200_DACT_GELU_NEW) k = EK_DGELU;
+      else if (a->dact == MB200_DACT_RELU) k = EK_DRELU;
+    } else if (!rope && !a->act && !a->dact && !aux && !a->accumulate && nres > 0) {
+      if (nres == 2) k = EK_RES2;
+      else if (a->res1) k = EK_RES1;
+    }
+    kp.epi_kind = k;
+  }
   kp.rope_tab = reinterpret_cast<const float2*>(a->rope_tab);
   kp.rope_mode = a->rope_tab ? a->rope_mode : 0;
   kp.rope_S = a->rope_S;
