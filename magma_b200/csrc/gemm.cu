@@ -73,10 +73,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue phase 2 (row-contiguous): the four epilogue warps run ONE warp per scheduler, so this code is latency-bound
-// unless it is straight-line with high ILP. epi_rows<> is therefore specialised at compile time on what the epilogue
-// does, fully unrolled over the 16 row-pairs of a 32x64 staging block, with pointer bumps instead of per-iteration
-// address arithmetic; the kernel dispatches once per tile on p.epi_kind (host-chosen) to an instantiation.
+// Epilogue. Accumulator rows live one-per-thread in TMEM; outputs (and residual / aux inputs) want row-contiguous
+// global access. Per 64-column group: phase 1 moves TMEM -> registers -> a per-warp XOR-swizzled smem block, phase 2
+// re-reads it so that 16 lanes x 4 columns cover one row segment (full 128-byte lines per row).
+// The four epilogue warps run ONE warp per scheduler, so phase 2 is latency-bound unless it is straight-line with
+// high ILP: epi_tile<> is specialised at compile time on what the epilogue does, fully unrolled over the 16 row pairs,
+// uses pointer bumps instead of per-row address arithmetic, and issues ALL global loads of a group (residuals, aux)
+// before anything is stored (a store may alias a later load as far as the compiler knows, which would serialise one
+// DRAM round trip per row pair). The kernel dispatches once per tile on p.epi_kind (chosen on the host).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
@@ -98,78 +102,246 @@ __device__ __forceinline__ uint2 f32x4_to_bf16(const float (&v)[4]) {
   u.y = *reinterpret_cast<uint32_t*>(&h1);
   return u;
 }
+__device__ __forceinline__ uint2 ldg64(const bf16* ptr) {
+  uint2 u;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(u.x), "=r"(u.y) : "l"(ptr));
+  return u;
+}
 
 enum { EK_GENERIC = 0, EK_PLAIN, EK_ROPE, EK_GELU, EK_GELU_AUX, EK_QGELU, EK_RELU, EK_DGELU, EK_DRELU, EK_RES1,
        EK_RES2, EK_ACCUM };
 
-// One 32-row x 64-column staging block, lanes with 4 valid columns only. stg_lane = smem address of this lane's float4
-// in row `rsub` (XOR-swizzled per row inside). Pointers are element pointers at (row0 + rsub, col).
-template <int ACT, int DACT, int NRES, bool AUX, bool ROPE, bool ACCUM, typename OutT>
-__device__ __forceinline__ void epi_rows(const GemmKernelParams& p, uint32_t stg_warp, int c4, int rsub, int nrows,
-                                         const float (&bv)[4], OutT* cptr, bf16* auxo, const bf16* auxi,
-                                         const bf16* r1, const bf16* r2, int row_first, int rope_p) {
-  const long long cstep = 2 * p.ldc, rstep = 2 * p.ld_res;
+struct EpiCtx {
+  uint32_t tmem_acc;  // TMEM address of this warp's lanes, column 0 of the accumulator buffer
+  uint32_t stg_s;     // smem address of this warp's staging block
+  uint64_t* tmem_full;
+  uint64_t* tmem_empty;
+  uint32_t full_phase;
+  long long boff;     // batch offset in C (elements)
+  int row0, nrows, n_blk, lane;
+};
+
+// slow per-lane path: any combination of epilogue options, any number (1..4) of valid columns. Used for float4
+// groups cut by the N edge and for option combinations without a specialised instantiation.
+template <typename OutT>
+__device__ __noinline__ void epi_lane_generic(const GemmKernelParams& p, const EpiCtx& c, int col, int nvalid, int rsub,
+                                              int c4) {
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias) {
 #pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (e < nvalid) bv[e] = __bfloat162float(p.bias[col + e]);
+  }
+  int rope_p = -1;
+  if (p.rope_mode != 0 && col < p.rope_ncols) {
+    const int dim = col % p.rope_hd;
+    if (dim < p.rope_rot) rope_p = dim >> 1;
+  }
   for (int it = 0; it < 16; ++it) {
     const int rl = it * 2 + rsub;
-    if (rl < nrows) {
-      const float4 sv = lds128(stg_warp + (uint32_t)(rl * 256 + ((((c4 >> 2)) ^ (rl & 15)) << 4)));
-      float v[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
-      if constexpr (ROPE) {
-        if (rope_p >= 0) {
-          const float2* tp = p.rope_tab + (long long)((row_first + rl) % p.rope_S) * (p.rope_rot >> 1) + rope_p;
-          const float2 cs0 = __ldg(tp), cs1 = __ldg(tp + 1);
-          const float sg = p.rope_mode > 0 ? 1.f : -1.f;
-          const float a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
-          v[0] = a0 * cs0.x - a1 * cs0.y * sg;
-          v[1] = a1 * cs0.x + a0 * cs0.y * sg;
-          v[2] = a2 * cs1.x - a3 * cs1.y * sg;
-          v[3] = a3 * cs1.x + a2 * cs1.y * sg;
-        }
+    if (rl >= c.nrows) continue;
+    const int row = c.row0 + rl;
+    const float4 sv = lds128(c.stg_s + (uint32_t)(rl * 256 + ((((c4 >> 2)) ^ (rl & 15)) << 4)));
+    float v[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
+    const long long coff = c.boff + (long long)row * p.ldc + col;
+    if (rope_p >= 0) {  // pairs never straddle the float4 (col % 4 == 0, rot % 4 == 0)
+      const float2* tp = p.rope_tab + (long long)(row % p.rope_S) * (p.rope_rot >> 1) + rope_p;
+      const float2 cs0 = __ldg(tp), cs1 = __ldg(tp + 1);
+      const float sg = p.rope_mode > 0 ? 1.f : -1.f;
+      const float a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+      v[0] = a0 * cs0.x - a1 * cs0.y * sg;
+      v[1] = a1 * cs0.x + a0 * cs0.y * sg;
+      v[2] = a2 * cs1.x - a3 * cs1.y * sg;
+      v[3] = a3 * cs1.x + a2 * cs1.y * sg;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e >= nvalid) continue;
+      float x = v[e];
+      if (p.aux_out) p.aux_out[coff + e] = __float2bfloat16(x);
+      if (p.act == MB200_ACT_GELU_NEW) x = gelu_new_f(x);
+      else if (p.act == MB200_ACT_QUICK_GELU) x = quick_gelu_f(x);
+      else if (p.act == MB200_ACT_RELU) x = fmaxf(x, 0.f);
+      if (p.dact) {
+        const float a = __bfloat162float(p.aux_in[coff + e]);
+        x = p.dact == MB200_DACT_GELU_NEW ? x * gelu_new_grad_f(a) : (a > 0.f ? x : 0.f);
       }
-      if constexpr (AUX) *reinterpret_cast<uint2*>(auxo + it * cstep) = f32x4_to_bf16(v);
-      if constexpr (ACT == MB200_ACT_GELU_NEW) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = gelu_new_f(v[e]);
-      } else if constexpr (ACT == MB200_ACT_QUICK_GELU) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = quick_gelu_f(v[e]);
-      } else if constexpr (ACT == MB200_ACT_RELU) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-      }
-      if constexpr (DACT != 0) {
-        float a[4];
-        bf16x4_to_f32(*reinterpret_cast<const uint2*>(auxi + it * cstep), a);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if constexpr (DACT == MB200_DACT_GELU_NEW) v[e] *= gelu_new_grad_f(a[e]);
-          else v[e] = a[e] > 0.f ? v[e] : 0.f;
-        }
-      }
-      if constexpr (NRES >= 1) {
-        float a[4];
-        bf16x4_to_f32(*reinterpret_cast<const uint2*>(r1 + it * rstep), a);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] += a[e];
-      }
-      if constexpr (NRES >= 2) {
-        float a[4];
-        bf16x4_to_f32(*reinterpret_cast<const uint2*>(r2 + it * rstep), a);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] += a[e];
-      }
+      const long long roff = c.boff + (long long)row * p.ld_res + col + e;
+      if (p.res1) x += __bfloat162float(p.res1[roff]);
+      if (p.res2) x += __bfloat162float(p.res2[roff]);
       if constexpr (sizeof(OutT) == 4) {
-        float4 o = make_float4(v[0], v[1], v[2], v[3]);
-        float* dst = reinterpret_cast<float*>(cptr) + it * cstep;
-        if constexpr (ACCUM) {
-          const float4 old = *reinterpret_cast<const float4*>(dst);
-          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-        }
-        *reinterpret_cast<float4*>(dst) = o;
+        float* dst = reinterpret_cast<float*>(p.C) + coff + e;
+        *dst = p.accumulate ? *dst + x : x;
       } else {
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(cptr) + it * cstep) = f32x4_to_bf16(v);
+        reinterpret_cast<bf16*>(p.C)[coff + e] = __float2bfloat16(x);
       }
+    }
+  }
+}
+
+template <int BN, int DACT, int NRES, bool ACCUM, bool GENERIC, int NLD>
+__device__ __forceinline__ void epi_preload(const GemmKernelParams& p, const EpiCtx& c, int g, int c4, int rsub,
+                                            long long cstep, long long rstep, uint2 (&pre)[NLD > 0 ? NLD : 1][16]) {
+  if constexpr (NLD > 0 && !GENERIC) {
+    const int col = c.n_blk * BN + g * 64 + c4;
+    if (col + 4 > p.N) return;
+    const long long aoff = c.boff + (long long)(c.row0 + rsub) * p.ldc + col;
+    const long long roff = c.boff + (long long)(c.row0 + rsub) * p.ld_res + col;
+    constexpr int kD = 0, kR1 = (DACT != 0 ? 1 : 0), kR2 = kR1 + 1, kA = kR1 + NRES;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      if (it * 2 + rsub < c.nrows) {
+        if constexpr (DACT != 0) pre[kD][it] = ldg64(p.aux_in + aoff + it * cstep);
+        if constexpr (NRES >= 1) pre[kR1][it] = ldg64(p.res1 + roff + it * rstep);
+        if constexpr (NRES >= 2) pre[kR2][it] = ldg64(p.res2 + roff + it * rstep);
+        if constexpr (ACCUM) {
+          const float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.C) + aoff + it * cstep);
+          pre[kA][it] = make_uint2(__float_as_uint(o.x), __float_as_uint(o.y));
+          pre[kA + 1][it] = make_uint2(__float_as_uint(o.z), __float_as_uint(o.w));
+        }
+      }
+    }
+  }
+}
+
+template <int BN, int ACT, int DACT, int NRES, bool AUX, bool ROPE, bool ACCUM, bool GENERIC, typename OutT>
+__device__ __forceinline__ void epi_tile(const GemmKernelParams& p, const EpiCtx& c) {
+  constexpr int NLD = (DACT != 0 ? 1 : 0) + NRES + (ACCUM ? 2 : 0);  // uint2 loads per row pair
+  const int lane = c.lane;
+  const int c4 = (lane & 15) * 4;
+  const int rsub = lane >> 4;
+  const int n_tile_end = min(p.N, (c.n_blk + 1) * BN);
+  const long long cstep = 2 * p.ldc, rstep = 2 * p.ld_res;
+  uint2 pre[NLD > 0 ? NLD : 1][16];
+
+  epi_preload<BN, DACT, NRES, ACCUM, GENERIC, NLD>(p, c, 0, c4, rsub, cstep, rstep, pre);  // overlaps the accumulator wait
+  mbar_wait(c.tmem_full, c.full_phase);
+  tc_fence_after();
+
+#pragma unroll 1
+  for (int g = 0; g < BN / 64; ++g) {
+    const int n0 = c.n_blk * BN + g * 64;
+    if (n0 >= p.N) break;  // warp-uniform
+    // ---- phase 1: TMEM -> registers -> per-warp smem staging (thread i owns accumulator row i) ----
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t rr[32];
+      tmem_ld_32x32(c.tmem_acc + (uint32_t)(g * 64 + h * 32), rr);
+      tmem_ld_wait();
+      const uint32_t drow = c.stg_s + (uint32_t)(lane * 256);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        sts128(drow + (uint32_t)(((((h * 32 + j) >> 2) ^ (lane & 15)) << 4)), __uint_as_float(rr[j]) * p.alpha,
+               __uint_as_float(rr[j + 1]) * p.alpha, __uint_as_float(rr[j + 2]) * p.alpha,
+               __uint_as_float(rr[j + 3]) * p.alpha);
+    }
+    if (n0 + 64 >= n_tile_end) {
+      // last column group: the accumulator has been fully read -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c.tmem_empty);
+    }
+    __syncwarp();
+    // ---- phase 2 ----
+    const int col = n0 + c4;
+    const int nvalid = p.N - col;
+    if (nvalid >= 4 && !GENERIC) {
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.bias) bf16x4_to_f32(ldg64(p.bias + col), bv);
+      int rope_p = -1;
+      if constexpr (ROPE) {
+        if (col < p.rope_ncols) {
+          const int dim = col % p.rope_hd;
+          if (dim < p.rope_rot) rope_p = dim >> 1;
+        }
+      }
+      const long long aoff = c.boff + (long long)(c.row0 + rsub) * p.ldc + col;
+      OutT* cptr = reinterpret_cast<OutT*>(p.C) + aoff;
+      bf16* auxo = AUX ? p.aux_out + aoff : nullptr;
+      constexpr int kFence = (ACT == MB200_ACT_GELU_NEW || ACT == MB200_ACT_QUICK_GELU || DACT == MB200_DACT_GELU_NEW) ? 1 : 4;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        // compiler scheduling fence: keeps the fully unrolled body from hoisting every smem read / conversion of all 16
+        // row pairs at once (register pressure); the global loads were all issued by epi_preload already
+        if (it % kFence == 0) asm volatile("" ::: "memory");
+        const int rl = it * 2 + rsub;
+        if (rl < c.nrows) {
+          const float4 sv = lds128(c.stg_s + (uint32_t)(rl * 256 + ((((c4 >> 2)) ^ (rl & 15)) << 4)));
+          float v[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
+          if constexpr (ROPE) {
+            if (rope_p >= 0) {
+              const float2* tp = p.rope_tab + (long long)((c.row0 + rl) % p.rope_S) * (p.rope_rot >> 1) + rope_p;
+              const float2 cs0 = __ldg(tp), cs1 = __ldg(tp + 1);
+              const float sg = p.rope_mode > 0 ? 1.f : -1.f;
+              const float a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+              v[0] = a0 * cs0.x - a1 * cs0.y * sg;
+              v[1] = a1 * cs0.x + a0 * cs0.y * sg;
+              v[2] = a2 * cs1.x - a3 * cs1.y * sg;
+              v[3] = a3 * cs1.x + a2 * cs1.y * sg;
+            }
+          }
+          if constexpr (AUX) *reinterpret_cast<uint2*>(auxo + it * cstep) = f32x4_to_bf16(v);
+          if constexpr (ACT == MB200_ACT_GELU_NEW) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = gelu_new_f(v[e]);
+          } else if constexpr (ACT == MB200_ACT_QUICK_GELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = quick_gelu_f(v[e]);
+          } else if constexpr (ACT == MB200_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          constexpr int kD = 0, kR1 = (DACT != 0 ? 1 : 0), kR2 = kR1 + 1, kA = kR1 + NRES;
+          if constexpr (DACT != 0) {
+            float a[4];
+            bf16x4_to_f32(pre[kD][it], a);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if constexpr (DACT == MB200_DACT_GELU_NEW) v[e] *= gelu_new_grad_f(a[e]);
+              else v[e] = a[e] > 0.f ? v[e] : 0.f;
+            }
+          }
+          if constexpr (NRES >= 1) {
+            float a[4];
+            bf16x4_to_f32(pre[kR1][it], a);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] += a[e];
+          }
+          if constexpr (NRES >= 2) {
+            float a[4];
+            bf16x4_to_f32(pre[kR2][it], a);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] += a[e];
+          }
+          if constexpr (sizeof(OutT) == 4) {
+            float4 o = make_float4(v[0], v[1], v[2], v[3]);
+            if constexpr (ACCUM) {
+              o.x += __uint_as_float(pre[kA][it].x);
+              o.y += __uint_as_float(pre[kA][it].y);
+              o.z += __uint_as_float(pre[kA + 1][it].x);
+              o.w += __uint_as_float(pre[kA + 1][it].y);
+            }
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(cptr) + it * cstep) = o;
+          } else {
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(cptr) + it * cstep) = f32x4_to_bf16(v);
+          }
+        }
+      }
+    } else if (GENERIC && nvalid > 0) {
+      epi_lane_generic<OutT>(p, c, col, nvalid < 4 ? nvalid : 4, rsub, c4);
+    }
+    __syncwarp();  // staging block is reused by the next column group
+    if (g + 1 < BN / 64)  // latency overlaps phase 1 of the next group
+      epi_preload<BN, DACT, NRES, ACCUM, GENERIC, NLD>(p, c, g + 1, c4, rsub, cstep, rstep, pre);
+  }
+  if constexpr (!GENERIC) {
+    // a float4 column group cut by the N edge (N % 4 != 0, e.g. the 50258-wide LM head) can only be in the LAST group
+    // of the tile, whose staging block is still intact: finish those lanes on the slow path, outside the hot loop.
+    if (p.N & 3) {
+      const int lastg = (n_tile_end - 1 - c.n_blk * BN) >> 6;
+      const int col = c.n_blk * BN + lastg * 64 + c4;
+      const int nvalid = p.N - col;
+      if (nvalid > 0 && nvalid < 4) epi_lane_generic<OutT>(p, c, col, nvalid, rsub, c4);
     }
   }
 }
@@ -311,203 +483,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int z0 = z % p.nb0, z1 = z / p.nb0;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-
-      const long long boff = (long long)z0 * p.c_bs0 + (long long)z1 * p.c_bs1;
-      float* stg = epi_stage + q * (32 * C_::kEpiPitch);
-      const uint32_t stg_s = smem_u32(stg);
-      const int row0 = m_blk * BM + q * 32;
-      const int nrows = max(0, min(32, p.M - row0));
-      const int n_tile_end = min(p.N, (n_blk + 1) * BN);
-      // coalesced phase-2 mapping: 16 lanes x 4 columns cover one 64-column row segment; 2 rows per instruction
-      const int c4 = (lane & 15) * 4;
-      const int rsub = lane >> 4;
-
-#pragma unroll 1
-      for (int g = 0; g < BN / 64; ++g) {
-        const int n0 = n_blk * BN + g * 64;
-        if (n0 >= p.N) break;  // warp-uniform
-        // ---- phase 1: TMEM -> registers -> per-warp smem staging (thread i owns accumulator row i) ----
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t rr[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + g * 64 + h * 32), rr);
-          tmem_ld_wait();
-          const uint32_t drow = stg_s + (uint32_t)(lane * 256);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            sts128(drow + (uint32_t)(((((h * 32 + j) >> 2) ^ (lane & 15)) << 4)), __uint_as_float(rr[j]) * p.alpha,
-                   __uint_as_float(rr[j + 1]) * p.alpha, __uint_as_float(rr[j + 2]) * p.alpha,
-                   __uint_as_float(rr[j + 3]) * p.alpha);
+      EpiCtx c;
+      c.tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      c.stg_s = smem_u32(epi_stage + q * (32 * C_::kEpiPitch));
+      c.tmem_full = &tmem_full[acc];
+      c.tmem_empty = &tmem_empty[acc];
+      c.full_phase = acc_phase;
+      c.boff = (long long)z0 * p.c_bs0 + (long long)z1 * p.c_bs1;
+      c.row0 = m_blk * BM + q * 32;
+      c.nrows = max(0, min(32, p.M - c.row0));
+      c.n_blk = n_blk;
+      c.lane = lane;
+#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM) epi_tile<BN, ACT, DACT, NRES, AUX, ROPE, ACCUM, false, OutT>(p, c)
+      if constexpr (sizeof(OutT) == 4) {
+        // fp32 outputs are attention scores and weight gradients: only plain / accumulate are specialised
+        switch (p.epi_kind) {
+          case EK_PLAIN: MB_EPI(0, 0, 0, false, false, false); break;
+          case EK_ACCUM: MB_EPI(0, 0, 0, false, false, true); break;
+          default: epi_tile<BN, 0, 0, 0, false, false, false, true, OutT>(p, c); break;
         }
-        if (n0 + 64 >= n_tile_end) {
-          // last column group of this tile: the accumulator has been fully read -> hand TMEM back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      } else {
+        switch (p.epi_kind) {
+          case EK_PLAIN: MB_EPI(0, 0, 0, false, false, false); break;
+          case EK_ROPE: MB_EPI(0, 0, 0, false, true, false); break;
+          case EK_GELU: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, false, false, false); break;
+          case EK_GELU_AUX: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, true, false, false); break;
+          case EK_QGELU: MB_EPI(MB200_ACT_QUICK_GELU, 0, 0, false, false, false); break;
+          case EK_RELU: MB_EPI(MB200_ACT_RELU, 0, 0, false, false, false); break;
+          case EK_DGELU: MB_EPI(0, MB200_DACT_GELU_NEW, 0, false, false, false); break;
+          case EK_DRELU: MB_EPI(0, MB200_DACT_RELU, 0, false, false, false); break;
+          case EK_RES1: MB_EPI(0, 0, 1, false, false, false); break;
+          case EK_RES2: MB_EPI(0, 0, 2, false, false, false); break;
+          default: epi_tile<BN, 0, 0, 0, false, false, false, true, OutT>(p, c); break;
         }
-        __syncwarp();
-        // ---- phase 2: fused epilogue in a row-contiguous layout (full 128-byte lines per row) ----
-        const int col = n0 + c4;
-        const int nvalid = p.N - col;  // > 0 columns of this lane's float4 are in range
-        float bv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.bias && nvalid > 0) {
-          if (nvalid >= 4) {
-            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
-            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-            bv[0] = f0.x; bv[1] = f0.y; bv[2] = f1.x; bv[3] = f1.y;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (e < nvalid) bv[e] = __bfloat162float(p.bias[col + e]);
-          }
-        }
-        int rope_p = -1;  // index of this lane's first rotary pair, or -1
-        if (p.rope_mode != 0 && col < p.rope_ncols) {
-          const int dim = col % p.rope_hd;
-          if (dim < p.rope_rot) rope_p = dim >> 1;
-        }
-        if (p.epi_kind != EK_GENERIC && nvalid >= 4) {
-          OutT* cptr = reinterpret_cast<OutT*>(p.C) + boff + (long long)(row0 + rsub) * p.ldc + col;
-          const long long aoff = boff + (long long)(row0 + rsub) * p.ldc + col;
-          const long long roff = boff + (long long)(row0 + rsub) * p.ld_res + col;
-          bf16* auxo = p.aux_out ? p.aux_out + aoff : nullptr;
-          const bf16* auxi = p.aux_in ? p.aux_in + aoff : nullptr;
-          const bf16* r1 = p.res1 ? p.res1 + roff : nullptr;
-          const bf16* r2 = p.res2 ? p.res2 + roff : nullptr;
-#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM) \
-  epi_rows<ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT>(p, stg_s, c4, rsub, nrows, bv, cptr, auxo, auxi, r1, r2, row0, rope_p)
-          switch (p.epi_kind) {
-            case EK_PLAIN: MB_EPI(0, 0, 0, false, false, false); break;
-            case EK_ROPE: MB_EPI(0, 0, 0, false, true, false); break;
-            case EK_GELU: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, false, false, false); break;
-            case EK_GELU_AUX: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, true, false, false); break;
-            case EK_QGELU: MB_EPI(MB200_ACT_QUICK_GELU, 0, 0, false, false, false); break;
-            case EK_RELU: MB_EPI(MB200_ACT_RELU, 0, 0, false, false, false); break;
-            case EK_DGELU: MB_EPI(0, MB200_DACT_GELU_NEW, 0, false, false, false); break;
-            case EK_DRELU: MB_EPI(0, MB200_DACT_RELU, 0, false, false, false); break;
-            case EK_RES1: MB_EPI(0, 0, 1, false, false, false); break;
-            case EK_RES2: MB_EPI(0, 0, 2, false, false, false); break;
-            case EK_ACCUM: MB_EPI(0, 0, 0, false, false, true); break;
-            default: break;
-          }
-#undef MB_EPI
-          __syncwarp();
-          continue;
-        }
-#pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const int rl = it * 2 + rsub;
-          const int row = m_blk * BM + q * 32 + rl;
-          if (row >= p.M || nvalid <= 0) continue;
-          const float4 sv = lds128(stg_s + (uint32_t)(rl * 256 + ((((c4 >> 2)) ^ (rl & 15)) << 4)));
-          float v[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
-          const long long coff = boff + (long long)row * p.ldc + col;
-          const bool full = nvalid >= 4;
-          if (rope_p >= 0) {
-            const float2* tp = p.rope_tab + (long long)(row % p.rope_S) * (p.rope_rot >> 1) + rope_p;
-            const float2 cs0 = __ldg(tp), cs1 = __ldg(tp + 1);
-            const float sg = p.rope_mode > 0 ? 1.f : -1.f;
-            const float a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
-            v[0] = a0 * cs0.x - a1 * cs0.y * sg;
-            v[1] = a1 * cs0.x + a0 * cs0.y * sg;
-            v[2] = a2 * cs1.x - a3 * cs1.y * sg;
-            v[3] = a3 * cs1.x + a2 * cs1.y * sg;
-          }
-          if (p.aux_out) {
-            bf16* dst = p.aux_out + coff;
-            if (full) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-              uint2 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0);
-              u.y = *reinterpret_cast<uint32_t*>(&h1);
-              *reinterpret_cast<uint2*>(dst) = u;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (e < nvalid) dst[e] = __float2bfloat16(v[e]);
-            }
-          }
-          if (p.act == MB200_ACT_GELU_NEW) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = gelu_new_f(v[e]);
-          } else if (p.act == MB200_ACT_QUICK_GELU) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = quick_gelu_f(v[e]);
-          } else if (p.act == MB200_ACT_RELU) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          if (p.dact) {
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
-            const bf16* src = p.aux_in + coff;
-            if (full) {
-              const uint2 u = *reinterpret_cast<const uint2*>(src);
-              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-              a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (e < nvalid) a[e] = __bfloat162float(src[e]);
-            }
-            if (p.dact == MB200_DACT_GELU_NEW) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] *= gelu_new_grad_f(a[e]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
-            }
-          }
-#pragma unroll
-          for (int ri = 0; ri < 2; ++ri) {
-            const bf16* rp = ri == 0 ? p.res1 : p.res2;
-            if (!rp) continue;
-            const bf16* src = rp + boff + (long long)row * p.ld_res + col;
-            if (full) {
-              const uint2 u = *reinterpret_cast<const uint2*>(src);
-              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-              v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (e < nvalid) v[e] += __bfloat162float(src[e]);
-            }
-          }
-          if constexpr (sizeof(OutT) == 4) {
-            float* dst = reinterpret_cast<float*>(p.C) + coff;
-            if (full) {
-              float4 o = make_float4(v[0], v[1], v[2], v[3]);
-              if (p.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(dst);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              *reinterpret_cast<float4*>(dst) = o;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (e < nvalid) dst[e] = p.accumulate ? dst[e] + v[e] : v[e];
-            }
-          } else {
-            bf16* dst = reinterpret_cast<bf16*>(p.C) + coff;
-            if (full) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-              uint2 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0);
-              u.y = *reinterpret_cast<uint32_t*>(&h1);
-              *reinterpret_cast<uint2*>(dst) = u;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (e < nvalid) dst[e] = __float2bfloat16(v[e]);
-            }
-          }
-        }
-        __syncwarp();  // staging buffer is reused by the next column group
       }
+#undef MB_EPI
     }
   }
 
