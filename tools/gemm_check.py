@@ -12,7 +12,7 @@ import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
-GROUPS = ["basic", "majors", "tails", "epilogue", "batched", "perf"]
+GROUPS = ["basic", "majors", "tails", "epilogue", "batched", "pair", "perf"]
 
 
 def ref_gemm(A, B, a_mn, b_mn):
@@ -178,6 +178,69 @@ def run_group(g):
         ops.gemm(pbuf[..., :T], v2, out=o2.permute(0, 2, 1, 3), b_mn=True)
         torch.cuda.synchronize()
         ok &= report("batched ViT PV T=257 (ragged K)", o2.permute(0, 2, 1, 3), pbuf[..., :T].float() @ v2.float())
+    elif g == "pair":
+        # the CTA-pair (cta_group::2) kernel, forced with force_bn=512
+        import torch.nn.functional as F
+
+        for a_mn in (False, True):
+            for b_mn in (False, True):
+                M, N, K = 512, 768, 320
+                A, B = mk((M, K), a_mn, dev), mk((N, K), b_mn, dev)
+                C = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, force_bn=512)
+                torch.cuda.synchronize()
+                ok &= report(f"pair majors a_mn={int(a_mn)} b_mn={int(b_mn)}", C, ref_gemm(A, B, a_mn, b_mn))
+                M, N, K = 300, 1002, 328
+                A, B = mk((M, K), a_mn, dev), mk((N, K), b_mn, dev)
+                buf = torch.full((M, 1008), 7.0, device=dev, dtype=torch.bfloat16)
+                ops.gemm(A, B, out=buf[:, :N], a_mn=a_mn, b_mn=b_mn, force_bn=512)
+                torch.cuda.synchronize()
+                ok &= report(f"pair tails a_mn={int(a_mn)} b_mn={int(b_mn)} M=300 N=1002 K=328", buf[:, :N], ref_gemm(A, B, a_mn, b_mn))
+                ok &= bool((buf[:, N:] == 7.0).all().item())
+        M, N, K = 1024, 4096, 4096
+        A, B = mk((M, K), False, dev), mk((N, K), False, dev)
+        C = ops.gemm(A, B, force_bn=512)
+        torch.cuda.synchronize()
+        ok &= report("pair 1024x4096x4096", C, ref_gemm(A, B, False, False))
+        M, N, K = 512, 1024, 256
+        A, B = mk((M, K), False, dev, 0.5), mk((N, K), False, dev, 0.125)
+        bias = torch.randn(N, device=dev).to(torch.bfloat16)
+        base = ref_gemm(A, B, False, False)
+        pre = base + bias.float()
+        aux = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        C = ops.gemm(A, B, bias=bias, act=ops.ACT_GELU_NEW, aux_out=aux, force_bn=512)
+        ok &= report("pair bias+gelu_new+aux", C, F.gelu(pre, approximate="tanh"))
+        ok &= report("pair aux_out", aux, pre)
+        r1, r2 = mk((M, N), False, dev), mk((M, N), False, dev)
+        C = ops.gemm(A, B, bias=bias, res1=r1, res2=r2, force_bn=512)
+        ok &= report("pair bias+res1+res2", C, pre + r1.float() + r2.float())
+        x = mk((M, N), False, dev)
+        C = ops.gemm(A, B, aux_in=x, dact=ops.DACT_RELU, force_bn=512)
+        ok &= report("pair dact relu", C, base * (x.float() > 0).float())
+        Cf = torch.ones(M, N, device=dev, dtype=torch.float32)
+        ops.gemm(A, B, out=Cf, accumulate=True, force_bn=512)
+        ok &= report("pair f32 accumulate", Cf, base + 1.0, tol=5e-3)
+        # batched (2 x 3 batches of 256 x 512 x 192)
+        Ab = mk((2, 3, 256, 192), False, dev)
+        Bb = mk((2, 3, 512, 192), False, dev)
+        Cb = ops.gemm(Ab, Bb, force_bn=512)
+        torch.cuda.synchronize()
+        ok &= report("pair batched", Cb, Ab.float() @ Bb.float().transpose(-1, -2))
+        # perf vs 1-CTA
+        for (M, N, K, bmn) in ((1024, 4096, 4096, False), (1024, 16384, 4096, False), (1024, 4096, 16384, True), (8192, 8192, 8192, False)):
+            A, B = mk((M, K), False, dev), mk((N, K), bmn, dev)
+            C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            for bn in (256, 512):
+                for _ in range(3):
+                    ops.gemm(A, B, out=C, b_mn=bmn, force_bn=bn)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    ops.gemm(A, B, out=C, b_mn=bmn, force_bn=bn)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 20
+                print(f"[PERF] M={M} N={N} K={K} bmn={int(bmn)} {'pair' if bn == 512 else '1cta'}: {ms*1000:.1f} us {2.0*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
     elif g == "perf":
         shapes = [
             (1024, 4096, 4096, False, False, "out/qkv-like fwd"),
