@@ -331,8 +331,8 @@ static int pick_bn(int M, int N, int K, int batches) {
 static bool use_gemm2() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("MB200_GEMM2");
-    v = e ? atoi(e) : 0;
+    const char* e = getenv("MB200_GEMM2");  // set MB200_GEMM2=0 to fall back to the 1-CTA kernel everywhere
+    v = e ? atoi(e) : 1;
   }
   return v != 0;
 }
