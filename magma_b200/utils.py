@@ -90,7 +90,11 @@ def init_distributed(backend="nccl"):
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            import datetime
+
+            # a short collective timeout: a rank that stops participating must fail fast, not hang the box
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                    timeout=datetime.timedelta(seconds=int(os.environ.get("MB200_NCCL_TIMEOUT_S", "180"))))
         else:
             dist.init_process_group(backend)
         return dist.get_rank(), world, local_rank
