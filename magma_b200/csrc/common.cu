@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace mb200 {
 
@@ -29,6 +30,15 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MB200_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
 }
 
 int check_arch() {

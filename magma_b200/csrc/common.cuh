@@ -36,6 +36,7 @@ int check_cuda(cudaError_t e, const char* what);
 
 int num_sms();
 int check_arch();  // 0 if the current device is sm_100, else MB200_E_ARCH
+bool pdl_enabled();  // env MB200_PDL (default on)
 
 // launch accounting (mb200_launch_count) and optional per-GEMM CUDA-event timing (mb200_prof_*)
 void count_launch(int n = 1);
@@ -237,6 +238,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ----
+// Kernels of the layer loop are launched with programmaticStreamSerialization: each CTA signals at its start that the
+// next kernel in the stream may be scheduled (onto SMs as they free up), and every kernel blocks in pdl_wait() until
+// its predecessor has fully completed and flushed before it touches global memory. The prologue of kernel N+1
+// (barrier init, TMEM allocation, descriptor prefetch, launch latency) thereby overlaps the tail of kernel N.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- misc math ----
 __device__ __forceinline__ float gelu_new_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
@@ -263,5 +272,25 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// launch with the programmatic-stream-serialization attribute (PDL); falls back to a plain launch when disabled
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace mb200

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(kLnThreads)
 layernorm_fwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ gamma,
                      const bf16* __restrict__ beta, bf16* __restrict__ y, long long ldy, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int d, float eps) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const int nvec = d >> 3;
@@ -127,6 +129,8 @@ __global__ void __launch_bounds__(kLnThreads)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x, long long ldx,
                      const bf16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const bf16* __restrict__ res, long long ldres, bf16* __restrict__ dx, long long lddx, int d) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const int nvec = d >> 3;
@@ -239,6 +243,8 @@ __global__ void rope_table_kernel(float2* __restrict__ tab, int S, int half, int
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, long long lds, long long s_bs, bf16* __restrict__ p,
                                    long long ldp, long long p_bs, int nz, int Sq, int Sk, float scale, int causal,
                                    int koff) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (wid >= (long long)nz * Sq) return;
@@ -260,6 +266,8 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, long long lds, l
 __global__ void softmax_bwd_kernel(const float* __restrict__ dp, long long lddp, long long dp_bs,
                                    const bf16* __restrict__ p, long long ldp, long long p_bs, bf16* __restrict__ ds,
                                    long long ldds, long long ds_bs, int nz, int Sq, int Sk, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (wid >= (long long)nz * Sq) return;
@@ -430,6 +438,8 @@ __global__ void ce_reduce_kernel(const float* __restrict__ row_loss, int M, cons
 static constexpr int kColsumRows = 64;  // rows per CTA: grid = (col strips of 64) x (row chunks) for parallelism
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ldx, int rows, int cols, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[8][64];
   const int cl = threadIdx.x & 31;        // column pair within the strip
   const int rg = threadIdx.x >> 5;        // row group 0..7
@@ -681,8 +691,8 @@ extern "C" int mb200_layernorm_fwd(const void* x, int64_t ldx, const void* gamma
   MB_REQUIRE(rows > 0 && d > 0 && d % 8 == 0 && d <= kLnThreads * kLnMaxVec * 8, MB200_E_SHAPE,
              "layernorm: d=%d must be a multiple of 8 and <= %d", d, kLnThreads * kLnMaxVec * 8);
   MB_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, MB200_E_ALIGN, "layernorm: row strides must be multiples of 8");
-  layernorm_fwd_kernel<<<rows, kLnThreads, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)gamma,
-                                                            (const bf16*)beta, (bf16*)y, ldy, mean, rstd, d, eps);
+  MB_CUDA(launch_pdl(layernorm_fwd_kernel, dim3(rows), dim3(kLnThreads), 0, ST(stream), (const bf16*)x, (long long)ldx,
+                     (const bf16*)gamma, (const bf16*)beta, (bf16*)y, (long long)ldy, mean, rstd, (int)d, eps));
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -695,9 +705,9 @@ extern "C" int mb200_layernorm_bwd(const void* dy, int64_t lddy, const void* x, 
              "layernorm_bwd: bad d=%d", d);
   MB_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && (!res || ldres % 8 == 0), MB200_E_ALIGN,
              "layernorm_bwd: row strides must be multiples of 8");
-  layernorm_bwd_kernel<<<rows, kLnThreads, 0, ST(stream)>>>((const bf16*)dy, lddy, (const bf16*)x, ldx,
-                                                            (const bf16*)gamma, mean, rstd, (const bf16*)res, ldres,
-                                                            (bf16*)dx, lddx, d);
+  MB_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(rows), dim3(kLnThreads), 0, ST(stream), (const bf16*)dy,
+                     (long long)lddy, (const bf16*)x, (long long)ldx, (const bf16*)gamma, mean, rstd, (const bf16*)res,
+                     (long long)ldres, (bf16*)dx, (long long)lddx, (int)d));
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -736,8 +746,9 @@ extern "C" int mb200_softmax_fwd(const float* s, int64_t lds, int64_t s_bs, void
                                  void* stream) {
   MB_ENTER();
   const long long warps = (long long)nz * Sq;
-  softmax_fwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ST(stream)>>>(s, lds, s_bs, (bf16*)p, ldp, p_bs, nz, Sq,
-                                                                          Sk, scale, causal, koff);
+  MB_CUDA(launch_pdl(softmax_fwd_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, ST(stream), s, (long long)lds,
+                     (long long)s_bs, (bf16*)p, (long long)ldp, (long long)p_bs, (int)nz, (int)Sq, (int)Sk, scale,
+                     (int)causal, (int)koff));
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -747,8 +758,9 @@ extern "C" int mb200_softmax_bwd(const float* dp, int64_t lddp, int64_t dp_bs, c
                                  int32_t Sk, float scale, void* stream) {
   MB_ENTER();
   const long long warps = (long long)nz * Sq;
-  softmax_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ST(stream)>>>(dp, lddp, dp_bs, (const bf16*)p, ldp, p_bs,
-                                                                          (bf16*)ds, ldds, ds_bs, nz, Sq, Sk, scale);
+  MB_CUDA(launch_pdl(softmax_bwd_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, ST(stream), dp,
+                     (long long)lddp, (long long)dp_bs, (const bf16*)p, (long long)ldp, (long long)p_bs, (bf16*)ds,
+                     (long long)ldds, (long long)ds_bs, (int)nz, (int)Sq, (int)Sk, scale));
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -804,7 +816,8 @@ extern "C" int mb200_colsum(const void* x, int64_t ldx, int32_t rows, int32_t co
   MB_REQUIRE(cols % 2 == 0 && ldx % 2 == 0, MB200_E_ALIGN, "colsum: cols and ldx must be even");
   if (!accumulate) MB_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), ST(stream)));
   dim3 grid((cols + 63) / 64, (rows + kColsumRows - 1) / kColsumRows);
-  colsum_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)x, ldx, rows, cols, out);
+  MB_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, ST(stream), (const bf16*)x, (long long)ldx, (int)rows, (int)cols,
+                     out));
   MB_LAUNCH_CHECK();
   return 0;
 }

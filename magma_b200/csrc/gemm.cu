@@ -44,6 +44,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
 
+  pdl_trigger();  // the next kernel may start its prologue on SMs as they become free
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -66,6 +67,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above overlapped the previous kernel; global memory is touched only from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -285,7 +287,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     const double flops = 2.0 * kp.M * (double)kp.N * kp.K * nb;
     const double bytes = nb * (2.0 * ((double)kp.M * kp.K + (double)kp.N * kp.K) + (double)sizeof(OutT) * kp.M * kp.N);
     GemmProfScope prof(stream, flops, bytes);
-    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(tmA, tmB, kp);
+    MB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg<BN>::kSmemBytes, stream, tmA, tmB, kp));
   }
   count_launch();
   MB_CUDA(cudaGetLastError());

@@ -48,6 +48,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_kb = (p.K + BK - 1) / BK;
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -68,6 +69,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -218,7 +220,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKer
     const double flops = 2.0 * kp.M * (double)kp.N * kp.K * nb;
     const double bytes = nb * (2.0 * ((double)kp.M * kp.K + (double)kp.N * kp.K) + (double)sizeof(OutT) * kp.M * kp.N);
     GemmProfScope prof(stream, flops, bytes);
-    kern<<<clusters * 2, kThreads, kSmem2, stream>>>(tmA, tmB, kp);
+    MB_CUDA(launch_pdl(kern, dim3(clusters * 2), dim3(kThreads), kSmem2, stream, tmA, tmB, kp));
   }
   count_launch();
   MB_CUDA(cudaGetLastError());
