@@ -295,6 +295,18 @@ int mb200_vit_forward(const mb200_vit_model* m, const void* images, void* feats,
 /* Fused KV-cache attention for one decode step (Sq = 1): q/k/v come from the fused qkv row [B][3][H][hd] (already
  * rotated); k,v are appended to the cache at position `pos`, then softmax(q K^T / sqrt(hd)) V over [0, pos].
  * Replaces the torch.cat cache growth + _attn of hf:gptj/modeling_gptj.py:209-214,136-149 per step. */
+/* Fused causal self-attention for sequences that fit one tile (S <= 128, head_dim a multiple of 64, <= 256): one CTA
+ * per (batch, head), S = QK^T / softmax / PV entirely on-chip (TMEM + smem). qkv is the fused, already-rotated
+ * [B*S][3][H][hd] buffer; P (bf16 [B,H,S,ldP]) is saved for the backward pass; O is [B,S,H,hd] with row stride ldo.
+ * GPTJAttention._attn, hf:gptj/modeling_gptj.py:136-149. */
+int mb200_attn_fwd_tile(const void* qkv, int64_t ld_qkv, void* P, int64_t ldP, void* O, int64_t ldo, int32_t B,
+                        int32_t S, int32_t H, int32_t hd, void* stream);
+/* Backward of the above: dqkv [B*S][3][H][hd] receives dQ, dK (inverse rotary applied through rope_tab, which may be
+ * NULL) and dV. */
+int mb200_attn_bwd_tile(const void* qkv, int64_t ld_qkv, const void* dO, int64_t ld_do, const void* P, int64_t ldP,
+                        void* dqkv, int64_t ld_dqkv, const float* rope_tab, int32_t rot, int32_t B, int32_t S, int32_t H,
+                        int32_t hd, void* stream);
+
 int mb200_attn_decode(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, void* out, int64_t ld_out,
                       int32_t B, int32_t H, int32_t hd, int32_t S_kv_max, int32_t pos, void* stream);
 

@@ -164,5 +164,6 @@ EXPORTED_SYMBOLS = [
     "mb200_vit_assemble", "mb200_argmax", "mb200_add", "mb200_sumsq", "mb200_adamw_step",
     "mb200_cast_f32_to_bf16", "mb200_cast_bf16_to_f32",
     "mb200_gptj_workspace_bytes", "mb200_gptj_forward", "mb200_gptj_backward",
-    "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode",
+    "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode", "mb200_attn_fwd_tile",
+    "mb200_attn_bwd_tile",
 ]

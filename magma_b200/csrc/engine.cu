@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 extern "C" {
 int mb200_layernorm_fwd(const void*, int64_t, const void*, const void*, void*, int64_t, float*, float*, int32_t,
@@ -33,6 +34,21 @@ int mb200_vit_assemble(void*, const void*, const void*, const void*, int32_t, in
 namespace mb200 {
 
 int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream);
+bool attn_tile_supported(int S, int hd);
+int attn_fwd_tile(const bf16* qkv, long long ld_qkv, bf16* P, long long ldP, bf16* O, long long ldo, int B, int S, int H,
+                  int hd, cudaStream_t st);
+int attn_bwd_tile(const bf16* qkv, long long ld_qkv, const bf16* dO, long long ld_do, const bf16* P, long long ldP,
+                  bf16* dqkv, long long ld_dqkv, const float* rope_tab, int rot, int B, int S, int H, int hd,
+                  cudaStream_t st);
+
+static bool use_attn_tile() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MB200_ATTN_TILE");  // 0 = always use the GEMM-based attention path
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
 
 #define MB_TRY(expr)        \
   do {                      \
@@ -431,6 +447,19 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
       attn_decode_kernel<<<B * H, kDecThreads, smem, st>>>(a.qkv, 3 * d, kc, vc, a.attn_o, d, H, hd, Smax, pos0);
       count_launch();
       MB_CUDA(cudaGetLastError());
+    } else if (use_attn_tile() && attn_tile_supported(S, hd) && pos0 == 0) {
+      // whole sequence in one tile: fused QK^T / softmax / PV kernel, one CTA per (batch, head)
+      if (kcache) {
+        bf16* kc = kcache + (size_t)l * cache_layer;
+        bf16* vc = vcache + (size_t)l * cache_layer;
+        const long long tot = (long long)B * S * H * (hd / 8);
+        int grid = (int)((tot + 255) / 256);
+        if (grid > num_sms() * 8) grid = num_sms() * 8;
+        kv_append_kernel<<<grid, 256, 0, st>>>(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0);
+        count_launch();
+        MB_CUDA(cudaGetLastError());
+      }
+      MB_TRY(attn_fwd_tile(a.qkv, 3 * d, a.P, P.ldP, a.attn_o, d, B, S, H, hd, st));
     } else {
       Mat Q = mat(a.qkv, 3 * d, 0, hd, (long long)S * 3 * d);
       Mat Kk, Vv;
@@ -611,7 +640,9 @@ static int gptj_backward(const mb200_gptj_model* m, bf16* dx, float loss_scale, 
       dh_acc = P.da;
     }
     MB_TRY(gemm(st, M, d, d, mat(da, d), mat(L.w_out, d, 1), P.dattn_o, d, 0));  // d(attn_o) = da Wo
-    {
+    if (use_attn_tile() && attn_tile_supported(S, hd)) {
+      MB_TRY(attn_bwd_tile(a.qkv, 3 * d, P.dattn_o, d, a.P, P.ldP, P.dqkv, 3 * d, P.rope_tab, m->rotary_dim, B, S, H, hd, st));
+    } else {
       const long long qb0 = hd, qb1 = (long long)S * 3 * d;           // fused-qkv batch strides (h, b)
       const long long pb0 = (long long)S * P.ldP, pb1 = (long long)H * S * P.ldP;
       Mat dO = mat(P.dattn_o, d, 0, hd, (long long)S * d);

@@ -423,7 +423,8 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
 
   const bool amn = a->A.mn_major != 0, bmn = a->B.mn_major != 0;
   const bool f32 = a->c_dtype == MB200_F32;
-  if (force2 || (bn == 256 && a->M > 128 && a->N >= 256 && !a->force_bn && use_gemm2())) {
+  // (short-K problems are dominated by per-tile fixed cost, where the 1-CTA kernel with narrower tiles does better)
+  if (force2 || (bn == 256 && a->M > 128 && a->N >= 256 && a->K >= 512 && !a->force_bn && use_gemm2())) {
     // CTA-pair kernel: 256x256 tile per pair, each SM stages its own 128 A rows and HALF of the B tile
     // (64 B/clk of L2->SM traffic per SM instead of 96), 6-stage ring
     rc = make_operand_map(&tmB, a->B, a->N, a->K, a->nb0, a->nb1, 128);
