@@ -286,3 +286,23 @@ def adamw_step(master, grad, m1, m2, shadow, lr, beta1, beta2, eps, wd, grad_sca
                                  ctypes.c_float(beta2), ctypes.c_float(eps), ctypes.c_float(wd),
                                  ctypes.c_float(grad_scale), _ptr(gnorm_sq), ctypes.c_float(max_norm), int(step),
                                  int(zero_grad), _stream()))
+
+
+def attn_fwd_tile(qkv, B, S, H, hd):
+    """Fused single-tile causal attention (S <= 128). qkv: bf16 [B*S, 3*H*hd] already rotated.
+    Returns (O [B*S, H*hd], P [B, H, S, ldP])."""
+    ldP = (S + 7) // 8 * 8
+    P = torch.zeros(B, H, S, ldP, dtype=torch.bfloat16, device=qkv.device)
+    O = torch.empty(B * S, H * hd, dtype=torch.bfloat16, device=qkv.device)
+    check(lib().mb200_attn_fwd_tile(_ptr(qkv), ctypes.c_int64(qkv.stride(0)), _ptr(P), ctypes.c_int64(ldP), _ptr(O),
+                                    ctypes.c_int64(H * hd), B, S, H, hd, _stream()))
+    return O, P
+
+
+def attn_bwd_tile(qkv, dO, P, B, S, H, hd, rope_tab=None, rot=0):
+    """Backward of attn_fwd_tile -> dqkv [B*S, 3*H*hd] (inverse rotary applied to dq, dk when rope_tab is given)."""
+    dqkv = torch.empty_like(qkv)
+    check(lib().mb200_attn_bwd_tile(_ptr(qkv), ctypes.c_int64(qkv.stride(0)), _ptr(dO), ctypes.c_int64(dO.stride(0)),
+                                    _ptr(P), ctypes.c_int64(P.stride(2)), _ptr(dqkv), ctypes.c_int64(dqkv.stride(0)),
+                                    _ptr(rope_tab), int(rot), B, S, H, hd, _stream()))
+    return dqkv
