@@ -41,6 +41,36 @@ int attn_bwd_tile(const bf16* qkv, long long ld_qkv, const bf16* dO, long long l
                   bf16* dqkv, long long ld_dqkv, const float* rope_tab, int rot, int B, int S, int H, int hd,
                   cudaStream_t st);
 
+// Two-stream execution of the parallel-residual block: the attention branch (qkv -> attention -> out_proj) and the MLP
+// branch (fc_in -> fc_out) only meet at the block's final sum, so they are issued on two streams (fork after ln_1, join
+// before the sum). Kernels of one branch fill the SMs the other leaves idle (64 pair-tiles on 74 SM pairs for the
+// N = 4096 GEMMs, 128-thread attention CTAs, kernel tails).
+static bool use_two_streams() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MB200_TWO_STREAM");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork[64], join[64];
+  bool ok = false;
+};
+static SideStream& side_stream() {
+  static SideStream ss;
+  if (!ss.ok) {
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess) {
+      ss.ok = true;
+      for (int i = 0; i < 64 && ss.ok; ++i)
+        ss.ok = cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+  }
+  return ss;
+}
+
 static bool use_attn_tile() {
   static int v = -1;
   if (v < 0) {
@@ -109,6 +139,7 @@ struct GptjPlan {
   bf16* g0;
   bf16* g1;
   bf16* dt;
+  bf16* dt2;      // second adapter-hidden gradient buffer (attention adapter runs on the side stream)
   bf16* dm;
   bf16* dhact;
   bf16* dh_mlp;
@@ -173,6 +204,7 @@ static int make_plan(GptjPlan& P, const mb200_gptj_model* m, int B, int S, int S
     P.g1 = c.take<bf16>(M * d);
     const int rmax = rm > ra ? rm : ra;
     P.dt = rmax ? c.take<bf16>(M * rmax) : nullptr;
+    P.dt2 = ra ? c.take<bf16>(M * ra) : nullptr;
     P.dm = c.take<bf16>(M * d);
     P.dhact = c.take<bf16>(M * dff);
     P.dh_mlp = c.take<bf16>(M * d);
@@ -183,6 +215,7 @@ static int make_plan(GptjPlan& P, const mb200_gptj_model* m, int B, int S, int S
     P.da = c.take<bf16>(M * d);
   } else {
     P.dlogits = nullptr;
+    P.dt2 = nullptr;
     P.g0 = P.g1 = P.dt = P.dm = P.dhact = P.dh_mlp = P.dattn_o = P.dqkv = P.dS = P.dh = P.da = nullptr;
   }
   P.bytes = align_up(c.off, 256);
@@ -417,6 +450,8 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
   const size_t cache_layer = (size_t)B * H * Smax * hd;
 
   MB_TRY(mb200_rope_table(P.rope_tab, S, m->rotary_dim, pos0, st));
+  SideStream& SS = side_stream();
+  const bool two = use_two_streams() && SS.ok && M >= 256;  // decode steps stay on one stream
   const bf16* xin = x;
   if (training) {
     MB_CUDA(cudaMemcpyAsync(P.acts[0].x_in, x, (size_t)M * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
@@ -429,6 +464,12 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
                           : ((l & 1) ? P.x_final : P.acts[0].x_in);
     // ln_1 (one LN feeds both branches of the parallel-residual block)
     MB_TRY(mb200_layernorm_fwd(xin, d, L.ln1_g, L.ln1_b, a.h, d, a.mean, a.rstd, M, d, m->ln_eps, st));
+    cudaStream_t sa = st;  // stream of the attention branch
+    if (two) {
+      MB_CUDA(cudaEventRecord(SS.fork[l], st));
+      MB_CUDA(cudaStreamWaitEvent(SS.s, SS.fork[l], 0));
+      sa = SS.s;
+    }
     // fused q/k/v projection with the rotary embedding applied in the GEMM epilogue (q and k column ranges)
     {
       Epi e;
@@ -438,13 +479,13 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
       e.rope_hd = hd;
       e.rope_rot = m->rotary_dim;
       e.rope_ncols = 2 * d;
-      MB_TRY(gemm(st, M, 3 * d, d, mat(a.h, d), mat(L.w_qkv, d), a.qkv, 3 * d, 0, e));
+      MB_TRY(gemm(sa, M, 3 * d, d, mat(a.h, d), mat(L.w_qkv, d), a.qkv, 3 * d, 0, e));
     }
     if (kcache && S == 1) {
       bf16* kc = kcache + (size_t)l * cache_layer;
       bf16* vc = vcache + (size_t)l * cache_layer;
       const size_t smem = (((size_t)(pos0 + 1) + 31) & ~(size_t)31) * 4 + 32 * 4;
-      attn_decode_kernel<<<B * H, kDecThreads, smem, st>>>(a.qkv, 3 * d, kc, vc, a.attn_o, d, H, hd, Smax, pos0);
+      attn_decode_kernel<<<B * H, kDecThreads, smem, sa>>>(a.qkv, 3 * d, kc, vc, a.attn_o, d, H, hd, Smax, pos0);
       count_launch();
       MB_CUDA(cudaGetLastError());
     } else if (use_attn_tile() && attn_tile_supported(S, hd) && pos0 == 0) {
@@ -455,11 +496,11 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
         const long long tot = (long long)B * S * H * (hd / 8);
         int grid = (int)((tot + 255) / 256);
         if (grid > num_sms() * 8) grid = num_sms() * 8;
-        kv_append_kernel<<<grid, 256, 0, st>>>(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0);
+        kv_append_kernel<<<grid, 256, 0, sa>>>(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0);
         count_launch();
         MB_CUDA(cudaGetLastError());
       }
-      MB_TRY(attn_fwd_tile(a.qkv, 3 * d, a.P, P.ldP, a.attn_o, d, B, S, H, hd, st));
+      MB_TRY(attn_fwd_tile(a.qkv, 3 * d, a.P, P.ldP, a.attn_o, d, B, S, H, hd, sa));
     } else {
       Mat Q = mat(a.qkv, 3 * d, 0, hd, (long long)S * 3 * d);
       Mat Kk, Vv;
@@ -469,7 +510,7 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
         const long long tot = (long long)B * S * H * (hd / 8);
         int grid = (int)((tot + 255) / 256);
         if (grid > num_sms() * 8) grid = num_sms() * 8;
-        kv_append_kernel<<<grid, 256, 0, st>>>(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0);
+        kv_append_kernel<<<grid, 256, 0, sa>>>(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0);
         count_launch();
       MB_CUDA(cudaGetLastError());
         Kk = mat(kc, hd, 0, (long long)Smax * hd, (long long)H * Smax * hd);
@@ -479,11 +520,11 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
         Vv = mat(a.qkv + 2 * d, 3 * d, 1, hd, (long long)S * 3 * d);
       }
       // scores = Q K^T (fp32), P = softmax(scores / sqrt(hd) + causal mask), O = P V
-      MB_TRY(gemm(st, S, Sk, hd, Q, Kk, P.scores, P.ldS, 1, Epi(), H, B, (long long)S * P.ldS,
+      MB_TRY(gemm(sa, S, Sk, hd, Q, Kk, P.scores, P.ldS, 1, Epi(), H, B, (long long)S * P.ldS,
                   (long long)H * S * P.ldS));
       MB_TRY(mb200_softmax_fwd(P.scores, P.ldS, (long long)S * P.ldS, a.P, P.ldP, (long long)S * P.ldP, B * H, S, Sk,
-                               scale, 1, Sk - S, st));
-      MB_TRY(gemm(st, S, hd, Sk, mat(a.P, P.ldP, 0, (long long)S * P.ldP, (long long)H * S * P.ldP), Vv, a.attn_o, d,
+                               scale, 1, Sk - S, sa));
+      MB_TRY(gemm(sa, S, hd, Sk, mat(a.P, P.ldP, 0, (long long)S * P.ldP, (long long)H * S * P.ldP), Vv, a.attn_o, d,
                   0, Epi(), H, B, hd, (long long)S * d));
     }
     // attention output projection; ax = attention branch + residual x
@@ -491,19 +532,20 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
       Epi e;
       e.res1 = xin;
       e.ld_res = d;
-      MB_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), P.ax, d, 0, e));
+      MB_TRY(gemm(sa, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), P.ax, d, 0, e));
     } else if (m->attn_adapter == MB200_ADAPTER_NORMAL) {
       // AdapterWrapper: adapter(attn_out) + attn_out   (magma/adapters.py:109-116)
-      MB_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), a.a_out, d, 0));
-      MB_TRY(adapter_fwd(st, L.attn_ad, M, d, m->attn_adapter_r, a.a_out, a.t_attn, P.ax, a.a_out, xin));
+      MB_TRY(gemm(sa, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), a.a_out, d, 0));
+      MB_TRY(adapter_fwd(sa, L.attn_ad, M, d, m->attn_adapter_r, a.a_out, a.t_attn, P.ax, a.a_out, xin));
     } else {
       // ParallelAdapterWrapper: attn(h) + adapter(h), h = ln_1 output   (magma/adapters.py:85-92)
       Epi e;
       e.res1 = xin;
       e.ld_res = d;
-      MB_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), a.a_out, d, 0, e));
-      MB_TRY(adapter_fwd(st, L.attn_ad, M, d, m->attn_adapter_r, a.h, a.t_attn, P.ax, a.a_out, nullptr));
+      MB_TRY(gemm(sa, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), a.a_out, d, 0, e));
+      MB_TRY(adapter_fwd(sa, L.attn_ad, M, d, m->attn_adapter_r, a.h, a.t_attn, P.ax, a.a_out, nullptr));
     }
+    if (two) MB_CUDA(cudaEventRecord(SS.join[l], sa));
     // MLP: fc_in + bias + gelu_new (pre-activation saved for backward), then fc_out + bias
     {
       Epi e;
@@ -513,6 +555,7 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
       MB_TRY(gemm(st, M, dff, d, mat(a.h, d), mat(L.w_fc_in, d), P.hact, dff, 0, e));
     }
     if (m->mlp_adapter == MB200_ADAPTER_NONE) {
+      if (two) MB_CUDA(cudaStreamWaitEvent(st, SS.join[l], 0));  // ax is consumed by the fc_out epilogue
       Epi e;
       e.bias = L.b_fc_out;
       e.res1 = P.ax;
@@ -523,9 +566,11 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
       Epi e;
       e.bias = L.b_fc_out;
       MB_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), a.mlp_out, d, 0, e));
+      if (two) MB_CUDA(cudaStreamWaitEvent(st, SS.join[l], 0));  // ax is consumed by the adapter's up-projection
       MB_TRY(adapter_fwd(st, L.mlp_ad, M, d, m->mlp_adapter_r, a.mlp_out, a.t_mlp, xout, a.mlp_out, P.ax));
     } else {
       // ParallelAdapter: mlp(h) + adapter(h)   (magma/adapters.py:63-66)
+      if (two) MB_CUDA(cudaStreamWaitEvent(st, SS.join[l], 0));
       Epi e;
       e.bias = L.b_fc_out;
       e.res1 = P.ax;
@@ -594,6 +639,10 @@ static int gptj_backward(const mb200_gptj_model* m, bf16* dx, float loss_scale, 
   const float scale = 1.0f / sqrtf((float)hd);
   // gradient w.r.t. the residual stream entering layer l lives in g[(l) & 1]
   auto gbuf = [&](int l) { return (l & 1) ? P.g1 : P.g0; };
+  SideStream& SS = side_stream();
+  // parallel adapters thread the ln_1-output gradient through both chains sequentially: keep those on one stream
+  const bool twob = use_two_streams() && SS.ok && M >= 256 && m->mlp_adapter != MB200_ADAPTER_PARALLEL &&
+                    m->attn_adapter != MB200_ADAPTER_PARALLEL;
 
   if (layer_hi == m->n_layer) {
     // dxf = loss_scale * dlogits Wlm ; g = LN_f backward
@@ -609,6 +658,13 @@ static int gptj_backward(const mb200_gptj_model* m, bf16* dx, float loss_scale, 
     const bf16* g = gbuf(l + 1);
     bf16* gout = (l == 0 && dx) ? dx : gbuf(l);
     const bf16* dh_acc = nullptr;  // running sum of gradients w.r.t. h = ln_1 output
+    cudaStream_t sa = st;
+    if (twob) {
+      // fork BEFORE the MLP chain is enqueued: g (complete on st here) feeds both chains
+      MB_CUDA(cudaEventRecord(SS.fork[l], st));
+      MB_CUDA(cudaStreamWaitEvent(SS.s, SS.fork[l], 0));
+      sa = SS.s;
+    }
 
     // ---- MLP branch ----
     const bf16* dm = g;
@@ -630,32 +686,32 @@ static int gptj_backward(const mb200_gptj_model* m, bf16* dx, float loss_scale, 
       MB_TRY(gemm(st, M, d, dff, mat(P.dhact, dff), mat(L.w_fc_in, d, 1), P.dh_mlp, d, 0, e2));
       dh_acc = P.dh_mlp;
     }
-    // ---- attention branch ----
+    // ---- attention branch (side stream when two-stream execution is on) ----
     const bf16* da = g;
     if (m->attn_adapter == MB200_ADAPTER_NORMAL) {
-      MB_TRY(adapter_bwd(st, L.attn_ad, M, d, m->attn_adapter_r, g, a.a_out, a.t_attn, P.dt, P.da, g, accumulate));
+      MB_TRY(adapter_bwd(sa, L.attn_ad, M, d, m->attn_adapter_r, g, a.a_out, a.t_attn, twob ? P.dt2 : P.dt, P.da, g, accumulate));
       da = P.da;
     } else if (m->attn_adapter == MB200_ADAPTER_PARALLEL) {
-      MB_TRY(adapter_bwd(st, L.attn_ad, M, d, m->attn_adapter_r, g, a.h, a.t_attn, P.dt, P.da, dh_acc, accumulate));
+      MB_TRY(adapter_bwd(sa, L.attn_ad, M, d, m->attn_adapter_r, g, a.h, a.t_attn, P.dt, P.da, dh_acc, accumulate));
       dh_acc = P.da;
     }
-    MB_TRY(gemm(st, M, d, d, mat(da, d), mat(L.w_out, d, 1), P.dattn_o, d, 0));  // d(attn_o) = da Wo
+    MB_TRY(gemm(sa, M, d, d, mat(da, d), mat(L.w_out, d, 1), P.dattn_o, d, 0));  // d(attn_o) = da Wo
     if (use_attn_tile() && attn_tile_supported(S, hd)) {
-      MB_TRY(attn_bwd_tile(a.qkv, 3 * d, P.dattn_o, d, a.P, P.ldP, P.dqkv, 3 * d, P.rope_tab, m->rotary_dim, B, S, H, hd, st));
+      MB_TRY(attn_bwd_tile(a.qkv, 3 * d, P.dattn_o, d, a.P, P.ldP, P.dqkv, 3 * d, P.rope_tab, m->rotary_dim, B, S, H, hd, sa));
     } else {
       const long long qb0 = hd, qb1 = (long long)S * 3 * d;           // fused-qkv batch strides (h, b)
       const long long pb0 = (long long)S * P.ldP, pb1 = (long long)H * S * P.ldP;
       Mat dO = mat(P.dattn_o, d, 0, hd, (long long)S * d);
       Mat dO_mn = mat(P.dattn_o, d, 1, hd, (long long)S * d);
       // dP = dO V^T (fp32)
-      MB_TRY(gemm(st, S, S, hd, dO, mat(a.qkv + 2 * d, 3 * d, 0, qb0, qb1), P.scores, P.ldS, 1, Epi(), H, B,
+      MB_TRY(gemm(sa, S, S, hd, dO, mat(a.qkv + 2 * d, 3 * d, 0, qb0, qb1), P.scores, P.ldS, 1, Epi(), H, B,
                   (long long)S * P.ldS, (long long)H * S * P.ldS));
       // dV = P^T dO
-      MB_TRY(gemm(st, S, hd, S, mat(a.P, P.ldP, 1, pb0, pb1), dO_mn, P.dqkv + 2 * d, 3 * d, 0, Epi(), H, B, qb0,
+      MB_TRY(gemm(sa, S, hd, S, mat(a.P, P.ldP, 1, pb0, pb1), dO_mn, P.dqkv + 2 * d, 3 * d, 0, Epi(), H, B, qb0,
                   qb1));
       // dS = P * (dP - rowsum(dP * P)) / sqrt(hd)
       MB_TRY(mb200_softmax_bwd(P.scores, P.ldS, (long long)S * P.ldS, a.P, P.ldP, pb0, P.dS, P.ldP, pb0, B * H, S, S,
-                               scale, st));
+                               scale, sa));
       // dQ = dS K ; dK = dS^T Q (gradients w.r.t. the rotated q, k) with the inverse rotation fused in the epilogue
       Epi er;
       er.rope_tab = P.rope_tab;
@@ -664,10 +720,14 @@ static int gptj_backward(const mb200_gptj_model* m, bf16* dx, float loss_scale, 
       er.rope_hd = hd;
       er.rope_rot = m->rotary_dim;
       er.rope_ncols = hd;
-      MB_TRY(gemm(st, S, hd, S, mat(P.dS, P.ldP, 0, pb0, pb1), mat(a.qkv + d, 3 * d, 1, qb0, qb1), P.dqkv, 3 * d, 0,
+      MB_TRY(gemm(sa, S, hd, S, mat(P.dS, P.ldP, 0, pb0, pb1), mat(a.qkv + d, 3 * d, 1, qb0, qb1), P.dqkv, 3 * d, 0,
                   er, H, B, qb0, qb1));
-      MB_TRY(gemm(st, S, hd, S, mat(P.dS, P.ldP, 1, pb0, pb1), mat(a.qkv, 3 * d, 1, qb0, qb1), P.dqkv + d, 3 * d, 0,
+      MB_TRY(gemm(sa, S, hd, S, mat(P.dS, P.ldP, 1, pb0, pb1), mat(a.qkv, 3 * d, 1, qb0, qb1), P.dqkv + d, 3 * d, 0,
                   er, H, B, qb0, qb1));
+    }
+    if (twob) {
+      MB_CUDA(cudaEventRecord(SS.join[l], sa));
+      MB_CUDA(cudaStreamWaitEvent(st, SS.join[l], 0));
     }
     {
       Epi e;
