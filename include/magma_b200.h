@@ -114,6 +114,10 @@ typedef struct {
   int32_t rope_mode;
   const void* rope_tab;
   int32_t rope_S, rope_hd, rope_rot, rope_ncols;
+  /* optional split-K workspace for small-M (M <= 128, unbatched) weight-streaming GEMMs: fp32, ZERO on entry (the
+   * library leaves it zero again), at least M * round_up(N, 4) * 4 bytes. NULL = never split K. */
+  void* splitk_ws;
+  int64_t splitk_ws_bytes;
 } mb200_gemm_args;
 
 int mb200_gemm(const mb200_gemm_args* args, void* stream);

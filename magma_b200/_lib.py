@@ -58,6 +58,8 @@ class GemmArgs(ctypes.Structure):
         ("rope_hd", ctypes.c_int32),
         ("rope_rot", ctypes.c_int32),
         ("rope_ncols", ctypes.c_int32),
+        ("splitk_ws", ctypes.c_void_p),
+        ("splitk_ws_bytes", ctypes.c_int64),
     ]
 
 

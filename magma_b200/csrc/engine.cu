@@ -48,8 +48,8 @@ int attn_bwd_tile(const bf16* qkv, long long ld_qkv, const bf16* dO, long long l
 static bool use_two_streams() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("MB200_TWO_STREAM");
-    v = e ? atoi(e) : 1;
+    const char* e = getenv("MB200_TWO_STREAM");  // measured: no gain at B=8,S=128 (33.34 vs 33.40 ms) -> off by default
+    v = e ? atoi(e) : 0;
   }
   return v != 0;
 }
@@ -135,6 +135,8 @@ struct GptjPlan {
   float* row_loss;
   int* n_valid;
   float* rope_tab;  // [S][rot/2] (cos, sin) for positions pos0 .. pos0+S-1
+  float* splitk_ws;  // fp32 [min(M,128)][max N] split-K workspace for small-M (decode) GEMMs, kept zero between uses
+  size_t splitk_bytes;
   // backward temporaries
   bf16* g0;
   bf16* g1;
@@ -198,6 +200,13 @@ static int make_plan(GptjPlan& P, const mb200_gptj_model* m, int B, int S, int S
   P.row_loss = c.take<float>(M);
   P.n_valid = c.take<int>(4);
   P.rope_tab = c.take<float>((size_t)S * m->rotary_dim);
+  {
+    size_t maxn = (size_t)3 * d;
+    if ((size_t)dff > maxn) maxn = dff;
+    if ((size_t)P.ldv > maxn) maxn = (size_t)P.ldv;
+    P.splitk_bytes = M <= 128 ? (size_t)M * maxn * sizeof(float) : 0;
+    P.splitk_ws = P.splitk_bytes ? c.take<float>(P.splitk_bytes / sizeof(float)) : nullptr;
+  }
   if (training) {
     P.dlogits = c.take<bf16>(M * (size_t)P.ldv);
     P.g0 = c.take<bf16>(M * d);
@@ -249,6 +258,10 @@ struct Epi {
   int rope_mode = 0, rope_S = 0, rope_hd = 0, rope_rot = 0, rope_ncols = 0;
 };
 
+// split-K workspace of the pass being issued (set by gptj_forward for small-M passes, else null)
+static thread_local float* g_splitk_ws = nullptr;
+static thread_local size_t g_splitk_bytes = 0;
+
 static int gemm(cudaStream_t st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, int c_f32,
                 const Epi& e = Epi(), int nb0 = 1, int nb1 = 1, long long c_bs0 = 0, long long c_bs1 = 0) {
   mb200_gemm_args g;
@@ -289,6 +302,8 @@ static int gemm(cudaStream_t st, int M, int N, int K, Mat A, Mat B, void* C, lon
   g.rope_hd = e.rope_hd;
   g.rope_rot = e.rope_rot;
   g.rope_ncols = e.rope_ncols;
+  g.splitk_ws = g_splitk_ws;
+  g.splitk_ws_bytes = (long long)g_splitk_bytes;
   return gemm_impl(&g, st);
 }
 
@@ -450,6 +465,11 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
   const size_t cache_layer = (size_t)B * H * Smax * hd;
 
   MB_TRY(mb200_rope_table(P.rope_tab, S, m->rotary_dim, pos0, st));
+  struct SplitKScope {  // the workspace is only valid while this pass is being issued
+    SplitKScope(float* w, size_t b) { g_splitk_ws = w; g_splitk_bytes = b; }
+    ~SplitKScope() { g_splitk_ws = nullptr; g_splitk_bytes = 0; }
+  } splitk_scope(P.splitk_ws, P.splitk_bytes);
+  if (P.splitk_ws) MB_CUDA(cudaMemsetAsync(P.splitk_ws, 0, P.splitk_bytes, st));
   SideStream& SS = side_stream();
   const bool two = use_two_streams() && SS.ok && M >= 256;  // decode steps stay on one stream
   const bf16* xin = x;

@@ -74,14 +74,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < p.total_tiles * p.split_k; w += gridDim.x) {
+        const int t = w / p.split_k, ks = w - t * p.split_k;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const int tpb = p.tiles_m * p.tiles_n;
         const int z = t / tpb;
         const int r = t - z * tpb;
         const int m_blk = r % p.tiles_m;
         const int n_blk = r / p.tiles_m;
         const int z0 = z % p.nb0, z1 = z / p.nb0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], C_::kStageBytes);
           uint8_t* sa = smem_a + stage * C_::kABytes;
@@ -121,13 +123,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      for (int w = blockIdx.x; w < p.total_tiles * p.split_k; w += gridDim.x, ++it) {
+        const int ks = w % p.split_k;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_a + stage * C_::kABytes);
@@ -136,7 +140,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc(sa + k * a_kadv, a_lbo, 1024);
             const uint64_t db = make_smem_desc(sb + k * b_kadv, b_lbo, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == kStages) {
@@ -151,7 +155,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (int w = blockIdx.x; w < p.total_tiles * p.split_k; w += gridDim.x, ++it) {
+      const int t = w / p.split_k;
       const int tpb = p.tiles_m * p.tiles_n;
       const int z = t / tpb;
       const int r = t - z * tpb;
@@ -176,12 +181,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if constexpr (sizeof(OutT) == 4) {
         // fp32 outputs are attention scores and weight gradients: only plain / accumulate are specialised
         switch (p.epi_kind) {
+          case EK_SPLITK:
           case EK_PLAIN: MB_EPI(0, 0, 0, false, false, false); break;
           case EK_ACCUM: MB_EPI(0, 0, 0, false, false, true); break;
           default: epi_tile<BN, 0, 0, 0, false, false, false, true, OutT>(p, c); break;
         }
       } else {
         switch (p.epi_kind) {
+          case EK_SPLITK:
           case EK_PLAIN: MB_EPI(0, 0, 0, false, false, false); break;
           case EK_ROPE: MB_EPI(0, 0, 0, false, true, false); break;
           case EK_GELU: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, false, false, false); break;
@@ -204,6 +211,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<C_::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// split-K finalize: C = epilogue(ws), and the workspace is zeroed again for its next use. One thread per float4.
+// ---------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void splitk_finalize_kernel(const GemmKernelParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int ncol4 = (p.N + 3) >> 2;
+  const long long total = (long long)p.M * ncol4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / ncol4);
+    const int col = (int)(i - (long long)row * ncol4) * 4;
+    const int nvalid = min(4, p.N - col);
+    float* w = p.splitk_ws + (long long)row * p.ld_ws + col;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = e < nvalid ? w[e] : 0.f;
+      if (e < nvalid) w[e] = 0.f;
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e < nvalid) v[e] += __bfloat162float(p.bias[col + e]);
+    }
+    if (p.rope_mode != 0 && col < p.rope_ncols && (col % p.rope_hd) < p.rope_rot) {
+      const int rp = (col % p.rope_hd) >> 1;
+      const float2* tp = p.rope_tab + (long long)(row % p.rope_S) * (p.rope_rot >> 1) + rp;
+      const float2 cs0 = __ldg(tp), cs1 = __ldg(tp + 1);
+      const float sg = p.rope_mode > 0 ? 1.f : -1.f;
+      const float a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+      v[0] = a0 * cs0.x - a1 * cs0.y * sg;
+      v[1] = a1 * cs0.x + a0 * cs0.y * sg;
+      v[2] = a2 * cs1.x - a3 * cs1.y * sg;
+      v[3] = a3 * cs1.x + a2 * cs1.y * sg;
+    }
+    const long long coff = (long long)row * p.ldc + col;
+    const long long roff = (long long)row * p.ld_res + col;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e >= nvalid) continue;
+      float x = v[e];
+      if (p.aux_out) p.aux_out[coff + e] = __float2bfloat16(x);
+      if (p.act == MB200_ACT_GELU_NEW) x = gelu_new_f(x);
+      else if (p.act == MB200_ACT_QUICK_GELU) x = quick_gelu_f(x);
+      else if (p.act == MB200_ACT_RELU) x = fmaxf(x, 0.f);
+      if (p.dact) {
+        const float a = __bfloat162float(p.aux_in[coff + e]);
+        x = p.dact == MB200_DACT_GELU_NEW ? x * gelu_new_grad_f(a) : (a > 0.f ? x : 0.f);
+      }
+      if (p.res1) x += __bfloat162float(p.res1[roff + e]);
+      if (p.res2) x += __bfloat162float(p.res2[roff + e]);
+      if constexpr (sizeof(OutT) == 4) {
+        float* dst = reinterpret_cast<float*>(p.C) + coff + e;
+        *dst = p.accumulate ? *dst + x : x;
+      } else {
+        reinterpret_cast<bf16*>(p.C)[coff + e] = __float2bfloat16(x);
+      }
+    }
   }
 }
 
@@ -281,7 +350,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  const long long items = (long long)kp.total_tiles * kp.split_k;
+  int grid = items < num_sms() ? (int)items : num_sms();
   {
     const double nb = (double)kp.total_tiles / ((double)kp.tiles_m * kp.tiles_n);
     const double flops = 2.0 * kp.M * (double)kp.N * kp.K * nb;
@@ -423,6 +493,51 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
 
   const bool amn = a->A.mn_major != 0, bmn = a->B.mn_major != 0;
   const bool f32 = a->c_dtype == MB200_F32;
+  kp.split_k = 1;
+  kp.kb_per_split = (a->K + BK - 1) / BK;
+  kp.splitk_ws = nullptr;
+  kp.ld_ws = 0;
+  // Small-M GEMMs (decode: M = batch) stream the weights once and are HBM-bound: what matters is bytes in flight, i.e.
+  // wide tiles on (nearly) every SM. Split K so that tiles x splits covers the machine; partials meet in an fp32
+  // workspace (red.global.add) and the fused epilogue runs in a small finalize kernel that re-zeroes the workspace.
+  if (a->splitk_ws && a->M <= 128 && a->nb0 * a->nb1 == 1 && a->K >= 1024 && !a->force_bn) {
+    const int bn_s = a->N >= 256 ? 256 : (a->N > 64 ? 128 : 64);
+    const int tiles = (a->N + bn_s - 1) / bn_s;
+    const int num_kb = (a->K + BK - 1) / BK;
+    int split = num_sms() / tiles;
+    if (split > num_kb / 4) split = num_kb / 4;
+    const long long ld_ws = (a->N + 3) / 4 * 4;
+    if (split > 1 && (size_t)a->M * ld_ws * sizeof(float) <= (size_t)a->splitk_ws_bytes) {
+      const int kb_per = (num_kb + split - 1) / split;
+      split = (num_kb + kb_per - 1) / kb_per;  // every split owns at least one k-block
+      bn = bn_s;
+      rc = make_operand_map(&tmB, a->B, a->N, a->K, a->nb0, a->nb1, bn);
+      if (rc) return rc;
+      kp.tiles_n = tiles;
+      kp.total_tiles = kp.tiles_m * tiles;
+      kp.split_k = split;
+      kp.kb_per_split = kb_per;
+      kp.splitk_ws = reinterpret_cast<float*>(a->splitk_ws);
+      kp.ld_ws = ld_ws;
+      GemmKernelParams kg = kp;  // the GEMM itself only accumulates partials
+      kg.epi_kind = EK_SPLITK;
+      kg.bias = nullptr;
+      int r2;
+      switch (bn) {
+        case 64: r2 = dispatch_major<64, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
+        case 128: r2 = dispatch_major<128, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
+        default: r2 = dispatch_major<256, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
+      }
+      if (r2) return r2;
+      const long long n4 = (long long)a->M * ((a->N + 3) / 4);
+      const int fgrid = (int)((n4 + 255) / 256 > 2048 ? 2048 : (n4 + 255) / 256);
+      kp.alpha = 1.f;  // already applied to the partials
+      if (f32) MB_CUDA(launch_pdl(splitk_finalize_kernel<float>, dim3(fgrid), dim3(256), 0, stream, kp));
+      else MB_CUDA(launch_pdl(splitk_finalize_kernel<bf16>, dim3(fgrid), dim3(256), 0, stream, kp));
+      count_launch();
+      return 0;
+    }
+  }
   // (short-K problems are dominated by per-tile fixed cost, where the 1-CTA kernel with narrower tiles does better)
   if (force2 || (bn == 256 && a->M > 128 && a->N >= 256 && a->K >= 512 && !a->force_bn && use_gemm2())) {
     // CTA-pair kernel: 256x256 tile per pair, each SM stages its own 128 A rows and HALF of the B tile

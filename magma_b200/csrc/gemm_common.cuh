@@ -42,6 +42,11 @@ struct GemmKernelParams {
   int rope_mode;           // +1 forward, -1 inverse (transpose rotation)
   int rope_S, rope_hd, rope_rot, rope_ncols;
   int epi_kind;  // EK_*: which specialised epilogue handles full float4 column groups (0 = generic only)
+  // split-K (small-M / weight-streaming GEMMs, e.g. decode): work item = (tile, k-range); partial tiles are reduced
+  // with fp32 red.global.add into splitk_ws [M][ld_ws] and the fused epilogue runs in splitk_finalize_kernel
+  int split_k, kb_per_split;
+  float* splitk_ws;
+  long long ld_ws;
 };
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, SWIZZLE_128B, version 1)
@@ -93,7 +98,7 @@ __device__ __forceinline__ uint2 ldg64(const bf16* ptr) {
 }
 
 enum { EK_GENERIC = 0, EK_PLAIN, EK_ROPE, EK_GELU, EK_GELU_AUX, EK_QGELU, EK_RELU, EK_DGELU, EK_DRELU, EK_RES1,
-       EK_RES2, EK_ACCUM };
+       EK_RES2, EK_ACCUM, EK_SPLITK };
 
 struct EpiCtx {
   uint32_t tmem_acc;  // TMEM address of this warp's lanes, column 0 of the accumulator buffer
@@ -233,7 +238,24 @@ __device__ __forceinline__ void epi_tile(const GemmKernelParams& p, const EpiCtx
     // ---- phase 2 ----
     const int col = n0 + c4;
     const int nvalid = p.N - col;
-    if (nvalid >= 4 && !GENERIC) {
+    if (p.epi_kind == EK_SPLITK) {
+      // partial tile of a split-K work item: accumulate into the fp32 workspace (epilogue runs in the finalize kernel)
+      if (nvalid > 0) {
+        float* wrow = p.splitk_ws + (long long)(c.row0 + rsub) * p.ld_ws + col;
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int rl = it * 2 + rsub;
+          if (rl < c.nrows) {
+            const float4 sv = lds128(c.stg_s + (uint32_t)(rl * 256 + ((((c4 >> 2)) ^ (rl & 15)) << 4)));
+            float* w = wrow + (long long)it * 2 * p.ld_ws;
+            atomicAdd(w, sv.x);
+            if (nvalid > 1) atomicAdd(w + 1, sv.y);
+            if (nvalid > 2) atomicAdd(w + 2, sv.z);
+            if (nvalid > 3) atomicAdd(w + 3, sv.w);
+          }
+        }
+      }
+    } else if (nvalid >= 4 && !GENERIC) {
       float bv[4] = {0.f, 0.f, 0.f, 0.f};
       if (p.bias) bf16x4_to_f32(ldg64(p.bias + col), bv);
       int rope_p = -1;
@@ -323,6 +345,7 @@ __device__ __forceinline__ void epi_tile(const GemmKernelParams& p, const EpiCtx
       epi_preload<BN, DACT, NRES, ACCUM, GENERIC, NLD>(p, c, g + 1, c4, rsub, cstep, rstep, pre);
   }
   if constexpr (!GENERIC) {
+    if (p.epi_kind == EK_SPLITK) return;
     // a float4 column group cut by the N edge (N % 4 != 0, e.g. the 50258-wide LM head) can only be in the LAST group
     // of the tile, whose staging block is still intact: finish those lanes on the slow path, outside the hot loop.
     if (p.N & 3) {

@@ -58,6 +58,7 @@ def gemm(
     rope_hd=0,
     rope_rot=0,
     rope_ncols=0,
+    splitk_ws=None,
 ):
     """C[..., M, N] = epilogue(alpha * A @ B^T) on the tcgen05 GEMM core.
 
@@ -111,6 +112,8 @@ def gemm(
     if rope_tab is not None and rope_mode:
         g.rope_tab, g.rope_mode = rope_tab.data_ptr(), int(rope_mode)
         g.rope_S, g.rope_hd, g.rope_rot, g.rope_ncols = int(rope_S), int(rope_hd), int(rope_rot), int(rope_ncols)
+    if splitk_ws is not None:
+        g.splitk_ws, g.splitk_ws_bytes = splitk_ws.data_ptr(), splitk_ws.numel() * splitk_ws.element_size()
     check(lib().mb200_gemm(ctypes.byref(g), _stream()))
     return out
 

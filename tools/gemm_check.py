@@ -12,7 +12,7 @@ import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
-GROUPS = ["basic", "majors", "tails", "epilogue", "batched", "pair", "perf"]
+GROUPS = ["basic", "majors", "tails", "epilogue", "batched", "pair", "splitk", "perf"]
 
 
 def ref_gemm(A, B, a_mn, b_mn):
@@ -241,6 +241,48 @@ def run_group(g):
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 20
                 print(f"[PERF] M={M} N={N} K={K} bmn={int(bmn)} {'pair' if bn == 512 else '1cta'}: {ms*1000:.1f} us {2.0*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    elif g == "splitk":
+        import torch.nn.functional as F
+
+        ws = torch.zeros(32 * 50304, device=dev, dtype=torch.float32)
+        for (M, N, K, bmn) in ((32, 4096, 4096, False), (32, 12288, 4096, False), (32, 4096, 16384, False),
+                               (32, 1024, 4096, False), (7, 50258, 4096, False), (32, 4096, 4096, True), (100, 1000, 2048, False)):
+            A, B = mk((M, K), False, dev, 0.5), mk((N, K), bmn, dev, 0.125)
+            ldc = (N + 63) // 64 * 64
+            bias = torch.randn(N, device=dev).to(torch.bfloat16)
+            res = mk((M, ldc), False, dev)[:, :N]
+            C = torch.empty(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+            ops.gemm(A, B, out=C, b_mn=bmn, bias=bias, act=ops.ACT_GELU_NEW, res1=res, splitk_ws=ws)
+            torch.cuda.synchronize()
+            want = F.gelu(ref_gemm(A, B, False, bmn) + bias.float(), approximate="tanh") + res.float()
+            ok &= report(f"splitk M={M} N={N} K={K} bmn={int(bmn)} bias+gelu+res", C, want)
+            ok &= bool((ws == 0).all().item())  # workspace left zero
+        # rope epilogue through the finalize kernel (decode qkv): M=4 rows at position 9
+        Sx, H, hd, rot = 1, 4, 256, 64
+        A2, B2 = mk((4, 4096), False, dev, 0.5), mk((3 * H * hd, 4096), False, dev, 0.05)
+        tab = ops.rope_table(1, rot, pos0=9, device=dev)
+        kw = dict(rope_tab=tab, rope_mode=1, rope_S=1, rope_hd=hd, rope_rot=rot, rope_ncols=2 * H * hd)
+        a = ops.gemm(A2, B2, splitk_ws=ws, **kw)
+        b = ops.gemm(A2, B2, **kw)
+        torch.cuda.synchronize()
+        ok &= report("splitk rope epilogue == single-pass rope epilogue", a, b.float())
+        for (M, N, K) in ((32, 12288, 4096), (32, 16384, 4096), (32, 4096, 16384), (32, 4096, 4096), (32, 1024, 4096), (32, 50258, 4096)):
+            A, B = mk((M, K), False, dev), mk((N, K), False, dev)
+            ldc = (N + 63) // 64 * 64
+            C = torch.empty(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+            for use in (False, True):
+                kw = dict(splitk_ws=ws) if use else {}
+                for _ in range(3):
+                    ops.gemm(A, B, out=C, **kw)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    ops.gemm(A, B, out=C, **kw)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 20
+                print(f"[PERF] M={M} N={N} K={K} {'splitk' if use else 'single'}: {ms*1000:.1f} us  {N*K*2/ms/1e6:.0f} GB/s weights", flush=True)
     elif g == "perf":
         shapes = [
             (1024, 4096, 4096, False, False, "out/qkv-like fwd"),
