@@ -114,8 +114,8 @@ typedef struct {
   int32_t rope_mode;
   const void* rope_tab;
   int32_t rope_S, rope_hd, rope_rot, rope_ncols;
-  /* optional split-K workspace for small-M (M <= 128, unbatched) weight-streaming GEMMs: fp32, ZERO on entry (the
-   * library leaves it zero again), at least M * round_up(N, 4) * 4 bytes. NULL = never split K. */
+  /* optional split-K scratch for small-M (M <= 128, unbatched) long-K GEMMs: fp32, splits * M * round_up(N, 4) * 4
+   * bytes are used (the split count adapts to the size given). Contents need no initialisation. NULL = never split. */
   void* splitk_ws;
   int64_t splitk_ws_bytes;
 } mb200_gemm_args;

@@ -135,7 +135,7 @@ struct GptjPlan {
   float* row_loss;
   int* n_valid;
   float* rope_tab;  // [S][rot/2] (cos, sin) for positions pos0 .. pos0+S-1
-  float* splitk_ws;  // fp32 [min(M,128)][max N] split-K workspace for small-M (decode) GEMMs, kept zero between uses
+  float* splitk_ws;  // fp32 split-K scratch for small-M (decode) GEMMs: [splits][M][N]
   size_t splitk_bytes;
   // backward temporaries
   bf16* g0;
@@ -200,13 +200,8 @@ static int make_plan(GptjPlan& P, const mb200_gptj_model* m, int B, int S, int S
   P.row_loss = c.take<float>(M);
   P.n_valid = c.take<int>(4);
   P.rope_tab = c.take<float>((size_t)S * m->rotary_dim);
-  {
-    size_t maxn = (size_t)3 * d;
-    if ((size_t)dff > maxn) maxn = dff;
-    if ((size_t)P.ldv > maxn) maxn = (size_t)P.ldv;
-    P.splitk_bytes = M <= 128 ? (size_t)M * maxn * sizeof(float) : 0;
-    P.splitk_ws = P.splitk_bytes ? c.take<float>(P.splitk_bytes / sizeof(float)) : nullptr;
-  }
+  P.splitk_bytes = M <= 128 ? (size_t)16 * M * d * sizeof(float) : 0;  // 16 splits of an [M, d] output
+  P.splitk_ws = P.splitk_bytes ? c.take<float>(P.splitk_bytes / sizeof(float)) : nullptr;
   if (training) {
     P.dlogits = c.take<bf16>(M * (size_t)P.ldv);
     P.g0 = c.take<bf16>(M * d);
@@ -469,7 +464,6 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
     SplitKScope(float* w, size_t b) { g_splitk_ws = w; g_splitk_bytes = b; }
     ~SplitKScope() { g_splitk_ws = nullptr; g_splitk_bytes = 0; }
   } splitk_scope(P.splitk_ws, P.splitk_bytes);
-  if (P.splitk_ws) MB_CUDA(cudaMemsetAsync(P.splitk_ws, 0, P.splitk_bytes, st));
   SideStream& SS = side_stream();
   const bool two = use_two_streams() && SS.ok && M >= 256;  // decode steps stay on one stream
   const bf16* xin = x;

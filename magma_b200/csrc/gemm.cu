@@ -171,6 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       c.tmem_full = &tmem_full[acc];
       c.tmem_empty = &tmem_empty[acc];
       c.empty_remote = 0;
+      c.ks = w - t * p.split_k;
       c.full_phase = acc_phase;
       c.boff = (long long)z0 * p.c_bs0 + (long long)z1 * p.c_bs1;
       c.row0 = m_blk * BM + q * 32;
@@ -215,7 +216,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
-// split-K finalize: C = epilogue(ws), and the workspace is zeroed again for its next use. One thread per float4.
+// split-K finalize: C = epilogue(sum over splits of ws[split]). One thread per float4 of the output.
 // ---------------------------------------------------------------------------------------------
 template <typename OutT>
 __global__ void splitk_finalize_kernel(const GemmKernelParams p) {
@@ -227,12 +228,13 @@ __global__ void splitk_finalize_kernel(const GemmKernelParams p) {
     const int row = (int)(i / ncol4);
     const int col = (int)(i - (long long)row * ncol4) * 4;
     const int nvalid = min(4, p.N - col);
-    float* w = p.splitk_ws + (long long)row * p.ld_ws + col;
-    float v[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      v[e] = e < nvalid ? w[e] : 0.f;
-      if (e < nvalid) w[e] = 0.f;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ks = 0; ks < p.split_k; ++ks) {  // fixed summation order -> bitwise reproducible
+      const float4 w4 = *reinterpret_cast<const float4*>(p.splitk_ws + ((long long)ks * p.M + row) * p.ld_ws + col);
+      v[0] += w4.x;
+      v[1] += w4.y;
+      v[2] += w4.z;
+      v[3] += w4.w;
     }
     if (p.bias) {
 #pragma unroll
@@ -498,16 +500,19 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   kp.splitk_ws = nullptr;
   kp.ld_ws = 0;
   // Small-M GEMMs (decode: M = batch) stream the weights once and are HBM-bound: what matters is bytes in flight, i.e.
-  // wide tiles on (nearly) every SM. Split K so that tiles x splits covers the machine; partials meet in an fp32
-  // workspace (red.global.add) and the fused epilogue runs in a small finalize kernel that re-zeroes the workspace.
-  if (a->splitk_ws && a->M <= 128 && a->nb0 * a->nb1 == 1 && a->K >= 1024 && !a->force_bn) {
+  // wide tiles on (nearly) every SM. For the long-K / narrow-N shape (GPT-J fc_out: N = 4096, K = 16384 -> 16 tiles)
+  // K is split so that tiles x splits covers the machine (measured 80 -> 49 us at M = 32); the wide shapes already
+  // run >= 96 CTAs and get slower with the extra pass. Partials go to per-split fp32 slices; a small finalize kernel
+  // sums them in fixed order (deterministic) and applies the fused epilogue.
+  if (a->splitk_ws && a->M <= 128 && a->nb0 * a->nb1 == 1 && a->K >= 8192 && a->N <= 8192 && !a->force_bn) {
     const int bn_s = a->N >= 256 ? 256 : (a->N > 64 ? 128 : 64);
     const int tiles = (a->N + bn_s - 1) / bn_s;
     const int num_kb = (a->K + BK - 1) / BK;
     int split = num_sms() / tiles;
     if (split > num_kb / 4) split = num_kb / 4;
     const long long ld_ws = (a->N + 3) / 4 * 4;
-    if (split > 1 && (size_t)a->M * ld_ws * sizeof(float) <= (size_t)a->splitk_ws_bytes) {
+    while (split > 1 && (size_t)split * a->M * ld_ws * sizeof(float) > (size_t)a->splitk_ws_bytes) --split;
+    if (split > 1) {
       const int kb_per = (num_kb + split - 1) / split;
       split = (num_kb + kb_per - 1) / kb_per;  // every split owns at least one k-block
       bn = bn_s;

@@ -164,6 +164,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       c.tmem_full = &tmem_full[acc];
       c.tmem_empty = &tmem_empty[acc];
       c.empty_remote = rank != 0;
+      c.ks = 0;
       c.full_phase = acc_phase;
       c.boff = (long long)z0 * p.c_bs0 + (long long)z1 * p.c_bs1;
       c.row0 = m_blk * BM + q * 32;

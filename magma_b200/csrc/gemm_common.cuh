@@ -43,7 +43,8 @@ struct GemmKernelParams {
   int rope_S, rope_hd, rope_rot, rope_ncols;
   int epi_kind;  // EK_*: which specialised epilogue handles full float4 column groups (0 = generic only)
   // split-K (small-M / weight-streaming GEMMs, e.g. decode): work item = (tile, k-range); partial tiles are reduced
-  // with fp32 red.global.add into splitk_ws [M][ld_ws] and the fused epilogue runs in splitk_finalize_kernel
+  // written to splitk_ws [split][M][ld_ws] (fp32) and summed in fixed order, with the fused epilogue, by
+  // splitk_finalize_kernel
   int split_k, kb_per_split;
   float* splitk_ws;
   long long ld_ws;
@@ -109,6 +110,7 @@ struct EpiCtx {
   uint32_t full_phase;
   long long boff;     // batch offset in C (elements)
   int row0, nrows, n_blk, lane;
+  int ks;             // split-K index of this work item (0 when K is not split)
 };
 
 // slow per-lane path: any combination of epilogue options, any number (1..4) of valid columns. Used for float4
@@ -239,19 +241,16 @@ __device__ __forceinline__ void epi_tile(const GemmKernelParams& p, const EpiCtx
     const int col = n0 + c4;
     const int nvalid = p.N - col;
     if (p.epi_kind == EK_SPLITK) {
-      // partial tile of a split-K work item: accumulate into the fp32 workspace (epilogue runs in the finalize kernel)
+      // partial tile of a split-K work item: plain fp32 stores into this split's slice of the workspace (deterministic:
+      // the finalize kernel sums the slices in a fixed order and applies the fused epilogue)
       if (nvalid > 0) {
-        float* wrow = p.splitk_ws + (long long)(c.row0 + rsub) * p.ld_ws + col;
+        float* wrow = p.splitk_ws + ((long long)c.ks * p.M + (c.row0 + rsub)) * p.ld_ws + col;
 #pragma unroll 4
         for (int it = 0; it < 16; ++it) {
           const int rl = it * 2 + rsub;
           if (rl < c.nrows) {
             const float4 sv = lds128(c.stg_s + (uint32_t)(rl * 256 + ((((c4 >> 2)) ^ (rl & 15)) << 4)));
-            float* w = wrow + (long long)it * 2 * p.ld_ws;
-            atomicAdd(w, sv.x);
-            if (nvalid > 1) atomicAdd(w + 1, sv.y);
-            if (nvalid > 2) atomicAdd(w + 2, sv.z);
-            if (nvalid > 3) atomicAdd(w + 3, sv.w);
+            *reinterpret_cast<float4*>(wrow + (long long)it * 2 * p.ld_ws) = sv;  // ld_ws % 4 == 0: padded columns exist
           }
         }
       }
