@@ -21,11 +21,12 @@
 
 namespace mb200 {
 
-template <int BN, bool A_MN, bool B_MN, typename OutT>
+template <int BN, bool A_MN, bool B_MN, typename OutT, int AROWS = BM>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmKernelParams p) {
-  using C_ = Cfg<BN>;
+  static_assert(AROWS == BM || !A_MN, "the 32-row A ring is only implemented for K-major A");
+  using C_ = Cfg<BN, AROWS>;
   constexpr int kStages = C_::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -343,13 +344,13 @@ int make_operand_map(CUtensorMap* out, const mb200_operand& op, int rows, int K,
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT>
+template <int BN, bool A_MN, bool B_MN, typename OutT, int AROWS = BM>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& kp,
                        cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, OutT>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, OutT, AROWS>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AROWS>::kSmemBytes));
     attr_set = true;
   }
   const long long items = (long long)kp.total_tiles * kp.split_k;
@@ -359,7 +360,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     const double flops = 2.0 * kp.M * (double)kp.N * kp.K * nb;
     const double bytes = nb * (2.0 * ((double)kp.M * kp.K + (double)kp.N * kp.K) + (double)sizeof(OutT) * kp.M * kp.N);
     GemmProfScope prof(stream, flops, bytes);
-    MB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg<BN>::kSmemBytes, stream, tmA, tmB, kp));
+    MB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg<BN, AROWS>::kSmemBytes, stream, tmA, tmB, kp));
   }
   count_launch();
   MB_CUDA(cudaGetLastError());
@@ -373,6 +374,14 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
   if (!a_mn && b_mn) return launch_gemm<BN, false, true, OutT>(tmA, tmB, kp, s);
   if (a_mn && !b_mn) return launch_gemm<BN, true, false, OutT>(tmA, tmB, kp, s);
   return launch_gemm<BN, true, true, OutT>(tmA, tmB, kp, s);
+}
+
+// small-M (M <= 32, K-major A, bf16 out): 32-row A ring
+template <int BN>
+static int dispatch_small(bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& kp,
+                          cudaStream_t s) {
+  if (b_mn) return launch_gemm<BN, false, true, bf16, 32>(tmA, tmB, kp, s);
+  return launch_gemm<BN, false, false, bf16, 32>(tmA, tmB, kp, s);
 }
 
 static int pick_bn(int M, int N, int K, int batches) {
@@ -434,7 +443,10 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   MB_REQUIRE(bn == 64 || bn == 128 || bn == 256, MB200_E_ARG, "gemm: force_bn must be 64/128/256 (or 512 = 2-CTA)");
 
   CUtensorMap tmA, tmB;
-  rc = make_operand_map(&tmA, a->A, a->M, a->K, a->nb0, a->nb1, BM);
+  // small-M problems (decode: M = batch <= 32) stage only a 32-row A box per k-block (see Cfg<BN, AROWS>)
+  const bool small_m = a->M <= 32 && a->A.mn_major == 0 && a->nb0 * a->nb1 == 1 && a->c_dtype == MB200_BF16 &&
+                       a->force_bn != 512;
+  rc = make_operand_map(&tmA, a->A, a->M, a->K, a->nb0, a->nb1, small_m ? 32 : BM);
   if (rc) return rc;
   rc = make_operand_map(&tmB, a->B, a->N, a->K, a->nb0, a->nb1, bn);
   if (rc) return rc;
@@ -528,10 +540,18 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
       kg.epi_kind = EK_SPLITK;
       kg.bias = nullptr;
       int r2;
-      switch (bn) {
-        case 64: r2 = dispatch_major<64, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
-        case 128: r2 = dispatch_major<128, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
-        default: r2 = dispatch_major<256, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
+      if (small_m) {
+        switch (bn) {
+          case 64: r2 = dispatch_small<64>(bmn, tmA, tmB, kg, stream); break;
+          case 128: r2 = dispatch_small<128>(bmn, tmA, tmB, kg, stream); break;
+          default: r2 = dispatch_small<256>(bmn, tmA, tmB, kg, stream); break;
+        }
+      } else {
+        switch (bn) {
+          case 64: r2 = dispatch_major<64, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
+          case 128: r2 = dispatch_major<128, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
+          default: r2 = dispatch_major<256, bf16>(amn, bmn, tmA, tmB, kg, stream); break;
+        }
       }
       if (r2) return r2;
       const long long n4 = (long long)a->M * ((a->N + 3) / 4);
@@ -552,6 +572,13 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
     kp.tiles_m = (a->M + 255) / 256;  // cluster tiles along M
     kp.total_tiles = kp.tiles_m * kp.tiles_n * a->nb0 * a->nb1;
     return launch_gemm2(tmA, tmB, kp, amn, bmn, f32, stream);
+  }
+  if (small_m) {
+    switch (bn) {
+      case 64: return dispatch_small<64>(bmn, tmA, tmB, kp, stream);
+      case 128: return dispatch_small<128>(bmn, tmA, tmB, kp, stream);
+      default: return dispatch_small<256>(bmn, tmA, tmB, kp, stream);
+    }
   }
   switch (bn) {
     case 64:

@@ -11,16 +11,23 @@ static constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
 static constexpr int kThreads = 256; // 8 warps
 static constexpr int kSmemBudget = 192 * 1024;  // operand ring; + 34 KB epilogue staging + barriers < 227 KB
 
-template <int BN>
+// AROWS = rows of A actually staged per k-block. 128 normally. 32 for small-M (decode) problems: only a 32-row TMA box
+// is loaded per stage and the A slots are packed 4 KB apart; the UMMA descriptor still spans 128 rows (16 KB), so
+// rows 32..127 of the product are computed from whatever follows in shared memory — those TMEM lanes are never stored.
+// The freed shared memory goes to deeper rings: what bounds a weight-streaming GEMM is bytes of B in flight per SM.
+template <int BN, int AROWS = BM>
 struct Cfg {
-  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kABytes = AROWS * BK * 2;  // slot stride of the A ring
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kAWindow = BM * BK * 2;    // bytes an MMA reads starting at an A slot
+  static constexpr int kMaxStages = AROWS == BM ? 8 : 16;
+  static constexpr int kStagesRaw = (kSmemBudget - (kAWindow - kABytes)) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers; 128/256/512 — powers of two
   static constexpr int kEpiPitch = 64;      // floats per staged row; 16-byte chunks XOR-swizzled by (row & 15)
   static constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;  // per-warp [32 rows][64 cols] fp32 staging, 4 warps
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 struct GemmKernelParams {

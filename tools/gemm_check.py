@@ -12,7 +12,7 @@ import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
-GROUPS = ["basic", "majors", "tails", "epilogue", "batched", "pair", "splitk", "perf"]
+GROUPS = ["basic", "majors", "tails", "epilogue", "batched", "pair", "splitk", "smallm", "perf"]
 
 
 def ref_gemm(A, B, a_mn, b_mn):
@@ -285,6 +285,39 @@ def run_group(g):
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 20
                 print(f"[PERF] M={M} N={N} K={K} {'splitk' if use else 'single'}: {ms*1000:.1f} us  {N*K*2/ms/1e6:.0f} GB/s weights", flush=True)
+    elif g == "smallm":
+        # M <= 32: 32-row A ring (deeper pipeline). All tile widths, both B majors, fused epilogues, ragged N/K.
+        import torch.nn.functional as F
+
+        for M in (1, 7, 32):
+            for (N, K, bmn) in ((4096, 4096, False), (1000, 328, True), (12288, 4096, False), (264, 16384, False)):
+                A, B = mk((M, K), False, dev, 0.5), mk((N, K), bmn, dev, 0.125)
+                ldc = (N + 63) // 64 * 64
+                bias = torch.randn(N, device=dev).to(torch.bfloat16)
+                res = mk((M, ldc), False, dev)[:, :N]
+                C = torch.full((M, ldc), 7.0, device=dev, dtype=torch.bfloat16)
+                ops.gemm(A, B, out=C[:, :N], b_mn=bmn, bias=bias, act=ops.ACT_RELU, res1=res)
+                torch.cuda.synchronize()
+                want = F.relu(ref_gemm(A, B, False, bmn) + bias.float()) + res.float()
+                ok &= report(f"smallm M={M} N={N} K={K} bmn={int(bmn)}", C[:, :N], want)
+                ok &= bool((C[:, N:] == 7.0).all().item())
+        for bn in (64, 128, 256):
+            A, B = mk((32, 512), False, dev), mk((512, 512), False, dev)
+            ok &= report(f"smallm forced bn={bn}", ops.gemm(A, B, force_bn=bn), ref_gemm(A, B, False, False))
+        for (M, N, K) in ((32, 12288, 4096), (32, 16384, 4096), (32, 4096, 4096), (32, 1024, 4096), (32, 4096, 1024)):
+            A, B = mk((M, K), False, dev), mk((N, K), False, dev)
+            C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                ops.gemm(A, B, out=C)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                ops.gemm(A, B, out=C)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"[PERF] smallm M={M} N={N} K={K}: {ms*1000:.1f} us  {N*K*2/ms/1e6:.0f} GB/s weights", flush=True)
     elif g == "perf":
         shapes = [
             (1024, 4096, 4096, False, False, "out/qkv-like fwd"),
