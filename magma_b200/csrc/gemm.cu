@@ -84,24 +84,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m_blk = r % p.tiles_m;
         const int n_blk = r / p.tiles_m;
         const int z0 = z % p.nb0, z1 = z / p.nb0;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; kb += C_::kKS) {
+          const int nsub = min(C_::kKS, kb1 - kb);  // k-blocks carried by this stage
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], C_::kStageBytes);
-          uint8_t* sa = smem_a + stage * C_::kABytes;
-          uint8_t* sb = smem_b + stage * C_::kBBytes;
-          if constexpr (A_MN) {
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(nsub * (C_::kASub + C_::kBSub)));
+          for (int j = 0; j < nsub; ++j) {
+            uint8_t* sa = smem_a + stage * C_::kABytes + j * C_::kASub;
+            uint8_t* sb = smem_b + stage * C_::kBBytes + j * C_::kBSub;
+            const int kc = (kb + j) * BK;
+            if constexpr (A_MN) {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              tma_load_4d(sa + i * 8192, &tmA, &full_bar[stage], m_blk * BM + i * 64, kb * BK, z0, z1);
-          } else {
-            tma_load_4d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM, z0, z1);
-          }
-          if constexpr (B_MN) {
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_4d(sa + i * 8192, &tmA, &full_bar[stage], m_blk * BM + i * 64, kc, z0, z1);
+            } else {
+              tma_load_4d(sa, &tmA, &full_bar[stage], kc, m_blk * BM, z0, z1);
+            }
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_4d(sb + i * 8192, &tmB, &full_bar[stage], n_blk * BN + i * 64, kb * BK, z0, z1);
-          } else {
-            tma_load_4d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN, z0, z1);
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_4d(sb + i * 8192, &tmB, &full_bar[stage], n_blk * BN + i * 64, kc, z0, z1);
+            } else {
+              tma_load_4d(sb, &tmB, &full_bar[stage], kc, n_blk * BN, z0, z1);
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -132,16 +136,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; kb += C_::kKS) {
+          const int nsub = min(C_::kKS, kb1 - kb);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * C_::kABytes);
-          const uint32_t sb = smem_u32(smem_b + stage * C_::kBBytes);
+          for (int j = 0; j < nsub; ++j) {
+            const uint32_t sa = smem_u32(smem_a + stage * C_::kABytes + j * C_::kASub);
+            const uint32_t sb = smem_u32(smem_b + stage * C_::kBBytes + j * C_::kBSub);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * a_kadv, a_lbo, 1024);
-            const uint64_t db = make_smem_desc(sb + k * b_kadv, b_lbo, 1024);
-            umma_bf16(d_tmem, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_smem_desc(sa + k * a_kadv, a_lbo, 1024);
+              const uint64_t db = make_smem_desc(sb + k * b_kadv, b_lbo, 1024);
+              umma_bf16(d_tmem, da, db, idesc, ((kb - kb0) | j | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == kStages) {
@@ -420,6 +427,62 @@ static bool use_gemm2() {
   return v != 0;
 }
 
+// Small-M (decode, M = batch <= 32) GEMMs stream their weight matrix once and are HBM-bound: what matters is bytes in
+// flight, i.e. every SM pulling weights all the time. The plan picks the tile width and a K split so that
+// tiles x splits covers the 148 SMs evenly. Time model, constants fitted to tools/smallm_bench.py --grid on B200
+// (profiles/r01_smallm_grid.log):
+//   t = t_item + waves * bytes_per_item / rate_per_sm + (split > 1 ? t_finalize : 0),
+//   rate_per_sm = min(per-SM TMA streaming rate (bytes in flight / latency), all-SM HBM rate / active SMs).
+struct SmallPlan {
+  int bn, split;
+};
+static SmallPlan plan_small_m(int N, int K, int M, size_t ws_bytes) {
+  const int sms = num_sms();
+  const int num_kb = (K + BK - 1) / BK;
+  const double kHbmRate = 5.3e12, kItem = 4e-6, kFinalize = 4e-6;
+  SmallPlan best{64, 1};
+  double best_t = 1e300;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && N <= bn / 2) continue;
+    const int tiles = (N + bn - 1) / bn;
+    for (int split = 1; split <= 16; ++split) {
+      if (split > 1) {
+        if (num_kb / split < 8) break;
+        if ((size_t)split * M * ((N + 3) / 4 * 4) * sizeof(float) > ws_bytes) break;
+      }
+      const int kb_per = (num_kb + split - 1) / split;
+      const int eff_split = (num_kb + kb_per - 1) / kb_per;
+      const long long items = (long long)tiles * eff_split;
+      const long long waves = (items + sms - 1) / sms;
+      const double active = (double)(items < sms ? items : sms);
+      const double sm_rate = bn == 64 ? 46e9 : 62e9;  // 96 KB vs 128 KB of weights in flight per SM
+      const double eff = bn == 64 ? 0.88 : (bn == 256 ? 0.95 : 1.0);  // same decomposition, measured relative rate
+      const double rate = eff * (sm_rate < kHbmRate / active ? sm_rate : kHbmRate / active);
+      const double t = kItem + waves * ((double)kb_per * bn * BK * 2 / rate) + (eff_split > 1 ? kFinalize : 0.0);
+      if (t < best_t - 1e-12) {
+        best_t = t;
+        best = SmallPlan{bn, eff_split};
+      }
+    }
+  }
+  // experiments: MB200_SMALLM_BN / MB200_SMALLM_SPLIT override the plan (tools/smallm_bench.py)
+  if (const char* e = getenv("MB200_SMALLM_BN")) {
+    const int v = atoi(e);
+    if (v == 64 || v == 128 || v == 256) best.bn = v;
+  }
+  if (const char* e = getenv("MB200_SMALLM_SPLIT")) {
+    int v = atoi(e);
+    if (v >= 1) {
+      while (v > 1 && ((size_t)v * M * ((N + 3) / 4 * 4) * sizeof(float) > ws_bytes || num_kb / v < 1)) --v;
+      const int kb_per = (num_kb + v - 1) / v;
+      best.split = (num_kb + kb_per - 1) / kb_per;
+    }
+  }
+  return best;
+}
+
 int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   MB_REQUIRE(a != nullptr, MB200_E_ARG, "null gemm args");
   MB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->nb0 > 0 && a->nb1 > 0, MB200_E_SHAPE,
@@ -446,6 +509,12 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   // small-M problems (decode: M = batch <= 32) stage only a 32-row A box per k-block (see Cfg<BN, AROWS>)
   const bool small_m = a->M <= 32 && a->A.mn_major == 0 && a->nb0 * a->nb1 == 1 && a->c_dtype == MB200_BF16 &&
                        a->force_bn != 512;
+  int plan_split = 1;
+  if (small_m && !a->force_bn) {
+    const SmallPlan pl = plan_small_m(a->N, a->K, a->M, a->splitk_ws ? (size_t)a->splitk_ws_bytes : 0);
+    bn = pl.bn;
+    plan_split = pl.split;
+  }
   rc = make_operand_map(&tmA, a->A, a->M, a->K, a->nb0, a->nb1, small_m ? 32 : BM);
   if (rc) return rc;
   rc = make_operand_map(&tmB, a->B, a->N, a->K, a->nb0, a->nb1, bn);
@@ -511,17 +580,20 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   kp.kb_per_split = (a->K + BK - 1) / BK;
   kp.splitk_ws = nullptr;
   kp.ld_ws = 0;
-  // Small-M GEMMs (decode: M = batch) stream the weights once and are HBM-bound: what matters is bytes in flight, i.e.
-  // wide tiles on (nearly) every SM. For the long-K / narrow-N shape (GPT-J fc_out: N = 4096, K = 16384 -> 16 tiles)
-  // K is split so that tiles x splits covers the machine (measured 80 -> 49 us at M = 32); the wide shapes already
-  // run >= 96 CTAs and get slower with the extra pass. Partials go to per-split fp32 slices; a small finalize kernel
-  // sums them in fixed order (deterministic) and applies the fused epilogue.
-  if (a->splitk_ws && a->M <= 128 && a->nb0 * a->nb1 == 1 && a->K >= 8192 && a->N <= 8192 && !a->force_bn) {
-    const int bn_s = a->N >= 256 ? 256 : (a->N > 64 ? 128 : 64);
+  // Split-K for small M (see plan_small_m; for 32 < M <= 128 only the long-K / narrow-N shape, GPT-J fc_out, is split:
+  // measured 80 -> 49 us at M = 32). Partials go to per-split fp32 slices; a small finalize kernel sums them in fixed
+  // order (deterministic) and applies the fused epilogue.
+  const bool split_mid = !small_m && a->splitk_ws && a->M <= 128 && a->nb0 * a->nb1 == 1 && a->K >= 8192 &&
+                         a->N <= 8192 && !a->force_bn;
+  if (plan_split > 1 || split_mid) {
+    const int bn_s = small_m ? bn : (a->N >= 256 ? 256 : (a->N > 64 ? 128 : 64));
     const int tiles = (a->N + bn_s - 1) / bn_s;
     const int num_kb = (a->K + BK - 1) / BK;
-    int split = num_sms() / tiles;
-    if (split > num_kb / 4) split = num_kb / 4;
+    int split = plan_split;
+    if (split_mid) {
+      split = num_sms() / tiles;
+      if (split > num_kb / 4) split = num_kb / 4;
+    }
     const long long ld_ws = (a->N + 3) / 4 * 4;
     while (split > 1 && (size_t)split * a->M * ld_ws * sizeof(float) > (size_t)a->splitk_ws_bytes) --split;
     if (split > 1) {

@@ -15,14 +15,21 @@ static constexpr int kSmemBudget = 192 * 1024;  // operand ring; + 34 KB epilogu
 // is loaded per stage and the A slots are packed 4 KB apart; the UMMA descriptor still spans 128 rows (16 KB), so
 // rows 32..127 of the product are computed from whatever follows in shared memory — those TMEM lanes are never stored.
 // The freed shared memory goes to deeper rings: what bounds a weight-streaming GEMM is bytes of B in flight per SM.
+//
+// In that mode a ring stage also carries kKS consecutive k-blocks (4 at BN = 64, 2 at BN = 128): the single MMA-issuing
+// thread spends ~350 cycles per barrier round trip (try_wait + fence + 4 tcgen05.mma + commit), which hides under the
+// 512 tensor-pipe cycles of a 128x256 k-block but not under the 128 cycles of a 128x64 one.
 template <int BN, int AROWS = BM>
 struct Cfg {
-  static constexpr int kABytes = AROWS * BK * 2;  // slot stride of the A ring
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kKS = AROWS == BM ? 1 : (BN == 64 ? 4 : (BN == 128 ? 2 : 1));  // k-blocks per ring stage
+  static constexpr int kASub = AROWS * BK * 2;    // bytes of one k-block of A (sub-slot stride)
+  static constexpr int kBSub = BN * BK * 2;
+  static constexpr int kABytes = kASub * kKS;     // slot stride of the A ring
+  static constexpr int kBBytes = kBSub * kKS;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAWindow = BM * BK * 2;    // bytes an MMA reads starting at an A slot
   static constexpr int kMaxStages = AROWS == BM ? 8 : 16;
-  static constexpr int kStagesRaw = (kSmemBudget - (kAWindow - kABytes)) / kStageBytes;
+  static constexpr int kStagesRaw = (kSmemBudget - (kAWindow - kASub)) / kStageBytes;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers; 128/256/512 — powers of two
   static constexpr int kEpiPitch = 64;      // floats per staged row; 16-byte chunks XOR-swizzled by (row & 15)
