@@ -7,6 +7,8 @@ gradient of the ~0.24 B trainable parameters, which live in one flat fp32 arena:
 arena slices over NCCL on a side stream as soon as the backward pass has finished the layers they belong to
 (backward is issued in layer chunks), so the exchange overlaps the remaining backward; the fused AdamW kernel then
 applies 1/world averaging, global-norm clipping and the bf16 weight refresh in one pass."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -15,7 +17,9 @@ from .utils import reduce_losses
 
 
 class B200Engine:
-    def __init__(self, model, config, n_buckets: int = 4, betas=(0.9, 0.95), eps=1e-8):
+    def __init__(self, model, config, n_buckets: int = None, betas=(0.9, 0.95), eps=1e-8):
+        if n_buckets is None:  # gradient buckets of the overlapped all-reduce (tuning knob)
+            n_buckets = int(os.environ.get("MB200_DP_BUCKETS", "4"))
         self.module = model
         self.config = config
         self.world = dist.get_world_size() if dist.is_initialized() else 1

@@ -385,7 +385,7 @@ def group_generate(dev):
     model.eval()
     images, _ = O.synthetic_batch(cfg, 2, 32, seed=4)
     images = images.to(torch.bfloat16).float()
-    text = torch.randint(0, 900, (2, 5))
+    text = torch.randint(0, 900, (2, 5), generator=torch.Generator().manual_seed(11))
     emb_o = O.magma_embed([images, text], w16, cfg)
     emb = model.embed([images.to(dev), text.to(dev)])
     ok &= report("embed([image, text])", emb, emb_o, 3e-2)
@@ -393,9 +393,27 @@ def group_generate(dev):
     toks = model.generate(emb, max_steps=12, temperature=0.0, decode=False).cpu()
     n = min(toks.shape[1], toks_o.shape[1])
     same = bool((toks[:, :n] == toks_o[:, :n]).all())
-    agree = float((toks[:, :n] == toks_o[:, :n]).float().mean())
-    ok &= agree > 0.9
-    print(f"[{'OK' if agree > 0.9 else 'FAIL'}] greedy generate token agreement {agree:.3f} (exact={same}) "
+    # Free-running greedy decoding is chaotic after the first differing token, so the criterion is per row: tokens agree
+    # up to the first divergence, and at that position the fp32 oracle itself is at a near-tie between its token and
+    # ours (margin below 10x the bf16 logit error, 5e-2 of the logit rms); a larger margin is a real defect.
+    s0 = emb_o.shape[1]
+    good = True
+    for r in range(toks.shape[0]):
+        diff = (toks[r, :n] != toks_o[r, :n]).nonzero()
+        if diff.numel() == 0:
+            continue
+        p = int(diff[0])
+        prefix = torch.cat([emb_o[r:r + 1], torch.nn.functional.embedding(toks_o[r:r + 1, s0:p], w16["lm.transformer.wte.weight"])], 1)
+        _, lg, _ = O.gptj_lm(prefix, w16, cfg)
+        lg = lg[0, -1].float()
+        margin = float(lg[toks_o[r, p]] - lg[toks[r, p]])
+        tol = 5e-2 * float(lg.pow(2).mean().sqrt())
+        row_ok = 0 <= margin < tol
+        print(f"    row {r}: first divergence at new token {p - s0}, oracle margin {margin:.4f} (tie tolerance {tol:.4f}) "
+              f"-> {'near-tie' if row_ok else 'MISMATCH'}", flush=True)
+        good &= row_ok
+    ok &= good
+    print(f"[{'OK' if good else 'FAIL'}] greedy generate vs oracle (exact={same}) "
           f"ours={toks[0, -12:].tolist()} oracle={toks_o[0, -12:].tolist()}", flush=True)
     # KV-cache decode path == full recompute (self-consistency, logits level)
     lm = model.lm
