@@ -42,7 +42,8 @@ enum {
   MB200_ACT_NONE = 0,
   MB200_ACT_GELU_NEW = 1,   /* GPT-J MLP: transformers/activations.py:59-66 (NewGELUActivation) */
   MB200_ACT_QUICK_GELU = 2, /* CLIP ViT MLP: x * sigmoid(1.702 x) */
-  MB200_ACT_RELU = 3        /* magma/adapters.py:11 (Adapter default activation) */
+  MB200_ACT_RELU = 3,       /* magma/adapters.py:11 (Adapter default activation) */
+  MB200_ACT_RELU_POST = 4   /* ReLU applied AFTER the residual adds: relu(A.B + bias + res) (CLIP Bottleneck output) */
 };
 /* epilogue activation-derivative multiplier (backward): out = acc * f'(aux_in) */
 enum {
@@ -174,6 +175,14 @@ int mb200_patchify(const void* img, void* patches, int64_t ldp, int32_t B, int32
 /* x[b,0] = cls + pos[0]; x[b,1+p] = pe[b,p] + pos[1+p]  (CLIP VisionTransformer.forward token assembly). */
 int mb200_vit_assemble(void* x, const void* pe, const void* cls, const void* pos, int32_t B, int32_t T, int32_t w,
                        void* stream);
+/* Conv-trunk encoders (CLIP ModifiedResNet behind magma/image_encoders.py:65-74), NHWC bf16 activations:
+ * images [B,C<=8,H,W] -> [B,H,W,8] (zero-padded channels); 3x3 / pad 1 / stride 1|2 im2col -> [B*Ho*Wo][9*C] in
+ * (kh, kw, c) column order; nn.AvgPool2d(k) -> [B,H/k,W/k,C]. C must be a multiple of 8. The convolutions themselves
+ * are mb200_gemm calls with the folded BatchNorm as bias (act RELU, or RELU_POST after the residual). */
+int mb200_nchw_to_nhwc8(const void* src, void* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+int mb200_im2col3x3(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
+                    void* stream);
+int mb200_avgpool_nhwc(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* stream);
 /* torch.argmax(logits.float(), -1) (magma/sampling.py:92,97): lowest index wins ties. */
 int mb200_argmax(const void* x, int64_t ldx, int32_t rows, int32_t V, int64_t* out, void* stream);
 int mb200_add(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);

@@ -531,6 +531,72 @@ __global__ void vit_assemble_kernel(bf16* __restrict__ x, const bf16* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Conv-trunk support (CLIP ModifiedResNet, image_encoders.py:65-74). Activations are NHWC bf16, so a 1x1 convolution is
+// a plain GEMM over [B*H*W, C]; a 3x3 convolution is im2col (column order (kh, kw, c), matching weights packed as
+// [Cout][3][3][Cin]) followed by the same GEMM with the folded BatchNorm as bias. All three kernels move 16-byte
+// vectors of 8 channels and are HBM-bound.
+// ---------------------------------------------------------------------------------------------
+// images [B, C<=8, H, W] bf16 -> [B, H, W, 8] bf16, channels C..7 zero (so that the stem's K = 9*8 is TMA-aligned)
+__global__ void nchw_to_nhwc8_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int C, int H, int W) {
+  const long long hw = (long long)H * W, total = (long long)B * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, px = i - b * hw;
+    alignas(16) bf16 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < C ? src[(b * C + c) * hw + px] : __float2bfloat16(0.f);
+    *reinterpret_cast<uint4*>(dst + i * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+// src [B,H,W,C] -> dst [B*Ho*Wo][9*C], 3x3 window, padding 1, stride s (Ho = (H-1)/s + 1); out-of-image taps are zero
+__global__ void im2col3x3_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int C,
+                                 int stride, int Ho, int Wo) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * Ho * Wo * 9 * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const int tap = (int)((i / cv) % 9);
+    const long long row = i / (9LL * cv);
+    const int wo = (int)(row % Wo);
+    const int ho = (int)((row / Wo) % Ho);
+    const long long b = row / ((long long)Wo * Ho);
+    const int hi = ho * stride - 1 + tap / 3, wi = wo * stride - 1 + tap % 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+      v = __ldg(reinterpret_cast<const uint4*>(src + ((b * H + hi) * W + wi) * C) + c8);
+    reinterpret_cast<uint4*>(dst)[i] = v;  // (row, tap, c8) is exactly the linear index
+  }
+}
+// nn.AvgPool2d(k) on NHWC: dst [B, H/k, W/k, C], fp32 accumulation
+__global__ void avgpool_nhwc_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int C,
+                                    int k) {
+  const int cv = C >> 3, Ho = H / k, Wo = W / k;
+  const long long total = (long long)B * Ho * Wo * cv;
+  const float inv = 1.f / (float)(k * k);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long long px = i / cv;
+    const int wo = (int)(px % Wo);
+    const int ho = (int)((px / Wo) % Ho);
+    const long long b = px / ((long long)Wo * Ho);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((b * H + ho * k + dy) * W + wo * k + dx) * C) + c8);
+        const bf16* e = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += __bfloat162float(e[c]);
+      }
+    alignas(16) bf16 o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = __float2bfloat16(acc[c] * inv);
+    reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // argmax over the last dim of bf16 rows, compared in fp32 like sampling.py:92,97 (logits.float(); argmax).
 // Ties resolve to the LOWEST index (torch.argmax on CPU/CUDA returns the first maximal element).
 // ---------------------------------------------------------------------------------------------
@@ -853,6 +919,39 @@ extern "C" int mb200_vit_assemble(void* x, const void* pe, const void* cls, cons
   MB_ENTER();
   vit_assemble_kernel<<<grid_for((long long)B * T * w, 256), 256, 0, ST(stream)>>>(
       (bf16*)x, (const bf16*)pe, (const bf16*)cls, (const bf16*)pos, B, T, w);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_nchw_to_nhwc8(const void* src, void* dst, int32_t B, int32_t C, int32_t H, int32_t W,
+                                   void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(C >= 1 && C <= 8 && B > 0 && H > 0 && W > 0, MB200_E_SHAPE, "nchw_to_nhwc8: B=%d C=%d H=%d W=%d", B, C, H, W);
+  nchw_to_nhwc8_kernel<<<grid_for((long long)B * H * W, 256), 256, 0, ST(stream)>>>((const bf16*)src, (bf16*)dst, B, C,
+                                                                                   H, W);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_im2col3x3(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
+                                void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2), MB200_E_SHAPE,
+             "im2col3x3: B=%d H=%d W=%d C=%d (multiple of 8) stride=%d (1 or 2)", B, H, W, C, stride);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  im2col3x3_kernel<<<grid_for((long long)B * Ho * Wo * 9 * (C / 8), 256), 256, 0, ST(stream)>>>(
+      (const bf16*)src, (bf16*)dst, B, H, W, C, stride, Ho, Wo);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_avgpool_nhwc(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k,
+                                   void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(B > 0 && k >= 1 && H >= k && W >= k && C > 0 && C % 8 == 0, MB200_E_SHAPE,
+             "avgpool_nhwc: B=%d H=%d W=%d C=%d (multiple of 8) k=%d", B, H, W, C, k);
+  avgpool_nhwc_kernel<<<grid_for((long long)B * (H / k) * (W / k) * (C / 8), 256), 256, 0, ST(stream)>>>(
+      (const bf16*)src, (bf16*)dst, B, H, W, C, k);
   MB_LAUNCH_CHECK();
   return 0;
 }

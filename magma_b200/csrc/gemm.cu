@@ -276,6 +276,7 @@ __global__ void splitk_finalize_kernel(const GemmKernelParams p) {
       }
       if (p.res1) x += __bfloat162float(p.res1[roff + e]);
       if (p.res2) x += __bfloat162float(p.res2[roff + e]);
+      if (p.act == MB200_ACT_RELU_POST) x = fmaxf(x, 0.f);
       if constexpr (sizeof(OutT) == 4) {
         float* dst = reinterpret_cast<float*>(p.C) + coff + e;
         *dst = p.accumulate ? *dst + x : x;
@@ -557,7 +558,8 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
     } else if (!rope && !a->act && nres == 0 && !aux && !a->accumulate) {
       if (a->dact == MB200_DACT_GELU_NEW) k = EK_DGELU;
       else if (a->dact == MB200_DACT_RELU) k = EK_DRELU;
-    } else if (!rope && !a->act && !a->dact && !aux && !a->accumulate && nres > 0) {
+    } else if (!rope && (!a->act || a->act == MB200_ACT_RELU_POST) && !a->dact && !aux && !a->accumulate &&
+               nres > 0) {
       if (nres == 2) k = EK_RES2;
       else if (a->res1) k = EK_RES1;
     }

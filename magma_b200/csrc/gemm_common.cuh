@@ -175,6 +175,7 @@ __device__ __noinline__ void epi_lane_generic(const GemmKernelParams& p, const E
       const long long roff = c.boff + (long long)row * p.ld_res + col + e;
       if (p.res1) x += __bfloat162float(p.res1[roff]);
       if (p.res2) x += __bfloat162float(p.res2[roff]);
+      if (p.act == MB200_ACT_RELU_POST) x = fmaxf(x, 0.f);
       if constexpr (sizeof(OutT) == 4) {
         float* dst = reinterpret_cast<float*>(p.C) + coff + e;
         *dst = p.accumulate ? *dst + x : x;
@@ -335,6 +336,12 @@ __device__ __forceinline__ void epi_tile(const GemmKernelParams& p, const EpiCtx
             bf16x4_to_f32(pre[kR2][it], a);
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] += a[e];
+          }
+          if constexpr (NRES >= 1) {
+            if (p.act == MB200_ACT_RELU_POST) {  // warp-uniform
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
           }
           if constexpr (sizeof(OutT) == 4) {
             float4 o = make_float4(v[0], v[1], v[2], v[3]);

@@ -5,9 +5,15 @@ neither package is vendored. This module implements CLIP's VisionTransformer fam
 im2col + tcgen05 GEMM, 24x [LN -> QKV GEMM+bias -> attention -> out GEMM+bias+residual -> LN -> fc GEMM+bias+
 QuickGELU -> proj GEMM+bias+residual], ln_post(CLS) @ proj) with openai/CLIP's parameter names, and extends the
 reference's name table with `clip_vit_large` (ViT-L/14, BASELINE.json config 2) following the reference's own ViT
-convention (pooled [b, D] features; `"clip"` = ViT-B/32 -> 512, image_prefix.py:18). The conv-trunk encoders
-(`nfresnet50`, `clip_resnet`, `clip_resnet_large`) are a later row of the scope table and raise.
+convention (pooled [b, D] features; `"clip"` = ViT-B/32 -> 512, image_prefix.py:18).
+
+CLIP's conv trunks (`clip_resnet` = RN50x4, `clip_resnet_large` = RN50x16, the encoder MAGMA_v1.yml ships with) are
+implemented as `B200ModifiedResNet`: NHWC bf16 activations, 1x1 convolutions as plain tcgen05 GEMMs, 3x3 convolutions
+as im2col + GEMM, eval-mode BatchNorm folded into the packed weights / GEMM bias, ReLU and the bottleneck residual in
+the GEMM epilogue, the anti-aliasing average pools as one HBM-bound kernel; attention pool replaced by the
+"b d h w -> b (h w) d" reshape exactly as the reference does (image_encoders.py:69-74). timm's `nfresnet50` raises.
 """
+from collections import OrderedDict
 import ctypes
 
 import torch
@@ -169,11 +175,170 @@ class B200VisionTransformer(nn.Module):
         return feats
 
 
+# name -> (layers, width, input_resolution) of CLIP's ModifiedResNet family (output dim = width * 32)
+RESNET_CONFIGS = {
+    "clip_resnet": ((4, 6, 10, 6), 80, 288),          # RN50x4 (image_encoders.py:58-59) -> 2560
+    "RN50x4": ((4, 6, 10, 6), 80, 288),
+    "clip_resnet_large": ((6, 8, 18, 8), 96, 384),    # RN50x16 (image_encoders.py:60-61) -> 3072, 12x12 = 144 tokens
+    "RN50x16": ((6, 8, 18, 8), 96, 384),
+}
+
+
+def register_resnet(name, layers, width, input_resolution):
+    """Add a ModifiedResNet geometry under `name` (must contain "clip") — used by the tests for small trunks."""
+    from . import image_prefix
+
+    RESNET_CONFIGS[name] = (tuple(layers), width, input_resolution)
+    image_prefix.ENCODER_OUT_DIMS[name] = width * 32
+    image_prefix.ENCODER_SEQ_LENS[name] = (input_resolution // 32) ** 2
+
+
+class _Conv2d(nn.Module):
+    def __init__(self, ci, co, k, device):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(co, ci, k, k, dtype=torch.float32, device=device), requires_grad=False)
+
+
+class _BatchNorm(nn.Module):
+    """Eval-mode BatchNorm2d parameters/buffers under torch's names (so CLIP / MAGMA checkpoints load)."""
+
+    def __init__(self, c, device):
+        super().__init__()
+        self.eps = 1e-5
+        self.weight = nn.Parameter(torch.ones(c, dtype=torch.float32, device=device), requires_grad=False)
+        self.bias = nn.Parameter(torch.zeros(c, dtype=torch.float32, device=device), requires_grad=False)
+        self.register_buffer("running_mean", torch.zeros(c, dtype=torch.float32, device=device))
+        self.register_buffer("running_var", torch.ones(c, dtype=torch.float32, device=device))
+        self.register_buffer("num_batches_tracked", torch.zeros((), dtype=torch.long, device=device))
+
+
+def fold_conv_bn(conv_w: torch.Tensor, bn: "_BatchNorm", pad_cin_to: int = 0):
+    """Conv (no bias) followed by eval BatchNorm == conv with weight W * s and bias (beta - mean * s),
+    s = gamma / sqrt(var + eps). Returns (packed bf16 [Cout, kh*kw*Cin] in (kh, kw, c) column order — the order
+    mb200_im2col3x3 writes —, bf16 bias [Cout])."""
+    s = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    w = conv_w.float() * s[:, None, None, None]
+    b = bn.bias.float() - bn.running_mean.float() * s
+    if pad_cin_to and w.shape[1] < pad_cin_to:
+        w = torch.cat([w, w.new_zeros(w.shape[0], pad_cin_to - w.shape[1], *w.shape[2:])], 1)
+    packed = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    return packed.to(torch.bfloat16).contiguous(), b.to(torch.bfloat16).contiguous()
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, inplanes, planes, stride, device):
+        super().__init__()
+        self.stride = stride
+        self.conv1, self.bn1 = _Conv2d(inplanes, planes, 1, device), _BatchNorm(planes, device)
+        self.conv2, self.bn2 = _Conv2d(planes, planes, 3, device), _BatchNorm(planes, device)
+        self.conv3, self.bn3 = _Conv2d(planes, planes * 4, 1, device), _BatchNorm(planes * 4, device)
+        self.downsample = None
+        if stride > 1 or inplanes != planes * 4:  # CLIP names: downsample.{-1: AvgPool2d, 0: conv, 1: bn}
+            self.downsample = nn.Sequential(OrderedDict([("-1", nn.AvgPool2d(stride)),
+                                                         ("0", _Conv2d(inplanes, planes * 4, 1, device)),
+                                                         ("1", _BatchNorm(planes * 4, device))]))
+
+
+class B200ModifiedResNet(nn.Module):
+    """CLIP ModifiedResNet trunk with openai/CLIP state-dict names (conv1..3 / bn1..3, layer{1..4}.{i}.{conv1,bn1,
+    conv2,bn2,conv3,bn3,downsample.{0,1}}); `attnpool` is the reshape "b d h w -> b (h w) d" of
+    magma/image_encoders.py:69-74, so forward returns [b, (R/32)^2, width*32]. Forward only (frozen encoder)."""
+
+    def __init__(self, layers, width, input_resolution, device=None):
+        super().__init__()
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        assert width % 16 == 0 and input_resolution % 32 == 0, "channel counts must be multiples of 8 (16-byte rows)"
+        self._device = dev
+        self.input_resolution, self.width, self.layers_cfg = input_resolution, width, tuple(layers)
+        self.output_dim = width * 32
+        self.conv1, self.bn1 = _Conv2d(3, width // 2, 3, dev), _BatchNorm(width // 2, dev)
+        self.conv2, self.bn2 = _Conv2d(width // 2, width // 2, 3, dev), _BatchNorm(width // 2, dev)
+        self.conv3, self.bn3 = _Conv2d(width // 2, width, 3, dev), _BatchNorm(width, dev)
+        inpl = width
+        for li, n in enumerate(self.layers_cfg):
+            planes, blocks = width * (2 ** li), []
+            for b in range(n):
+                blocks.append(_Bottleneck(inpl, planes, 2 if (b == 0 and li > 0) else 1, dev))
+                inpl = planes * 4
+            setattr(self, f"layer{li + 1}", nn.Sequential(*blocks))
+        self._packed = None
+
+    @torch.no_grad()
+    def init_weights(self, seed=0):
+        g = torch.Generator(device=self._device).manual_seed(seed)
+        for name, p in self.named_parameters():
+            if p.ndim == 4:
+                fan = p.shape[1] * p.shape[2] * p.shape[3]
+                p.data.copy_(torch.randn(p.shape, generator=g, device=self._device) * (2.0 / fan) ** 0.5)
+            elif name.endswith("bn3.weight") or name.endswith("downsample.1.weight"):
+                p.data.fill_(0.5)
+        self._packed = None
+        return self
+
+    def invalidate(self):
+        self._packed = None
+
+    def load_state_dict(self, *a, **kw):
+        self._packed = None
+        return super().load_state_dict(*a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):  # reached when a parent module loads a checkpoint
+        self._packed = None
+        return super()._load_from_state_dict(*a, **kw)
+
+    def blocks(self):
+        for li in range(4):
+            yield from getattr(self, f"layer{li + 1}")
+
+    def _pack(self):
+        if self._packed is None:
+            pk = {"stem": [fold_conv_bn(self.conv1.weight, self.bn1, pad_cin_to=8), fold_conv_bn(self.conv2.weight, self.bn2),
+                           fold_conv_bn(self.conv3.weight, self.bn3)], "blocks": []}
+            for blk in self.blocks():
+                ds = fold_conv_bn(blk.downsample[1].weight, blk.downsample[2]) if blk.downsample is not None else None
+                pk["blocks"].append((fold_conv_bn(blk.conv1.weight, blk.bn1), fold_conv_bn(blk.conv2.weight, blk.bn2),
+                                     fold_conv_bn(blk.conv3.weight, blk.bn3), ds))
+            self._packed = pk
+        return self._packed
+
+    def forward(self, x):
+        """[b, 3, R, R] -> [b, (R/32)^2, width*32]."""
+        if any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
+            raise MB200Error("training the image encoder (freeze_img_encoder: false) is not supported: the conv trunk "
+                             "runs with eval-mode BatchNorm folded into its weights and has no backward pass")
+        B, C, R, R2 = x.shape
+        if C != 3 or R != self.input_resolution or R2 != R:
+            raise ValueError(f"expected [b,3,{self.input_resolution},{self.input_resolution}], got {tuple(x.shape)}")
+        pk = self._pack()
+        x = ops.nchw_to_nhwc8(x.to(device=self._device, dtype=torch.bfloat16).contiguous())
+
+        def conv3x3(t, wb, stride):
+            cols, Ho, Wo = ops.im2col3x3(t, stride)
+            return ops.gemm(cols, wb[0], bias=wb[1], act=ops.ACT_RELU).view(t.shape[0], Ho, Wo, -1)
+
+        def conv1x1(t, wb, **kw):
+            return ops.gemm(t.reshape(-1, t.shape[-1]), wb[0], bias=wb[1], **kw).view(*t.shape[:3], -1)
+
+        x = conv3x3(x, pk["stem"][0], 2)
+        x = conv3x3(x, pk["stem"][1], 1)
+        x = conv3x3(x, pk["stem"][2], 1)
+        x = ops.avgpool_nhwc(x, 2)
+        for blk, (w1, w2, w3, wd) in zip(self.blocks(), pk["blocks"]):
+            out = conv1x1(x, w1, act=ops.ACT_RELU)
+            out = conv3x3(out, w2, 1)
+            if blk.stride > 1:
+                out = ops.avgpool_nhwc(out, blk.stride)
+            idn = x
+            if wd is not None:
+                idn = conv1x1(ops.avgpool_nhwc(x, blk.stride) if blk.stride > 1 else x, wd)
+            x = conv1x1(out, w3, act=ops.ACT_RELU_POST, res1=idn.reshape(-1, idn.shape[-1]))  # relu(bn3(conv3) + identity)
+        return x.reshape(B, -1, x.shape[-1])
+
+
 def clip_encoder(device=None, name: str = "clip") -> nn.Module:
     """magma/image_encoders.py:48-76."""
-    if name in ("clip_resnet", "RN50x4", "clip_resnet_large", "RN50x16"):
-        raise NotImplementedError(f"CLIP ModifiedResNet encoder '{name}' (conv trunk) is not re-backed yet "
-                                  "(SURVEY.md §8f rank 1); use 'clip' or 'clip_vit_large'")
+    if name in RESNET_CONFIGS:
+        return B200ModifiedResNet(*RESNET_CONFIGS[name], device=device)
     if name not in VIT_CONFIGS:
         raise ValueError(f"encoder {name} not recognized")
     return B200VisionTransformer(*VIT_CONFIGS[name], device=device)
@@ -182,7 +347,7 @@ def clip_encoder(device=None, name: str = "clip") -> nn.Module:
 def get_image_encoder(name: str, device=None, pretrained: bool = False) -> nn.Module:
     """magma/image_encoders.py:79-91. Weights are uninitialised/random: no checkpoint source exists offline."""
     if name == "nfresnet50":
-        raise NotImplementedError("nfresnet50 (timm conv trunk) is not re-backed yet (SURVEY.md §8f rank 1)")
-    if "clip" in name or name in VIT_CONFIGS:
+        raise NotImplementedError("nfresnet50 (timm NF-ResNet conv trunk) is not re-backed (SURVEY.md §8f rank 1)")
+    if "clip" in name or name in VIT_CONFIGS or name in RESNET_CONFIGS:
         return clip_encoder(device=device, name=name)
     raise ValueError(f"image encoder {name} not recognized")

@@ -101,9 +101,11 @@ class ImagePrefix(nn.Module):
         feats = self.enc(x)  # image_prefix.py:83
         if feats.ndim == 4:
             feats = feats[:, :, 0, 0]  # "b d 1 1 -> b d" (:86-87)
-        elif feats.ndim == 3:
-            assert self.encoder_type in ENCODER_SEQ_LENS
-            raise NotImplementedError("sequence-output (conv trunk) encoders are not re-backed yet")
+        seq_shape = None
+        if feats.ndim == 3:  # conv trunks: one token per spatial position, projected individually (:89-93)
+            assert self.encoder_type in ENCODER_SEQ_LENS and feats.shape[1] == self.out_seq_len, tuple(feats.shape)
+            seq_shape = (feats.shape[0], feats.shape[1], self.out_dim)
+            feats = feats.reshape(-1, feats.shape[-1])
         else:
             assert feats.ndim == 2
         feats = feats.to(torch.bfloat16).contiguous()
@@ -112,9 +114,11 @@ class ImagePrefix(nn.Module):
         lnw = self.ln.weight if self.use_layernorm else None
         lnb = self.ln.bias if self.use_layernorm else None
         if torch.is_grad_enabled() and self.proj.weight.requires_grad:
-            return _PrefixFn.apply(self, feats, self.proj.weight, self.proj.bias, lnw, lnb)
-        with torch.no_grad():
-            return _PrefixFn.forward(_NoCtx(), self, feats, self.proj.weight, self.proj.bias, lnw, lnb)
+            out = _PrefixFn.apply(self, feats, self.proj.weight, self.proj.bias, lnw, lnb)
+        else:
+            with torch.no_grad():
+                out = _PrefixFn.forward(_NoCtx(), self, feats, self.proj.weight, self.proj.bias, lnw, lnb)
+        return out.view(seq_shape) if seq_shape is not None else out
 
 
 class _NoCtx:

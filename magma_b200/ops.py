@@ -7,7 +7,7 @@ import torch
 from . import _lib
 from ._lib import GemmArgs, check, lib
 
-ACT_NONE, ACT_GELU_NEW, ACT_QUICK_GELU, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU_NEW, ACT_QUICK_GELU, ACT_RELU, ACT_RELU_POST = 0, 1, 2, 3, 4
 DACT_NONE, DACT_GELU_NEW, DACT_RELU = 0, 1, 3
 
 
@@ -266,6 +266,34 @@ def argmax(x, V=None):
     out = torch.empty(rows, dtype=torch.int64, device=x.device)
     check(lib().mb200_argmax(_ptr(x), ctypes.c_int64(x.stride(0)), rows, V, _ptr(out), _stream()))
     return out
+
+
+def nchw_to_nhwc8(x):
+    """[B, C<=8, H, W] bf16 -> [B, H, W, 8] bf16 with zero-padded channels (conv-trunk stem input)."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.ndim == 4
+    B, C, H, W = x.shape
+    y = torch.empty(B, H, W, 8, dtype=torch.bfloat16, device=x.device)
+    check(lib().mb200_nchw_to_nhwc8(_ptr(x), _ptr(y), B, C, H, W, _stream()))
+    return y
+
+
+def im2col3x3(x, stride=1):
+    """NHWC [B,H,W,C] bf16 -> [B*Ho*Wo, 9*C] bf16 (3x3, padding 1), columns ordered (kh, kw, c)."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.ndim == 4
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    y = torch.empty(B * Ho * Wo, 9 * C, dtype=torch.bfloat16, device=x.device)
+    check(lib().mb200_im2col3x3(_ptr(x), _ptr(y), B, H, W, C, stride, _stream()))
+    return y, Ho, Wo
+
+
+def avgpool_nhwc(x, k):
+    """nn.AvgPool2d(k) on NHWC bf16: [B,H,W,C] -> [B,H//k,W//k,C]."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.ndim == 4
+    B, H, W, C = x.shape
+    y = torch.empty(B, H // k, W // k, C, dtype=torch.bfloat16, device=x.device)
+    check(lib().mb200_avgpool_nhwc(_ptr(x), _ptr(y), B, H, W, C, k, _stream()))
+    return y
 
 
 def add(a, b, c=None):

@@ -56,6 +56,10 @@ class OracleConfig:
     vit_patch: int = 14
     vit_image: int = 224
     vit_mlp: int = 4096
+    # conv trunk (openai/CLIP ModifiedResNet: RN50x16 = width 96, layers (6,8,18,8), 384 px; RN50x4 = 80, (4,6,10,6), 288)
+    rn_width: int = 96
+    rn_layers: tuple = (6, 8, 18, 8)
+    rn_image: int = 384
     eos_token: int = 50256
     image_token: int = 50257
 
@@ -255,6 +259,77 @@ def vit_forward(images, w, cfg: OracleConfig, pre="image_prefix.enc"):
         x = x + F.linear(h, w[f"{p}.mlp.c_proj.weight"], w[f"{p}.mlp.c_proj.bias"])
     pooled = layer_norm(x[:, 0], w[f"{pre}.ln_post.weight"], w[f"{pre}.ln_post.bias"])
     return pooled @ w[f"{pre}.proj"]
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP ModifiedResNet (RN50x4 / RN50x16) with the attention pool replaced by "b d h w -> b (h w) d"
+# (magma/image_encoders.py:65-74). PARITY UNPINNED: openai/CLIP is not vendored and nothing in this image carries its
+# ModifiedResNet, so this follows the published architecture (CLIP model.py: Bottleneck / ModifiedResNet — 3-conv stem
+# with stride-2 first conv and a 2x2 average pool, anti-aliased bottlenecks where the stride is an average pool after
+# conv2 and in front of the 1x1 downsample conv, BatchNorm in eval mode) with its state-dict names.
+# ------------------------------------------------------------------------------------------------
+def _bn_eval(x, w, p, eps=1e-5):
+    return F.batch_norm(x, w[f"{p}.running_mean"], w[f"{p}.running_var"], w[f"{p}.weight"], w[f"{p}.bias"], False, 0.0, eps)
+
+
+def resnet_block_specs(cfg: OracleConfig):
+    """[(name, inplanes, planes, stride)] for layer1..layer4 (CLIP model.py ModifiedResNet._make_layer)."""
+    specs, inpl = [], cfg.rn_width
+    for li, n in enumerate(cfg.rn_layers):
+        planes = cfg.rn_width * (2 ** li)
+        for b in range(n):
+            specs.append((f"layer{li + 1}.{b}", inpl, planes, 2 if (b == 0 and li > 0) else 1))
+            inpl = planes * 4
+    return specs
+
+
+def resnet_forward(images, w, cfg: OracleConfig, pre="image_prefix.enc"):
+    x = images
+    for i, stride in ((1, 2), (2, 1), (3, 1)):  # stem
+        x = F.relu(_bn_eval(F.conv2d(x, w[f"{pre}.conv{i}.weight"], stride=stride, padding=1), w, f"{pre}.bn{i}"))
+    x = F.avg_pool2d(x, 2)
+    for name, inpl, planes, stride in resnet_block_specs(cfg):
+        p = f"{pre}.{name}"
+        out = F.relu(_bn_eval(F.conv2d(x, w[f"{p}.conv1.weight"]), w, f"{p}.bn1"))
+        out = F.relu(_bn_eval(F.conv2d(out, w[f"{p}.conv2.weight"], padding=1), w, f"{p}.bn2"))
+        if stride > 1:
+            out = F.avg_pool2d(out, stride)
+        out = _bn_eval(F.conv2d(out, w[f"{p}.conv3.weight"]), w, f"{p}.bn3")
+        idn = x
+        if stride > 1 or inpl != planes * 4:
+            idn = F.avg_pool2d(x, stride) if stride > 1 else x
+            idn = _bn_eval(F.conv2d(idn, w[f"{p}.downsample.0.weight"]), w, f"{p}.downsample.1")
+        x = F.relu(out + idn)
+    B, D = x.shape[:2]
+    return x.reshape(B, D, -1).permute(0, 2, 1)  # image_encoders.py:71-73
+
+
+def init_resnet_weights(cfg: OracleConfig, seed=0, pre="image_prefix.enc", dtype=torch.float32):
+    """He-normal convs, BatchNorm statistics away from (0, 1) so that folding errors show."""
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+
+    def conv(name, co, ci, k):
+        w[f"{name}.weight"] = (torch.randn(co, ci, k, k, generator=g) * math.sqrt(2.0 / (ci * k * k))).to(dtype)
+
+    def bn(name, c, gain=1.0):
+        w[f"{name}.weight"] = (gain * (1.0 + 0.1 * torch.randn(c, generator=g))).to(dtype)
+        w[f"{name}.bias"] = (0.1 * torch.randn(c, generator=g)).to(dtype)
+        w[f"{name}.running_mean"] = (0.1 * torch.randn(c, generator=g)).to(dtype)
+        w[f"{name}.running_var"] = (1.0 + 0.2 * torch.rand(c, generator=g)).to(dtype)
+
+    wd = cfg.rn_width
+    conv(f"{pre}.conv1", wd // 2, 3, 3), bn(f"{pre}.bn1", wd // 2)
+    conv(f"{pre}.conv2", wd // 2, wd // 2, 3), bn(f"{pre}.bn2", wd // 2)
+    conv(f"{pre}.conv3", wd, wd // 2, 3), bn(f"{pre}.bn3", wd)
+    for name, inpl, planes, stride in resnet_block_specs(cfg):
+        p = f"{pre}.{name}"
+        conv(f"{p}.conv1", planes, inpl, 1), bn(f"{p}.bn1", planes)
+        conv(f"{p}.conv2", planes, planes, 3), bn(f"{p}.bn2", planes)
+        conv(f"{p}.conv3", planes * 4, planes, 1), bn(f"{p}.bn3", planes * 4, gain=0.5)
+        if stride > 1 or inpl != planes * 4:
+            conv(f"{p}.downsample.0", planes * 4, inpl, 1), bn(f"{p}.downsample.1", planes * 4, gain=0.5)
+    return w
 
 
 # ------------------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-GROUPS = ["ops", "lm", "lm_variants", "vit", "magma", "generate", "fullsize"]
+GROUPS = ["ops", "lm", "lm_variants", "vit", "resnet", "magma", "generate", "fullsize"]
 
 
 def rel(got, want):
@@ -282,7 +282,106 @@ def group_vit(dev):
     return ok
 
 
-def build_magma(cfg, w16, dev, S, dropout=0.0):
+def im2col3x3_reference(x_nhwc, stride):
+    """torch statement of mb200_im2col3x3: [B,H,W,C] -> [B*Ho*Wo, 9*C], zero padding 1, columns (kh, kw, c)."""
+    import torch
+    import torch.nn.functional as F
+
+    B, H, W, C = x_nhwc.shape
+    xp = F.pad(x_nhwc, (0, 0, 1, 1, 1, 1))
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    taps = [xp[:, kh:kh + (Ho - 1) * stride + 1:stride, kw:kw + (Wo - 1) * stride + 1:stride, :]
+            for kh in range(3) for kw in range(3)]
+    return torch.stack(taps, 3).reshape(B * Ho * Wo, 9 * C)
+
+
+def group_resnet(dev):
+    """Conv-trunk row: layout kernels bit-exact vs torch, RELU_POST epilogue, a small CLIP
+    ModifiedResNet against the oracle restatement, and Magma.forward/backward through the 3-D feature path."""
+    import torch
+    import torch.nn.functional as F
+    from magma_b200 import ops
+    from magma_b200.image_encoders import B200ModifiedResNet, register_resnet
+    from oracle import magma_oracle as O
+
+    ok = True
+    torch.manual_seed(3)
+    img = torch.randn(2, 3, 20, 28).to(torch.bfloat16)
+    got = ops.nchw_to_nhwc8(img.to(dev)).cpu()
+    want = torch.zeros(2, 20, 28, 8, dtype=torch.bfloat16)
+    want[..., :3] = img.permute(0, 2, 3, 1)
+    same = bool(torch.equal(got, want))
+    ok &= same
+    print(f"[{'OK' if same else 'FAIL'}] nchw_to_nhwc8 bit-exact", flush=True)
+    for (B, H, W, C, st) in ((2, 9, 7, 16, 1), (2, 9, 7, 16, 2), (1, 12, 12, 40, 2), (3, 6, 10, 8, 1)):
+        x = torch.randn(B, H, W, C).to(torch.bfloat16)
+        got, Ho, Wo = ops.im2col3x3(x.to(dev), st)
+        same = bool(torch.equal(got.cpu(), im2col3x3_reference(x, st)))
+        ok &= same
+        print(f"[{'OK' if same else 'FAIL'}] im2col3x3 B={B} H={H} W={W} C={C} stride={st} bit-exact", flush=True)
+    for (B, H, W, C, k) in ((2, 8, 12, 16, 2), (1, 9, 9, 24, 3), (2, 7, 9, 8, 2)):
+        x = torch.randn(B, H, W, C).to(torch.bfloat16)
+        want = F.avg_pool2d(x.float().permute(0, 3, 1, 2), k).permute(0, 2, 3, 1)
+        ok &= report(f"avgpool_nhwc k={k} H={H} W={W}", ops.avgpool_nhwc(x.to(dev), k), want, 4e-3)
+    # relu(A.B + bias + res): RELU_POST on the specialised (N % 4 == 0) and the generic (ragged N) epilogue
+    for (M, N, K) in ((300, 256, 136), (70, 100, 72)):
+        A = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        Bm = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev).to(torch.bfloat16)
+        ldr = (N + 7) // 8 * 8
+        res = torch.randn(M, ldr, device=dev).to(torch.bfloat16)[:, :N]
+        got = torch.empty(M, ldr, device=dev, dtype=torch.bfloat16)[:, :N]
+        ops.gemm(A, Bm, out=got, bias=bias, act=ops.ACT_RELU_POST, res1=res)
+        want = F.relu(A.float() @ Bm.float().t() + bias.float() + res.float())
+        ok &= report(f"gemm RELU_POST epilogue M={M} N={N} K={K}", got, want, 1e-2)
+    # trunk vs oracle
+    for cfg in (O.OracleConfig(rn_width=16, rn_layers=(1, 2, 1, 1), rn_image=64),
+                O.OracleConfig(rn_width=32, rn_layers=(2, 1, 2, 1), rn_image=96)):
+        w = {k: v.to(torch.bfloat16).float() if v.ndim == 4 else v for k, v in O.init_resnet_weights(cfg, seed=4).items()}
+        net = B200ModifiedResNet(cfg.rn_layers, cfg.rn_width, cfg.rn_image, device=dev)
+        sd = {k[len("image_prefix.enc."):]: v for k, v in w.items()}
+        missing, unexpected = net.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+        x = torch.randn(2, 3, cfg.rn_image, cfg.rn_image).to(torch.bfloat16).float()
+        want = O.resnet_forward(x, w, cfg)
+        got = net(x.to(dev))
+        torch.cuda.synchronize()
+        ok &= got.shape == want.shape
+        ok &= report(f"ModifiedResNet forward width={cfg.rn_width} layers={cfg.rn_layers} {cfg.rn_image}px -> "
+                     f"{tuple(got.shape)}", got, want, 3e-2)
+    # Magma with the conv trunk: prefix = one token per spatial position (fixed 4 tokens here)
+    cfg = small_cfg(rn_width=16, rn_layers=(1, 1, 1, 1), rn_image=64, enc_out_dim=512)
+    S, B = 32, 2
+    w = boost_adapters(O.init_weights(cfg, seed=6, with_vit=False), True)
+    w["image_prefix.proj.weight"] = w["image_prefix.proj.weight"][: cfg.d]  # Linear(enc_out_dim, d): per-token projection
+    w["image_prefix.proj.bias"] = w["image_prefix.proj.bias"][: cfg.d]
+    w.update(O.init_resnet_weights(cfg, seed=7))
+    w16 = {k: (v.to(torch.bfloat16).float() if "running" not in k and ".bn" not in k and "downsample.1" not in k else v)
+           for k, v in w.items()}
+    register_resnet("clip_resnet_tiny", cfg.rn_layers, cfg.rn_width, cfg.rn_image)
+    model = build_magma(cfg, w16, dev, S, encoder_name="clip_resnet_tiny", image_size=cfg.rn_image)
+    model.eval()
+    images = torch.randn(B, 3, cfg.rn_image, cfg.rn_image).to(torch.bfloat16).float()
+    _, captions = O.synthetic_batch(cfg, B, S, seed=12, prefix_len=4)
+    trainable = [k for k in w16 if ".adapter." in k or k.startswith("image_prefix.proj") or k.startswith("image_prefix.ln")]
+    params = {k: v.clone().requires_grad_(k in trainable) for k, v in w16.items()}
+    prefix_o = O.image_prefix_from_features(O.resnet_forward(images, params, cfg), params, cfg, fixed_seq=True)
+    loss_o, logits_o, _ = O.magma_forward(None, captions, params, cfg, input_embeddings=prefix_o)
+    loss_o.backward()
+    out = model(images.to(dev), captions.to(dev))
+    out.loss.backward()
+    torch.cuda.synchronize()
+    ok &= report("magma(conv trunk) loss", out.loss.reshape(1), loss_o.detach().reshape(1), 5e-3)
+    ok &= report("magma(conv trunk) logits", out.logits, logits_o.detach(), 3e-2)
+    sd = dict(model.named_parameters())
+    worst = max(rel(sd[k].grad, params[k].grad)[0] for k in trainable)
+    good = worst < 5e-2
+    ok &= good
+    print(f"[{'OK' if good else 'FAIL'}] magma(conv trunk) trainable grads worst rel_fro={worst:.3e}", flush=True)
+    return ok
+
+
+def build_magma(cfg, w16, dev, S, dropout=0.0, encoder_name="clip_vit_tiny", image_size=None):
     import torch
     from magma_b200.config import MultimodalConfig
     from magma_b200.image_encoders import register_vit
@@ -291,10 +390,10 @@ def build_magma(cfg, w16, dev, S, dropout=0.0):
 
     register_vit("clip_vit_tiny", cfg.vit_width, cfg.vit_layers, cfg.vit_heads, cfg.vit_patch, cfg.vit_image,
                  cfg.vit_mlp, cfg.enc_out_dim)
-    mc = MultimodalConfig(batch_size=2, train_steps=1, encoder_name="clip_vit_tiny",
+    mc = MultimodalConfig(batch_size=2, train_steps=1, encoder_name=encoder_name,
                           adapter_config={"mlp": dict(cfg.mlp_adapter)} if cfg.mlp_adapter else None,
                           image_seq_len=cfg.image_seq_len, image_embed_dropout_prob=dropout,
-                          use_image_embed_layernorm=True, image_size=cfg.vit_image, seq_len=S)
+                          use_image_embed_layernorm=True, image_size=image_size or cfg.vit_image, seq_len=S)
     mc._lm_config = GPTJConfig(vocab_size=cfg.vocab, hidden_size=cfg.d, num_layers=cfg.n_layer, num_heads=cfg.n_head,
                                rotary_dim=cfg.rotary_dim)
     model = Magma(mc, device=dev, init_seed=None)
@@ -302,7 +401,7 @@ def build_magma(cfg, w16, dev, S, dropout=0.0):
     missing, unexpected = model.load_state_dict(w16, strict=False)
     # Magma registers lm.transformer.wte / .h a second time as word_embedding / transformer (magma/magma.py:52-53):
     # those alias keys share storage with the lm.* keys that were loaded
-    missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
+    missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer.")) and not k.endswith("num_batches_tracked")]
     assert not unexpected and not missing, (missing, unexpected)
     model.lm.invalidate()
     model.lm.attach_arena(model.arena)
