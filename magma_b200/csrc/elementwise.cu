@@ -549,22 +549,24 @@ __global__ void nchw_to_nhwc8_kernel(const bf16* __restrict__ src, bf16* __restr
   }
 }
 // src [B,H,W,C] -> dst [B*Ho*Wo][9*C], 3x3 window, padding 1, stride s (Ho = (H-1)/s + 1); out-of-image taps are zero
+template <typename Idx>  // 32-bit index arithmetic whenever the vector count allows it (the divisions dominate otherwise)
 __global__ void im2col3x3_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int C,
                                  int stride, int Ho, int Wo) {
-  const int cv = C >> 3;
-  const long long total = (long long)B * Ho * Wo * 9 * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
-    const int tap = (int)((i / cv) % 9);
-    const long long row = i / (9LL * cv);
-    const int wo = (int)(row % Wo);
-    const int ho = (int)((row / Wo) % Ho);
-    const long long b = row / ((long long)Wo * Ho);
+  const Idx cv = (Idx)(C >> 3);
+  const Idx total = (Idx)B * Ho * Wo * 9 * cv;
+  for (Idx i = blockIdx.x * (Idx)blockDim.x + threadIdx.x; i < total; i += (Idx)gridDim.x * blockDim.x) {
+    const Idx t = i / cv;
+    const int c8 = (int)(i - t * cv);
+    const Idx row = t / 9;
+    const int tap = (int)(t - row * 9);
+    const Idx r2 = row / Wo;
+    const int wo = (int)(row - r2 * Wo);
+    const Idx b = r2 / Ho;
+    const int ho = (int)(r2 - b * Ho);
     const int hi = ho * stride - 1 + tap / 3, wi = wo * stride - 1 + tap % 3;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-      v = __ldg(reinterpret_cast<const uint4*>(src + ((b * H + hi) * W + wi) * C) + c8);
+      v = __ldg(reinterpret_cast<const uint4*>(src + (((long long)b * H + hi) * W + wi) * C) + c8);
     reinterpret_cast<uint4*>(dst)[i] = v;  // (row, tap, c8) is exactly the linear index
   }
 }
@@ -939,8 +941,13 @@ extern "C" int mb200_im2col3x3(const void* src, void* dst, int32_t B, int32_t H,
   MB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2), MB200_E_SHAPE,
              "im2col3x3: B=%d H=%d W=%d C=%d (multiple of 8) stride=%d (1 or 2)", B, H, W, C, stride);
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  im2col3x3_kernel<<<grid_for((long long)B * Ho * Wo * 9 * (C / 8), 256), 256, 0, ST(stream)>>>(
-      (const bf16*)src, (bf16*)dst, B, H, W, C, stride, Ho, Wo);
+  const long long nvec = (long long)B * Ho * Wo * 9 * (C / 8);
+  if (nvec < (1LL << 31) - (1LL << 24))  // headroom for the grid-stride increment
+    im2col3x3_kernel<unsigned int><<<grid_for(nvec, 256), 256, 0, ST(stream)>>>((const bf16*)src, (bf16*)dst, B, H, W, C,
+                                                                                stride, Ho, Wo);
+  else
+    im2col3x3_kernel<long long><<<grid_for(nvec, 256), 256, 0, ST(stream)>>>((const bf16*)src, (bf16*)dst, B, H, W, C,
+                                                                             stride, Ho, Wo);
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -15,6 +15,7 @@ the GEMM epilogue, the anti-aliasing average pools as one HBM-bound kernel; atte
 """
 from collections import OrderedDict
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -262,6 +263,7 @@ class B200ModifiedResNet(nn.Module):
                 inpl = planes * 4
             setattr(self, f"layer{li + 1}", nn.Sequential(*blocks))
         self._packed = None
+        self._graphs = {}
 
     @torch.no_grad()
     def init_weights(self, seed=0):
@@ -309,8 +311,40 @@ class B200ModifiedResNet(nn.Module):
         B, C, R, R2 = x.shape
         if C != 3 or R != self.input_resolution or R2 != R:
             raise ValueError(f"expected [b,3,{self.input_resolution},{self.input_resolution}], got {tuple(x.shape)}")
+        x = x.to(device=self._device, dtype=torch.bfloat16).contiguous()
+        if os.environ.get("MB200_RESNET_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(x)
+        return self._forward_eager(x)
+
+    def _forward_graphed(self, x):
+        """The trunk is ~300 short launches with static shapes: replay them as one CUDA graph per batch size (the
+        host-side launch cost, not the GPU, bounds the eager version). The result is copied out of the graph's static
+        buffer, so it stays valid across later calls."""
+        B = x.shape[0]
+        entry = self._graphs.get(B)
+        if entry is None or entry[3] is not self._pack():
+            pk = self._pack()
+            static_in = torch.empty_like(x)
+            static_in.copy_(x)
+            s = torch.cuda.Stream(device=self._device)
+            s.wait_stream(torch.cuda.current_stream(self._device))
+            with torch.cuda.stream(s):
+                self._forward_eager(static_in)  # warm-up outside capture (function attributes, allocator)
+            torch.cuda.current_stream(self._device).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._forward_eager(static_in)
+            entry = (g, static_in, static_out, pk)
+            self._graphs[B] = entry
+        g, static_in, static_out, _ = entry
+        static_in.copy_(x)
+        g.replay()
+        return static_out.clone()
+
+    def _forward_eager(self, x):
+        B = x.shape[0]
         pk = self._pack()
-        x = ops.nchw_to_nhwc8(x.to(device=self._device, dtype=torch.bfloat16).contiguous())
+        x = ops.nchw_to_nhwc8(x)
 
         def conv3x3(t, wb, stride):
             cols, Ho, Wo = ops.im2col3x3(t, stride)

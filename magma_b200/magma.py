@@ -248,8 +248,8 @@ class Magma(nn.Module):
 
     @classmethod
     def from_checkpoint(cls, config_path, checkpoint_path, device="cuda"):
-        """magma/magma.py:278-301. The published checkpoint uses the fork's parameter names; mapping them onto
-        this module's names is the checkpoint-adapter row of the scope table."""
+        """magma/magma.py:278-301. The published checkpoint uses the fork's parameter names; checkpoint.py maps them
+        onto this module's names and a mismatch raises instead of loading partially."""
         import os
 
         if not os.path.exists(checkpoint_path):
@@ -259,7 +259,16 @@ class Magma(nn.Module):
         if "module" in sd.keys():
             sd = sd["module"]
         print_main(f"loading magma checkpoint from: {checkpoint_path}")
-        model.load_state_dict(sd, strict=False)
+        from .checkpoint import convert_reference_state_dict
+
+        sd, report = convert_reference_state_dict(sd)  # fork GPT-Neo names -> HF GPT-J names (checkpoint.py)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer.")) and
+                   not k.endswith("num_batches_tracked")]
+        if missing or unexpected:
+            raise RuntimeError(f"checkpoint does not match the model: {len(missing)} missing (e.g. {missing[:4]}), "
+                               f"{len(unexpected)} unexpected (e.g. {list(unexpected)[:4]}); "
+                               f"{len(report['renamed'])} keys were renamed, {len(report['dropped'])} dropped")
         model.finalize()
         print_main("magma successfully loaded")
         model.eval()

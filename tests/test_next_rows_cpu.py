@@ -83,3 +83,23 @@ def test_factory_dispatch():
     with pytest.raises(ValueError):
         ie.get_image_encoder("clip_unknown")
     assert isinstance(ie.get_image_encoder("clip_resnet", device="cpu"), ie.B200ModifiedResNet)
+
+
+def test_checkpoint_key_adapter_round_trip():
+    """Fork-named (GPT-Neo lineage) LM keys map onto the HF GPT-J names and back; CLIP's own mlp.c_fc / c_proj names
+    under image_prefix.enc are left alone; causal-mask buffers are dropped (magma_b200/checkpoint.py)."""
+    from magma_b200.checkpoint import convert_reference_state_dict, to_reference_names
+
+    cfg = O.OracleConfig(d=64, n_layer=2, n_head=2, rotary_dim=16, vocab=128, vit_width=32, vit_layers=1, vit_heads=2,
+                         vit_patch=8, vit_image=16, vit_mlp=64, enc_out_dim=32,
+                         attn_adapter={"adapter_type": "normal", "downsample_factor": 8})
+    w = O.init_weights(cfg)
+    ref = to_reference_names(w)
+    assert "lm.transformer.h.0.attn.attn_block.attention.q_proj.weight" in ref
+    assert "lm.transformer.h.1.mlp.0.c_fc.weight" in ref and "lm.transformer.h.1.mlp.0.fc_in.weight" not in ref
+    assert "image_prefix.enc.transformer.resblocks.0.mlp.c_fc.weight" in ref
+    ref["lm.transformer.h.0.attn.attn_block.attention.bias"] = torch.zeros(1)
+    ref["lm.transformer.h.0.attn.attn_block.attention.masked_bias"] = torch.zeros(1)
+    back, report = convert_reference_state_dict(ref)
+    assert set(back) == set(w) and not report["collisions"] and len(report["dropped"]) == 2
+    assert all(torch.equal(back[k], w[k]) for k in w)

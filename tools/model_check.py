@@ -347,6 +347,13 @@ def group_resnet(dev):
         got = net(x.to(dev))
         torch.cuda.synchronize()
         ok &= got.shape == want.shape
+        again = net(x.to(dev))  # second call replays the captured CUDA graph
+        os.environ["MB200_RESNET_GRAPH"] = "0"
+        eager = net(x.to(dev))
+        del os.environ["MB200_RESNET_GRAPH"]
+        same = bool(torch.equal(got, again)) and bool(torch.equal(got, eager))
+        ok &= same
+        print(f"[{'OK' if same else 'FAIL'}] CUDA-graph replay == eager launches, bit-exact", flush=True)
         ok &= report(f"ModifiedResNet forward width={cfg.rn_width} layers={cfg.rn_layers} {cfg.rn_image}px -> "
                      f"{tuple(got.shape)}", got, want, 3e-2)
     # Magma with the conv trunk: prefix = one token per spatial position (fixed 4 tokens here)
