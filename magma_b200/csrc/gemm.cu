@@ -587,13 +587,20 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   // order (deterministic) and applies the fused epilogue.
   const bool split_mid = !small_m && a->splitk_ws && a->M <= 128 && a->nb0 * a->nb1 == 1 && a->K >= 8192 &&
                          a->N <= 8192 && !a->force_bn;
-  if (plan_split > 1 || split_mid) {
-    const int bn_s = small_m ? bn : (a->N >= 256 ? 256 : (a->N > 64 ? 128 : 64));
+  // Larger M with few tiles and a long K (conv-trunk 3x3 convolutions of the late stages: M = 1152, N = 768,
+  // K = 6912 -> 27 tiles of 108 k-blocks): one SM pulls operands at <= ~60 GB/s, so 27 busy SMs are bandwidth-starved
+  // (measured 115 us, ~100 TFLOP/s); split K until tiles x splits covers the machine.
+  const int bn_few = a->N >= 256 ? 256 : (a->N > 64 ? 128 : 64);
+  const bool split_few = !small_m && !split_mid && a->splitk_ws && a->M > 128 && a->nb0 * a->nb1 == 1 &&
+                         a->K >= 2048 && !a->force_bn &&
+                         2 * kp.tiles_m * ((a->N + bn_few - 1) / bn_few) <= num_sms();
+  if (plan_split > 1 || split_mid || split_few) {
+    const int bn_s = small_m ? bn : bn_few;
     const int tiles = (a->N + bn_s - 1) / bn_s;
     const int num_kb = (a->K + BK - 1) / BK;
     int split = plan_split;
-    if (split_mid) {
-      split = num_sms() / tiles;
+    if (split_mid || split_few) {
+      split = num_sms() / (tiles * kp.tiles_m);
       if (split > num_kb / 4) split = num_kb / 4;
     }
     const long long ld_ws = (a->N + 3) / 4 * 4;

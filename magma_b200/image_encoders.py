@@ -264,6 +264,7 @@ class B200ModifiedResNet(nn.Module):
             setattr(self, f"layer{li + 1}", nn.Sequential(*blocks))
         self._packed = None
         self._graphs = {}
+        self._splitk_ws = None
 
     @torch.no_grad()
     def init_weights(self, seed=0):
@@ -346,12 +347,16 @@ class B200ModifiedResNet(nn.Module):
         pk = self._pack()
         x = ops.nchw_to_nhwc8(x)
 
+        if self._splitk_ws is None:  # fp32 split-K scratch for the few-tile / long-K convolutions of the late stages
+            self._splitk_ws = torch.empty(16 << 20, dtype=torch.float32, device=self._device)
+        ws = self._splitk_ws
+
         def conv3x3(t, wb, stride):
             cols, Ho, Wo = ops.im2col3x3(t, stride)
-            return ops.gemm(cols, wb[0], bias=wb[1], act=ops.ACT_RELU).view(t.shape[0], Ho, Wo, -1)
+            return ops.gemm(cols, wb[0], bias=wb[1], act=ops.ACT_RELU, splitk_ws=ws).view(t.shape[0], Ho, Wo, -1)
 
         def conv1x1(t, wb, **kw):
-            return ops.gemm(t.reshape(-1, t.shape[-1]), wb[0], bias=wb[1], **kw).view(*t.shape[:3], -1)
+            return ops.gemm(t.reshape(-1, t.shape[-1]), wb[0], bias=wb[1], splitk_ws=ws, **kw).view(*t.shape[:3], -1)
 
         x = conv3x3(x, pk["stem"][0], 2)
         x = conv3x3(x, pk["stem"][1], 1)

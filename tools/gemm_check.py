@@ -246,7 +246,8 @@ def run_group(g):
 
         ws = torch.full((16 * 128 * 8192,), float('nan'), device=dev, dtype=torch.float32)  # scratch needs no init
         for (M, N, K, bmn) in ((32, 4096, 16384, False), (32, 4096, 8192, True), (7, 1002, 8200, False),
-                               (100, 1000, 16384, False), (32, 4096, 4096, False)):
+                               (100, 1000, 16384, False), (32, 4096, 4096, False),
+                               (1152, 768, 6912, False), (300, 248, 2120, True)):  # few tiles, long K, M > 128
             A, B = mk((M, K), False, dev, 0.5), mk((N, K), bmn, dev, 0.125)
             ldc = (N + 63) // 64 * 64
             bias = torch.randn(N, device=dev).to(torch.bfloat16)
