@@ -185,6 +185,13 @@ int mb200_im2col3x3(const void* src, void* dst, int32_t B, int32_t H, int32_t W,
 int mb200_avgpool_nhwc(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* stream);
 /* torch.argmax(logits.float(), -1) (magma/sampling.py:92,97): lowest index wins ties. */
 int mb200_argmax(const void* x, int64_t ldx, int32_t rows, int32_t V, int64_t* out, void* stream);
+/* One sampled token per row for temperature > 0 (magma/sampling.py:97-105): top_k_filter (:22-30, off when top_k == 0),
+ * top_p_filter including its inverted-nucleus comparison (:7-19, off when top_p == 0; ties ordered by index = a stable
+ * sort), softmax(logits / temperature) and one multinomial draw from Philox(seed, row, offset). logits bf16 or f32
+ * [rows, V] with row stride ld; keep_mask (optional, [rows, V] bytes) receives 1 where a token survives both filters. */
+int mb200_sample(const void* logits, int32_t dtype, int64_t ld, int32_t rows, int32_t V, float temperature,
+                 int32_t top_k, float top_p, uint64_t seed, uint64_t offset, int64_t* tokens, uint8_t* keep_mask,
+                 void* stream);
 int mb200_add(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
 
 /* Fused AdamW over a flat fp32 arena (torch.optim.AdamW(betas=(0.9,0.95)) of train.py:96-101) with global-norm

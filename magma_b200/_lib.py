@@ -164,7 +164,7 @@ EXPORTED_SYMBOLS = [
     "mb200_softmax_fwd", "mb200_softmax_bwd", "mb200_build_labels", "mb200_embed_assemble", "mb200_embed_gather",
     "mb200_cross_entropy", "mb200_colsum", "mb200_dropout_fwd", "mb200_dropout_apply", "mb200_patchify",
     "mb200_nchw_to_nhwc8", "mb200_im2col3x3", "mb200_avgpool_nhwc",
-    "mb200_vit_assemble", "mb200_argmax", "mb200_add", "mb200_sumsq", "mb200_adamw_step",
+    "mb200_vit_assemble", "mb200_argmax", "mb200_sample", "mb200_add", "mb200_sumsq", "mb200_adamw_step",
     "mb200_cast_f32_to_bf16", "mb200_cast_bf16_to_f32",
     "mb200_gptj_workspace_bytes", "mb200_gptj_forward", "mb200_gptj_backward",
     "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode", "mb200_attn_fwd_tile",

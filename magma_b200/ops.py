@@ -296,6 +296,19 @@ def avgpool_nhwc(x, k):
     return y
 
 
+def sample(logits, temperature, top_k=0, top_p=0.0, seed=0, offset=0, return_mask=False):
+    """One token per row of `logits` [rows, V] (bf16 or fp32, unit column stride) sampled like magma/sampling.py:97-105
+    (top-k filter, the reference's nucleus filter, softmax(logits / T), multinomial)."""
+    assert logits.ndim == 2 and logits.stride(1) == 1 and logits.dtype in (torch.bfloat16, torch.float32)
+    rows, V = logits.shape
+    out = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    mask = torch.empty(rows, V, dtype=torch.uint8, device=logits.device) if return_mask else None
+    check(lib().mb200_sample(_ptr(logits), 0 if logits.dtype == torch.bfloat16 else 1, ctypes.c_int64(logits.stride(0)), rows, V,
+                             ctypes.c_float(temperature), int(top_k), ctypes.c_float(top_p), ctypes.c_uint64(seed & (2**64 - 1)),
+                             ctypes.c_uint64(offset), _ptr(out), _ptr(mask), _stream()))
+    return (out, mask) if return_mask else out
+
+
 def add(a, b, c=None):
     y = torch.empty_like(a)
     check(lib().mb200_add(_ptr(a), _ptr(b), _ptr(c), _ptr(y), ctypes.c_int64(a.numel()), _stream()))

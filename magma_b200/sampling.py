@@ -16,7 +16,8 @@ from . import ops
 
 def top_p_filter(logits, threshold: float = 0.9):
     """magma/sampling.py:7-19 — reproduced including its inverted-nucleus comparison (`cum_probs < 1 - threshold`,
-    shifted right by one). Runs with torch ops: sampling (T > 0) is a later row of the scope table (§8f rank 4)."""
+    shifted right by one). This torch statement is the public filter function of the reference API; `generate` itself
+    samples with the fused device kernel (`ops.sample` -> mb200_sample), which applies the same rule without a sort."""
     sorted_logits, sorted_indices = torch.sort(logits, descending=True)
     cum_probs = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
     sorted_indices_to_remove = cum_probs < (1 - threshold)
@@ -58,6 +59,8 @@ def generate(model, embeddings, max_steps: int = 100, temperature: float = 0.7, 
     cache = None
     n_done = max_steps
     all_eos = torch.zeros(max_steps, dtype=torch.bool, device=dev)
+    # Philox seed of this call, drawn from torch's CPU generator: reproducible under torch.manual_seed, new per call
+    sample_seed = int(torch.randint(0, 2**62, (1,)).item()) if temperature != 0.0 else 0
     for i in range(max_steps):
         if i == 0:
             from .language_model import KVCache
@@ -71,13 +74,9 @@ def generate(model, embeddings, max_steps: int = 100, temperature: float = 0.7, 
         if temperature == 0.0:
             next_token = ops.argmax(logits.contiguous() if logits.stride(-1) != 1 else logits, logits.shape[-1])  # :97
         else:
-            lg = logits.float()                                                 # :92
-            if top_k > 0:
-                lg = top_k_filter(lg, k=top_k)
-            if top_p > 0:
-                lg = top_p_filter(lg, threshold=top_p)
-            probs = F.softmax(lg / temperature, dim=-1)
-            next_token = torch.multinomial(probs, num_samples=1).squeeze(1)
+            # :92-105 in one launch: top-k filter, the reference's nucleus filter, softmax(logits / T), multinomial
+            lg = logits if logits.stride(-1) == 1 else logits.contiguous()
+            next_token = ops.sample(lg, temperature, top_k=top_k, top_p=top_p, seed=sample_seed, offset=i)
         out[:, s + i] = next_token                                              # :107
         if eos_token is not None:
             all_eos[i] = (next_token == eos_token).all()                        # :109, evaluated lazily

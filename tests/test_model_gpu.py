@@ -13,7 +13,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("group", ["lm", "lm_variants", "vit", "resnet", "magma", "generate"])
+@pytest.mark.parametrize("group", ["lm", "lm_variants", "vit", "resnet", "magma", "generate", "sampling"])
 def test_model_group(group):
     import torch
 

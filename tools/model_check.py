@@ -7,7 +7,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-GROUPS = ["ops", "lm", "lm_variants", "vit", "resnet", "magma", "generate", "fullsize"]
+GROUPS = ["ops", "lm", "lm_variants", "vit", "resnet", "magma", "generate", "sampling", "fullsize"]
 
 
 def rel(got, want):
@@ -531,6 +531,86 @@ def group_generate(dev):
     l_step = lm.decode_logits(nxt, c)
     full = lm(inputs_embeds=torch.cat([emb, nxt], 1)).logits[:, -1]
     ok &= report("decode step (KV cache) == full forward", l_step, full, 2e-2)
+    return ok
+
+
+def reference_keep_mask(logits, top_k, top_p):
+    """magma/sampling.py:7-30 with a STABLE descending sort (ties ordered by index): which tokens survive the filters."""
+    import torch
+    import torch.nn.functional as F
+
+    x = logits.float().clone()
+    if top_k > 0:
+        order = torch.sort(x, dim=-1, descending=True, stable=True).indices
+        keep = torch.zeros_like(x, dtype=torch.bool).scatter_(1, order[:, :top_k], True)
+        x = x.masked_fill(~keep, float("-inf"))
+    if top_p > 0:
+        sl, idx = torch.sort(x, dim=-1, descending=True, stable=True)
+        rem = torch.cumsum(F.softmax(sl, dim=-1), dim=-1) < (1 - top_p)
+        rem[..., 1:] = rem[..., :-1].clone()
+        rem[..., 0] = False
+        x = x.masked_fill(torch.zeros_like(rem).scatter_(1, idx, rem), float("-inf"))
+    return x > float("-inf")
+
+
+def group_sampling(dev):
+    """mb200_sample (§8f rank 4): filter masks against the reference rule, draw statistics, generate(T > 0)."""
+    import torch
+    import torch.nn.functional as F
+    from magma_b200 import ops
+
+    ok = True
+    g = torch.Generator().manual_seed(5)
+    V = 50258
+    peaked = torch.randn(6, V, generator=g) * 4.0            # trained-LM-like: top-1 mass >= 0.1 in most rows
+    flat = torch.randn(6, V, generator=g) * 0.05             # random-init-like: thousands of ranks below 1 - p
+    mid = torch.randn(6, V, generator=g) * 1.5
+    cases = [("peaked fp32", peaked, 0, 0.9, 0), ("mid fp32", mid, 0, 0.9, 0), ("flat fp32", flat, 0, 0.9, 3),
+             ("top-k only", mid, 50, 0.0, 0), ("top-k + top-p", mid, 200, 0.9, 0), ("top-k=1", mid, 1, 0.9, 0),
+             ("mid bf16 (ties)", mid.to(torch.bfloat16), 0, 0.9, 0), ("top-k bf16 (ties)", mid.to(torch.bfloat16), 40, 0.5, 0),
+             ("flat bf16 (ties)", flat.to(torch.bfloat16), 0, 0.9, 3), ("p=0.5 mid", mid, 0, 0.5, 1)]
+    for name, lg, k, p, slack in cases:
+        want = reference_keep_mask(lg, k, p)
+        tok, mask = ops.sample(lg.to(dev), 0.7, top_k=k, top_p=p, seed=1, offset=0, return_mask=True)
+        diff = (mask.cpu().bool() != want).sum(1)
+        inside = bool(mask.cpu().bool().gather(1, tok.cpu()[:, None]).all())
+        good = int(diff.max()) <= slack and inside
+        ok &= good
+        print(f"[{'OK' if good else 'FAIL'}] filters {name}: kept {want.sum(1).tolist()} mask mismatches/row {diff.tolist()} "
+              f"(allowed {slack}: fp32 cumsum rounding at the boundary rank), sampled token kept={inside}", flush=True)
+    # draw statistics: 20000 independent rows of one small distribution vs softmax(logits / T)
+    Vs, T = 48, 0.7
+    base = torch.randn(Vs, generator=g) * 1.5
+    rows = base[None, :].expand(20000, Vs).contiguous()
+    tok = ops.sample(rows.to(dev), T, top_k=0, top_p=0.0, seed=123, offset=7).cpu()
+    freq = torch.bincount(tok, minlength=Vs).float() / tok.numel()
+    probs = F.softmax(base / T, -1)
+    z = ((freq - probs).abs() / (probs * (1 - probs) / tok.numel()).sqrt().clamp_min(1e-9)).max().item()
+    good = z < 5.0
+    ok &= good
+    print(f"[{'OK' if good else 'FAIL'}] multinomial draw: max |freq - p| = {z:.2f} sigma over {Vs} tokens, 20000 rows", flush=True)
+    again = ops.sample(rows.to(dev), T, seed=123, offset=7).cpu()
+    other = ops.sample(rows.to(dev), T, seed=123, offset=8).cpu()
+    good = bool(torch.equal(tok, again)) and not bool(torch.equal(tok, other))
+    ok &= good
+    print(f"[{'OK' if good else 'FAIL'}] same (seed, offset) reproduces, next offset differs", flush=True)
+    # generate with T > 0 runs end to end and is reproducible under torch.manual_seed
+    from oracle import magma_oracle as O
+
+    cfg = small_cfg()
+    w16 = {k: v.to(torch.bfloat16).float() for k, v in O.init_weights(cfg, seed=9).items()}
+    model = build_magma(cfg, w16, dev, 32)
+    model.eval()
+    images, _ = O.synthetic_batch(cfg, 2, 32, seed=4)
+    emb = model.embed([images.to(torch.bfloat16).to(dev), torch.randint(0, 900, (2, 5), generator=g).to(dev)])
+    torch.manual_seed(77)
+    a = model.generate(emb, max_steps=10, temperature=0.7, top_k=0, top_p=0.9, decode=False).cpu()
+    torch.manual_seed(77)
+    b = model.generate(emb, max_steps=10, temperature=0.7, top_k=0, top_p=0.9, decode=False).cpu()
+    c = model.generate(emb, max_steps=10, temperature=0.7, top_k=20, top_p=0.0, decode=False).cpu()
+    good = bool(torch.equal(a, b)) and a.shape[1] > emb.shape[1] and int(a[:, emb.shape[1]:].max()) < cfg.vocab and c.shape[0] == 2
+    ok &= good
+    print(f"[{'OK' if good else 'FAIL'}] generate(T=0.7, top_p=0.9) reproducible under manual_seed: {a[0, emb.shape[1]:].tolist()}", flush=True)
     return ok
 
 
