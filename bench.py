@@ -107,8 +107,13 @@ def cpu_reference_run(steps, warmup, budget_s, n_threads=None):
 
     from oracle import magma_oracle as O
 
-    if n_threads:
-        torch.set_num_threads(n_threads)
+    if not n_threads:
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host core it can
+        try:
+            n_threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n_threads = os.cpu_count() or 1
+    torch.set_num_threads(n_threads)
     cores = torch.get_num_threads()
     cfg = O.OracleConfig()
     t0 = time.time()
