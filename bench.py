@@ -21,6 +21,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -43,21 +44,81 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock / throttle-reason samples DURING the timed region. Primary: NVML polled from a thread every 10 ms
+    (first sample immediately, so even a 0.3 s region is covered); fallback: an `nvidia-smi -lms 100` child process
+    (slow to start: it must already be running when the region begins, so construct the sampler before the warm-up
+    and call mark() when the timed region starts)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, nvml=None):
+        self.samples, self.t_mark, self.p, self.f, self.thread = [], None, None, None, None
+        self._stop = threading.Event()
+        self.h = self.nvml = None
+        try:
+            if nvml is None:
+                import pynvml as nvml
+            nvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            self.h = nvml.nvmlDeviceGetHandleByIndex(int(ids[gpu_index]) if gpu_index < len(ids) else gpu_index)
+            self.nvml = nvml
+            self.max_mhz = float(nvml.nvmlDeviceGetMaxClockInfo(self.h, nvml.NVML_CLOCK_SM))
+            self._poll()  # fails here, not in the thread, if a query is unsupported
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nvml = self.h = None
+            self._start_smi(gpu_index)
+
+    def _reasons(self):
+        for fn in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            if hasattr(self.nvml, fn):
+                return int(getattr(self.nvml, fn)(self.h))
+        return 0
+
+    def _poll(self):
+        self.samples.append((time.time(), float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)),
+                             self._reasons()))
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._poll()
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def _start_smi(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark(self):
+        """The timed region starts now: only later samples count (NVML path)."""
+        self.t_mark = time.time()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            try:
+                self._poll()
+            except Exception:
+                pass
+            rows = [r for r in self.samples if self.t_mark is None or r[0] >= self.t_mark] or self.samples[-1:]
+            sm = sorted(r[1] for r in rows)
+            bits = 0
+            for r in rows:
+                bits |= r[2]
+            return {"sm_mhz": statistics.median(sm[len(sm) // 2:]), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(n for m, n in self.REASONS if bits & m), "samples": len(sm), "source": "nvml"}
         if self.p is None:
             return out
         self.p.terminate()
@@ -81,7 +142,7 @@ class ClockSampler:
         if sm:
             busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
             out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+                   "samples": len(sm), "source": "nvidia-smi"}
         return out
 
 
@@ -109,10 +170,17 @@ def cpu_reference_run(steps, warmup, budget_s, n_threads=None):
 
     if not n_threads:
         # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host core it can
+        # (physical cores: 128 hyper-threads on the 64-core box ran this 30x slower than 64 threads)
         try:
             n_threads = len(os.sched_getaffinity(0))
         except AttributeError:
             n_threads = os.cpu_count() or 1
+        try:
+            import psutil
+
+            n_threads = max(1, min(n_threads, psutil.cpu_count(logical=False) or n_threads))
+        except Exception:
+            pass
     torch.set_num_threads(n_threads)
     cores = torch.get_num_threads()
     cfg = O.OracleConfig()
@@ -239,10 +307,12 @@ def run_b200(args):
         return ms
 
     # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # running before the warm-up (see its docstring)
     for i in range(max(args.warmup, 3)):
         loss = device_step(i)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     launches0 = L.mb200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
