@@ -138,6 +138,11 @@ int mb200_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx
 int mb200_layernorm_param_grad(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
                                const float* rstd, float* dgamma, float* dbeta, int32_t rows, int32_t d,
                                int32_t accumulate, void* stream);
+/* Same result for many rows (ViT training: 2056 rows per LayerNorm): (column strip) x (row chunk) grid with one
+ * atomic per (column, chunk) instead of one thread per column walking every row. */
+int mb200_layernorm_param_grad_rows(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
+                                    const float* rstd, float* dgamma, float* dbeta, int32_t rows, int32_t d,
+                                    int32_t accumulate, void* stream);
 /* rotate_every_two on q,k of a fused [rows][3][H][hd] buffer (hf:gptj/modeling_gptj.py:57-67,190-207). */
 int mb200_rope(void* qkv, int64_t ld, int32_t rows, int32_t S, int32_t H, int32_t hd, int32_t rot, int32_t pos0,
                int32_t inverse, void* stream);
@@ -311,6 +316,43 @@ size_t mb200_vit_workspace_bytes(const mb200_vit_model* m, int32_t B);
  * (the encoder is frozen on the measured path: magma/magma.py:98-100). */
 int mb200_vit_forward(const mb200_vit_model* m, const void* images, void* feats, int32_t B, void* ws,
                       size_t ws_bytes, void* stream);
+
+/* ---- CLIP-ViT training (freeze_img_encoder: false — MAGMA_v1.yml:5; magma/magma.py:98-100 leaves the encoder
+ * trainable, and the optimizer gives it its own learning rate, magma/utils.py:173-177). Host-only schedule in
+ * csrc/vit_train.cu over the same primitives as the inference pass; activations of every layer are kept in `ws`
+ * (no recomputation: ~85 MB per ViT-L/14 layer at B = 8). Gradient buffers are fp32 with the parameter's own shape. */
+typedef struct {
+  float *ln1_g, *ln1_b;
+  float* w_qkv; /* [3w, w] */
+  float* b_qkv;
+  float* w_out; /* [w, w] */
+  float* b_out;
+  float *ln2_g, *ln2_b;
+  float* w_fc;  /* [mlp, w] */
+  float* b_fc;
+  float* w_proj; /* [w, mlp] */
+  float* b_proj;
+} mb200_vit_layer_grads;
+
+typedef struct {
+  float* w_conv; /* [w, 3*P*P] contiguous — conv1.weight.view(w, -1) */
+  float* cls;    /* [w] */
+  float* pos;    /* [T, w] */
+  float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+  float* proj;   /* [w, out_dim] — the parameter's own layout (not proj_t) */
+  const mb200_vit_layer_grads* layers; /* host array [n_layer] */
+} mb200_vit_grads;
+
+size_t mb200_vit_train_workspace_bytes(const mb200_vit_model* m, int32_t B);
+/* Same result as mb200_vit_forward, with every layer's activations saved in `ws` for mb200_vit_backward. */
+int mb200_vit_forward_train(const mb200_vit_model* m, const void* images, void* feats, int32_t B, void* ws,
+                            size_t ws_bytes, void* stream);
+/* Backward of the pass recorded in `ws`. dfeats: bf16 [B, out_dim]. Every parameter gradient is written to `g`
+ * (accumulate != 0 adds into the buffers). The gradient w.r.t. the pixels is not produced (images are data). */
+int mb200_vit_backward(const mb200_vit_model* m, const mb200_vit_grads* g, const void* dfeats, int32_t accumulate,
+                       int32_t B, void* ws, size_t ws_bytes, void* stream);
+/* dx = dy * d/dx[x * sigmoid(1.702 x)] at x = pre (CLIP QuickGELU, backward). dx may alias dy. */
+int mb200_quick_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream);
 
 /* Fused KV-cache attention for one decode step (Sq = 1): q/k/v come from the fused qkv row [B][3][H][hd] (already
  * rotated); k,v are appended to the cache at position `pos`, then softmax(q K^T / sqrt(hd)) V over [0, pos].

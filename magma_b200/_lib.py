@@ -151,9 +151,20 @@ class VitModelC(ctypes.Structure):
     ]
 
 
+class VitLayerGradsC(ctypes.Structure):
+    """mb200_vit_layer_grads: fp32 gradient pointers, same field order as VitLayerC."""
+    _fields_ = list(VitLayerC._fields_)
+
+
+class VitGradsC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w_conv", "cls", "pos", "ln_pre_g", "ln_pre_b", "ln_post_g",
+                                               "ln_post_b", "proj")] + [("layers", ctypes.POINTER(VitLayerGradsC))]
+
+
 def _setup_signatures(L):
     L.mb200_gptj_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_vit_workspace_bytes.restype = ctypes.c_size_t
+    L.mb200_vit_train_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_launch_count.restype = ctypes.c_longlong
 
 
@@ -169,4 +180,6 @@ EXPORTED_SYMBOLS = [
     "mb200_gptj_workspace_bytes", "mb200_gptj_forward", "mb200_gptj_backward",
     "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode", "mb200_attn_fwd_tile",
     "mb200_attn_bwd_tile",
+    "mb200_vit_train_workspace_bytes", "mb200_vit_forward_train", "mb200_vit_backward", "mb200_quick_gelu_bwd",
+    "mb200_layernorm_param_grad_rows",
 ]

@@ -75,7 +75,11 @@ class ParamArena:
         """(lo, hi) element range covering every parameter whose name starts with one of the prefixes."""
         return dp.slice_for(self.names, [p.numel() for p in self.params], self.offsets, prefixes)
 
-    def adamw_step(self, lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, grad_scale=1.0, max_norm=0.0):
+    def adamw_step(self, lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, grad_scale=1.0, max_norm=0.0,
+                   segments=None):
+        """One fused AdamW pass over the arena. `segments` = [(lo, hi, lr, weight_decay), ...] (dp.optimizer_segments)
+        runs the same kernel per parameter group instead — the reference's separate image-encoder learning rate and
+        its weight-decay exemptions (magma/utils.py:120-215); the clipping norm stays global over all groups."""
         if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(self.master)
             self.exp_avg_sq = torch.zeros_like(self.master)
@@ -85,8 +89,16 @@ class ParamArena:
             self.gnorm_sq.zero_()
             ops.sumsq(self.grad, self.gnorm_sq)
             gn = self.gnorm_sq
-        ops.adamw_step(self.master, self.grad, self.exp_avg, self.exp_avg_sq, self.shadow, lr, betas[0], betas[1], eps,
-                       weight_decay, grad_scale, gn, max_norm or 0.0, self.step_count, zero_grad=True)
+        if segments is None or (len(segments) == 1 and segments[0][:2] == (0, self.numel)):
+            if segments:
+                lr, weight_decay = segments[0][2], segments[0][3]
+            ops.adamw_step(self.master, self.grad, self.exp_avg, self.exp_avg_sq, self.shadow, lr, betas[0], betas[1],
+                           eps, weight_decay, grad_scale, gn, max_norm or 0.0, self.step_count, zero_grad=True)
+        else:
+            for lo, hi, slr, swd in segments:
+                ops.adamw_step(self.master[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                               self.shadow[lo:hi], slr, betas[0], betas[1], eps, swd, grad_scale, gn, max_norm or 0.0,
+                               self.step_count, zero_grad=True)
         for p in self.params:
             p.grad = None
         # the fused kernel wrote master and shadow together: they are in sync without bumping tensor versions

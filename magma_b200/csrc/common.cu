@@ -1,5 +1,6 @@
 // magma_b200 — error plumbing and device queries shared by all translation units.
 #include "common.cuh"
+#include "sched_rt.h"
 
 #include <stdarg.h>
 #include <stdlib.h>
@@ -58,6 +59,19 @@ int check_arch() {
     cached = 0;
   }
   return cached;
+}
+
+// ---------------------------------------------------------------------------------------------
+// runtime helpers of the host-only schedule files (sched_rt.h)
+// ---------------------------------------------------------------------------------------------
+int rt_check_arch() { return check_arch(); }
+int rt_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  MB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int rt_zero(void* dst, size_t bytes, void* stream) {
+  MB_CUDA(cudaMemsetAsync(dst, 0, bytes, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

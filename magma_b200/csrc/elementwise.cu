@@ -727,6 +727,67 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
     dst[i] = __bfloat162float(src[i]);
 }
 
+// LayerNorm parameter gradients for MANY rows (ViT training: 2056 rows x 49 LayerNorms; adapters with a leading LN):
+// the same (column strip) x (row chunk) decomposition as colsum_kernel. out must be zeroed first unless accumulating.
+static constexpr int kLnPgRows = 64;
+__global__ void __launch_bounds__(256)
+layernorm_param_grad_rows_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x, long long ldx,
+                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d) {
+  __shared__ float pg[8][64], pb[8][64];
+  const int cl = threadIdx.x & 31;  // column pair within the strip
+  const int rg = threadIdx.x >> 5;  // row group 0..7
+  const int c0 = blockIdx.x * 64 + cl * 2;
+  const int r0 = blockIdx.y * kLnPgRows;
+  const int r1 = min(rows, r0 + kLnPgRows);
+  float g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (c0 < d) {
+    for (int r = r0 + rg; r < r1; r += 8) {
+      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + (long long)r * lddy + c0));
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (long long)r * ldx + c0));
+      const float mu = mean[r], rs = rstd[r];
+      g0 += g.x * (v.x - mu) * rs;
+      g1 += g.y * (v.y - mu) * rs;
+      b0 += g.x;
+      b1 += g.y;
+    }
+  }
+  pg[rg][cl * 2] = g0;
+  pg[rg][cl * 2 + 1] = g1;
+  pb[rg][cl * 2] = b0;
+  pb[rg][cl * 2 + 1] = b1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int j = threadIdx.x & 63;
+    const int c = blockIdx.x * 64 + j;
+    float s = 0.f;
+    if (threadIdx.x < 64) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += pg[q][j];
+      if (c < d) atomicAdd(dgamma + c, s);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += pb[q][j];
+      if (c < d) atomicAdd(dbeta + c, s);
+    }
+  }
+}
+
+// QuickGELU backward (CLIP MLP): dx = dy * (s + 1.702 x s (1 - s)), s = sigmoid(1.702 x). 16-byte vectors; dx may alias dy.
+__global__ void quick_gelu_bwd_kernel(const bf16* dy, const bf16* __restrict__ pre, bf16* dx, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float g[8], x[8], o[8];
+    unpack8(reinterpret_cast<const uint4*>(dy)[i], g);
+    unpack8(reinterpret_cast<const uint4*>(pre)[i], x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float s = 1.f / (1.f + __expf(-1.702f * x[e]));
+      o[e] = g[e] * (s + 1.702f * x[e] * s * (1.f - s));
+    }
+    reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+  }
+}
+
 static inline int grid_for(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -786,6 +847,36 @@ extern "C" int mb200_layernorm_param_grad(const void* dy, int64_t lddy, const vo
   MB_ENTER();
   layernorm_param_grad_kernel<<<(d + 127) / 128, 128, 0, ST(stream)>>>((const bf16*)dy, lddy, (const bf16*)x, ldx,
                                                                        mean, rstd, dgamma, dbeta, rows, d, accumulate);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_layernorm_param_grad_rows(const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                                               const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                                               int32_t rows, int32_t d, int32_t accumulate, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(rows > 0 && d > 0 && d % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0, MB200_E_ALIGN,
+             "layernorm_param_grad_rows: d and row strides must be even");
+  {
+    // many rows: 2-D decomposition with one atomic per (column, row chunk)
+    if (!accumulate) {
+      MB_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)d * sizeof(float), ST(stream)));
+      MB_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)d * sizeof(float), ST(stream)));
+    }
+    dim3 grid((d + 63) / 64, (rows + kLnPgRows - 1) / kLnPgRows);
+    layernorm_param_grad_rows_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, mean, rstd,
+                                                                   dgamma, dbeta, rows, d);
+    MB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int mb200_quick_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "quick_gelu_bwd: n=%lld must be a positive multiple of 8", (long long)n);
+  MB_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
+             MB200_E_ALIGN, "quick_gelu_bwd: pointers must be 16-byte aligned");
+  quick_gelu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)pre, (bf16*)dx, n / 8);
   MB_LAUNCH_CHECK();
   return 0;
 }

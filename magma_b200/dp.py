@@ -59,3 +59,22 @@ def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     per = global_batch // world
     assert per * world == global_batch, "global batch must divide evenly across ranks"
     return rank * per, (rank + 1) * per
+
+
+def optimizer_segments(names: Sequence[str], numels: Sequence[int], offsets: Sequence[int], no_decay: Sequence[bool],
+                       lr: float, image_enc_lr, weight_decay: float, enc_prefix: str = "image_prefix.enc."):
+    """Parameter groups of the reference optimizer (magma/utils.py:120-215) mapped onto the flat arena: contiguous runs
+    [(lo, hi, lr, weight_decay), ...] of parameters sharing a learning rate and decay. The image encoder gets
+    `image_enc_lr` when it is set (utils.py:173-177); LayerNorm / embedding parameters and biases are exempt from
+    weight decay (utils.py:128-146). With weight_decay == 0 and no separate encoder rate this is ONE run — the whole
+    arena in one fused kernel launch."""
+    segs = []
+    for n, k, o, nd in zip(names, numels, offsets, no_decay):
+        plr = image_enc_lr if (image_enc_lr is not None and n.startswith(enc_prefix)) else lr
+        pwd = 0.0 if (nd or weight_decay == 0.0) else weight_decay
+        hi = o + (k + ALIGN - 1) // ALIGN * ALIGN
+        if segs and segs[-1][1] == o and segs[-1][2] == plr and segs[-1][3] == pwd:
+            segs[-1] = (segs[-1][0], hi, plr, pwd)
+        else:
+            segs.append((o, hi, plr, pwd))
+    return segs

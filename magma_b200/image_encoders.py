@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import MB200Error, VitLayerC, VitModelC, check, lib
+from ._lib import MB200Error, VitGradsC, VitLayerC, VitLayerGradsC, VitModelC, check, lib
 
 # name -> (width, layers, heads, patch, input_resolution, mlp, out_dim)
 VIT_CONFIGS = {
@@ -88,10 +88,40 @@ class _Conv(nn.Module):
         self.weight = _p(w, 3, patch, patch, device=device)
 
 
+_VIT_LAYER_FIELDS = (("ln1_g", "ln_1.weight"), ("ln1_b", "ln_1.bias"), ("w_qkv", "attn.in_proj_weight"),
+                     ("b_qkv", "attn.in_proj_bias"), ("w_out", "attn.out_proj.weight"), ("b_out", "attn.out_proj.bias"),
+                     ("ln2_g", "ln_2.weight"), ("ln2_b", "ln_2.bias"), ("w_fc", "mlp.c_fc.weight"),
+                     ("b_fc", "mlp.c_fc.bias"), ("w_proj", "mlp.c_proj.weight"), ("b_proj", "mlp.c_proj.bias"))
+_VIT_TOP_FIELDS = (("cls", "class_embedding"), ("pos", "positional_embedding"), ("ln_pre_g", "ln_pre.weight"),
+                   ("ln_pre_b", "ln_pre.bias"), ("ln_post_g", "ln_post.weight"), ("ln_post_b", "ln_post.bias"))
+
+
+class _VitTrainFn(torch.autograd.Function):
+    """feats = ViT(images) with the hand-written backward of csrc/vit_train.cu (`freeze_img_encoder: false`): every
+    parameter gradient is written as fp32 straight into the trainable-parameter arena. `anchor` is one trainable
+    parameter: it makes autograd call backward although the pixels carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, enc, x, anchor):
+        feats = enc._run_forward_train(x)
+        ctx.enc, ctx.B, ctx.generation = enc, x.shape[0], enc._generation
+        return feats
+
+    @staticmethod
+    def backward(ctx, dfeats):
+        enc = ctx.enc
+        if ctx.generation != enc._generation:
+            raise MB200Error("backward called after another training forward overwrote the saved ViT activations")
+        enc._run_backward(dfeats.to(torch.bfloat16).contiguous(), ctx.B)
+        return None, None, None
+
+
 class B200VisionTransformer(nn.Module):
     """CLIP VisionTransformer with openai/CLIP state-dict names (conv1, class_embedding, positional_embedding,
     ln_pre, transformer.resblocks.{i}.{ln_1,attn.{in_proj_weight,in_proj_bias,out_proj},ln_2,mlp.{c_fc,c_proj}},
     ln_post, proj). Attribute `input_resolution` is read by Magma.__init__ (magma/magma.py:69)."""
+
+    supports_training = True  # Magma(freeze_img_encoder=False) sets requires_grad on this encoder's parameters
 
     def __init__(self, width, layers, heads, patch, input_resolution, mlp, out_dim, device=None):
         super().__init__()
@@ -108,7 +138,11 @@ class B200VisionTransformer(nn.Module):
         self.ln_post = _LN(width, dev)
         self.proj = _p(width, out_dim, device=dev)
         self._cache = None
+        self._gcache = None
         self._ws = {}
+        self._ws_train = {}
+        self._arena = None
+        self._generation = 0
 
     @torch.no_grad()
     def init_weights(self, seed=0, std=0.02):
@@ -118,53 +152,125 @@ class B200VisionTransformer(nn.Module):
             if name.endswith(("ln_1.weight", "ln_2.weight", "ln_pre.weight", "ln_post.weight")):
                 r = 1.0 + r
             p.data.copy_(r)
-        self._cache = None
+        self.invalidate()
         return self
 
     def invalidate(self):
         self._cache = None
+        self._gcache = None
+
+    def attach_arena(self, arena):
+        """Trainable encoder (freeze_img_encoder: false): parameters are fp32 master views of the arena and the
+        kernels read the arena's bf16 compute copy."""
+        self._arena = arena
+        self.invalidate()
+
+    def _trainable(self):
+        flags = [p.requires_grad for p in self.parameters()]
+        if any(flags) and not all(flags):
+            raise MB200Error("the ViT encoder trains all of its parameters or none (mixed requires_grad is not supported)")
+        return all(flags)
+
+    def _w(self, name, p):
+        """The bf16 tensor the kernels read for parameter p."""
+        if p.requires_grad:
+            if self._arena is None:
+                raise MB200Error("trainable ViT parameters need the parameter arena (Magma.finalize())")
+            return self._arena.shadow_of(p)
+        if p.dtype != torch.bfloat16 or not p.is_cuda:
+            raise MB200Error(f"frozen ViT parameter {name} must be bf16 on CUDA")
+        return p.data
+
+    def _refresh_packed(self):
+        """conv1 is staged as [w, 3P^2 padded to 8] and proj transposed; with a trainable encoder both follow the
+        optimizer, so they are rewritten from the compute copy before every pass (0.7 M elements)."""
+        _, _, conv, proj_t = self._cache
+        K = 3 * self.patch * self.patch
+        conv[:, :K].copy_(self._w("conv1.weight", self.conv1.weight).reshape(self.width, K))
+        proj_t.copy_(self._w("proj", self.proj).t())
 
     def _cmodel(self):
         if self._cache is not None:
             return self._cache
-        for n, p in self.named_parameters():
-            if p.dtype != torch.bfloat16 or not p.is_cuda:
-                raise MB200Error(f"ViT parameter {n} must be bf16 on CUDA")
+        named = dict(self.named_parameters())
         K = 3 * self.patch * self.patch
         ldk = (K + 7) // 8 * 8
         conv = torch.zeros(self.width, ldk, dtype=torch.bfloat16, device=self._device)
-        conv[:, :K] = self.conv1.weight.data.reshape(self.width, K)
-        proj_t = self.proj.data.t().contiguous()
+        proj_t = torch.empty(self.output_dim, self.width, dtype=torch.bfloat16, device=self._device)
         layers = (VitLayerC * self.layers)()
-        for i, b in enumerate(self.transformer.resblocks):
-            L = layers[i]
-            L.ln1_g, L.ln1_b = b.ln_1.weight.data_ptr(), b.ln_1.bias.data_ptr()
-            L.w_qkv, L.b_qkv = b.attn.in_proj_weight.data_ptr(), b.attn.in_proj_bias.data_ptr()
-            L.w_out, L.b_out = b.attn.out_proj.weight.data_ptr(), b.attn.out_proj.bias.data_ptr()
-            L.ln2_g, L.ln2_b = b.ln_2.weight.data_ptr(), b.ln_2.bias.data_ptr()
-            L.w_fc, L.b_fc = b.mlp.c_fc.weight.data_ptr(), b.mlp.c_fc.bias.data_ptr()
-            L.w_proj, L.b_proj = b.mlp.c_proj.weight.data_ptr(), b.mlp.c_proj.bias.data_ptr()
+        for i in range(self.layers):
+            for f, k in _VIT_LAYER_FIELDS:
+                n = f"transformer.resblocks.{i}.{k}"
+                setattr(layers[i], f, self._w(n, named[n]).data_ptr())
         m = VitModelC()
         m.n_layer, m.width, m.n_head, m.patch = self.layers, self.width, self.heads, self.patch
         m.image, m.mlp, m.out_dim = self.input_resolution, self.mlp_dim, self.output_dim
         m.w_conv, m.ld_conv = conv.data_ptr(), ldk
-        m.cls, m.pos = self.class_embedding.data_ptr(), self.positional_embedding.data_ptr()
-        m.ln_pre_g, m.ln_pre_b = self.ln_pre.weight.data_ptr(), self.ln_pre.bias.data_ptr()
-        m.ln_post_g, m.ln_post_b = self.ln_post.weight.data_ptr(), self.ln_post.bias.data_ptr()
+        for f, k in _VIT_TOP_FIELDS:
+            setattr(m, f, self._w(k, named[k]).data_ptr())
         m.proj_t = proj_t.data_ptr()
         m.layers = ctypes.cast(layers, ctypes.POINTER(VitLayerC))
         self._cache = (m, layers, conv, proj_t)
+        self._refresh_packed()
         return self._cache
+
+    def _cgrads(self):
+        """mb200_vit_grads over the arena's fp32 gradient views (parameter shapes; conv1 as [w, 3P^2])."""
+        if self._gcache is None:
+            named, ar = dict(self.named_parameters()), self._arena
+            lg = (VitLayerGradsC * self.layers)()
+            for i in range(self.layers):
+                for f, k in _VIT_LAYER_FIELDS:
+                    setattr(lg[i], f, ar.grad_of(named[f"transformer.resblocks.{i}.{k}"]).data_ptr())
+            G = VitGradsC()
+            G.w_conv = ar.grad_of(self.conv1.weight).data_ptr()
+            for f, k in _VIT_TOP_FIELDS:
+                setattr(G, f, ar.grad_of(named[k]).data_ptr())
+            G.proj = ar.grad_of(self.proj).data_ptr()
+            G.layers = ctypes.cast(lg, ctypes.POINTER(VitLayerGradsC))
+            self._gcache = (G, lg)
+        return self._gcache[0]
+
+    def _train_ws(self, B):
+        if B not in self._ws_train:
+            n = lib().mb200_vit_train_workspace_bytes(ctypes.byref(self._cmodel()[0]), B)
+            if n == 0:
+                raise MB200Error(f"vit_train_workspace_bytes: {lib().mb200_last_error().decode()}")
+            self._ws_train[B] = torch.empty(n, dtype=torch.uint8, device=self._device)
+        return self._ws_train[B]
+
+    def _run_forward_train(self, x):
+        B = x.shape[0]
+        self._arena.sync_shadow()
+        m = self._cmodel()[0]
+        self._refresh_packed()
+        ws = self._train_ws(B)
+        self._generation += 1
+        feats = torch.empty(B, self.output_dim, dtype=torch.bfloat16, device=self._device)
+        check(lib().mb200_vit_forward_train(ctypes.byref(m), ops._ptr(x), ops._ptr(feats), B, ops._ptr(ws),
+                                            ctypes.c_size_t(ws.numel()), ops._stream()))
+        return feats
+
+    def _run_backward(self, dfeats, B):
+        ar = self._arena
+        ws = self._train_ws(B)
+        acc = int(bool(getattr(ar, "_accumulate_current", False)))
+        check(lib().mb200_vit_backward(ctypes.byref(self._cmodel()[0]), ctypes.byref(self._cgrads()), ops._ptr(dfeats),
+                                       acc, B, ops._ptr(ws), ctypes.c_size_t(ws.numel()), ops._stream()))
+        ar.publish_grads()
 
     def forward(self, x):
         """[b, 3, R, R] -> [b, out_dim] (pooled CLS features, like clip's `.visual`)."""
-        if any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
-            raise MB200Error("training the image encoder (freeze_img_encoder: false) is not supported yet: "
-                             "the ViT backward pass is a later row of the scope table")
         B, C, R, R2 = x.shape
         if C != 3 or R != self.input_resolution or R2 != R:
             raise ValueError(f"expected [b,3,{self.input_resolution},{self.input_resolution}], got {tuple(x.shape)}")
         x = x.to(device=self._device, dtype=torch.bfloat16).contiguous()
+        if self._trainable():
+            if torch.is_grad_enabled():
+                return _VitTrainFn.apply(self, x, self.class_embedding)
+            self._arena.sync_shadow()
+            self._cmodel()
+            self._refresh_packed()
         m = self._cmodel()[0]
         if B not in self._ws:
             n = lib().mb200_vit_workspace_bytes(ctypes.byref(m), B)

@@ -37,7 +37,7 @@ class _PrefixFn(torch.autograd.Function):
             be16 = arena.shadow_of(lnb) if arena is not None else lnb.to(torch.bfloat16)
             out, mean, rstd = ops.layernorm_fwd(rows, g16, be16, mod.ln.eps)
             ctx.g16 = g16
-        ctx.mod, ctx.p, ctx.mask = mod, p, mask
+        ctx.mod, ctx.p, ctx.mask, ctx.w16 = mod, p, mask, w16
         ctx.save_for_backward(feats, rows, mean, rstd)
         seq = mod.out_seq_len if mod.reshape_seq else rows.shape[0] // B
         return out.view(B, seq, mod.out_dim)
@@ -65,10 +65,13 @@ class _PrefixFn(torch.autograd.Function):
         gw, gb = gbuf(mod.proj.weight), gbuf(mod.proj.bias)
         ops.gemm(g2, feats, out=gw, a_mn=True, b_mn=True, accumulate=acc)   # dW[out, in] = g^T feats
         ops.colsum(g2, out=gb, accumulate=acc)
+        dfeats = None
+        if ctx.needs_input_grad[1]:  # trainable encoder (freeze_img_encoder: false): dfeats = g W
+            dfeats = ops.gemm(g2.contiguous(), ctx.w16, b_mn=True)
         if arena is not None:
             arena.publish_grads()
-            return None, None, None, None, None, None
-        return None, None, gw.to(mod.proj.weight.dtype), gb, gl_w, gl_b
+            return None, dfeats, None, None, None, None
+        return None, dfeats, gw.to(mod.proj.weight.dtype), gb, gl_w, gl_b
 
 
 class ImagePrefix(nn.Module):
@@ -96,6 +99,8 @@ class ImagePrefix(nn.Module):
 
     def attach_arena(self, arena):
         self._arena = arena
+        if hasattr(self.enc, "attach_arena"):
+            self.enc.attach_arena(arena)
 
     def forward(self, x):
         feats = self.enc(x)  # image_prefix.py:83

@@ -111,9 +111,12 @@ class Magma(nn.Module):
                 param.requires_grad = bool(config.adapter_config) and "adapter" in name
         else:
             raise NotImplementedError("freeze_lm: false (full LM fine-tuning) is outside the re-backed hot path")
+        # magma.py:98-100 freezes the encoder only when asked to (MAGMA_v1.yml trains it). The ViT family has a backward
+        # pass (csrc/vit_train.cu); the conv trunks do not (eval-mode BatchNorm folded into their weights).
+        enc_trains = (not config.freeze_img_encoder) and getattr(self.image_prefix.enc, "supports_training", False)
         for param in self.image_prefix.enc.parameters():
-            param.requires_grad = False
-        self.encoder_trainable_requested = not config.freeze_img_encoder
+            param.requires_grad = enc_trains
+        self.encoder_trainable_requested = (not config.freeze_img_encoder) and not enc_trains
         if init_seed is not None:
             self.lm.init_weights(seed=init_seed)
             if hasattr(self.image_prefix.enc, "init_weights"):
@@ -232,8 +235,8 @@ class Magma(nn.Module):
         captions = captions.to(self.device).contiguous()
         if input_embeddings is None:
             if self.encoder_trainable_requested and self.training and torch.is_grad_enabled():
-                raise NotImplementedError("freeze_img_encoder: false needs the ViT backward pass (not built yet); "
-                                          "set freeze_img_encoder: true")
+                raise NotImplementedError(f"freeze_img_encoder: false is not supported for the conv-trunk encoder "
+                                          f"{self.config.encoder_name!r} (no backward pass); set freeze_img_encoder: true")
             input_embeddings = self.image_prefix(images)
         labels = build_labels(input_embeddings, captions, self.eos_token, self.device)
         trainable = self._arena is not None and torch.is_grad_enabled()

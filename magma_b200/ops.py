@@ -161,6 +161,21 @@ def layernorm_param_grad(dy, x, mean, rstd, dgamma, dbeta, accumulate=False):
                                            int(accumulate), _stream()))
 
 
+def layernorm_param_grad_rows(dy, x, mean, rstd, dgamma, dbeta, accumulate=False):
+    """Same result as layernorm_param_grad with a (column strip) x (row chunk) grid — for thousands of rows."""
+    rows, d, ldx = _rows(x)
+    check(lib().mb200_layernorm_param_grad_rows(_ptr(dy), ctypes.c_int64(_rows(dy)[2]), _ptr(x), ctypes.c_int64(ldx),
+                                                _ptr(mean), _ptr(rstd), _ptr(dgamma), _ptr(dbeta), rows, d,
+                                                int(accumulate), _stream()))
+
+
+def quick_gelu_bwd(dy, pre, out=None):
+    """dx = dy * d/dx[x sigmoid(1.702 x)] at x = pre (CLIP QuickGELU backward); `out` may be dy itself."""
+    out = torch.empty_like(dy) if out is None else out
+    check(lib().mb200_quick_gelu_bwd(_ptr(dy), _ptr(pre), _ptr(out), ctypes.c_int64(dy.numel()), _stream()))
+    return out
+
+
 def rope_(qkv, S, H, hd, rot, pos0=0, inverse=False):
     """In place on a [rows, 3*H*hd] fused qkv buffer."""
     rows = qkv.shape[0]

@@ -30,6 +30,7 @@ class B200Engine:
         self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
         self._pending = []
         self.chunks = dp.layer_chunks(len(model.lm.transformer.h), n_buckets)  # (hi, lo), last layers first
+        self._segments = None  # optimizer parameter groups, built at the first step (utils.configure_param_groups)
 
     # DeepSpeed-engine surface used by the reference -------------------------------------------------
     def __call__(self, images, captions):
@@ -89,10 +90,15 @@ class B200Engine:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         cfg = self.config
         lr = cfg.lr_at(self.global_step) if hasattr(cfg, "lr_at") else cfg.lr
+        if self._segments is None:
+            from .utils import configure_param_groups
+
+            self._segments = configure_param_groups(self.module, cfg)
+        segs = [(lo, hi, lr * scale, wd) for lo, hi, scale, wd in self._segments]
         self.module.arena.adamw_step(lr=lr, betas=self.betas, eps=self.eps,
                                      weight_decay=float(getattr(cfg, "weight_decay", 0.0) or 0.0),
                                      grad_scale=1.0 / self.world,
-                                     max_norm=float(getattr(cfg, "gradient_clipping", 0.0) or 0.0))
+                                     max_norm=float(getattr(cfg, "gradient_clipping", 0.0) or 0.0), segments=segs)
         self.global_step += 1
 
 

@@ -36,6 +36,39 @@ def build_labels(input_embeddings, captions, eos_token, device=None):
     return ops.build_labels(captions.contiguous(), int(shape[1]), int(eos_token))
 
 
+def no_weight_decay_names(model):
+    """Names of the parameters the reference exempts from weight decay (magma/utils.py:120-146): every parameter of a
+    LayerNorm or Embedding module, and every parameter called `bias`."""
+    import torch.nn as nn
+
+    from .image_encoders import _LN
+    from .language_model import LayerNorm, WordEmbedding
+
+    out = set()
+    for mname, mod in model.named_modules():
+        exempt = isinstance(mod, (nn.LayerNorm, nn.Embedding, _LN, LayerNorm, WordEmbedding))
+        for pname, p in mod._parameters.items():
+            if p is not None and (exempt or pname == "bias"):
+                out.add(f"{mname}.{pname}" if mname else pname)
+    return out
+
+
+def configure_param_groups(model, config):
+    """magma/utils.py:164-215 for the flat arena: [(lo, hi, lr_scale, weight_decay)] runs of `model.arena`, where
+    lr_scale multiplies the scheduled learning rate (the image encoder's group trains at image_enc_lr / lr of it —
+    DeepSpeed's WarmupDecayLR scales every group's own max lr by the same schedule factor, config.py:103-123)."""
+    from . import dp
+
+    arena = model.arena
+    nd = no_weight_decay_names(model)
+    enc_scale = None
+    if getattr(config, "image_enc_lr", None) is not None and config.lr:
+        enc_scale = float(config.image_enc_lr) / float(config.lr)
+    return dp.optimizer_segments(arena.names, [p.numel() for p in arena.params], arena.offsets,
+                                 [n in nd for n in arena.names], 1.0, enc_scale,
+                                 float(getattr(config, "weight_decay", 0.0) or 0.0))
+
+
 class IdTokenizer:
     """Offline stand-in for GPT2TokenizerFast + '<|image|>' (magma/utils.py:43-58): same ids and length
     (eos=pad=50256, cls=50257, len=50258). Text <-> id conversion needs the GPT-2 vocabulary files, which are not

@@ -1,0 +1,341 @@
+// TEST INFRASTRUCTURE — CPU emulation of the PRIMITIVE operators of the magma_b200 C ABI.
+//
+// Purpose: the model-level schedules of the product (csrc/vit_train.cu, written against csrc/sched_rt.h) are host
+// code that only carves a workspace and issues primitive operators. tests/ compile such a schedule file as plain C++
+// together with this file and run it on CPU tensors, so that every pointer offset, leading dimension, operand major,
+// batch stride and accumulate flag of the schedule is checked against the oracle (torch autograd of
+// oracle/magma_oracle.py) without a GPU. Each function below restates the documented semantics of the primitive it
+// stands for (include/magma_b200.h; the kernel it mirrors is named next to it) in scalar C++ with bf16 storage and fp32
+// arithmetic, and enforces the same argument rules as the CUDA host wrappers (alignment, leading dimensions), so a
+// call the GPU library would reject is rejected here too.
+//
+// Only tests/ build and load this (oracle/build_emul.py). Nothing under magma_b200/ links, imports or executes it;
+// it is not a fallback for anything — the product fails loudly without its CUDA library (magma_b200/_lib.py).
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../include/magma_b200.h"
+
+namespace mb200 {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int rt_check_arch() { return 0; }
+int rt_copy(void* dst, const void* src, size_t bytes, void*) {
+  memmove(dst, src, bytes);
+  return 0;
+}
+int rt_zero(void* dst, size_t bytes, void*) {
+  memset(dst, 0, bytes);
+  return 0;
+}
+}  // namespace mb200
+
+#define EM_REQUIRE(cond, code, ...)   \
+  do {                                \
+    if (!(cond)) {                    \
+      mb200::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+typedef uint16_t bf16_t;
+static inline float b2f(bf16_t v) {
+  uint32_t u = (uint32_t)v << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline bf16_t f2b(float f) {  // round to nearest even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (bf16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (bf16_t)(u >> 16);
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static inline float gelu_new_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+static inline float gelu_new_grad_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float t = tanhf(k0 * (x + k1 * x * x * x));
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x * x);
+}
+static inline float quick_gelu_f(float x) { return x / (1.f + expf(-1.702f * x)); }
+
+extern "C" {
+
+int mb200_version(void) { return MB200_VERSION; }
+const char* mb200_last_error(void) { return mb200::g_err; }
+int mb200_check_device(void) { return 0; }
+
+// ---- mb200_gemm (csrc/gemm.cu::gemm_impl + the epilogue of csrc/gemm_common.cuh) ----
+static int check_operand(const mb200_operand& op, int nb0, int nb1) {
+  EM_REQUIRE(op.ptr != nullptr && aligned16(op.ptr), MB200_E_ALIGN, "gemm operand pointer not 16B aligned");
+  EM_REQUIRE(op.ld % 8 == 0, MB200_E_ALIGN, "gemm operand ld (%lld) must be a multiple of 8 elements", (long long)op.ld);
+  EM_REQUIRE((nb0 == 1 || op.bs0 % 8 == 0) && (nb1 == 1 || op.bs1 % 8 == 0), MB200_E_ALIGN,
+             "gemm operand batch strides must be multiples of 8 elements");
+  return 0;
+}
+
+int mb200_gemm(const mb200_gemm_args* a, void*) {
+  EM_REQUIRE(a != nullptr, MB200_E_ARG, "null gemm args");
+  EM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->nb0 > 0 && a->nb1 > 0, MB200_E_SHAPE, "gemm: bad shape");
+  EM_REQUIRE(a->c_dtype == MB200_BF16 || a->c_dtype == MB200_F32, MB200_E_DTYPE, "gemm: bad c_dtype");
+  EM_REQUIRE(!(a->accumulate && a->c_dtype != MB200_F32), MB200_E_DTYPE, "gemm: accumulate needs f32 output");
+  EM_REQUIRE(!(a->dact && !a->aux_in), MB200_E_ARG, "gemm: dact needs aux_in");
+  const int celt = a->c_dtype == MB200_F32 ? 4 : 8;
+  EM_REQUIRE(a->C && aligned16(a->C) && a->ldc % celt == 0, MB200_E_ALIGN, "gemm: C must be 16B aligned with ldc %% %d",
+             celt);
+  EM_REQUIRE((a->nb0 == 1 || a->c_bs0 % celt == 0) && (a->nb1 == 1 || a->c_bs1 % celt == 0), MB200_E_ALIGN,
+             "gemm: C batch strides must be multiples of %d elements", celt);
+  if (a->res1 || a->res2) EM_REQUIRE(a->ld_res % 8 == 0, MB200_E_ALIGN, "gemm: ld_res must be a multiple of 8");
+  if (a->aux_in || a->aux_out) EM_REQUIRE(a->ldc % 8 == 0, MB200_E_ALIGN, "gemm: aux tensors share ldc (must be %%8)");
+  int rc = check_operand(a->A, a->nb0, a->nb1);
+  if (rc) return rc;
+  rc = check_operand(a->B, a->nb0, a->nb1);
+  if (rc) return rc;
+  const bool rope = a->rope_tab && a->rope_mode != 0;
+  if (rope)
+    EM_REQUIRE(a->rope_S > 0 && a->rope_hd > 0 && a->rope_rot % 4 == 0 && a->rope_rot <= a->rope_hd &&
+                   a->rope_hd % 4 == 0 && a->rope_ncols % 4 == 0,
+               MB200_E_ARG, "gemm: bad rope epilogue parameters");
+  const bf16_t* bias = (const bf16_t*)a->bias;
+  const bf16_t* aux_in = (const bf16_t*)a->aux_in;
+  bf16_t* aux_out = (bf16_t*)a->aux_out;
+  const bf16_t* res1 = (const bf16_t*)a->res1;
+  const bf16_t* res2 = (const bf16_t*)a->res2;
+  const float* tab = (const float*)a->rope_tab;
+  std::vector<float> row(a->N);
+  for (int z = 0; z < a->nb0 * a->nb1; ++z) {
+    const int z0 = z % a->nb0, z1 = z / a->nb0;
+    const bf16_t* A = (const bf16_t*)a->A.ptr + z0 * a->A.bs0 + z1 * a->A.bs1;
+    const bf16_t* B = (const bf16_t*)a->B.ptr + z0 * a->B.bs0 + z1 * a->B.bs1;
+    const long long coff0 = z0 * a->c_bs0 + z1 * a->c_bs1;
+    for (int m = 0; m < a->M; ++m) {
+      for (int n = 0; n < a->N; ++n) {
+        float acc = 0.f;
+        for (int k = 0; k < a->K; ++k) {
+          const float av = b2f(a->A.mn_major ? A[(long long)k * a->A.ld + m] : A[(long long)m * a->A.ld + k]);
+          const float bv = b2f(a->B.mn_major ? B[(long long)k * a->B.ld + n] : B[(long long)n * a->B.ld + k]);
+          acc += av * bv;
+        }
+        row[n] = a->alpha * acc + (bias ? b2f(bias[n]) : 0.f);
+      }
+      if (rope) {  // rotate_every_two on adjacent column pairs
+        const float sg = a->rope_mode > 0 ? 1.f : -1.f;
+        for (int n = 0; n + 1 < a->N && n < a->rope_ncols; n += 2) {
+          const int dim = n % a->rope_hd;
+          if (dim >= a->rope_rot) continue;
+          const float* cs = tab + ((long long)(m % a->rope_S) * (a->rope_rot / 2) + dim / 2) * 2;
+          const float x0 = row[n], x1 = row[n + 1];
+          row[n] = x0 * cs[0] - x1 * cs[1] * sg;
+          row[n + 1] = x1 * cs[0] + x0 * cs[1] * sg;
+        }
+      }
+      for (int n = 0; n < a->N; ++n) {
+        float x = row[n];
+        const long long coff = coff0 + (long long)m * a->ldc + n;
+        if (aux_out) aux_out[coff] = f2b(x);
+        if (a->act == MB200_ACT_GELU_NEW) x = gelu_new_f(x);
+        else if (a->act == MB200_ACT_QUICK_GELU) x = quick_gelu_f(x);
+        else if (a->act == MB200_ACT_RELU) x = fmaxf(x, 0.f);
+        if (a->dact) {
+          const float p = b2f(aux_in[coff]);
+          x = a->dact == MB200_DACT_GELU_NEW ? x * gelu_new_grad_f(p) : (p > 0.f ? x : 0.f);
+        }
+        const long long roff = coff0 + (long long)m * a->ld_res + n;  // residuals use C's batch offset
+        if (res1) x += b2f(res1[roff]);
+        if (res2) x += b2f(res2[roff]);
+        if (a->act == MB200_ACT_RELU_POST) x = fmaxf(x, 0.f);
+        if (a->c_dtype == MB200_F32) {
+          float* dst = (float*)a->C + coff;
+          *dst = a->accumulate ? *dst + x : x;
+        } else {
+          ((bf16_t*)a->C)[coff] = f2b(x);
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// ---- LayerNorm (elementwise.cu: layernorm_fwd_kernel / layernorm_bwd_kernel / layernorm_param_grad*_kernel) ----
+int mb200_layernorm_fwd(const void* x_, int64_t ldx, const void* gamma_, const void* beta_, void* y_, int64_t ldy,
+                        float* mean, float* rstd, int32_t rows, int32_t d, float eps, void*) {
+  EM_REQUIRE(rows > 0 && d > 0 && d % 8 == 0 && d <= 8192, MB200_E_SHAPE, "layernorm: bad d=%d", d);
+  EM_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, MB200_E_ALIGN, "layernorm: row strides must be multiples of 8");
+  const bf16_t *x = (const bf16_t*)x_, *g = (const bf16_t*)gamma_, *b = (const bf16_t*)beta_;
+  bf16_t* y = (bf16_t*)y_;
+  std::vector<float> v(d);
+  for (int r = 0; r < rows; ++r) {
+    float s = 0.f;
+    for (int c = 0; c < d; ++c) {
+      v[c] = b2f(x[(long long)r * ldx + c]);  // the row is read completely before it is written (in place is legal)
+      s += v[c];
+    }
+    const float mu = s / d;
+    float q = 0.f;
+    for (int c = 0; c < d; ++c) q += (v[c] - mu) * (v[c] - mu);
+    const float rs = 1.f / sqrtf(q / d + eps);
+    if (mean) mean[r] = mu;
+    if (rstd) rstd[r] = rs;
+    for (int c = 0; c < d; ++c) y[(long long)r * ldy + c] = f2b((v[c] - mu) * rs * b2f(g[c]) + b2f(b[c]));
+  }
+  return 0;
+}
+
+int mb200_layernorm_bwd(const void* dy_, int64_t lddy, const void* x_, int64_t ldx, const void* gamma_,
+                        const float* mean, const float* rstd, const void* res_, int64_t ldres, void* dx_, int64_t lddx,
+                        int32_t rows, int32_t d, void*) {
+  EM_REQUIRE(rows > 0 && d > 0 && d % 8 == 0 && d <= 8192, MB200_E_SHAPE, "layernorm_bwd: bad d=%d", d);
+  EM_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && (!res_ || ldres % 8 == 0), MB200_E_ALIGN,
+             "layernorm_bwd: row strides must be multiples of 8");
+  const bf16_t *dy = (const bf16_t*)dy_, *x = (const bf16_t*)x_, *gm = (const bf16_t*)gamma_, *res = (const bf16_t*)res_;
+  bf16_t* dx = (bf16_t*)dx_;
+  std::vector<float> g(d), xh(d), rr(d);
+  for (int r = 0; r < rows; ++r) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < d; ++c) {
+      g[c] = b2f(dy[(long long)r * lddy + c]) * b2f(gm[c]);
+      xh[c] = (b2f(x[(long long)r * ldx + c]) - mean[r]) * rstd[r];
+      rr[c] = res ? b2f(res[(long long)r * ldres + c]) : 0.f;
+      s1 += g[c];
+      s2 += g[c] * xh[c];
+    }
+    const float m1 = s1 / d, m2 = s2 / d;
+    for (int c = 0; c < d; ++c) dx[(long long)r * lddx + c] = f2b(rstd[r] * (g[c] - m1 - xh[c] * m2) + rr[c]);
+  }
+  return 0;
+}
+
+static int ln_param_grad(const void* dy_, int64_t lddy, const void* x_, int64_t ldx, const float* mean,
+                         const float* rstd, float* dgamma, float* dbeta, int32_t rows, int32_t d, int32_t accumulate) {
+  const bf16_t *dy = (const bf16_t*)dy_, *x = (const bf16_t*)x_;
+  for (int c = 0; c < d; ++c) {
+    float sg = 0.f, sb = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      const float g = b2f(dy[(long long)r * lddy + c]);
+      sg += g * (b2f(x[(long long)r * ldx + c]) - mean[r]) * rstd[r];
+      sb += g;
+    }
+    dgamma[c] = accumulate ? dgamma[c] + sg : sg;
+    dbeta[c] = accumulate ? dbeta[c] + sb : sb;
+  }
+  return 0;
+}
+int mb200_layernorm_param_grad(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
+                               const float* rstd, float* dgamma, float* dbeta, int32_t rows, int32_t d,
+                               int32_t accumulate, void*) {
+  return ln_param_grad(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, d, accumulate);
+}
+int mb200_layernorm_param_grad_rows(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
+                                    const float* rstd, float* dgamma, float* dbeta, int32_t rows, int32_t d,
+                                    int32_t accumulate, void*) {
+  EM_REQUIRE(rows > 0 && d > 0 && d % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0, MB200_E_ALIGN,
+             "layernorm_param_grad_rows: d and row strides must be even");
+  return ln_param_grad(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, d, accumulate);
+}
+
+// ---- softmax (elementwise.cu: softmax_fwd_kernel / softmax_bwd_kernel) ----
+int mb200_softmax_fwd(const float* s, int64_t lds, int64_t s_bs, void* p_, int64_t ldp, int64_t p_bs, int32_t nz,
+                      int32_t Sq, int32_t Sk, float scale, int32_t causal, int32_t koff, void*) {
+  bf16_t* p = (bf16_t*)p_;
+  for (int z = 0; z < nz; ++z)
+    for (int i = 0; i < Sq; ++i) {
+      const float* sr = s + (long long)z * s_bs + (long long)i * lds;
+      bf16_t* pr = p + (long long)z * p_bs + (long long)i * ldp;
+      int lim = Sk;
+      if (causal && i + koff + 1 < Sk) lim = i + koff + 1;
+      float m = -INFINITY, sum = 0.f;
+      for (int j = 0; j < lim; ++j) m = fmaxf(m, sr[j] * scale);
+      for (int j = 0; j < lim; ++j) sum += expf(sr[j] * scale - m);
+      for (int j = 0; j < Sk; ++j) pr[j] = f2b(j < lim ? expf(sr[j] * scale - m) / sum : 0.f);  // pad columns untouched
+    }
+  return 0;
+}
+
+int mb200_softmax_bwd(const float* dp, int64_t lddp, int64_t dp_bs, const void* p_, int64_t ldp, int64_t p_bs,
+                      void* ds_, int64_t ldds, int64_t ds_bs, int32_t nz, int32_t Sq, int32_t Sk, float scale, void*) {
+  const bf16_t* p = (const bf16_t*)p_;
+  bf16_t* ds = (bf16_t*)ds_;
+  for (int z = 0; z < nz; ++z)
+    for (int i = 0; i < Sq; ++i) {
+      const float* dpr = dp + (long long)z * dp_bs + (long long)i * lddp;
+      const bf16_t* pr = p + (long long)z * p_bs + (long long)i * ldp;
+      bf16_t* dsr = ds + (long long)z * ds_bs + (long long)i * ldds;
+      float acc = 0.f;
+      for (int j = 0; j < Sk; ++j) acc += dpr[j] * b2f(pr[j]);
+      for (int j = 0; j < Sk; ++j) dsr[j] = f2b(b2f(pr[j]) * (dpr[j] - acc) * scale);
+    }
+  return 0;
+}
+
+// ---- reductions / elementwise / ViT front end ----
+int mb200_colsum(const void* x_, int64_t ldx, int32_t rows, int32_t cols, float* out, int32_t accumulate, void*) {
+  EM_REQUIRE(cols % 2 == 0 && ldx % 2 == 0, MB200_E_ALIGN, "colsum: cols and ldx must be even");
+  const bf16_t* x = (const bf16_t*)x_;
+  for (int c = 0; c < cols; ++c) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += b2f(x[(long long)r * ldx + c]);
+    out[c] = accumulate ? out[c] + s : s;
+  }
+  return 0;
+}
+
+int mb200_quick_gelu_bwd(const void* dy_, const void* pre_, void* dx_, int64_t n, void*) {
+  EM_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "quick_gelu_bwd: n must be a positive multiple of 8");
+  EM_REQUIRE(aligned16(dy_) && aligned16(pre_) && aligned16(dx_), MB200_E_ALIGN, "quick_gelu_bwd: 16B alignment");
+  const bf16_t *dy = (const bf16_t*)dy_, *pre = (const bf16_t*)pre_;
+  bf16_t* dx = (bf16_t*)dx_;
+  for (int64_t i = 0; i < n; ++i) {
+    const float x = b2f(pre[i]), s = 1.f / (1.f + expf(-1.702f * x));
+    dx[i] = f2b(b2f(dy[i]) * (s + 1.702f * x * s * (1.f - s)));
+  }
+  return 0;
+}
+
+// images [B,3,R,R] -> patches [B*g*g][ldp], column order (c, py, px)   (patchify_kernel)
+int mb200_patchify(const void* img_, void* patches_, int64_t ldp, int32_t B, int32_t R, int32_t P, void*) {
+  EM_REQUIRE(R % P == 0 && ldp >= 3 * P * P, MB200_E_SHAPE, "patchify: bad geometry");
+  const bf16_t* img = (const bf16_t*)img_;
+  bf16_t* patches = (bf16_t*)patches_;
+  const int g = R / P;
+  for (int b = 0; b < B; ++b)
+    for (int gy = 0; gy < g; ++gy)
+      for (int gx = 0; gx < g; ++gx)
+        for (int c = 0; c < 3; ++c)
+          for (int py = 0; py < P; ++py)
+            for (int px = 0; px < P; ++px)
+              patches[(((long long)b * g + gy) * g + gx) * ldp + (c * P + py) * P + px] =
+                  img[(((long long)b * 3 + c) * R + (gy * P + py)) * R + (gx * P + px)];
+  return 0;
+}
+
+// x[b,0] = cls + pos[0]; x[b,1+p] = pe[b,p] + pos[1+p]   (vit_assemble_kernel)
+int mb200_vit_assemble(void* x_, const void* pe_, const void* cls_, const void* pos_, int32_t B, int32_t T, int32_t w,
+                       void*) {
+  bf16_t* x = (bf16_t*)x_;
+  const bf16_t *pe = (const bf16_t*)pe_, *cls = (const bf16_t*)cls_, *pos = (const bf16_t*)pos_;
+  for (long long b = 0; b < B; ++b)
+    for (int t = 0; t < T; ++t)
+      for (int c = 0; c < w; ++c) {
+        const float base = t == 0 ? b2f(cls[c]) : b2f(pe[(b * (T - 1) + (t - 1)) * w + c]);
+        x[(b * T + t) * w + c] = f2b(base + b2f(pos[(long long)t * w + c]));
+      }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+"""GPU tests of code written AFTER this round's GPU budget was spent: none of it has run on a B200 yet.
+
+Everything here is marked xfail(strict=False): a pass shows up as XPASS, a failure as XFAIL, and either way the verified
+suite in the other files stays green. The file sorts last on purpose. What was checked without a GPU: the ViT training
+schedule was dry-run on the CPU against the oracle's autograd (tests/test_sched_emul_cpu.py), the optimizer
+parameter-group logic is pure host code (tests/test_param_groups_cpu.py). First job of the next round: run this file,
+fix what fails, drop the xfail marks and move the tests into test_ops_gpu.py / test_model_gpu.py."""
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="written after the round's GPU budget was spent; not yet run on a B200",
+                                strict=False)]
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def test_quick_gelu_bwd_matches_autograd():
+    import torch
+
+    from magma_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    pre = (torch.randn(257, 4096, generator=g) * 2).to(torch.bfloat16)
+    dy = torch.randn(257, 4096, generator=g).to(torch.bfloat16)
+    x = pre.float().requires_grad_(True)
+    (x * torch.sigmoid(1.702 * x)).backward(dy.float())
+    out = ops.quick_gelu_bwd(dy.to(dev), pre.to(dev))
+    assert _rel(out, x.grad) < 5e-3
+    buf = dy.to(dev).clone()
+    ops.quick_gelu_bwd(buf, pre.to(dev), out=buf)  # in place
+    assert torch.equal(buf, out)
+
+
+def test_layernorm_param_grad_rows_matches_the_small_kernel_and_fp32():
+    import torch
+
+    from magma_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    rows, d = 2056, 1024
+    x = torch.randn(rows, d, generator=g).to(torch.bfloat16).to(dev)
+    dy = torch.randn(rows, d, generator=g).to(torch.bfloat16).to(dev)
+    gamma = torch.ones(d, dtype=torch.bfloat16, device=dev)
+    beta = torch.zeros(d, dtype=torch.bfloat16, device=dev)
+    _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-5)
+    xh = (x.float() - mean[:, None]) * rstd[:, None]
+    want_g, want_b = (dy.float() * xh).sum(0), dy.float().sum(0)
+    dg = torch.full((d,), 3.0, dtype=torch.float32, device=dev)
+    db = torch.full((d,), 3.0, dtype=torch.float32, device=dev)
+    ops.layernorm_param_grad_rows(dy, x, mean, rstd, dg, db, accumulate=False)
+    assert _rel(dg, want_g) < 1e-4 and _rel(db, want_b) < 1e-4
+    ops.layernorm_param_grad_rows(dy, x, mean, rstd, dg, db, accumulate=True)
+    assert _rel(dg, 2 * want_g) < 1e-4 and _rel(db, 2 * want_b) < 1e-4
+    dg2, db2 = torch.empty_like(dg), torch.empty_like(db)
+    ops.layernorm_param_grad(dy, x, mean, rstd, dg2, db2, accumulate=False)
+    assert _rel(dg2, want_g) < 1e-4 and _rel(db2, want_b) < 1e-4
+
+
+def _build(dev, freeze_enc, S=32, image_enc_lr=None, weight_decay=0.0):
+    import torch
+
+    from magma_b200.config import MultimodalConfig
+    from magma_b200.image_encoders import register_vit
+    from magma_b200.language_model import GPTJConfig
+    from magma_b200.magma import Magma
+    from oracle import magma_oracle as O
+    from tools.model_check import boost_adapters, small_cfg
+
+    cfg = small_cfg()
+    w = boost_adapters(O.init_weights(cfg, seed=5), True)
+    for k in w:  # larger encoder weights than the 0.02 init: encoder gradients well above bf16 noise
+        if k.startswith("image_prefix.enc.") and k.endswith(("in_proj_weight", "out_proj.weight", "c_fc.weight",
+                                                              "c_proj.weight", "conv1.weight", ".proj")):
+            w[k] = w[k] * 3
+    w16 = {k: v.to(torch.bfloat16).float() for k, v in w.items()}
+    register_vit("clip_vit_tiny", cfg.vit_width, cfg.vit_layers, cfg.vit_heads, cfg.vit_patch, cfg.vit_image,
+                 cfg.vit_mlp, cfg.enc_out_dim)
+    mc = MultimodalConfig(batch_size=2, train_steps=1, encoder_name="clip_vit_tiny",
+                          adapter_config={"mlp": dict(cfg.mlp_adapter)}, image_seq_len=cfg.image_seq_len,
+                          image_embed_dropout_prob=0.0, use_image_embed_layernorm=True, image_size=cfg.vit_image,
+                          seq_len=S, freeze_img_encoder=freeze_enc, image_enc_lr=image_enc_lr, weight_decay=weight_decay,
+                          lr=1e-2, warmup_num_steps=2)
+    mc._lm_config = GPTJConfig(vocab_size=cfg.vocab, hidden_size=cfg.d, num_layers=cfg.n_layer, num_heads=cfg.n_head,
+                               rotary_dim=cfg.rotary_dim)
+    model = Magma(mc, device=dev, init_seed=None)
+    model.eos_token, model.image_token = cfg.eos_token, cfg.image_token
+    missing, unexpected = model.load_state_dict(w16, strict=False)
+    missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
+    assert not missing and not unexpected, (missing, unexpected)
+    model.lm.invalidate()
+    model.lm.attach_arena(model.arena)
+    model.image_prefix.enc.invalidate()
+    return model, mc, cfg, w16
+
+
+def test_trainable_vit_gradients_match_oracle_autograd():
+    """freeze_img_encoder: false (MAGMA_v1.yml:5): d loss / d (every ViT parameter) through LM -> prefix -> encoder."""
+    import torch
+
+    from oracle import magma_oracle as O
+
+    dev = torch.device("cuda:0")
+    S, B = 32, 3
+    model, mc, cfg, w16 = _build(dev, freeze_enc=False, S=S)
+    model.eval()
+    images, captions = O.synthetic_batch(cfg, B, S, seed=11)
+    images = images.to(torch.bfloat16).float()
+    trainable = [k for k in w16 if ".adapter." in k or k.startswith("image_prefix.")]
+    params = {k: v.clone().requires_grad_(k in trainable) for k, v in w16.items()}
+    loss_o, _, _ = O.magma_forward(images, captions, params, cfg)
+    loss_o.backward()
+    out = model(images.to(dev), captions.to(dev))
+    assert abs(float(out.loss) - float(loss_o)) < 2e-2
+    out.loss.backward()
+    sd = dict(model.named_parameters())
+    assert all(sd[k].requires_grad for k in trainable)
+    bad = {k: round(_rel(sd[k].grad, params[k].grad), 4) for k in trainable
+           if _rel(sd[k].grad, params[k].grad) > (1.5e-1 if ".adapter.0." in k else 8e-2)}
+    assert not bad, bad
+    # gradient accumulation: a second identical pass doubles every encoder gradient
+    g1 = {k: sd[k].grad.clone() for k in trainable if k.startswith("image_prefix.enc.")}
+    model(images.to(dev), captions.to(dev)).loss.backward()
+    assert max(_rel(sd[k].grad, 2 * g1[k]) for k in g1) < 1e-2
+
+
+def test_frozen_vit_is_unchanged_by_the_training_path():
+    """The saved-activation forward must produce the same features as the inference forward (same kernels, same order)."""
+    import torch
+
+    from oracle import magma_oracle as O
+
+    dev = torch.device("cuda:0")
+    model_t, _, cfg, _ = _build(dev, freeze_enc=False)
+    model_f, _, _, _ = _build(dev, freeze_enc=True)
+    images, _ = O.synthetic_batch(cfg, 3, 32, seed=2)
+    x = images.to(dev).to(torch.bfloat16)
+    f_train = model_t.image_prefix.enc(x)          # autograd path (grad enabled, trainable)
+    with torch.no_grad():
+        f_eval = model_t.image_prefix.enc(x)       # inference kernel schedule over the arena's compute copy
+    f_frozen = model_f.image_prefix.enc(x)
+    assert torch.equal(f_eval, f_frozen)
+    assert _rel(f_train, f_frozen) < 1e-6
+
+
+def test_encoder_learning_rate_group_and_weight_decay_exemptions():
+    """magma/utils.py:164-215: the encoder's parameters move at image_enc_lr / lr of the others' rate."""
+    import torch
+
+    from magma_b200.train_loop import B200Engine
+    from oracle import magma_oracle as O
+
+    dev = torch.device("cuda:0")
+    model, mc, cfg, _ = _build(dev, freeze_enc=False, image_enc_lr=1e-2 * 1e-3, weight_decay=0.0)
+    model.train()
+    images, captions = O.synthetic_batch(cfg, 2, 32, seed=4)
+    eng = B200Engine(model, mc, n_buckets=2)
+    sd = {k: p for k, p in model.named_parameters() if p.requires_grad}
+    before = {k: p.detach().clone() for k, p in sd.items()}
+    for _ in range(3):
+        out = eng(images.to(dev).to(torch.bfloat16), captions.to(dev))
+        eng.backward(out.loss)
+        eng.step()
+    enc = [float((sd[k].detach() - before[k]).abs().max()) for k in sd if k.startswith("image_prefix.enc.")]
+    oth = [float((sd[k].detach() - before[k]).abs().max()) for k in sd if not k.startswith("image_prefix.enc.")]
+    # Adam's step is ~lr per element: the encoder's largest move is ~1e-3 of the others'
+    assert max(enc) > 0 and max(oth) > 0
+    assert max(enc) < 5e-3 * max(oth), (max(enc), max(oth))
+    segs = eng._segments
+    assert len(segs) == 3 and segs[1][2] == pytest.approx(1e-3)
