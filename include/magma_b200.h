@@ -56,6 +56,10 @@ int mb200_version(void);
 const char* mb200_last_error(void);
 /* 0 when the current CUDA device is sm_100 (B200), MB200_E_ARCH otherwise. */
 int mb200_check_device(void);
+/* Limit the persistent GEMM grids to n_sms SMs (0 = all, the default; also env MB200_GEMM_SMS). Data-parallel training
+ * may leave a few SMs free for NCCL's CTAs so the gradient all-reduce overlaps the backward GEMMs. Returns the limit in
+ * effect. */
+int mb200_set_gemm_sm_limit(int n_sms);
 /* number of kernels this library has launched since load (bench.py reports the delta as gpu_launches). */
 long long mb200_launch_count(void);
 /* optional per-launch CUDA-event timing of the GEMM core (used by bench.py for the roofline numbers):

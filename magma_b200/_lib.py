@@ -181,5 +181,5 @@ EXPORTED_SYMBOLS = [
     "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode", "mb200_attn_fwd_tile",
     "mb200_attn_bwd_tile",
     "mb200_vit_train_workspace_bytes", "mb200_vit_forward_train", "mb200_vit_backward", "mb200_quick_gelu_bwd",
-    "mb200_layernorm_param_grad_rows",
+    "mb200_layernorm_param_grad_rows", "mb200_set_gemm_sm_limit",
 ]

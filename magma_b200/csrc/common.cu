@@ -33,6 +33,20 @@ int num_sms() {
   return n;
 }
 
+// SMs the persistent GEMM kernels may occupy (0 = all). Data-parallel training can leave a few SMs to NCCL's CTAs so the
+// gradient all-reduce overlaps the backward GEMMs instead of waiting for gaps between them.
+static int g_gemm_sm_limit = -1;
+int gemm_sms() {
+  if (g_gemm_sm_limit < 0) {
+    const char* e = getenv("MB200_GEMM_SMS");
+    g_gemm_sm_limit = e ? atoi(e) : 0;
+    if (g_gemm_sm_limit < 0) g_gemm_sm_limit = 0;
+  }
+  const int n = num_sms();
+  return (g_gemm_sm_limit >= 2 && g_gemm_sm_limit < n) ? g_gemm_sm_limit : n;
+}
+void set_gemm_sm_limit(int n) { g_gemm_sm_limit = n < 0 ? 0 : n; }
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -142,6 +156,7 @@ int prof_read(double* ms, double* flops, double* bytes, long long* n) {
 }  // namespace mb200
 
 namespace mb200 {
+void set_gemm_sm_limit(int n);
 const char* last_error();
 long long launches();
 void prof_enable(int on);
@@ -157,6 +172,10 @@ extern "C" int mb200_prof_read(double* gemm_ms, double* gemm_flops, double* gemm
   return mb200::prof_read(gemm_ms, gemm_flops, gemm_bytes, gemm_launches);
 }
 
+extern "C" int mb200_set_gemm_sm_limit(int n_sms) {
+  mb200::set_gemm_sm_limit(n_sms);
+  return mb200::gemm_sms();
+}
 extern "C" int mb200_version(void) { return MB200_VERSION; }
 extern "C" const char* mb200_last_error(void) { return mb200::last_error(); }
 extern "C" int mb200_check_device(void) { return mb200::check_arch(); }

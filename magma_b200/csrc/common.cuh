@@ -35,6 +35,7 @@ int check_cuda(cudaError_t e, const char* what);
   } while (0)
 
 int num_sms();
+int gemm_sms();  // SMs the persistent GEMM grids may use: num_sms() unless limited (mb200_set_gemm_sm_limit / MB200_GEMM_SMS)
 int check_arch();  // 0 if the current device is sm_100, else MB200_E_ARCH
 bool pdl_enabled();  // env MB200_PDL (default on)
 

@@ -362,7 +362,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     attr_set = true;
   }
   const long long items = (long long)kp.total_tiles * kp.split_k;
-  int grid = items < num_sms() ? (int)items : num_sms();
+  int grid = items < gemm_sms() ? (int)items : gemm_sms();
   {
     const double nb = (double)kp.total_tiles / ((double)kp.tiles_m * kp.tiles_n);
     const double flops = 2.0 * kp.M * (double)kp.N * kp.K * nb;

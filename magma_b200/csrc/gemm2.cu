@@ -214,7 +214,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKer
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
     attr_set = true;
   }
-  const int max_clusters = num_sms() / 2;
+  const int max_clusters = gemm_sms() / 2;
   const int clusters = kp.total_tiles < max_clusters ? kp.total_tiles : max_clusters;
   {
     const double nb = (double)kp.total_tiles / ((double)kp.tiles_m * kp.tiles_n);

@@ -47,11 +47,19 @@ def slice_for(names: Sequence[str], numels: Sequence[int], offsets: Sequence[int
     return lo, hi
 
 
-def allreduce_slice(flat_grad: torch.Tensor, lo, hi, group=None):
-    """SUM all-reduce of one contiguous arena slice (averaging by 1/world is folded into the optimizer kernel)."""
+def allreduce_slice(flat_grad: torch.Tensor, lo, hi, group=None, comm_dtype=None):
+    """SUM all-reduce of one contiguous arena slice (averaging by 1/world is folded into the optimizer kernel).
+    comm_dtype=torch.bfloat16 exchanges a bf16 copy of the slice (half the NVLink bytes; the reference exchanged fp16
+    gradients under DeepSpeed fp16, train.py:103-111) and writes the summed values back into the fp32 arena."""
     if lo is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
-    return dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=group)
+    view = flat_grad[lo:hi]
+    if comm_dtype is None or comm_dtype == view.dtype:
+        return dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+    buf = view.to(comm_dtype)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    view.copy_(buf)
+    return None
 
 
 def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:

@@ -28,6 +28,14 @@ class B200Engine:
         self.global_step = 0
         self.betas, self.eps = betas, eps
         self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
+        # experimental data-parallel knobs (both off by default): exchange gradients as bf16, and keep a
+        # few SMs out of the persistent GEMM grids so NCCL's CTAs run beside the backward GEMMs
+        self.comm_dtype = torch.bfloat16 if os.environ.get("MB200_DP_BF16", "0") == "1" else None
+        gemm_sms = int(os.environ.get("MB200_DP_GEMM_SMS", "0"))
+        if self.world > 1 and gemm_sms > 0:
+            from ._lib import lib
+
+            lib().mb200_set_gemm_sm_limit(gemm_sms)
         self._pending = []
         self.chunks = dp.layer_chunks(len(model.lm.transformer.h), n_buckets)  # (hi, lo), last layers first
         self._segments = None  # optimizer parameter groups, built at the first step (utils.configure_param_groups)
@@ -55,7 +63,7 @@ class B200Engine:
         ev.record(torch.cuda.current_stream())
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            dp.allreduce_slice(arena.grad, lo, hi)
+            dp.allreduce_slice(arena.grad, lo, hi, comm_dtype=self.comm_dtype)
 
     def backward(self, loss):
         """engine.backward (train_loop.py:18): loss/grad_accum scaling, chunked backward with overlapped all-reduce

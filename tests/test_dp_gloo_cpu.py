@@ -97,6 +97,14 @@ def _worker(rank, world, port, q):
         flat /= world  # the product folds this into the fused AdamW kernel (grad_scale = 1/world)
         _, g_full = loss_and_grads(X)
         ok = all(torch.allclose(flat[o:o + n].view(s), g, atol=1e-5) for g, o, n, s in zip(g_full, offs, numels, shapes))
+        # bf16 exchange option: same sums up to bf16 rounding of each rank's contribution, result back in fp32
+        flat2 = torch.zeros(total)
+        for g, o, n in zip(g_local, offs, numels):
+            flat2[o:o + n] = g.reshape(-1)
+        dp.allreduce_slice(flat2, 0, total, comm_dtype=torch.bfloat16)
+        flat2 /= world
+        ok = ok and flat2.dtype == torch.float32 and \
+            ((flat2 - flat).norm() / flat.norm()).item() < 1e-2 and not torch.equal(flat2, flat)
         # reduce_losses (magma/utils.py:26-34)
         from magma_b200.utils import reduce_losses
 
