@@ -110,3 +110,19 @@ def test_config_loads_reference_style_yaml(tmp_path):
     assert c.lr_at(0) == 0.0 and abs(c.lr_at(100) - 8e-4) < 1e-12 and c.lr_at(300000) == 0.0
     with pytest.raises(TypeError):
         MultimodalConfig(batch_size=1, train_steps=1, dataset_type="new")  # unknown keys rejected like the reference
+
+
+def test_shipped_and_reference_configs_load():
+    """configs/*.yml of this repo and, when the reference tree is mounted (build container only), the reference's own
+    MAGMA_v1.yml load through the same schema (magma/config.py:20-94)."""
+    from magma_b200.config import MultimodalConfig
+
+    c = MultimodalConfig.from_yml(os.path.join(ROOT, "configs", "MAGMA_v1_vit.yml"))
+    assert c.encoder_name == "clip_vit_large" and c.freeze_img_encoder and c.seq_len == 128
+    t = MultimodalConfig.from_yml(os.path.join(ROOT, "configs", "MAGMA_v1_vit_trainable_encoder.yml"))
+    assert not t.freeze_img_encoder and t.image_enc_lr == 2.0e-6
+    ref = "/root/reference/configs/MAGMA_v1.yml"
+    if os.path.exists(ref):
+        r = MultimodalConfig.from_yml(ref)
+        assert r.encoder_name == "clip_resnet_large" and not r.freeze_img_encoder and r.image_enc_lr == 2.0e-6
+        assert r.adapter_config == {"mlp": {"adapter_type": "normal", "downsample_factor": 4}}
