@@ -172,3 +172,29 @@ def test_encoder_learning_rate_group_and_weight_decay_exemptions():
     assert max(enc) < 5e-3 * max(oth), (max(enc), max(oth))
     segs = eng._segments
     assert len(segs) == 3 and segs[1][2] == pytest.approx(1e-3)
+
+
+def test_preprocess_inputs_image_and_text_to_embeddings(tmp_path):
+    """magma/magma.py:176-212: [ImageInput, str] -> transforms / tokenizer -> embed -> [1, L_img + n_tokens, d]."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from magma_b200.image_input import ImageInput
+
+    dev = torch.device("cuda:0")
+    model, mc, cfg, _ = _build(dev, freeze_enc=True)
+    model.eval()
+    assert model.transforms is not None
+    rng = np.random.default_rng(0)
+    p = tmp_path / "img.png"
+    Image.fromarray(rng.integers(0, 256, (90, 120, 3), dtype=np.uint8), "RGB").save(p)
+    text = "abc"  # the offline IdTokenizer maps bytes to ids < 256 < vocab
+    emb = model.preprocess_inputs([ImageInput(str(p)), text])
+    n_tok = len(model.tokenizer.encode(text))
+    assert emb.shape == (1, cfg.image_seq_len + n_tok, cfg.d)
+    pix = model.transforms(Image.open(p))
+    ref = model.embed([pix, model.tokenizer.encode(text, return_tensors="pt")])
+    assert torch.equal(emb, ref)
+    with pytest.raises(Exception, match="Invalid input type"):
+        model.preprocess_inputs([3.14])
