@@ -53,3 +53,77 @@ def to_reference_names(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
             nk = nk.replace(".fc_in.", ".c_fc.").replace(".fc_out.", ".c_proj.")
         out[nk] = v
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Training-state checkpoints: what the reference does through the DeepSpeed engine
+# (`model_engine.save_checkpoint(save_dir, client_state=sd)` / `load_checkpoint`, magma/utils.py:89-117) for
+# B200Engine. Directory layout follows DeepSpeed's so `Magma.from_checkpoint` and the reference's tools find the files:
+#   <save_dir>/latest                                   text file holding the tag
+#   <save_dir>/<tag>/mp_rank_00_model_states.pt         {"module": state_dict, "global_step", "client_state"...}
+#   <save_dir>/<tag>/b200_optim_states.pt               fp32 master / Adam moments of the flat arena + counters
+# ------------------------------------------------------------------------------------------------
+import os
+
+
+def arena_optimizer_state(arena) -> Dict[str, object]:
+    """Everything needed to resume the fused AdamW exactly: the fp32 master copy (the bf16 compute copy is derived from
+    it), both moments, the step counter, and the parameter names/offsets as a layout check."""
+    return {
+        "names": list(arena.names), "offsets": list(arena.offsets), "numel": int(arena.numel),
+        "master": arena.master.detach().cpu().clone(),
+        "exp_avg": None if arena.exp_avg is None else arena.exp_avg.detach().cpu().clone(),
+        "exp_avg_sq": None if arena.exp_avg_sq is None else arena.exp_avg_sq.detach().cpu().clone(),
+        "step_count": int(arena.step_count),
+    }
+
+
+def load_arena_optimizer_state(arena, st: Dict[str, object], load_optimizer_states: bool = True) -> None:
+    """Inverse of arena_optimizer_state. A layout mismatch (different trainable set / order) raises."""
+    if list(st["names"]) != list(arena.names) or list(st["offsets"]) != list(arena.offsets) or \
+            int(st["numel"]) != int(arena.numel):
+        raise RuntimeError("optimizer checkpoint does not match the model's trainable-parameter arena "
+                           f"({len(st['names'])} vs {len(arena.names)} tensors, {st['numel']} vs {arena.numel} elements)")
+    arena.master.copy_(st["master"].to(arena.master.device))
+    if load_optimizer_states and st["exp_avg"] is not None:
+        if arena.exp_avg is None:
+            arena.exp_avg = torch.zeros_like(arena.master)
+            arena.exp_avg_sq = torch.zeros_like(arena.master)
+        arena.exp_avg.copy_(st["exp_avg"].to(arena.master.device))
+        arena.exp_avg_sq.copy_(st["exp_avg_sq"].to(arena.master.device))
+        arena.step_count = int(st["step_count"])
+    arena.sync_shadow(force=True)  # refresh the bf16 compute copy the kernels read
+
+
+def save_training_checkpoint(save_dir, tag, module_state: Dict[str, torch.Tensor], optim_state, client_state,
+                             reference_names: bool = False) -> str:
+    d = os.path.join(str(save_dir), str(tag))
+    os.makedirs(d, exist_ok=True)
+    sd = {k: v.detach().cpu() for k, v in module_state.items()}
+    if reference_names:
+        sd = to_reference_names(sd)
+    payload = {"module": sd}
+    payload.update(client_state or {})
+    torch.save(payload, os.path.join(d, "mp_rank_00_model_states.pt"))
+    torch.save(optim_state, os.path.join(d, "b200_optim_states.pt"))
+    with open(os.path.join(str(save_dir), "latest"), "w") as f:
+        f.write(str(tag))
+    return d
+
+
+def read_training_checkpoint(load_dir, tag=None):
+    """-> (path, model payload, optimizer state) or (None, None, None) when there is nothing to load (DeepSpeed returns
+    a None path in that case and the reference's load_model then starts from step 0, magma/utils.py:112-116)."""
+    latest = os.path.join(str(load_dir), "latest")
+    if tag is None:
+        if not os.path.exists(latest):
+            return None, None, None
+        tag = open(latest).read().strip()
+    d = os.path.join(str(load_dir), str(tag))
+    mp = os.path.join(d, "mp_rank_00_model_states.pt")
+    if not os.path.exists(mp):
+        return None, None, None
+    payload = torch.load(mp, map_location="cpu", weights_only=False)
+    op = os.path.join(d, "b200_optim_states.pt")
+    optim = torch.load(op, map_location="cpu", weights_only=False) if os.path.exists(op) else None
+    return d, payload, optim

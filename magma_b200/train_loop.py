@@ -110,6 +110,60 @@ class B200Engine:
         self.global_step += 1
 
 
+    # DeepSpeed-engine checkpoint surface (magma/utils.py:89-117 call these through save_model / load_model) ----------
+    def save_checkpoint(self, save_dir, tag=None, client_state=None, trainable_only=True):
+        """Writes <save_dir>/<tag>/{mp_rank_00_model_states.pt, b200_optim_states.pt} and <save_dir>/latest (rank 0).
+        trainable_only keeps the 12 GB of frozen LM / encoder weights out of the file (they never change); pass False
+        for a self-contained checkpoint `Magma.from_checkpoint` can load on its own."""
+        from . import checkpoint as ck
+
+        tag = tag if tag is not None else f"global_step{self.global_step}"
+        if dist.is_initialized() and dist.get_rank() != 0:
+            dist.barrier()
+            return True
+        model = self.module
+        trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+        sd = {k: v for k, v in model.state_dict().items()
+              if not k.startswith(("word_embedding.", "transformer.")) and (not trainable_only or k in trainable)}
+        state = dict(client_state or {})
+        state.update({"global_step_engine": self.global_step, "micro_step": self.micro_step,
+                      "trainable_only": bool(trainable_only)})
+        ck.save_training_checkpoint(save_dir, tag, sd, ck.arena_optimizer_state(model.arena), state)
+        if dist.is_initialized():
+            dist.barrier()
+        return True
+
+    def load_checkpoint(self, load_dir, tag=None, load_optimizer_states=True, load_lr_scheduler_states=True):
+        """-> (load_path, client_state) like DeepSpeed; (None, None) when nothing is found. The learning-rate schedule is
+        a pure function of the step counter here (config.lr_at), so restoring the counter restores the scheduler."""
+        from . import checkpoint as ck
+
+        path, payload, optim = ck.read_training_checkpoint(load_dir, tag)
+        if path is None:
+            return None, None
+        model = self.module
+        sd = payload.pop("module")
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        if unexpected:
+            raise RuntimeError(f"checkpoint has {len(unexpected)} keys the model does not (e.g. {list(unexpected)[:4]})")
+        if not payload.get("trainable_only", False):
+            missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
+            if missing:
+                raise RuntimeError(f"checkpoint lacks {len(missing)} model keys (e.g. {missing[:4]})")
+        if optim is not None:
+            ck.load_arena_optimizer_state(model.arena, optim, load_optimizer_states)
+        else:
+            model.arena.sync_shadow(force=True)
+        if load_lr_scheduler_states:
+            self.global_step = int(payload.get("global_step_engine", payload.get("global_step", 0)))
+            self.micro_step = int(payload.get("micro_step", 0))
+        model.lm.invalidate()
+        model.lm.attach_arena(model.arena)
+        if hasattr(model.image_prefix.enc, "invalidate"):
+            model.image_prefix.enc.invalidate()
+        return path, payload
+
+
 def _to_device(images, captions):
     return images.cuda(non_blocking=True).to(torch.bfloat16), captions.cuda(non_blocking=True)
 

@@ -26,6 +26,56 @@ def reduce_losses(losses):
     return losses
 
 
+def cycle(loader):
+    """magma/utils.py:37-40 — endless iterator over a DataLoader (what train_step's `next(train_loader)` pulls from)."""
+    while True:
+        for data in loader:
+            yield data
+
+
+def collate_fn(batch_data, seq_len=2048):
+    """magma/datasets/dataset.py:155-160: [(image [1,3,R,R], caption ids [1,n]), ...] -> (images [b,3,R,R],
+    captions [b, <=seq_len])."""
+    images, captions = zip(*batch_data)
+    return torch.cat(images), torch.cat([c[:, :seq_len] for c in captions])
+
+
+def count_parameters(model):
+    """magma/utils.py:241-245 — number of trainable parameters."""
+    return sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+def get_world_info():
+    """magma/utils.py:255-259."""
+    return int(os.environ["LOCAL_RANK"]), int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+
+
+def save_model(model_engine, save_dir, global_step, config=None):
+    """magma/utils.py:89-96 — config.yml next to the engine checkpoint, client state {global_step, config}."""
+    import yaml
+
+    os.makedirs(save_dir, exist_ok=True)
+    cfg = config.to_dict() if config is not None else None
+    if cfg is not None and is_main():
+        with open(os.path.join(str(save_dir), "config.yml"), "w") as f:
+            yaml.dump(cfg, f, default_flow_style=False)
+    model_engine.save_checkpoint(save_dir, client_state={"global_step": global_step, "config": cfg})
+
+
+def load_model(model_engine, load_dir, load_optimizer_states=True, load_lr_scheduler_states=True):
+    """magma/utils.py:99-117 — returns the global step to resume from, 0 when nothing could be loaded."""
+    try:
+        load_path, sd = model_engine.load_checkpoint(load_dir, load_optimizer_states=load_optimizer_states,
+                                                     load_lr_scheduler_states=load_lr_scheduler_states)
+    except AssertionError as e:
+        load_path, sd = None, None
+        print(e)
+    if load_path is None:
+        print("Model loading failed - starting from global step 0")
+        return 0
+    return sd["global_step"]
+
+
 def build_labels(input_embeddings, captions, eos_token, device=None):
     """Drop-in for magma/utils.py:334-364 (same signature). The Python double loop of the reference (one device
     sync per token) is one integer kernel here; the result is bit-identical."""

@@ -198,3 +198,40 @@ def test_preprocess_inputs_image_and_text_to_embeddings(tmp_path):
     assert torch.equal(emb, ref)
     with pytest.raises(Exception, match="Invalid input type"):
         model.preprocess_inputs([3.14])
+
+
+def test_engine_checkpoint_resume_continues_the_same_trajectory(tmp_path):
+    """save_model / load_model (magma/utils.py:89-117) through B200Engine.save_checkpoint / load_checkpoint: a run
+    resumed from the checkpoint reproduces the losses of the uninterrupted run (same data, dropout off)."""
+    import torch
+
+    from magma_b200.train_loop import B200Engine
+    from magma_b200.utils import load_model, save_model
+    from oracle import magma_oracle as O
+
+    dev = torch.device("cuda:0")
+    model, mc, cfg, _ = _build(dev, freeze_enc=True)
+    model.train()
+    images, captions = O.synthetic_batch(cfg, 2, 32, seed=4)
+    x, c = images.to(dev).to(torch.bfloat16), captions.to(dev)
+
+    def steps(engine, n):
+        out = []
+        for _ in range(n):
+            o = engine(x, c)
+            engine.backward(o.loss)
+            engine.step()
+            out.append(float(o.loss))
+        return out
+
+    eng = B200Engine(model, mc, n_buckets=2)
+    steps(eng, 3)
+    save_model(eng, str(tmp_path), eng.global_step, config=mc)
+    want = steps(eng, 3)
+    model2, mc2, _, _ = _build(dev, freeze_enc=True)   # fresh weights as loaded from the (frozen) base model
+    model2.train()
+    eng2 = B200Engine(model2, mc2, n_buckets=2)
+    assert load_model(eng2, str(tmp_path)) == 3 and eng2.global_step == 3
+    got = steps(eng2, 3)
+    assert max(abs(a - b) for a, b in zip(got, want)) < 2e-3, (got, want)
+    assert load_model(eng2, str(tmp_path / "missing")) == 0
