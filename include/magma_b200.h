@@ -358,6 +358,70 @@ int mb200_vit_backward(const mb200_vit_model* m, const mb200_vit_grads* g, const
 /* dx = dy * d/dx[x * sigmoid(1.702 x)] at x = pre (CLIP QuickGELU, backward). dx may alias dy. */
 int mb200_quick_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream);
 
+/* ---- GPT-J + adapters, general training schedule (csrc/gptj_sched.cu, host-only). Same arithmetic as
+ * mb200_gptj_forward/backward (training, no KV cache) for EVERY adapter form of the reference: normal / parallel /
+ * scaled_parallel (learnable scalar adapter_scale, magma/adapters.py:57-61), each with or without the leading
+ * LayerNorm (add_layernorm, adapters.py:16-17), on the MLP and / or the attention branch (magma/magma.py:102-174).
+ * Attention runs as batched GEMMs + softmax kernels. The fast runtime above covers the forms the shipped configs use;
+ * this one is what language_model.py selects for the others. */
+typedef struct {
+  const void* wd; /* [r, d] bf16 */
+  const void* bd;
+  const void* wu; /* [d, r] */
+  const void* bu;
+  const void* ln_g; /* leading LayerNorm weight / bias [d] bf16, or NULL */
+  const void* ln_b;
+  const float* scale; /* DEVICE fp32 scalar (adapter_scale) or NULL = 1 */
+  float *g_wd, *g_bd, *g_wu, *g_bu; /* fp32 gradients, parameter shapes; g_wd == NULL => adapter frozen */
+  float *g_ln_g, *g_ln_b;
+  float* g_scale; /* fp32 [1] */
+} mb200_adapter_ex;
+
+typedef struct {
+  const void* ln1_g;
+  const void* ln1_b;
+  const void* w_qkv;
+  const void* w_out;
+  const void* w_fc_in;
+  const void* b_fc_in;
+  const void* w_fc_out;
+  const void* b_fc_out;
+  mb200_adapter_ex mlp_ad;
+  mb200_adapter_ex attn_ad;
+} mb200_gptj_layer_ex;
+
+typedef struct {
+  int32_t n_layer, d, n_head, rotary_dim;
+  int32_t vocab;
+  int32_t d_ff;
+  int32_t mlp_adapter; /* MB200_ADAPTER_* */
+  int32_t mlp_adapter_r;
+  int32_t attn_adapter;
+  int32_t attn_adapter_r;
+  float ln_eps;
+  int32_t _pad;
+  const mb200_gptj_layer_ex* layers;
+  const void* lnf_g;
+  const void* lnf_b;
+  const void* w_lm;
+  const void* b_lm;
+} mb200_gptj_model_ex;
+
+size_t mb200_gptj_sched_workspace_bytes(const mb200_gptj_model_ex* m, int32_t B, int32_t S);
+/* x bf16 [B,S,d]; labels int64 [B,S] or NULL; logits bf16 [B*S][ldv] or NULL (kept in the workspace then);
+ * loss fp32 [1] (device) when labels != NULL. Activations are saved in `ws` for the backward pass. */
+int mb200_gptj_sched_forward(const mb200_gptj_model_ex* m, const void* x, const int64_t* labels, void* logits,
+                             int64_t ldv, float* loss, int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream);
+/* dx: bf16 [B,S,d] gradient w.r.t. x (or NULL). accumulate != 0 adds into the fp32 gradient buffers. */
+int mb200_gptj_sched_backward(const mb200_gptj_model_ex* m, void* dx, float loss_scale, int32_t accumulate, int32_t B,
+                              int32_t S, void* ws, size_t ws_bytes, void* stream);
+
+/* out = s[0] * u + r1 + r2 over n bf16 elements (s: DEVICE fp32 scalar or NULL = 1; r1, r2 optional) — the
+ * `* adapter_scale` of ParallelAdapter.forward (magma/adapters.py:63-66,85-92) with the residual sum folded in. */
+int mb200_scale_add(const void* u, const float* s, const void* r1, const void* r2, void* out, int64_t n, void* stream);
+/* out[0] (+)= sum_i a_i * b_i (fp32) over n bf16 elements — d loss / d adapter_scale. */
+int mb200_dot(const void* a, const void* b, int64_t n, float* out, int32_t accumulate, void* stream);
+
 /* Fused KV-cache attention for one decode step (Sq = 1): q/k/v come from the fused qkv row [B][3][H][hd] (already
  * rotated); k,v are appended to the cache at position `pos`, then softmax(q K^T / sqrt(hd)) V over [0, pos].
  * Replaces the torch.cat cache growth + _attn of hf:gptj/modeling_gptj.py:209-214,136-149 per step. */

@@ -151,6 +151,24 @@ class VitModelC(ctypes.Structure):
     ]
 
 
+class AdapterExC(ctypes.Structure):
+    """mb200_adapter_ex: adapter with the optional leading LayerNorm and the learnable scale (general schedule)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("wd", "bd", "wu", "bu", "ln_g", "ln_b", "scale", "g_wd", "g_bd", "g_wu",
+                                               "g_bu", "g_ln_g", "g_ln_b", "g_scale")]
+
+
+class GptjLayerExC(ctypes.Structure):
+    _fields_ = [
+        (n, ctypes.c_void_p)
+        for n in ("ln1_g", "ln1_b", "w_qkv", "w_out", "w_fc_in", "b_fc_in", "w_fc_out", "b_fc_out")
+    ] + [("mlp_ad", AdapterExC), ("attn_ad", AdapterExC)]
+
+
+class GptjModelExC(ctypes.Structure):
+    _fields_ = [(n, t) for n, t in GptjModelC._fields_ if n != "layers"]
+    _fields_.insert(12, ("layers", ctypes.POINTER(GptjLayerExC)))
+
+
 class VitLayerGradsC(ctypes.Structure):
     """mb200_vit_layer_grads: fp32 gradient pointers, same field order as VitLayerC."""
     _fields_ = list(VitLayerC._fields_)
@@ -165,6 +183,7 @@ def _setup_signatures(L):
     L.mb200_gptj_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_vit_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_vit_train_workspace_bytes.restype = ctypes.c_size_t
+    L.mb200_gptj_sched_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_launch_count.restype = ctypes.c_longlong
 
 
@@ -181,5 +200,6 @@ EXPORTED_SYMBOLS = [
     "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode", "mb200_attn_fwd_tile",
     "mb200_attn_bwd_tile",
     "mb200_vit_train_workspace_bytes", "mb200_vit_forward_train", "mb200_vit_backward", "mb200_quick_gelu_bwd",
-    "mb200_layernorm_param_grad_rows", "mb200_set_gemm_sm_limit",
+    "mb200_layernorm_param_grad_rows", "mb200_set_gemm_sm_limit", "mb200_scale_add", "mb200_dot",
+    "mb200_gptj_sched_workspace_bytes", "mb200_gptj_sched_forward", "mb200_gptj_sched_backward",
 ]

@@ -788,6 +788,47 @@ __global__ void quick_gelu_bwd_kernel(const bf16* dy, const bf16* __restrict__ p
   }
 }
 
+// out = s[0] * u + r1 + r2 (r1 / r2 optional; s == nullptr means 1): the `* adapter_scale` of ParallelAdapter.forward
+// (magma/adapters.py:63-66,85-92) with the block's residual sum folded in. s is a DEVICE scalar (a trainable parameter).
+__global__ void scale_add_kernel(const bf16* __restrict__ u, const float* __restrict__ s, const bf16* __restrict__ r1,
+                                 const bf16* __restrict__ r2, bf16* __restrict__ out, long long nvec) {
+  const float sc = s ? __ldg(s) : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    unpack8(reinterpret_cast<const uint4*>(u)[i], a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] *= sc;
+    if (r1) {
+      unpack8(reinterpret_cast<const uint4*>(r1)[i], b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += b[e];
+    }
+    if (r2) {
+      unpack8(reinterpret_cast<const uint4*>(r2)[i], b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += b[e];
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(a);
+  }
+}
+
+// out[0] += sum_i a_i * b_i (fp32): gradient of the adapter_scale scalar. One atomic per CTA; out zeroed first unless
+// accumulating.
+__global__ void __launch_bounds__(256)
+dot_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long nvec, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(reinterpret_cast<const uint4*>(a)[i], x);
+    unpack8(reinterpret_cast<const uint4*>(b)[i], y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += x[e] * y[e];
+  }
+  const float t = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, t);
+}
+
 static inline int grid_for(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -868,6 +909,30 @@ extern "C" int mb200_layernorm_param_grad_rows(const void* dy, int64_t lddy, con
                                                                    dgamma, dbeta, rows, d);
     MB_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" int mb200_scale_add(const void* u, const float* s, const void* r1, const void* r2, void* out, int64_t n,
+                               void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "scale_add: n=%lld must be a positive multiple of 8", (long long)n);
+  MB_REQUIRE(((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(r1) | reinterpret_cast<uintptr_t>(r2) |
+               reinterpret_cast<uintptr_t>(out)) & 15) == 0, MB200_E_ALIGN, "scale_add: pointers must be 16-byte aligned");
+  scale_add_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>((const bf16*)u, s, (const bf16*)r1, (const bf16*)r2,
+                                                                 (bf16*)out, n / 8);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_dot(const void* a, const void* b, int64_t n, float* out, int32_t accumulate, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "dot: n=%lld must be a positive multiple of 8", (long long)n);
+  MB_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0, MB200_E_ALIGN,
+             "dot: pointers must be 16-byte aligned");
+  if (!accumulate) MB_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ST(stream)));
+  const int grid = grid_for(n / 8, 256) > 1024 ? 1024 : grid_for(n / 8, 256);
+  dot_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)a, (const bf16*)b, n / 8, out);
+  MB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -1,0 +1,491 @@
+// magma_b200 — GPT-J + adapters, general training schedule (forward with saved activations + backward), host-only.
+//
+// engine.cu's runtime covers the adapter forms the reference's shipped configurations use (plain bottleneck, "normal"
+// and "parallel" wiring). The reference's Adapter classes have two more options — a leading LayerNorm
+// (`add_layernorm`, magma/adapters.py:16-17) and a learnable scalar on the parallel forms (`scaled_parallel`,
+// adapters.py:57-66,85-92) — and this file schedules the whole LM pass for ANY combination of them, on the MLP and / or
+// the attention branch (magma/magma.py:102-174), from the primitive operators of the C ABI only:
+//
+//   block (hf:gptj/modeling_gptj.py:400-413, parallel residual):  h = ln_1(x);  x' = attn(h) + mlp(h) + x
+//   Adapter.forward            adapters.py:38-39    y = A(z) + z            A(z) = Wu relu(Wd LN?(z) + bd) + bu
+//   ParallelAdapter.forward    adapters.py:63-66    y = module(h) + s * A(h)
+//   AdapterWrapper / ParallelAdapterWrapper         the same two on the attention output / input (:85-92,:109-116)
+//   LM head + shifted CE       hf:gptj/modeling_gptj.py:573,623 ; hf:loss/loss_utils.py:28-67
+//
+// Attention runs as strided batched GEMMs on the fused qkv buffer + the softmax kernels (the path engine.cu uses when
+// the fused single-tile kernel does not apply). The LM is frozen: dgrad through every GEMM, wgrad only for adapters.
+//
+// No kernels and no CUDA calls here (sched_rt.h): tests/test_sched_emul_cpu.py compiles this file as plain C++ against
+// oracle/cabi_emul.cpp and checks every adapter form against torch autograd of the oracle on the CPU.
+// Written after the round's GPU budget was spent: NOT YET RUN ON A B200.
+#include "sched_rt.h"
+
+#include <math.h>
+#include <string.h>
+
+namespace mb200 {
+namespace {
+
+typedef uint16_t bf16s;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off;
+  explicit Carver(void* b) : base(reinterpret_cast<uint8_t*>(b)), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Mat {
+  const void* p;
+  long long ld, bs0, bs1;
+  int mn;
+};
+inline Mat mat(const void* p, long long ld, int mn = 0, long long bs0 = 0, long long bs1 = 0) {
+  return Mat{p, ld, bs0, bs1, mn};
+}
+struct Epi {
+  float alpha = 1.f;
+  const void* bias = nullptr;
+  int act = 0;
+  void* aux_out = nullptr;
+  const void* aux_in = nullptr;
+  int dact = 0;
+  const void* res1 = nullptr;
+  const void* res2 = nullptr;
+  long long ld_res = 0;
+  int accumulate = 0;
+  const float* rope_tab = nullptr;
+  int rope_mode = 0, rope_S = 0, rope_hd = 0, rope_rot = 0, rope_ncols = 0;
+};
+
+int gemm(void* st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, int c_f32, const Epi& e = Epi(),
+         int nb0 = 1, int nb1 = 1, long long c_bs0 = 0, long long c_bs1 = 0) {
+  mb200_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.nb0 = nb0;
+  g.nb1 = nb1;
+  g.c_dtype = c_f32 ? MB200_F32 : MB200_BF16;
+  g.A.ptr = A.p;
+  g.A.ld = A.ld;
+  g.A.bs0 = A.bs0;
+  g.A.bs1 = A.bs1;
+  g.A.mn_major = A.mn;
+  g.B.ptr = B.p;
+  g.B.ld = B.ld;
+  g.B.bs0 = B.bs0;
+  g.B.bs1 = B.bs1;
+  g.B.mn_major = B.mn;
+  g.C = C;
+  g.ldc = ldc;
+  g.c_bs0 = c_bs0;
+  g.c_bs1 = c_bs1;
+  g.alpha = e.alpha;
+  g.act = e.act;
+  g.dact = e.dact;
+  g.accumulate = e.accumulate;
+  g.bias = e.bias;
+  g.aux_out = e.aux_out;
+  g.aux_in = e.aux_in;
+  g.res1 = e.res1;
+  g.res2 = e.res2;
+  g.ld_res = e.ld_res;
+  g.rope_tab = e.rope_tab;
+  g.rope_mode = e.rope_mode;
+  g.rope_S = e.rope_S;
+  g.rope_hd = e.rope_hd;
+  g.rope_rot = e.rope_rot;
+  g.rope_ncols = e.rope_ncols;
+  return mb200_gemm(&g, st);
+}
+
+// what one adapter keeps from forward to backward
+struct AdapterActs {
+  bf16s* zn;    // [M,d] LN(z) when the adapter has a leading LayerNorm
+  float* mean;  // [M]
+  float* rstd;  // [M]
+  bf16s* t;     // [M,r] hidden (post ReLU)
+  bf16s* u;     // [M,d] up-projection output before scaling (scaled_parallel only)
+};
+
+struct LayerActs {
+  bf16s* x_in;     // [M,d] residual stream entering the block
+  bf16s* h;        // [M,d] ln_1 output
+  float* mean;     // [M]
+  float* rstd;     // [M]
+  bf16s* qkv;      // [M,3d] after rotary
+  bf16s* P;        // [B,H,S,ldP]
+  bf16s* attn_o;   // [M,d] merged heads, before out_proj
+  bf16s* pre;      // [M,dff] fc_in pre-activation
+  bf16s* mlp_out;  // [M,d] fc_out output (input of a "normal" MLP adapter)
+  bf16s* a_out;    // [M,d] out_proj output (input of a "normal" attention adapter)
+  AdapterActs am, aa;
+};
+
+struct Plan {
+  int M, d, dff, H, hd, S, B, ldP;
+  long long ldv;
+  LayerActs acts[64];
+  float* scores;  // [B,H,S,ldP] fp32 (scores in forward, dP in backward)
+  bf16s *hact, *ax, *x_final, *xf_ln, *dlogits;
+  float *lnf_mean, *lnf_rstd, *row_loss, *rope_tab;
+  int* n_valid;
+  // backward temporaries
+  bf16s *g0, *g1, *gs, *dt, *dzn, *dm, *dhact, *dh_mlp, *dattn_o, *dqkv, *dS, *dh, *da, *dhp;
+  size_t bytes;
+};
+
+inline bool has_ln(const mb200_adapter_ex& a) { return a.ln_g != nullptr; }
+inline bool has_scale(const mb200_adapter_ex& a) { return a.scale != nullptr; }
+
+void carve_adapter(Carver& c, AdapterActs& a, const mb200_adapter_ex& ad, int kind, size_t M, size_t d, int r) {
+  a.zn = nullptr;
+  a.mean = a.rstd = nullptr;
+  a.t = a.u = nullptr;
+  if (kind == MB200_ADAPTER_NONE) return;
+  if (has_ln(ad)) {
+    a.zn = c.take<bf16s>(M * d);
+    a.mean = c.take<float>(M);
+    a.rstd = c.take<float>(M);
+  }
+  a.t = c.take<bf16s>(M * (size_t)r);
+  if (has_scale(ad)) a.u = c.take<bf16s>(M * d);
+}
+
+int make_plan(Plan& P, const mb200_gptj_model_ex* m, int B, int S, void* ws) {
+  MBS_REQUIRE(m && m->layers && m->n_layer > 0 && m->n_layer <= 64, MB200_E_SHAPE, "gptj_sched: n_layer out of range");
+  MBS_REQUIRE(B > 0 && S > 0 && m->n_head > 0 && m->d % m->n_head == 0 && m->d % 8 == 0 && m->d_ff % 8 == 0,
+              MB200_E_SHAPE, "gptj_sched: bad d / n_head / d_ff");
+  MBS_REQUIRE((m->d / m->n_head) % 8 == 0 && m->rotary_dim % 4 == 0 && m->rotary_dim <= m->d / m->n_head, MB200_E_SHAPE,
+              "gptj_sched: head_dim must be a multiple of 8 and rotary_dim a multiple of 4 within it");
+  for (int l = 0; l < m->n_layer; ++l) {
+    const mb200_gptj_layer_ex& L = m->layers[l];
+    MBS_REQUIRE(!(m->mlp_adapter == MB200_ADAPTER_NORMAL && has_scale(L.mlp_ad)) &&
+                    !(m->attn_adapter == MB200_ADAPTER_NORMAL && has_scale(L.attn_ad)),
+                MB200_E_ARG, "gptj_sched: adapter_scale exists on the parallel adapter forms only (adapters.py:57-61)");
+    MBS_REQUIRE((m->mlp_adapter == MB200_ADAPTER_NONE || (m->mlp_adapter_r > 0 && m->mlp_adapter_r % 8 == 0)) &&
+                    (m->attn_adapter == MB200_ADAPTER_NONE || (m->attn_adapter_r > 0 && m->attn_adapter_r % 8 == 0)),
+                MB200_E_SHAPE, "gptj_sched: adapter bottleneck widths must be positive multiples of 8");
+  }
+  Carver c(ws);
+  P.B = B;
+  P.S = S;
+  P.M = B * S;
+  P.d = m->d;
+  P.dff = m->d_ff;
+  P.H = m->n_head;
+  P.hd = m->d / m->n_head;
+  P.ldP = (int)align_up(S, 8);
+  P.ldv = (long long)align_up(m->vocab, 64);
+  const size_t M = P.M, d = P.d, dff = P.dff;
+  const size_t nP = (size_t)B * P.H * S * P.ldP;
+  for (int l = 0; l < m->n_layer; ++l) {
+    LayerActs& a = P.acts[l];
+    a.x_in = c.take<bf16s>(M * d);
+    a.h = c.take<bf16s>(M * d);
+    a.mean = c.take<float>(M);
+    a.rstd = c.take<float>(M);
+    a.qkv = c.take<bf16s>(M * 3 * d);
+    a.P = c.take<bf16s>(nP);
+    a.attn_o = c.take<bf16s>(M * d);
+    a.pre = c.take<bf16s>(M * dff);
+    a.mlp_out = c.take<bf16s>(M * d);
+    a.a_out = c.take<bf16s>(M * d);
+    carve_adapter(c, a.am, m->layers[l].mlp_ad, m->mlp_adapter, M, d, m->mlp_adapter_r);
+    carve_adapter(c, a.aa, m->layers[l].attn_ad, m->attn_adapter, M, d, m->attn_adapter_r);
+  }
+  P.scores = c.take<float>(nP);
+  P.hact = c.take<bf16s>(M * dff);
+  P.ax = c.take<bf16s>(M * d);
+  P.x_final = c.take<bf16s>(M * d);
+  P.xf_ln = c.take<bf16s>(M * d);
+  P.lnf_mean = c.take<float>(M);
+  P.lnf_rstd = c.take<float>(M);
+  P.row_loss = c.take<float>(M);
+  P.n_valid = c.take<int>(4);
+  P.rope_tab = c.take<float>((size_t)S * m->rotary_dim);
+  P.dlogits = c.take<bf16s>(M * (size_t)P.ldv);
+  const int rmax = m->mlp_adapter_r > m->attn_adapter_r ? m->mlp_adapter_r : m->attn_adapter_r;
+  P.g0 = c.take<bf16s>(M * d);
+  P.g1 = c.take<bf16s>(M * d);
+  P.gs = c.take<bf16s>(M * d);
+  P.dt = c.take<bf16s>(M * (size_t)(rmax > 0 ? rmax : 8));
+  P.dzn = c.take<bf16s>(M * d);
+  P.dm = c.take<bf16s>(M * d);
+  P.dhact = c.take<bf16s>(M * dff);
+  P.dh_mlp = c.take<bf16s>(M * d);
+  P.dattn_o = c.take<bf16s>(M * d);
+  P.dqkv = c.take<bf16s>(M * 3 * d);
+  P.dS = c.take<bf16s>(nP);
+  P.dh = c.take<bf16s>(M * d);
+  P.da = c.take<bf16s>(M * d);
+  P.dhp = c.take<bf16s>(M * d);
+  P.bytes = align_up(c.off, 256);
+  return 0;
+}
+
+// out = s * A(z) + res1 + res2, A(z) = Wu relu(Wd LN?(z) + bd) + bu   (s = 1 without adapter_scale)
+int adapter_fwd(void* st, const mb200_adapter_ex& ad, AdapterActs& a, int M, int d, int r, float eps, const bf16s* z,
+                bf16s* out, const bf16s* res1, const bf16s* res2) {
+  const bf16s* zin = z;
+  if (has_ln(ad)) {
+    MBS_TRY(mb200_layernorm_fwd(z, d, ad.ln_g, ad.ln_b, a.zn, d, a.mean, a.rstd, M, d, eps, st));
+    zin = a.zn;
+  }
+  Epi e1;
+  e1.bias = ad.bd;
+  e1.act = MB200_ACT_RELU;
+  MBS_TRY(gemm(st, M, r, d, mat(zin, d), mat(ad.wd, d), a.t, r, 0, e1));
+  Epi e2;
+  e2.bias = ad.bu;
+  if (!has_scale(ad)) {
+    e2.res1 = res1;
+    e2.res2 = res2;
+    e2.ld_res = d;
+    return gemm(st, M, d, r, mat(a.t, r), mat(ad.wu, r), out, d, 0, e2);
+  }
+  MBS_TRY(gemm(st, M, d, r, mat(a.t, r), mat(ad.wu, r), a.u, d, 0, e2));
+  return mb200_scale_add(a.u, ad.scale, res1, res2, out, (int64_t)M * d, st);
+}
+
+// g = dL/d(out) of adapter_fwd. dz_out = res + dL/dz through the adapter; parameter gradients accumulate or overwrite.
+int adapter_bwd(void* st, const mb200_adapter_ex& ad, const AdapterActs& a, const Plan& P, int M, int d, int r,
+                const bf16s* g, const bf16s* z, bf16s* dz_out, const bf16s* res, int acc) {
+  const bf16s* gu = g;  // gradient w.r.t. the up-projection output
+  if (has_scale(ad)) {
+    if (ad.g_scale) MBS_TRY(mb200_dot(g, a.u, (int64_t)M * d, ad.g_scale, acc, st));  // d s = <g, u>
+    MBS_TRY(mb200_scale_add(g, ad.scale, nullptr, nullptr, P.gs, (int64_t)M * d, st));   // gu = s * g
+    gu = P.gs;
+  }
+  const bf16s* zin = has_ln(ad) ? a.zn : z;
+  Epi e1;
+  e1.dact = MB200_DACT_RELU;
+  e1.aux_in = a.t;
+  MBS_TRY(gemm(st, M, r, d, mat(gu, d), mat(ad.wu, r, 1), P.dt, r, 0, e1));  // dt = (gu Wu) * 1[t > 0]
+  if (ad.g_wd) {
+    Epi ew;
+    ew.accumulate = acc;
+    MBS_TRY(gemm(st, d, r, M, mat(gu, d, 1), mat(a.t, r, 1), ad.g_wu, r, 1, ew));    // dWu[d,r] = gu^T t
+    MBS_TRY(mb200_colsum(gu, d, M, d, ad.g_bu, acc, st));
+    MBS_TRY(gemm(st, r, d, M, mat(P.dt, r, 1), mat(zin, d, 1), ad.g_wd, d, 1, ew));  // dWd[r,d] = dt^T zin
+    MBS_TRY(mb200_colsum(P.dt, r, M, r, ad.g_bd, acc, st));
+  }
+  if (!has_ln(ad)) {
+    Epi e2;
+    e2.res1 = res;
+    e2.ld_res = d;
+    return gemm(st, M, d, r, mat(P.dt, r), mat(ad.wd, d, 1), dz_out, d, 0, e2);  // dz = dt Wd (+ res)
+  }
+  MBS_TRY(gemm(st, M, d, r, mat(P.dt, r), mat(ad.wd, d, 1), P.dzn, d, 0));  // d LN(z)
+  if (ad.g_ln_g)
+    MBS_TRY(mb200_layernorm_param_grad_rows(P.dzn, d, z, d, a.mean, a.rstd, ad.g_ln_g, ad.g_ln_b, M, d, acc, st));
+  return mb200_layernorm_bwd(P.dzn, d, z, d, ad.ln_g, a.mean, a.rstd, res, d, dz_out, d, M, d, st);
+}
+
+int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels, bf16s* logits, long long ldv,
+            float* loss, int B, int S, void* ws, size_t ws_bytes, void* st) {
+  Plan P;
+  MBS_TRY(make_plan(P, m, B, S, ws));
+  MBS_REQUIRE(ws != nullptr && ws_bytes >= P.bytes, MB200_E_ARG, "gptj_sched_forward: workspace too small (%zu < %zu)",
+              ws_bytes, P.bytes);
+  const int M = P.M, d = P.d, dff = P.dff, H = P.H, hd = P.hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const long long qb0 = hd, qb1 = (long long)S * 3 * d;
+  const long long pb0 = (long long)S * P.ldP, pb1 = (long long)H * S * P.ldP;
+  MBS_TRY(mb200_rope_table(P.rope_tab, S, m->rotary_dim, 0, st));
+  MBS_TRY(rt_copy(P.acts[0].x_in, x, (size_t)M * d * sizeof(bf16s), st));
+  for (int l = 0; l < m->n_layer; ++l) {
+    const mb200_gptj_layer_ex& L = m->layers[l];
+    LayerActs& a = P.acts[l];
+    const bf16s* xin = a.x_in;
+    bf16s* xout = l + 1 < m->n_layer ? P.acts[l + 1].x_in : P.x_final;
+    MBS_TRY(mb200_layernorm_fwd(xin, d, L.ln1_g, L.ln1_b, a.h, d, a.mean, a.rstd, M, d, m->ln_eps, st));
+    {  // fused q/k/v projection, rotary embedding applied to the q and k column ranges in the epilogue
+      Epi e;
+      e.rope_tab = P.rope_tab;
+      e.rope_mode = 1;
+      e.rope_S = S;
+      e.rope_hd = hd;
+      e.rope_rot = m->rotary_dim;
+      e.rope_ncols = 2 * d;
+      MBS_TRY(gemm(st, M, 3 * d, d, mat(a.h, d), mat(L.w_qkv, d), a.qkv, 3 * d, 0, e));
+    }
+    // scores = Q K^T (fp32), P = softmax(scores / sqrt(hd) + causal mask), O = P V
+    MBS_TRY(gemm(st, S, S, hd, mat(a.qkv, 3 * d, 0, qb0, qb1), mat(a.qkv + d, 3 * d, 0, qb0, qb1), P.scores, P.ldP, 1,
+                 Epi(), H, B, pb0, pb1));
+    MBS_TRY(mb200_softmax_fwd(P.scores, P.ldP, pb0, a.P, P.ldP, pb0, B * H, S, S, scale, 1, 0, st));
+    MBS_TRY(gemm(st, S, hd, S, mat(a.P, P.ldP, 0, pb0, pb1), mat(a.qkv + 2 * d, 3 * d, 1, qb0, qb1), a.attn_o, d, 0, Epi(),
+                 H, B, hd, (long long)S * d));
+    // out_proj; ax = attention branch + residual x
+    if (m->attn_adapter == MB200_ADAPTER_NONE) {
+      Epi e;
+      e.res1 = xin;
+      e.ld_res = d;
+      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), P.ax, d, 0, e));
+    } else if (m->attn_adapter == MB200_ADAPTER_NORMAL) {  // AdapterWrapper: A(attn_out) + attn_out
+      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), a.a_out, d, 0));
+      MBS_TRY(adapter_fwd(st, L.attn_ad, a.aa, M, d, m->attn_adapter_r, m->ln_eps, a.a_out, P.ax, a.a_out, xin));
+    } else {  // ParallelAdapterWrapper: attn(h) + s * A(h)
+      Epi e;
+      e.res1 = xin;
+      e.ld_res = d;
+      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), a.a_out, d, 0, e));
+      MBS_TRY(adapter_fwd(st, L.attn_ad, a.aa, M, d, m->attn_adapter_r, m->ln_eps, a.h, P.ax, a.a_out, nullptr));
+    }
+    {  // fc_in + bias + gelu_new, pre-activation kept
+      Epi e;
+      e.bias = L.b_fc_in;
+      e.act = MB200_ACT_GELU_NEW;
+      e.aux_out = a.pre;
+      MBS_TRY(gemm(st, M, dff, d, mat(a.h, d), mat(L.w_fc_in, d), P.hact, dff, 0, e));
+    }
+    Epi eo;
+    eo.bias = L.b_fc_out;
+    if (m->mlp_adapter == MB200_ADAPTER_NONE) {
+      eo.res1 = P.ax;
+      eo.ld_res = d;
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), xout, d, 0, eo));
+    } else if (m->mlp_adapter == MB200_ADAPTER_NORMAL) {  // Sequential(mlp, Adapter): A(mlp(h)) + mlp(h)
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), a.mlp_out, d, 0, eo));
+      MBS_TRY(adapter_fwd(st, L.mlp_ad, a.am, M, d, m->mlp_adapter_r, m->ln_eps, a.mlp_out, xout, a.mlp_out, P.ax));
+    } else {  // ParallelAdapter: mlp(h) + s * A(h)
+      eo.res1 = P.ax;
+      eo.ld_res = d;
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), a.mlp_out, d, 0, eo));
+      MBS_TRY(adapter_fwd(st, L.mlp_ad, a.am, M, d, m->mlp_adapter_r, m->ln_eps, a.h, xout, a.mlp_out, nullptr));
+    }
+  }
+  // ln_f + LM head (+ shifted cross-entropy; the logits' gradient is written now, scaled in backward)
+  MBS_TRY(mb200_layernorm_fwd(P.x_final, d, m->lnf_g, m->lnf_b, P.xf_ln, d, P.lnf_mean, P.lnf_rstd, M, d, m->ln_eps, st));
+  bf16s* lg = logits ? logits : P.dlogits;
+  const long long ldl = logits ? ldv : P.ldv;
+  MBS_REQUIRE(ldl % 8 == 0 && ldl >= m->vocab, MB200_E_ALIGN, "gptj_sched_forward: ldv=%lld must be >= vocab and %%8", ldl);
+  {
+    Epi e;
+    e.bias = m->b_lm;
+    MBS_TRY(gemm(st, M, m->vocab, d, mat(P.xf_ln, d), mat(m->w_lm, d), lg, ldl, 0, e));
+  }
+  if (labels) {
+    MBS_REQUIRE(loss != nullptr, MB200_E_ARG, "gptj_sched_forward: labels given but loss pointer is NULL");
+    MBS_REQUIRE(ldl == P.ldv, MB200_E_ARG, "gptj_sched_forward: ldv must be %lld (vocab rounded up to 64)", P.ldv);
+    MBS_TRY(mb200_cross_entropy(lg, ldl, labels, B, S, m->vocab, P.row_loss, P.n_valid, loss, P.dlogits, 1.0f, st));
+  }
+  return 0;
+}
+
+int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int acc, int B, int S, void* ws, size_t ws_bytes,
+             void* st) {
+  Plan P;
+  MBS_TRY(make_plan(P, m, B, S, ws));
+  MBS_REQUIRE(ws != nullptr && ws_bytes >= P.bytes, MB200_E_ARG, "gptj_sched_backward: workspace too small");
+  const int M = P.M, d = P.d, dff = P.dff, H = P.H, hd = P.hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const long long qb0 = hd, qb1 = (long long)S * 3 * d;
+  const long long pb0 = (long long)S * P.ldP, pb1 = (long long)H * S * P.ldP;
+  // gradient w.r.t. the residual stream entering layer l lives in g[(l) & 1]
+  bf16s* gb[2] = {P.g0, P.g1};
+  {  // dxf = loss_scale * dlogits Wlm ; g = LN_f backward
+    Epi e;
+    e.alpha = loss_scale;
+    MBS_TRY(gemm(st, M, d, m->vocab, mat(P.dlogits, P.ldv), mat(m->w_lm, d, 1), P.dh, d, 0, e));
+    MBS_TRY(mb200_layernorm_bwd(P.dh, d, P.x_final, d, m->lnf_g, P.lnf_mean, P.lnf_rstd, nullptr, 0, gb[m->n_layer & 1], d,
+                                M, d, st));
+  }
+  for (int l = m->n_layer - 1; l >= 0; --l) {
+    const mb200_gptj_layer_ex& L = m->layers[l];
+    LayerActs& a = P.acts[l];
+    const bf16s* g = gb[(l + 1) & 1];
+    bf16s* gout = (l == 0 && dx) ? dx : gb[l & 1];
+    const bf16s* dh_acc = nullptr;  // running sum of gradients w.r.t. h = ln_1 output
+    // ---- MLP branch ----
+    const bf16s* dm = g;
+    if (m->mlp_adapter == MB200_ADAPTER_NORMAL) {
+      MBS_TRY(adapter_bwd(st, L.mlp_ad, a.am, P, M, d, m->mlp_adapter_r, g, a.mlp_out, P.dm, g, acc));
+      dm = P.dm;
+    } else if (m->mlp_adapter == MB200_ADAPTER_PARALLEL) {
+      MBS_TRY(adapter_bwd(st, L.mlp_ad, a.am, P, M, d, m->mlp_adapter_r, g, a.h, P.dm, nullptr, acc));
+      dh_acc = P.dm;
+    }
+    {
+      Epi e;
+      e.dact = MB200_DACT_GELU_NEW;
+      e.aux_in = a.pre;
+      MBS_TRY(gemm(st, M, dff, d, mat(dm, d), mat(L.w_fc_out, dff, 1), P.dhact, dff, 0, e));
+      Epi e2;
+      e2.res1 = dh_acc;
+      e2.ld_res = d;
+      MBS_TRY(gemm(st, M, d, dff, mat(P.dhact, dff), mat(L.w_fc_in, d, 1), P.dh_mlp, d, 0, e2));
+      dh_acc = P.dh_mlp;
+    }
+    // ---- attention branch ----
+    const bf16s* da = g;
+    if (m->attn_adapter == MB200_ADAPTER_NORMAL) {
+      MBS_TRY(adapter_bwd(st, L.attn_ad, a.aa, P, M, d, m->attn_adapter_r, g, a.a_out, P.da, g, acc));
+      da = P.da;
+    } else if (m->attn_adapter == MB200_ADAPTER_PARALLEL) {
+      MBS_TRY(adapter_bwd(st, L.attn_ad, a.aa, P, M, d, m->attn_adapter_r, g, a.h, P.dhp, dh_acc, acc));
+      dh_acc = P.dhp;
+    }
+    MBS_TRY(gemm(st, M, d, d, mat(da, d), mat(L.w_out, d, 1), P.dattn_o, d, 0));  // d(attn_o) = da Wo
+    {
+      Mat dO = mat(P.dattn_o, d, 0, hd, (long long)S * d);
+      Mat dO_mn = mat(P.dattn_o, d, 1, hd, (long long)S * d);
+      MBS_TRY(gemm(st, S, S, hd, dO, mat(a.qkv + 2 * d, 3 * d, 0, qb0, qb1), P.scores, P.ldP, 1, Epi(), H, B, pb0, pb1));
+      MBS_TRY(gemm(st, S, hd, S, mat(a.P, P.ldP, 1, pb0, pb1), dO_mn, P.dqkv + 2 * d, 3 * d, 0, Epi(), H, B, qb0, qb1));
+      MBS_TRY(mb200_softmax_bwd(P.scores, P.ldP, pb0, a.P, P.ldP, pb0, P.dS, P.ldP, pb0, B * H, S, S, scale, st));
+      Epi er;  // dQ, dK w.r.t. the rotated q, k: inverse rotation in the epilogue
+      er.rope_tab = P.rope_tab;
+      er.rope_mode = -1;
+      er.rope_S = S;
+      er.rope_hd = hd;
+      er.rope_rot = m->rotary_dim;
+      er.rope_ncols = hd;
+      MBS_TRY(gemm(st, S, hd, S, mat(P.dS, P.ldP, 0, pb0, pb1), mat(a.qkv + d, 3 * d, 1, qb0, qb1), P.dqkv, 3 * d, 0, er, H,
+                   B, qb0, qb1));
+      MBS_TRY(gemm(st, S, hd, S, mat(P.dS, P.ldP, 1, pb0, pb1), mat(a.qkv, 3 * d, 1, qb0, qb1), P.dqkv + d, 3 * d, 0, er, H,
+                   B, qb0, qb1));
+    }
+    {
+      Epi e;
+      e.res1 = dh_acc;
+      e.ld_res = d;
+      MBS_TRY(gemm(st, M, d, 3 * d, mat(P.dqkv, 3 * d), mat(L.w_qkv, d, 1), P.dh, d, 0, e));  // dh = dqkv Wqkv + ...
+    }
+    MBS_TRY(mb200_layernorm_bwd(P.dh, d, a.x_in, d, L.ln1_g, a.mean, a.rstd, g, d, gout, d, M, d, st));
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace mb200
+
+extern "C" size_t mb200_gptj_sched_workspace_bytes(const mb200_gptj_model_ex* m, int32_t B, int32_t S) {
+  mb200::Plan P;
+  if (mb200::make_plan(P, m, B, S, nullptr)) return 0;
+  return P.bytes;
+}
+
+extern "C" int mb200_gptj_sched_forward(const mb200_gptj_model_ex* m, const void* x, const int64_t* labels, void* logits,
+                                        int64_t ldv, float* loss, int32_t B, int32_t S, void* ws, size_t ws_bytes,
+                                        void* stream) {
+  int rc = mb200::rt_check_arch();
+  if (rc) return rc;
+  return mb200::forward(m, (const mb200::bf16s*)x, labels, (mb200::bf16s*)logits, ldv, loss, B, S, ws, ws_bytes, stream);
+}
+
+extern "C" int mb200_gptj_sched_backward(const mb200_gptj_model_ex* m, void* dx, float loss_scale, int32_t accumulate,
+                                         int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream) {
+  int rc = mb200::rt_check_arch();
+  if (rc) return rc;
+  return mb200::backward(m, (mb200::bf16s*)dx, loss_scale, accumulate, B, S, ws, ws_bytes, stream);
+}

@@ -18,7 +18,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import AdapterC, GptjLayerC, GptjModelC, MB200Error, check, lib
+from ._lib import (AdapterC, AdapterExC, GptjLayerC, GptjLayerExC, GptjModelC, GptjModelExC, MB200Error, check,
+                   lib)
 from .adapters import Adapter, AdapterWrapper, ParallelAdapter, ParallelAdapterWrapper
 from .arena import ParamArena
 
@@ -218,6 +219,7 @@ class B200GPTJForCausalLM(nn.Module):
         self._arena = None
         self._own_arena = False
         self._cmodel_cache = None
+        self._cmodel_ex_cache = None
         self._ws = {}
         self._generation = 0
         self._loss_scale_hint = None
@@ -261,6 +263,7 @@ class B200GPTJForCausalLM(nn.Module):
         self._arena = arena
         self._own_arena = False
         self._cmodel_cache = None
+        self._cmodel_ex_cache = None
 
     def _ensure_arena(self):
         if self._arena is None:
@@ -272,6 +275,86 @@ class B200GPTJForCausalLM(nn.Module):
         return self._arena
 
     # ---- C model struct ---------------------------------------------------------------------
+    def _general_schedule(self):
+        """True when an adapter uses an option the fast runtime (engine.cu) does not schedule — a leading LayerNorm
+        (add_layernorm, adapters.py:16-17) or the learnable adapter_scale (scaled_parallel, adapters.py:57-61). Those
+        models run through the general host-only schedule csrc/gptj_sched.cu (training / full-sequence passes only)."""
+        if getattr(self, "_force_general", False):  # test hook: cross-check the two schedules on the same model
+            return True
+        for blk in self.transformer.h:
+            for ad in (_split_mlp(blk.mlp)[2], _split_attn(blk.attn)[2]):
+                if ad is not None and (ad.add_layernorm or isinstance(getattr(ad, "adapter_scale", 1), nn.Parameter)):
+                    return True
+        return False
+
+    def _adapter_struct_ex(self, ad):
+        c = AdapterExC()
+        if ad is None:
+            return c
+        ar = self._arena
+        fields = [("wd", ad.down.weight), ("bd", ad.down.bias), ("wu", ad.up.weight), ("bu", ad.up.bias)]
+        if ad.add_layernorm:
+            fields += [("ln_g", ad.adapter[0].weight), ("ln_b", ad.adapter[0].bias)]
+        for cname, p in fields:
+            setattr(c, cname, ar.shadow_of(p).data_ptr())
+            if p.requires_grad:
+                setattr(c, "g_" + cname, ar.grad_of(p).data_ptr())
+        sc = getattr(ad, "adapter_scale", 1)
+        if isinstance(sc, nn.Parameter):  # read as fp32 straight from the arena's master copy
+            c.scale = sc.data.data_ptr()
+            if sc.requires_grad:
+                c.g_scale = ar.grad_of(sc).data_ptr()
+        return c
+
+    def _cmodel_ex(self):
+        """mb200_gptj_model_ex for the general schedule (same frozen-weight pointers, extended adapter tables)."""
+        self._ensure_arena()
+        if self._cmodel_ex_cache is not None:
+            return self._cmodel_ex_cache
+        cfg = self.config
+        n = len(self.transformer.h)
+        layers = (GptjLayerExC * n)()
+        kinds, rm, ra = set(), 0, 0
+        for l, blk in enumerate(self.transformer.h):
+            mk, mlp, mad = _split_mlp(blk.mlp)
+            ak, attn, aad = _split_attn(blk.attn)
+            kinds.add((mk, ak))
+            L = layers[l]
+            L.ln1_g, L.ln1_b = blk.ln_1.weight.data_ptr(), blk.ln_1.bias.data_ptr()
+            L.w_qkv, L.w_out = attn.fused_qkv().data_ptr(), attn.out_proj.weight.data_ptr()
+            L.w_fc_in, L.b_fc_in = mlp.fc_in.weight.data_ptr(), mlp.fc_in.bias.data_ptr()
+            L.w_fc_out, L.b_fc_out = mlp.fc_out.weight.data_ptr(), mlp.fc_out.bias.data_ptr()
+            L.mlp_ad, L.attn_ad = self._adapter_struct_ex(mad), self._adapter_struct_ex(aad)
+            rm = mad.bottleneck if mad is not None else rm
+            ra = aad.bottleneck if aad is not None else ra
+        if len(kinds) != 1:
+            raise MB200Error("all blocks must carry the same adapter configuration")
+        mk, ak = kinds.pop()
+        for name, p in self.named_parameters():
+            if "adapter" not in name and (p.dtype != torch.bfloat16 or not p.is_cuda):
+                raise MB200Error(f"frozen LM parameter {name} must be bf16 on CUDA (got {p.dtype}, {p.device})")
+        m = GptjModelExC()
+        m.n_layer, m.d, m.n_head, m.rotary_dim = n, cfg.hidden_size, cfg.num_heads, cfg.rotary_dim
+        m.vocab, m.d_ff = self.lm_head.weight.shape[0], cfg.intermediate_size
+        m.mlp_adapter, m.mlp_adapter_r, m.attn_adapter, m.attn_adapter_r = mk, rm, ak, ra
+        m.ln_eps = cfg.layer_norm_epsilon
+        m.layers = ctypes.cast(layers, ctypes.POINTER(GptjLayerExC))
+        m.lnf_g, m.lnf_b = self.transformer.ln_f.weight.data_ptr(), self.transformer.ln_f.bias.data_ptr()
+        m.w_lm, m.b_lm = self.lm_head.weight.data_ptr(), self.lm_head.bias.data_ptr()
+        self._cmodel_ex_cache = (m, layers)
+        return self._cmodel_ex_cache
+
+    def _workspace_ex(self, B, S):
+        key = ("ex", B, S)
+        if key not in self._ws:
+            nbytes = lib().mb200_gptj_sched_workspace_bytes(ctypes.byref(self._cmodel_ex()[0]), B, S)
+            if nbytes == 0:
+                raise MB200Error(lib().mb200_last_error().decode())
+            for k in [k for k in self._ws if k[0] == "ex"]:
+                del self._ws[k]
+            self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+        return self._ws[key]
+
     def _adapter_struct(self, ad, with_grad):
         c = AdapterC()
         if ad is None:
@@ -332,6 +415,7 @@ class B200GPTJForCausalLM(nn.Module):
     def invalidate(self):
         """Call after replacing parameters/modules (e.g. add_adapters) so the C model struct is rebuilt."""
         self._cmodel_cache = None
+        self._cmodel_ex_cache = None
         if self._own_arena:
             self._arena = None
 
@@ -358,6 +442,8 @@ class B200GPTJForCausalLM(nn.Module):
         x = x.to(torch.bfloat16).contiguous()
         if self._arena is not None or self.adapter_parameters():
             self._ensure_arena().sync_shadow()
+        if self._general_schedule():
+            return self._run_forward_general(x, labels, training, cache, last_only, want_hidden, want_logits)
         m, _ = self._cmodel()
         V, ldv = self.lm_head.weight.shape[0], self.ldv
         S_kv = cache.S_max if cache is not None else S
@@ -384,8 +470,42 @@ class B200GPTJForCausalLM(nn.Module):
             lg = logits.view(B, 1 if last_only else S, ldv)[..., :V]
         return (loss.squeeze(0) if loss is not None else None), lg
 
+    def _run_forward_general(self, x, labels, training, cache, last_only, want_hidden, want_logits):
+        """Full-sequence pass through csrc/gptj_sched.cu (adapters with add_layernorm / adapter_scale)."""
+        if cache is not None or last_only or want_hidden:
+            raise MB200Error("adapters with add_layernorm / scaled_parallel run through the general schedule, which has "
+                             "no KV-cache, last-position or hidden-state output (generate() is not supported for them)")
+        B, S, _ = x.shape
+        m = self._cmodel_ex()[0]
+        V, ldv = self.lm_head.weight.shape[0], self.ldv
+        ws = self._workspace_ex(B, S)
+        logits = torch.empty(B * S, ldv, dtype=torch.bfloat16, device=x.device) if want_logits else None
+        loss = torch.zeros(1, dtype=torch.float32, device=x.device) if labels is not None else None
+        if labels is not None:
+            labels = labels.to(device=x.device, dtype=torch.int64).contiguous()
+        self._generation += 1  # this schedule always records its activations in the workspace
+        check(lib().mb200_gptj_sched_forward(ctypes.byref(m), ops._ptr(x), ops._ptr(labels), ops._ptr(logits),
+                                             ctypes.c_int64(ldv), ops._ptr(loss), B, S, ops._ptr(ws),
+                                             ctypes.c_size_t(ws.numel()), ops._stream()))
+        self._last_hidden = None
+        lg = logits.view(B, S, ldv)[..., :V] if logits is not None else None
+        return (loss.squeeze(0) if loss is not None else None), lg
+
     def _run_backward(self, shape, loss_scale):
         B, S, d = shape
+        if self._general_schedule():
+            arena = self._arena
+            dx = torch.empty(B, S, d, dtype=torch.bfloat16, device=self._device)
+            ws = self._workspace_ex(B, S)
+            check(lib().mb200_gptj_sched_backward(ctypes.byref(self._cmodel_ex()[0]), ops._ptr(dx),
+                                                  ctypes.c_float(loss_scale), int(arena.grads_live()), B, S,
+                                                  ops._ptr(ws), ctypes.c_size_t(ws.numel()), ops._stream()))
+            if self._after_chunk is not None:  # one backward call: the gradient slices are exchanged afterwards
+                for hi, lo in (self._bwd_chunks or [(len(self.transformer.h), 0)]):
+                    self._after_chunk(hi, lo)
+            if self._own_arena:
+                arena.publish_grads()
+            return dx
         m, _ = self._cmodel()
         ws = self._workspace(B, S, S, True)
         arena = self._arena

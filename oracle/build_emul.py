@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE — builds oracle/_build/libsched_emul.so: the product's host-only schedule files
-(magma_b200/csrc/vit_train.cu, compiled as plain C++ — they contain no kernels and no CUDA calls, see
+(magma_b200/csrc/vit_train.cu and gptj_sched.cu, compiled as plain C++ — they contain no kernels and no CUDA calls, see
 magma_b200/csrc/sched_rt.h) linked against oracle/cabi_emul.cpp, the CPU emulation of the primitive C-ABI operators.
 tests/test_sched_emul_cpu.py loads it to dry-run the schedules against the oracle. Nothing in magma_b200/ uses it."""
 import os
@@ -8,7 +8,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT_DIR = os.path.join(ROOT, "oracle", "_build")
 OUT = os.path.join(OUT_DIR, "libsched_emul.so")
-SCHEDULES = [os.path.join(ROOT, "magma_b200", "csrc", "vit_train.cu")]
+SCHEDULES = [os.path.join(ROOT, "magma_b200", "csrc", "vit_train.cu"),
+             os.path.join(ROOT, "magma_b200", "csrc", "gptj_sched.cu")]
 EMUL = os.path.join(ROOT, "oracle", "cabi_emul.cpp")
 DEPS = SCHEDULES + [EMUL, os.path.join(ROOT, "magma_b200", "csrc", "sched_rt.h"),
                     os.path.join(ROOT, "include", "magma_b200.h")]

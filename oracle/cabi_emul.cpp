@@ -307,6 +307,82 @@ int mb200_quick_gelu_bwd(const void* dy_, const void* pre_, void* dx_, int64_t n
   return 0;
 }
 
+// out = s[0] * u + r1 + r2   (scale_add_kernel)
+int mb200_scale_add(const void* u_, const float* s, const void* r1_, const void* r2_, void* out_, int64_t n, void*) {
+  EM_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "scale_add: n must be a positive multiple of 8");
+  EM_REQUIRE(aligned16(u_) && aligned16(r1_) && aligned16(r2_) && aligned16(out_), MB200_E_ALIGN, "scale_add: alignment");
+  const bf16_t *u = (const bf16_t*)u_, *r1 = (const bf16_t*)r1_, *r2 = (const bf16_t*)r2_;
+  bf16_t* out = (bf16_t*)out_;
+  const float sc = s ? *s : 1.f;
+  for (int64_t i = 0; i < n; ++i) out[i] = f2b(b2f(u[i]) * sc + (r1 ? b2f(r1[i]) : 0.f) + (r2 ? b2f(r2[i]) : 0.f));
+  return 0;
+}
+
+// out[0] (+)= <a, b>   (dot_kernel)
+int mb200_dot(const void* a_, const void* b_, int64_t n, float* out, int32_t accumulate, void*) {
+  EM_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "dot: n must be a positive multiple of 8");
+  EM_REQUIRE(aligned16(a_) && aligned16(b_), MB200_E_ALIGN, "dot: alignment");
+  const bf16_t *a = (const bf16_t*)a_, *b = (const bf16_t*)b_;
+  double acc = 0.0;
+  for (int64_t i = 0; i < n; ++i) acc += (double)b2f(a[i]) * (double)b2f(b[i]);
+  out[0] = (accumulate ? out[0] : 0.f) + (float)acc;
+  return 0;
+}
+
+// (cos, sin) fp32 [S][rot/2][2]   (rope_table_kernel)
+int mb200_rope_table(float* tab, int32_t S, int32_t rot, int32_t pos0, void*) {
+  EM_REQUIRE(S > 0 && rot > 0 && rot % 2 == 0, MB200_E_SHAPE, "rope_table: bad S / rot");
+  const int half = rot / 2;
+  for (int s = 0; s < S; ++s)
+    for (int p = 0; p < half; ++p) {
+      const float inv_freq = 1.0f / powf(10000.0f, (float)(2 * p) / (float)rot);
+      const float ang = (float)(pos0 + s) * inv_freq;
+      tab[((long long)s * half + p) * 2] = cosf(ang);
+      tab[((long long)s * half + p) * 2 + 1] = sinf(ang);
+    }
+  return 0;
+}
+
+// shifted cross-entropy over bf16 logits, mean over valid targets; dlogits = grad_scale * (softmax - onehot) / n_valid,
+// zero rows where the target is ignored; dlogits may alias logits   (ce_count / ce_row / ce_reduce kernels)
+int mb200_cross_entropy(const void* logits_, int64_t ldv, const int64_t* labels, int32_t B, int32_t S, int32_t V,
+                        float* row_loss, int32_t* n_valid, float* loss, void* dlogits_, float grad_scale, void*) {
+  EM_REQUIRE(ldv % 8 == 0 && V <= ldv, MB200_E_ALIGN, "cross_entropy: ldv must be a multiple of 8 and >= V");
+  const bf16_t* logits = (const bf16_t*)logits_;
+  bf16_t* dlogits = (bf16_t*)dlogits_;
+  int nv = 0;
+  for (int i = 0; i < B * S; ++i)
+    if (i % S + 1 < S && labels[i + 1] != -100) ++nv;
+  *n_valid = nv;
+  const float gs = grad_scale / (float)(nv > 0 ? nv : 1);
+  double total = 0.0;
+  std::vector<float> f(V);
+  for (int row = 0; row < B * S; ++row) {
+    const int s = row % S;
+    const long long tgt = s + 1 < S ? labels[row + 1] : -100;
+    const bf16_t* lr = logits + (long long)row * ldv;
+    bf16_t* dr = dlogits ? dlogits + (long long)row * ldv : nullptr;
+    if (tgt == -100 || tgt < 0 || tgt >= V) {
+      row_loss[row] = 0.f;
+      if (dr)
+        for (int j = 0; j < V; ++j) dr[j] = f2b(0.f);
+      continue;
+    }
+    float m = -INFINITY, sum = 0.f;
+    for (int j = 0; j < V; ++j) {
+      f[j] = b2f(lr[j]);
+      m = fmaxf(m, f[j]);
+    }
+    for (int j = 0; j < V; ++j) sum += expf(f[j] - m);
+    row_loss[row] = m + logf(sum) - f[tgt];
+    total += row_loss[row];
+    if (dr)
+      for (int j = 0; j < V; ++j) dr[j] = f2b((expf(f[j] - m) / sum - (j == tgt ? 1.f : 0.f)) * gs);
+  }
+  *loss = (float)(total / (double)(nv > 0 ? nv : 1));
+  return 0;
+}
+
 // images [B,3,R,R] -> patches [B*g*g][ldp], column order (c, py, px)   (patchify_kernel)
 int mb200_patchify(const void* img_, void* patches_, int64_t ldp, int32_t B, int32_t R, int32_t P, void*) {
   EM_REQUIRE(R % P == 0 && ldp >= 3 * P * P, MB200_E_SHAPE, "patchify: bad geometry");

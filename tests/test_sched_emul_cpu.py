@@ -130,7 +130,7 @@ def test_vit_train_schedule_matches_oracle_autograd(emul):
     feats, grads = run_emul(emul, cfg, pre, w16, images, dfeats)
     assert rel(feats, feats_o) < 2e-2
     assert set(grads) == set(grads_o)
-    bad = {k: round(rel(g, grads_o[k]), 4) for k, g in grads.items() if rel(g, grads_o[k]) > 4e-2}
+    bad = {k: round(rel(g, grads_o[k]), 4) for k, g in grads.items() if rel(g, grads_o[k]) > 2.5e-2}
     assert not bad, bad  # bf16 activations vs the fp32 oracle
 
 
@@ -151,3 +151,171 @@ def test_vit_train_schedule_rejects_a_small_workspace(emul):
     feats = torch.empty(1, cfg.enc_out_dim, dtype=torch.bfloat16)
     rc = emul.mb200_vit_forward_train(ctypes.byref(m), ptr(images), ptr(feats), 1, ptr(ws), ctypes.c_size_t(1024), None)
     assert rc != 0 and b"workspace too small" in emul.mb200_last_error()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/gptj_sched.cu — GPT-J + adapters, every adapter form of the reference (magma/adapters.py, magma/magma.py:102-174)
+# ------------------------------------------------------------------------------------------------------------------
+from magma_b200._lib import AdapterExC, GptjLayerExC, GptjModelExC  # noqa: E402
+
+ADAPTER_KIND = {None: 0, "normal": 1, "parallel": 2, "scaled_parallel": 2}
+
+
+def lm_case(mlp, attn, mlp_ln=False, attn_ln=False, seed=0, B=2, S=12):
+    """Oracle weights for a tiny GPT-J with the requested adapter forms; adapter weights O(0.05) with the bottleneck
+    biases at +-3 so every ReLU is decided (bf16 and fp32 agree on the mask), LN / scale parameters non-trivial."""
+    cfg = O.OracleConfig(d=64, n_layer=2, n_head=4, rotary_dim=8, vocab=96,
+                         mlp_adapter=None if mlp is None else {"adapter_type": mlp, "downsample_factor": 4},
+                         attn_adapter=None if attn is None else {"adapter_type": attn, "downsample_factor": 8})
+    w = {k: v for k, v in O.init_weights(cfg, seed=seed, with_vit=False).items() if k.startswith("lm.")}
+    g = torch.Generator().manual_seed(seed + 7)
+    for k in list(w):
+        if ".adapter." in k:
+            w[k] = torch.randn(w[k].shape, generator=g) * (0.05 if k.endswith("weight") else 0.02)
+            if k.endswith("adapter.0.bias"):
+                w[k] = torch.where(torch.rand(w[k].shape, generator=g) < 0.5, -3.0, 3.0) + 0.02 * torch.randn(w[k].shape, generator=g)
+    for l in range(cfg.n_layer):
+        for loc, kind, ln in (("mlp", mlp, mlp_ln), ("attn", attn, attn_ln)):
+            if kind is None:
+                continue
+            pre = f"lm.transformer.h.{l}.{loc}" + (".1" if (loc == "mlp" and kind == "normal") else "")
+            if ln:  # add_layernorm shifts the Sequential indices by one (adapters.py:16-25)
+                for i, j in ((2, 3), (0, 1)):
+                    for s in ("weight", "bias"):
+                        w[f"{pre}.adapter.{j}.{s}"] = w.pop(f"{pre}.adapter.{i}.{s}")
+                w[f"{pre}.adapter.0.weight"] = 1.0 + 0.1 * torch.randn(cfg.d, generator=g)
+                w[f"{pre}.adapter.0.bias"] = 0.1 * torch.randn(cfg.d, generator=g)
+            if kind == "scaled_parallel":
+                w[f"lm.transformer.h.{l}.{loc}.adapter_scale"] = torch.tensor([0.7 + 0.2 * l])
+    w16 = {k: v.to(torch.bfloat16) for k, v in w.items()}
+    x = (torch.randn(B, S, cfg.d, generator=g) * 0.5).to(torch.bfloat16)
+    labels = torch.randint(0, cfg.vocab, (B, S), generator=g)
+    labels[:, :2] = -100
+    labels[0, 7:] = -100
+    return cfg, w16, x, labels
+
+
+def c_lm_model(cfg, w16, keep, with_grads=True):
+    """mb200_gptj_model_ex over the oracle-named bf16 tensors; returns (struct, {param name: fp32 grad tensor})."""
+    grads = {}
+    w32 = {}
+
+    def adapter(prefix, kind):
+        a = AdapterExC()
+        if kind is None:
+            return a
+        ln = f"{prefix}.adapter.3.weight" in w16
+        i0 = 1 if ln else 0
+        names = {"wd": f"{prefix}.adapter.{i0}.weight", "bd": f"{prefix}.adapter.{i0}.bias",
+                 "wu": f"{prefix}.adapter.{i0 + 2}.weight", "bu": f"{prefix}.adapter.{i0 + 2}.bias"}
+        if ln:
+            names.update({"ln_g": f"{prefix}.adapter.0.weight", "ln_b": f"{prefix}.adapter.0.bias"})
+        for f, n in names.items():
+            setattr(a, f, w16[n].data_ptr())
+            if with_grads:
+                grads[n] = torch.full(w16[n].shape, 5.0, dtype=torch.float32)
+                setattr(a, "g_" + f, grads[n].data_ptr())
+        sk = prefix.rsplit(".1", 1)[0] + ".adapter_scale" if prefix.endswith(".1") else prefix + ".adapter_scale"
+        if sk in w16:  # the scale is read as fp32 from the arena's master copy
+            w32[sk] = w16[sk].float().contiguous()
+            a.scale = w32[sk].data_ptr()
+            if with_grads:
+                grads[sk] = torch.full((1,), 5.0, dtype=torch.float32)
+                a.g_scale = grads[sk].data_ptr()
+        return a
+
+    mk = cfg.mlp_adapter["adapter_type"] if cfg.mlp_adapter else None
+    ak = cfg.attn_adapter["adapter_type"] if cfg.attn_adapter else None
+    layers = (GptjLayerExC * cfg.n_layer)()
+    for l in range(cfg.n_layer):
+        p = f"lm.transformer.h.{l}"
+        attn = f"{p}.attn" + ("" if ak is None else (".attn_block" if ak == "normal" else ".module"))
+        mlp = f"{p}.mlp" + ("" if mk is None else (".0" if mk == "normal" else ".module"))
+        qkv = torch.cat([w16[f"{attn}.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], 0).contiguous()
+        keep.append(qkv)
+        L = layers[l]
+        L.ln1_g, L.ln1_b = w16[f"{p}.ln_1.weight"].data_ptr(), w16[f"{p}.ln_1.bias"].data_ptr()
+        L.w_qkv, L.w_out = qkv.data_ptr(), w16[f"{attn}.out_proj.weight"].data_ptr()
+        L.w_fc_in, L.b_fc_in = w16[f"{mlp}.fc_in.weight"].data_ptr(), w16[f"{mlp}.fc_in.bias"].data_ptr()
+        L.w_fc_out, L.b_fc_out = w16[f"{mlp}.fc_out.weight"].data_ptr(), w16[f"{mlp}.fc_out.bias"].data_ptr()
+        L.mlp_ad = adapter(f"{p}.mlp.1" if mk == "normal" else f"{p}.mlp", mk)
+        L.attn_ad = adapter(f"{p}.attn", ak)
+    m = GptjModelExC()
+    m.n_layer, m.d, m.n_head, m.rotary_dim, m.vocab, m.d_ff = cfg.n_layer, cfg.d, cfg.n_head, cfg.rotary_dim, cfg.vocab, 4 * cfg.d
+    m.mlp_adapter, m.attn_adapter = ADAPTER_KIND[mk], ADAPTER_KIND[ak]
+    m.mlp_adapter_r = cfg.d // cfg.mlp_adapter["downsample_factor"] if mk else 0
+    m.attn_adapter_r = cfg.d // cfg.attn_adapter["downsample_factor"] if ak else 0
+    m.ln_eps = cfg.ln_eps
+    m.layers = ctypes.cast(layers, ctypes.POINTER(GptjLayerExC))
+    m.lnf_g, m.lnf_b = w16["lm.transformer.ln_f.weight"].data_ptr(), w16["lm.transformer.ln_f.bias"].data_ptr()
+    m.w_lm, m.b_lm = w16["lm.lm_head.weight"].data_ptr(), w16["lm.lm_head.bias"].data_ptr()
+    keep += [layers, w32]
+    return m, grads
+
+
+def run_lm_emul(L, cfg, w16, x, labels, accumulate=0):
+    keep = []
+    m, grads = c_lm_model(cfg, w16, keep)
+    B, S = labels.shape
+    L.mb200_gptj_sched_workspace_bytes.restype = ctypes.c_size_t
+    n = L.mb200_gptj_sched_workspace_bytes(ctypes.byref(m), B, S)
+    assert n > 0, L.mb200_last_error().decode()
+    ws = torch.empty(n + 256, dtype=torch.uint8)
+    wsp = ctypes.c_void_p(ws.data_ptr() + (-ws.data_ptr()) % 256)
+    ldv = (cfg.vocab + 63) // 64 * 64
+    logits = torch.zeros(B * S, ldv, dtype=torch.bfloat16)
+    loss = torch.zeros(1, dtype=torch.float32)
+    rc = L.mb200_gptj_sched_forward(ctypes.byref(m), ptr(x), ptr(labels), ptr(logits), ctypes.c_int64(ldv), ptr(loss), B, S,
+                                    wsp, ctypes.c_size_t(n), None)
+    assert rc == 0, L.mb200_last_error().decode()
+    dx = torch.empty_like(x)
+    rc = L.mb200_gptj_sched_backward(ctypes.byref(m), ptr(dx), ctypes.c_float(1.0), accumulate, B, S, wsp,
+                                     ctypes.c_size_t(n), None)
+    assert rc == 0, L.mb200_last_error().decode()
+    return float(loss), logits[:, : cfg.vocab].reshape(B, S, cfg.vocab), dx, grads
+
+
+FORMS = [
+    (None, None, False, False),                                  # plain GPT-J
+    ("normal", None, False, False),                              # MAGMA_v1.yml
+    ("normal", "normal", False, False),                          # MAGMA_v2.yml
+    ("parallel", "parallel", False, False),
+    ("normal", "normal", True, True),                            # add_layernorm (adapters.py:16-17)
+    ("scaled_parallel", "scaled_parallel", False, False),        # adapter_scale (adapters.py:57-61)
+    ("scaled_parallel", "normal", True, True),
+    ("parallel", "scaled_parallel", True, False),
+]
+
+
+@pytest.mark.parametrize("mlp,attn,mlp_ln,attn_ln", FORMS)
+def test_gptj_schedule_matches_oracle_autograd_for_every_adapter_form(emul, mlp, attn, mlp_ln, attn_ln):
+    cfg, w16, x, labels = lm_case(mlp, attn, mlp_ln, attn_ln)
+    params = {k: v.float().requires_grad_(".adapter" in k) for k, v in w16.items()}
+    xf = x.float().requires_grad_(True)
+    loss_o, logits_o, _ = O.gptj_lm(xf, params, cfg, labels=labels)
+    loss_o.backward()
+    loss, logits, dx, grads = run_lm_emul(emul, cfg, w16, x, labels)
+    assert abs(loss - float(loss_o.detach())) < 2e-2
+    assert rel(logits, logits_o.detach()) < 3e-2
+    assert rel(dx, xf.grad) < 2.5e-2
+    want = {k for k, v in params.items() if v.requires_grad}
+    assert set(grads) == want
+    bad = {k: round(rel(g, params[k].grad), 4) for k, g in grads.items() if rel(g, params[k].grad) > 2.5e-2}
+    assert not bad, bad
+
+
+def test_gptj_schedule_accumulates_and_validates(emul):
+    cfg, w16, x, labels = lm_case("scaled_parallel", "normal", True, True, seed=2)
+    _, _, _, g0 = run_lm_emul(emul, cfg, w16, x, labels, accumulate=0)   # overwrite: the 5.0 fill must vanish
+    _, _, _, g1 = run_lm_emul(emul, cfg, w16, x, labels, accumulate=1)   # add onto the 5.0 fill
+    for k in g0:
+        assert torch.allclose(g1[k], g0[k] + 5.0, rtol=1e-4, atol=1e-4), k
+    # adapter_scale on a "normal" adapter is rejected (the reference has no such form)
+    keep = []
+    m, _ = c_lm_model(cfg, w16, keep)
+    one = torch.ones(1)
+    layers = ctypes.cast(m.layers, ctypes.POINTER(GptjLayerExC))
+    layers[0].attn_ad.scale = one.data_ptr()
+    emul.mb200_gptj_sched_workspace_bytes.restype = ctypes.c_size_t
+    assert emul.mb200_gptj_sched_workspace_bytes(ctypes.byref(m), 2, 12) == 0
+    assert b"parallel adapter forms only" in emul.mb200_last_error()

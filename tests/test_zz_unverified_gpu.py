@@ -235,3 +235,116 @@ def test_engine_checkpoint_resume_continues_the_same_trajectory(tmp_path):
     got = steps(eng2, 3)
     assert max(abs(a - b) for a, b in zip(got, want)) < 2e-3, (got, want)
     assert load_model(eng2, str(tmp_path / "missing")) == 0
+
+
+def _variant_weights(cfg, mlp, attn, mlp_ln, attn_ln, seed=5):
+    """Oracle-named weights for adapter forms with add_layernorm / adapter_scale (same construction as
+    tests/test_sched_emul_cpu.py::lm_case, on the GPU test geometry)."""
+    import torch
+
+    from oracle import magma_oracle as O
+    from tools.model_check import boost_adapters
+
+    w = boost_adapters(O.init_weights(cfg, seed=seed), True)
+    g = torch.Generator().manual_seed(seed + 7)
+    for l in range(cfg.n_layer):
+        for loc, kind, ln in (("mlp", mlp, mlp_ln), ("attn", attn, attn_ln)):
+            if kind is None:
+                continue
+            pre = f"lm.transformer.h.{l}.{loc}" + (".1" if (loc == "mlp" and kind == "normal") else "")
+            if ln:
+                for i, j in ((2, 3), (0, 1)):
+                    for s in ("weight", "bias"):
+                        w[f"{pre}.adapter.{j}.{s}"] = w.pop(f"{pre}.adapter.{i}.{s}")
+                w[f"{pre}.adapter.0.weight"] = 1.0 + 0.1 * torch.randn(cfg.d, generator=g)
+                w[f"{pre}.adapter.0.bias"] = 0.1 * torch.randn(cfg.d, generator=g)
+            if kind == "scaled_parallel":
+                w[f"lm.transformer.h.{l}.{loc}.adapter_scale"] = torch.tensor([0.7 + 0.2 * l])
+    return {k: v.to(torch.bfloat16).float() for k, v in w.items()}
+
+
+@pytest.mark.parametrize("mlp,attn,mlp_ln,attn_ln", [("normal", "normal", True, True),
+                                                     ("scaled_parallel", "scaled_parallel", False, False),
+                                                     ("scaled_parallel", "normal", True, True)])
+def test_adapter_forms_with_layernorm_and_scale_match_oracle(mlp, attn, mlp_ln, attn_ln):
+    """add_layernorm (adapters.py:16-17) and scaled_parallel (adapters.py:57-61) through csrc/gptj_sched.cu."""
+    import torch
+
+    from magma_b200.config import MultimodalConfig
+    from magma_b200.image_encoders import register_vit
+    from magma_b200.language_model import GPTJConfig
+    from magma_b200.magma import Magma
+    from oracle import magma_oracle as O
+    from tools.model_check import small_cfg
+
+    dev = torch.device("cuda:0")
+    S, B = 32, 3
+    cfg = small_cfg(mlp_adapter={"adapter_type": mlp, "downsample_factor": 4},
+                    attn_adapter={"adapter_type": attn, "downsample_factor": 8})
+    w16 = _variant_weights(cfg, mlp, attn, mlp_ln, attn_ln)
+    register_vit("clip_vit_tiny", cfg.vit_width, cfg.vit_layers, cfg.vit_heads, cfg.vit_patch, cfg.vit_image,
+                 cfg.vit_mlp, cfg.enc_out_dim)
+    ac = {"mlp": {"adapter_type": mlp, "downsample_factor": 4, "add_layernorm": mlp_ln},
+          "attention": {"adapter_type": attn, "downsample_factor": 8, "add_layernorm": attn_ln}}
+    mc = MultimodalConfig(batch_size=2, train_steps=1, encoder_name="clip_vit_tiny", adapter_config=ac,
+                          image_seq_len=cfg.image_seq_len, image_embed_dropout_prob=0.0, use_image_embed_layernorm=True,
+                          image_size=cfg.vit_image, seq_len=S)
+    mc._lm_config = GPTJConfig(vocab_size=cfg.vocab, hidden_size=cfg.d, num_layers=cfg.n_layer, num_heads=cfg.n_head,
+                               rotary_dim=cfg.rotary_dim)
+    model = Magma(mc, device=dev, init_seed=None)
+    model.eos_token, model.image_token = cfg.eos_token, cfg.image_token
+    missing, unexpected = model.load_state_dict(w16, strict=False)
+    missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
+    assert not missing and not unexpected, (missing, unexpected)
+    model.lm.invalidate()
+    model.lm.attach_arena(model.arena)
+    model.image_prefix.enc.invalidate()
+    model.eval()
+    assert model.lm._general_schedule()
+    images, captions = O.synthetic_batch(cfg, B, S, seed=11)
+    images = images.to(torch.bfloat16).float()
+    trainable = [k for k in w16 if ".adapter" in k or k.startswith(("image_prefix.proj", "image_prefix.ln"))]
+    params = {k: v.clone().requires_grad_(k in trainable) for k, v in w16.items()}
+    loss_o, logits_o, _ = O.magma_forward(images, captions, params, cfg)
+    loss_o.backward()
+    out = model(images.to(dev), captions.to(dev))
+    assert abs(float(out.loss) - float(loss_o.detach())) < 2e-2
+    assert _rel(out.logits, logits_o.detach()) < 3e-2
+    out.loss.backward()
+    sd = dict(model.named_parameters())
+    bad = {k: round(_rel(sd[k].grad, params[k].grad), 4) for k in trainable
+           if _rel(sd[k].grad, params[k].grad) > 5e-2}
+    assert not bad, bad
+
+
+def test_general_schedule_agrees_with_the_fast_runtime():
+    """Two schedules, same kernels: csrc/gptj_sched.cu (batched-GEMM attention) against engine.cu (fused attention)
+    on the MAGMA_v1 adapter form — loss, logits and every trainable gradient."""
+    import torch
+
+    from oracle import magma_oracle as O
+
+    dev = torch.device("cuda:0")
+    model, mc, cfg, _ = _build(dev, freeze_enc=True)
+    model.eval()
+    images, captions = O.synthetic_batch(cfg, 3, 32, seed=11)
+    x, c = images.to(dev).to(torch.bfloat16), captions.to(dev)
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    sd = dict(model.named_parameters())
+
+    def run():
+        for p in model.parameters():
+            p.grad = None
+        model.arena.grad.zero_()
+        out = model(x, c)
+        out.loss.backward()
+        return float(out.loss), out.logits.float().clone(), {n: sd[n].grad.clone() for n in names}
+
+    l0, lg0, g0 = run()
+    model.lm._force_general = True
+    model.lm.invalidate()
+    model.lm.attach_arena(model.arena)
+    l1, lg1, g1 = run()
+    assert abs(l0 - l1) < 5e-3 and _rel(lg1, lg0) < 1e-2
+    bad = {n: round(_rel(g1[n], g0[n]), 4) for n in names if _rel(g1[n], g0[n]) > 2e-2}
+    assert not bad, bad
