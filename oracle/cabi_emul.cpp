@@ -383,6 +383,227 @@ int mb200_cross_entropy(const void* logits_, int64_t ldv, const int64_t* labels,
   return 0;
 }
 
+// ---- remaining primitives, so that host-side Python schedules (image_prefix.py, adapters.py, the conv trunk of
+// image_encoders.py, arena.py) can be dry-run on CPU tensors through magma_b200/ops.py (tests/conftest.py::emul_ops) ----
+long long mb200_launch_count(void) { return 0; }
+int mb200_prof_enable(int) { return 0; }
+int mb200_prof_read(double* a, double* b, double* c, long long* n) {
+  *a = *b = *c = 0.0;
+  *n = 0;
+  return 0;
+}
+int mb200_set_gemm_sm_limit(int) { return 148; }
+
+int mb200_rope(void* qkv_, int64_t ld, int32_t rows, int32_t S, int32_t H, int32_t hd, int32_t rot, int32_t pos0,
+               int32_t inverse, void*) {  // rope_kernel: in place on q and k of a fused [rows][3][H][hd] buffer
+  EM_REQUIRE(rot % 2 == 0 && rot <= hd && rows > 0, MB200_E_SHAPE, "rope: bad rot / hd");
+  bf16_t* qkv = (bf16_t*)qkv_;
+  for (long long r = 0; r < rows; ++r)
+    for (int which = 0; which < 2; ++which)
+      for (int h = 0; h < H; ++h)
+        for (int p = 0; p < rot / 2; ++p) {
+          const float inv_freq = 1.0f / powf(10000.0f, (float)(2 * p) / (float)rot);
+          const float ang = (float)(pos0 + (int)(r % S)) * inv_freq;
+          const float cs = cosf(ang), sn = inverse ? -sinf(ang) : sinf(ang);
+          bf16_t* q = qkv + r * ld + (long long)which * H * hd + (long long)h * hd + 2 * p;
+          const float x = b2f(q[0]), y = b2f(q[1]);
+          q[0] = f2b(x * cs - y * sn);
+          q[1] = f2b(y * cs + x * sn);
+        }
+  return 0;
+}
+
+int mb200_build_labels(const int64_t* captions, int64_t ldc, int64_t* labels, int32_t B, int32_t S, int32_t L,
+                       int64_t eos, void*) {  // build_labels_kernel
+  EM_REQUIRE(B > 0 && S > 0 && L >= 0 && L <= S, MB200_E_SHAPE, "build_labels: need 0 <= L <= S");
+  for (int b = 0; b < B; ++b) {
+    int first = S;
+    for (int s = L; s < S; ++s)
+      if (captions[(long long)b * ldc + (s - L)] == eos) {
+        first = s;
+        break;
+      }
+    for (int s = 0; s < S; ++s) {
+      int64_t v = s < L ? -100 : captions[(long long)b * ldc + (s - L)];
+      if (s > first) v = -100;
+      labels[(long long)b * S + s] = v;
+    }
+  }
+  return 0;
+}
+
+int mb200_embed_assemble(const int64_t* captions, int64_t ldc, const void* wte_, const void* prefix_, int32_t L, void* x_,
+                         int32_t B, int32_t S, int32_t d, int32_t vocab, void*) {  // embed_assemble_kernel
+  EM_REQUIRE(d % 8 == 0 && L >= 0 && L <= S, MB200_E_SHAPE, "embed_assemble: bad d / L / S");
+  const bf16_t *wte = (const bf16_t*)wte_, *prefix = (const bf16_t*)prefix_;
+  bf16_t* x = (bf16_t*)x_;
+  for (int b = 0; b < B; ++b)
+    for (int s = 0; s < S; ++s) {
+      const bf16_t* src;
+      if (s < L) {
+        src = prefix + ((long long)b * L + s) * d;
+      } else {
+        long long tok = captions[(long long)b * ldc + (s - L)];
+        if (tok < 0 || tok >= vocab) tok = 0;
+        src = wte + tok * (long long)d;
+      }
+      memcpy(x + ((long long)b * S + s) * d, src, (size_t)d * 2);
+    }
+  return 0;
+}
+
+int mb200_embed_gather(const int64_t* ids, const void* wte_, void* out_, int32_t n, int32_t d, int32_t vocab, void*) {
+  EM_REQUIRE(d % 8 == 0 && n > 0, MB200_E_SHAPE, "embed_gather: bad n / d");
+  const bf16_t* wte = (const bf16_t*)wte_;
+  bf16_t* out = (bf16_t*)out_;
+  for (int r = 0; r < n; ++r) {
+    long long tok = ids[r];
+    if (tok < 0 || tok >= vocab) tok = 0;
+    memcpy(out + (long long)r * d, wte + tok * (long long)d, (size_t)d * 2);
+  }
+  return 0;
+}
+
+static inline uint32_t hash32(uint64_t k) {  // the counter-based hash of dropout_fwd_kernel
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+int mb200_dropout_fwd(const void* x_, void* y_, uint8_t* mask, int64_t n, float p, uint64_t seed, void*) {
+  EM_REQUIRE(p >= 0.f && p < 1.f, MB200_E_ARG, "dropout: p out of range");
+  const bf16_t* x = (const bf16_t*)x_;
+  bf16_t* y = (bf16_t*)y_;
+  const float scale = 1.f / (1.f - p);
+  for (int64_t i = 0; i < n; ++i) {
+    const float u = (float)(hash32(seed * 0x9E3779B97F4A7C15ULL + (uint64_t)i) >> 8) * (1.0f / 16777216.0f);
+    mask[i] = u >= p ? 1 : 0;
+    y[i] = f2b(mask[i] ? b2f(x[i]) * scale : 0.f);
+  }
+  return 0;
+}
+int mb200_dropout_apply(const void* x_, const uint8_t* mask, void* y_, int64_t n, float p, void*) {
+  const bf16_t* x = (const bf16_t*)x_;
+  bf16_t* y = (bf16_t*)y_;
+  const float scale = 1.f / (1.f - p);
+  for (int64_t i = 0; i < n; ++i) y[i] = f2b(mask[i] ? b2f(x[i]) * scale : 0.f);
+  return 0;
+}
+
+int mb200_argmax(const void* x_, int64_t ldx, int32_t rows, int32_t V, int64_t* out, void*) {  // lowest index wins ties
+  const bf16_t* x = (const bf16_t*)x_;
+  for (int r = 0; r < rows; ++r) {
+    float best = -INFINITY;
+    int bi = 0;
+    for (int j = 0; j < V; ++j) {
+      const float v = b2f(x[(long long)r * ldx + j]);
+      if (v > best) {
+        best = v;
+        bi = j;
+      }
+    }
+    out[r] = bi;
+  }
+  return 0;
+}
+
+int mb200_add(const void* a_, const void* b_, const void* c_, void* y_, int64_t n, void*) {
+  EM_REQUIRE(n % 8 == 0, MB200_E_SHAPE, "add: n must be a multiple of 8");
+  const bf16_t *a = (const bf16_t*)a_, *b = (const bf16_t*)b_, *c = (const bf16_t*)c_;
+  bf16_t* y = (bf16_t*)y_;
+  for (int64_t i = 0; i < n; ++i) y[i] = f2b(b2f(a[i]) + (b2f(b[i]) + (c ? b2f(c[i]) : 0.f)));
+  return 0;
+}
+
+int mb200_sumsq(const float* x, int64_t n, float* out, void*) {
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += (double)x[i] * x[i];
+  out[0] += (float)s;
+  return 0;
+}
+
+// torch.optim.AdamW semantics with global-norm clipping and the bf16 refresh   (adamw_kernel)
+int mb200_adamw_step(float* w, float* g, float* m1, float* m2, void* shadow_, int64_t n, float lr, float b1, float b2,
+                     float eps, float wd, float grad_scale, const float* gnorm_sq, float max_norm, int32_t step,
+                     int32_t zero_grad, void*) {
+  EM_REQUIRE(step >= 1, MB200_E_ARG, "adamw: step must be >= 1");
+  EM_REQUIRE(n % 4 == 0, MB200_E_ALIGN, "adamw: n must be a multiple of 4");
+  bf16_t* shadow = (bf16_t*)shadow_;
+  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  float coef = grad_scale;
+  if (gnorm_sq != nullptr && max_norm > 0.f) coef *= fminf(1.f, max_norm / (sqrtf(*gnorm_sq) * grad_scale + 1e-6f));
+  const float inv_sqrt_bc2 = 1.f / sqrtf(bc2), stp = lr / bc1, decay = 1.f - lr * wd;
+  for (int64_t i = 0; i < n; ++i) {
+    const float gi = g[i] * coef;
+    float wi = w[i] * decay;
+    m1[i] = b1 * m1[i] + (1.f - b1) * gi;
+    m2[i] = b2 * m2[i] + (1.f - b2) * gi * gi;
+    wi -= stp * (m1[i] / (sqrtf(m2[i]) * inv_sqrt_bc2 + eps));
+    w[i] = wi;
+    if (shadow) shadow[i] = f2b(wi);
+    if (zero_grad) g[i] = 0.f;
+  }
+  return 0;
+}
+
+int mb200_cast_f32_to_bf16(const float* src, void* dst_, int64_t n, void*) {
+  bf16_t* dst = (bf16_t*)dst_;
+  for (int64_t i = 0; i < n; ++i) dst[i] = f2b(src[i]);
+  return 0;
+}
+int mb200_cast_bf16_to_f32(const void* src_, float* dst, int64_t n, void*) {
+  const bf16_t* src = (const bf16_t*)src_;
+  for (int64_t i = 0; i < n; ++i) dst[i] = b2f(src[i]);
+  return 0;
+}
+
+// conv-trunk support   (nchw_to_nhwc8_kernel / im2col3x3_kernel / avgpool_nhwc_kernel)
+int mb200_nchw_to_nhwc8(const void* src_, void* dst_, int32_t B, int32_t C, int32_t H, int32_t W, void*) {
+  EM_REQUIRE(C >= 1 && C <= 8 && B > 0 && H > 0 && W > 0, MB200_E_SHAPE, "nchw_to_nhwc8: bad shape");
+  const bf16_t* src = (const bf16_t*)src_;
+  bf16_t* dst = (bf16_t*)dst_;
+  const long long hw = (long long)H * W;
+  for (long long b = 0; b < B; ++b)
+    for (long long px = 0; px < hw; ++px)
+      for (int c = 0; c < 8; ++c) dst[(b * hw + px) * 8 + c] = c < C ? src[(b * C + c) * hw + px] : f2b(0.f);
+  return 0;
+}
+int mb200_im2col3x3(const void* src_, void* dst_, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, void*) {
+  EM_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2), MB200_E_SHAPE,
+             "im2col3x3: bad shape / stride");
+  const bf16_t* src = (const bf16_t*)src_;
+  bf16_t* dst = (bf16_t*)dst_;
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  for (long long b = 0; b < B; ++b)
+    for (int ho = 0; ho < Ho; ++ho)
+      for (int wo = 0; wo < Wo; ++wo)
+        for (int tap = 0; tap < 9; ++tap) {
+          const int hi = ho * stride - 1 + tap / 3, wi = wo * stride - 1 + tap % 3;
+          bf16_t* d = dst + ((((b * Ho + ho) * Wo + wo) * 9) + tap) * C;
+          if (hi >= 0 && hi < H && wi >= 0 && wi < W) memcpy(d, src + ((b * H + hi) * W + wi) * C, (size_t)C * 2);
+          else memset(d, 0, (size_t)C * 2);
+        }
+  return 0;
+}
+int mb200_avgpool_nhwc(const void* src_, void* dst_, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void*) {
+  EM_REQUIRE(B > 0 && k >= 1 && H >= k && W >= k && C > 0 && C % 8 == 0, MB200_E_SHAPE, "avgpool_nhwc: bad shape");
+  const bf16_t* src = (const bf16_t*)src_;
+  bf16_t* dst = (bf16_t*)dst_;
+  const int Ho = H / k, Wo = W / k;
+  for (long long b = 0; b < B; ++b)
+    for (int ho = 0; ho < Ho; ++ho)
+      for (int wo = 0; wo < Wo; ++wo)
+        for (int c = 0; c < C; ++c) {
+          float acc = 0.f;
+          for (int dy = 0; dy < k; ++dy)
+            for (int dx = 0; dx < k; ++dx) acc += b2f(src[((b * H + ho * k + dy) * W + wo * k + dx) * C + c]);
+          dst[((b * Ho + ho) * Wo + wo) * C + c] = f2b(acc / (float)(k * k));
+        }
+  return 0;
+}
+
 // images [B,3,R,R] -> patches [B*g*g][ldp], column order (c, py, px)   (patchify_kernel)
 int mb200_patchify(const void* img_, void* patches_, int64_t ldp, int32_t B, int32_t R, int32_t P, void*) {
   EM_REQUIRE(R % P == 0 && ldp >= 3 * P * P, MB200_E_SHAPE, "patchify: bad geometry");

@@ -31,3 +31,23 @@ def oracle_cfg_from_record(rec):
         enc_out_dim=vit["projection_dim"], use_image_embed_layernorm=True, vit_width=vit["hidden_size"],
         vit_layers=vit["num_hidden_layers"], vit_heads=vit["num_attention_heads"], vit_patch=vit["patch_size"],
         vit_image=vit["image_size"], vit_mlp=vit["intermediate_size"], eos_token=rec["eos"], image_token=rec["cls"])
+
+
+@pytest.fixture
+def emul_ops(monkeypatch):
+    """Host-side dry run: point magma_b200/ops.py at oracle/cabi_emul.cpp (the CPU emulation of the primitive C-ABI
+    operators) for the duration of ONE test, so the Python schedules built on ops.* (image_prefix.py, adapters.py, the
+    conv trunk, arena.py) run on CPU tensors and can be held to the oracle. Test infrastructure only: outside this
+    fixture `magma_b200._lib.lib()` loads the CUDA library or raises."""
+    import ctypes
+
+    from magma_b200 import _lib, ops
+    from oracle import build_emul
+
+    L = ctypes.CDLL(build_emul.build())
+    L.mb200_last_error.restype = ctypes.c_char_p
+    L.mb200_version.restype = ctypes.c_int
+    L.mb200_launch_count.restype = ctypes.c_longlong
+    monkeypatch.setattr(_lib, "_lib", L)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    return L
