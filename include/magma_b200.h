@@ -192,6 +192,21 @@ int mb200_nchw_to_nhwc8(const void* src, void* dst, int32_t B, int32_t C, int32_
 int mb200_im2col3x3(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
                     void* stream);
 int mb200_avgpool_nhwc(const void* src, void* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* stream);
+/* Conv-trunk TRAINING (freeze_img_encoder: false with a CLIP ModifiedResNet — what MAGMA_v1.yml / MAGMA_v2.yml ship):
+ * BatchNorm in training mode and the convolution backward pass on NHWC bf16 activations [rows = B*H*W][C].
+ *   col_moments   out1[c] = sum_r u', out2[c] = sum_r u' * v, u' = u * 1[mask > 0] (mask optional). Batch statistics with
+ *                 u = v = x; the two BatchNorm-backward reductions with u = dy, v = x, mask = the ReLU output.
+ *   channel_affine y = relu?(a1[c] * x1 * 1[mask > 0] + a2[c] * x2 + c0[c] + res) with fp32 per-channel coefficients
+ *                 (x2 / a2, c0, mask, res optional): BatchNorm forward (+ residual + ReLU), BatchNorm backward, ReLU
+ *                 backward.
+ *   col2im3x3     adjoint of mb200_im2col3x3: dcols [B*Ho*Wo][9*C] -> dx [B,H,W,C].
+ *   avgpool_nhwc_bwd adjoint of mb200_avgpool_nhwc: dy [B,H/k,W/k,C] -> dx [B,H,W,C]. */
+int mb200_col_moments(const void* u, int64_t ldu, const void* v, int64_t ldv, const void* mask, int64_t ldm, int32_t rows,
+                      int32_t cols, float* out1, float* out2, void* stream);
+int mb200_channel_affine(const void* x1, const float* a1, const void* x2, const float* a2, const float* c0,
+                         const void* mask, const void* res, int32_t relu, void* y, int64_t rows, int32_t C, void* stream);
+int mb200_col2im3x3(const void* dcols, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, void* stream);
+int mb200_avgpool_nhwc_bwd(const void* dy, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* stream);
 /* torch.argmax(logits.float(), -1) (magma/sampling.py:92,97): lowest index wins ties. */
 int mb200_argmax(const void* x, int64_t ldx, int32_t rows, int32_t V, int64_t* out, void* stream);
 /* One sampled token per row for temperature > 0 (magma/sampling.py:97-105): top_k_filter (:22-30, off when top_k == 0),

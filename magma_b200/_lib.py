@@ -202,4 +202,5 @@ EXPORTED_SYMBOLS = [
     "mb200_vit_train_workspace_bytes", "mb200_vit_forward_train", "mb200_vit_backward", "mb200_quick_gelu_bwd",
     "mb200_layernorm_param_grad_rows", "mb200_set_gemm_sm_limit", "mb200_scale_add", "mb200_dot",
     "mb200_gptj_sched_workspace_bytes", "mb200_gptj_sched_forward", "mb200_gptj_sched_backward",
+    "mb200_col_moments", "mb200_channel_affine", "mb200_col2im3x3", "mb200_avgpool_nhwc_bwd",
 ]

@@ -788,6 +788,151 @@ __global__ void quick_gelu_bwd_kernel(const bf16* dy, const bf16* __restrict__ p
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Conv-trunk TRAINING support (freeze_img_encoder: false with a CLIP ModifiedResNet — the configuration MAGMA_v1.yml
+// and MAGMA_v2.yml ship): BatchNorm in training mode and the convolution backward pass, NHWC bf16, HBM-bound.
+//   col_moments_kernel      per-channel sum(u') and sum(u' * v), u' = u * 1[mask > 0]:  batch statistics (u = v = x)
+//                           and the two BatchNorm-backward reductions (u = dy, v = x)
+//   channel_affine_kernel   y = relu?(a1[c] * x1 * 1[mask > 0] + a2[c] * x2 + c0[c] + res): BatchNorm forward
+//                           (+ residual + ReLU), BatchNorm backward, ReLU backward — coefficients are per channel, fp32
+//   col2im3x3_kernel        adjoint of im2col3x3_kernel (3x3, padding 1, stride 1|2): gather form, fp32 accumulation
+//   avgpool_nhwc_bwd_kernel adjoint of avgpool_nhwc_kernel
+// ---------------------------------------------------------------------------------------------
+static constexpr int kMomRows = 128;
+__global__ void __launch_bounds__(256)
+col_moments_kernel(const bf16* __restrict__ u, long long ldu, const bf16* __restrict__ v, long long ldv,
+                   const bf16* __restrict__ mask, long long ldm, int rows, int cols, float* __restrict__ out1,
+                   float* __restrict__ out2) {
+  __shared__ float p1[8][64], p2[8][64];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 64 + cl * 2;
+  const int r0 = blockIdx.y * kMomRows;
+  const int r1 = min(rows, r0 + kMomRows);
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (c0 < cols) {
+    for (int r = r0 + rg; r < r1; r += 8) {
+      float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(u + (long long)r * ldu + c0));
+      const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + (long long)r * ldv + c0));
+      if (mask) {
+        const float2 m = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(mask + (long long)r * ldm + c0));
+        if (!(m.x > 0.f)) x.x = 0.f;
+        if (!(m.y > 0.f)) x.y = 0.f;
+      }
+      a0 += x.x;
+      a1 += x.y;
+      b0 += x.x * y.x;
+      b1 += x.y * y.y;
+    }
+  }
+  p1[rg][cl * 2] = a0;
+  p1[rg][cl * 2 + 1] = a1;
+  p2[rg][cl * 2] = b0;
+  p2[rg][cl * 2 + 1] = b1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int j = threadIdx.x & 63;
+    const int c = blockIdx.x * 64 + j;
+    float s = 0.f;
+    if (threadIdx.x < 64) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += p1[q][j];
+      if (c < cols) atomicAdd(out1 + c, s);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += p2[q][j];
+      if (c < cols) atomicAdd(out2 + c, s);
+    }
+  }
+}
+
+__global__ void channel_affine_kernel(const bf16* __restrict__ x1, const float* __restrict__ a1,
+                                      const bf16* __restrict__ x2, const float* __restrict__ a2,
+                                      const float* __restrict__ c0, const bf16* __restrict__ mask,
+                                      const bf16* __restrict__ res, int relu, bf16* __restrict__ y, long long rows, int C) {
+  const int cv = C >> 3;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    float f[8], t[8];
+    unpack8(reinterpret_cast<const uint4*>(x1)[i], f);
+    if (mask) {
+      unpack8(reinterpret_cast<const uint4*>(mask)[i], t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (!(t[e] > 0.f)) f[e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = f[e] * __ldg(a1 + c + e) + (c0 ? __ldg(c0 + c + e) : 0.f);
+    if (x2) {
+      unpack8(reinterpret_cast<const uint4*>(x2)[i], t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += t[e] * __ldg(a2 + c + e);
+    }
+    if (res) {
+      unpack8(reinterpret_cast<const uint4*>(res)[i], t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += t[e];
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(f);
+  }
+}
+
+// dcols [B*Ho*Wo][9*C] -> dx [B,H,W,C]: dx[b,h,w] = sum over taps (kh,kw) with ho*s - 1 + kh = h, wo*s - 1 + kw = w
+__global__ void col2im3x3_kernel(const bf16* __restrict__ dcols, bf16* __restrict__ dx, int B, int H, int W, int C,
+                                 int stride, int Ho, int Wo) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    long long t = i / cv;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const long long b = t / H;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hn = h + 1 - kh;
+      if (hn < 0 || hn % stride != 0 || hn / stride >= Ho) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wn = w + 1 - kw;
+        if (wn < 0 || wn % stride != 0 || wn / stride >= Wo) continue;
+        const long long row = (b * Ho + hn / stride) * Wo + wn / stride;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dcols + (row * 9 + (kh * 3 + kw)) * C) + c8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    }
+    reinterpret_cast<uint4*>(dx)[i] = pack8(acc);
+  }
+}
+
+__global__ void avgpool_nhwc_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int H, int W, int C,
+                                        int k) {
+  const int cv = C >> 3, Ho = H / k, Wo = W / k;
+  const long long total = (long long)B * H * W * cv;
+  const float inv = 1.f / (float)(k * k);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    long long t = i / cv;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const long long b = t / H;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (h / k < Ho && w / k < Wo) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((b * Ho + h / k) * Wo + w / k) * C) + c8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] *= inv;
+    }
+    reinterpret_cast<uint4*>(dx)[i] = pack8(f);
+  }
+}
+
 // out = s[0] * u + r1 + r2 (r1 / r2 optional; s == nullptr means 1): the `* adapter_scale` of ParallelAdapter.forward
 // (magma/adapters.py:63-66,85-92) with the block's residual sum folded in. s is a DEVICE scalar (a trainable parameter).
 __global__ void scale_add_kernel(const bf16* __restrict__ u, const float* __restrict__ s, const bf16* __restrict__ r1,
@@ -909,6 +1054,58 @@ extern "C" int mb200_layernorm_param_grad_rows(const void* dy, int64_t lddy, con
                                                                    dgamma, dbeta, rows, d);
     MB_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" int mb200_col_moments(const void* u, int64_t ldu, const void* v, int64_t ldv, const void* mask, int64_t ldm,
+                                 int32_t rows, int32_t cols, float* out1, float* out2, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(rows > 0 && cols > 0 && cols % 2 == 0 && ldu % 2 == 0 && ldv % 2 == 0 && (!mask || ldm % 2 == 0),
+             MB200_E_ALIGN, "col_moments: cols and row strides must be even");
+  MB_CUDA(cudaMemsetAsync(out1, 0, (size_t)cols * sizeof(float), ST(stream)));
+  MB_CUDA(cudaMemsetAsync(out2, 0, (size_t)cols * sizeof(float), ST(stream)));
+  dim3 grid((cols + 63) / 64, (rows + kMomRows - 1) / kMomRows);
+  col_moments_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)u, ldu, (const bf16*)v, ldv, (const bf16*)mask, ldm, rows,
+                                                   cols, out1, out2);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_channel_affine(const void* x1, const float* a1, const void* x2, const float* a2, const float* c0,
+                                    const void* mask, const void* res, int32_t relu, void* y, int64_t rows, int32_t C,
+                                    void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && x1 && a1 && y && (!x2 || a2), MB200_E_ARG,
+             "channel_affine: C must be a multiple of 8, x1 / a1 / y non-null, a2 given with x2");
+  MB_REQUIRE(((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(mask) |
+               reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, MB200_E_ALIGN,
+             "channel_affine: pointers must be 16-byte aligned");
+  channel_affine_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, ST(stream)>>>(
+      (const bf16*)x1, a1, (const bf16*)x2, a2, c0, (const bf16*)mask, (const bf16*)res, relu, (bf16*)y, rows, C);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_col2im3x3(const void* dcols, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
+                               void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2), MB200_E_SHAPE,
+             "col2im3x3: B=%d H=%d W=%d C=%d (multiple of 8) stride=%d (1 or 2)", B, H, W, C, stride);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  col2im3x3_kernel<<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)dcols, (bf16*)dx, B,
+                                                                                          H, W, C, stride, Ho, Wo);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_avgpool_nhwc_bwd(const void* dy, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k,
+                                      void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(B > 0 && k >= 1 && H >= k && W >= k && C > 0 && C % 8 == 0, MB200_E_SHAPE,
+             "avgpool_nhwc_bwd: B=%d H=%d W=%d C=%d k=%d", B, H, W, C, k);
+  avgpool_nhwc_bwd_kernel<<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)dy, (bf16*)dx,
+                                                                                                B, H, W, C, k);
+  MB_LAUNCH_CHECK();
   return 0;
 }
 

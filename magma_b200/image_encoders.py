@@ -346,10 +346,41 @@ class _Bottleneck(nn.Module):
                                                          ("1", _BatchNorm(planes * 4, device))]))
 
 
+class _ResNetTrainFn(torch.autograd.Function):
+    """feats = trunk(images) with BatchNorm in TRAINING mode and the hand-scheduled backward of
+    B200ModifiedResNet._train_backward (`freeze_img_encoder: false` with a conv trunk — MAGMA_v1.yml / MAGMA_v2.yml).
+    Parameter gradients go straight into the arena; `anchor` is one trainable parameter (the pixels carry no gradient)."""
+
+    @staticmethod
+    def forward(ctx, enc, x, anchor):
+        feats, tape = enc._train_forward(x)
+        enc._generation += 1
+        ctx.enc, ctx.tape, ctx.generation = enc, tape, enc._generation
+        return feats
+
+    @staticmethod
+    def backward(ctx, dfeats):
+        enc = ctx.enc
+        enc._train_backward(ctx.tape, dfeats.to(torch.bfloat16).contiguous())
+        ctx.tape = None
+        return None, None, None
+
+
 class B200ModifiedResNet(nn.Module):
     """CLIP ModifiedResNet trunk with openai/CLIP state-dict names (conv1..3 / bn1..3, layer{1..4}.{i}.{conv1,bn1,
     conv2,bn2,conv3,bn3,downsample.{0,1}}); `attnpool` is the reshape "b d h w -> b (h w) d" of
-    magma/image_encoders.py:69-74, so forward returns [b, (R/32)^2, width*32]. Forward only (frozen encoder)."""
+    magma/image_encoders.py:69-74, so forward returns [b, (R/32)^2, width*32].
+
+    Frozen (the measured configuration): eval-mode BatchNorm folded into the packed weights, one CUDA graph per batch
+    size. Trainable (`freeze_img_encoder: false`, what MAGMA_v1.yml / v2.yml ship): BatchNorm in training mode (batch
+    statistics by `col_moments`, normalisation + residual + ReLU by `channel_affine`, running statistics updated with
+    momentum 0.1) and a hand-scheduled backward — BatchNorm / ReLU backward from the same two kernels, convolution
+    wgrad and dgrad as GEMMs over the saved im2col matrix (MN-major operands), `col2im3x3` and `avgpool_nhwc_bwd` as
+    the adjoints of the layout kernels. NOT YET RUN ON A B200; dry-run on the CPU against the
+    oracle's autograd in tests/test_host_dryrun_cpu.py."""
+
+    supports_training = True
+    bn_momentum = 0.1
 
     def __init__(self, layers, width, input_resolution, device=None):
         super().__init__()
@@ -371,6 +402,154 @@ class B200ModifiedResNet(nn.Module):
         self._packed = None
         self._graphs = {}
         self._splitk_ws = None
+        self._arena = None
+        self._generation = 0
+
+    def attach_arena(self, arena):
+        self._arena = arena
+        self._packed = None
+        self._graphs = {}
+
+    def _trainable(self):
+        flags = [p.requires_grad for p in self.parameters()]
+        if any(flags) and not all(flags):
+            raise MB200Error("the conv trunk trains all of its parameters or none (mixed requires_grad is not supported)")
+        return all(flags)
+
+    # ---- training path -------------------------------------------------------------------------------------------
+    def _w16(self, p):
+        """bf16 values of a (trainable, fp32) parameter: the arena's compute copy when there is one."""
+        if self._arena is not None and p.requires_grad:
+            return self._arena.shadow_of(p)
+        return p.data.to(torch.bfloat16)
+
+    def _pack_conv(self, conv, pad_cin_to=0):
+        """[Cout, Cin, k, k] -> bf16 [Cout, k*k*Cin] in the (kh, kw, c) column order im2col3x3 writes."""
+        w = self._w16(conv.weight)
+        if pad_cin_to and w.shape[1] < pad_cin_to:
+            w = torch.cat([w, w.new_zeros(w.shape[0], pad_cin_to - w.shape[1], *w.shape[2:])], 1)
+        return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+    def _put_grad(self, p, value, acc):
+        """Write / accumulate an fp32 gradient (parameter shape) for p: into the arena's view, or p.grad without one."""
+        value = value.to(torch.float32)
+        if self._arena is not None:
+            g = self._arena.grad_of(p)
+            g.add_(value) if acc else g.copy_(value)
+        else:
+            p.grad = value.clone() if (p.grad is None or not acc) else p.grad + value
+
+    def _conv_bn_fwd(self, tape, t, conv, bn, k, stride, relu, res=None, pad_cin_to=0, need_dx=True):
+        """conv (no bias) -> BatchNorm(batch statistics) [-> + res] [-> ReLU] on NHWC t; records what backward needs."""
+        B, H, W, Cin = t.shape
+        wp = self._pack_conv(conv, pad_cin_to)
+        if k == 3:
+            cols, Ho, Wo = ops.im2col3x3(t, stride)
+        else:
+            cols, Ho, Wo = t.reshape(-1, Cin), H, W
+        z = ops.gemm(cols, wp)                                    # conv output, [R, Cout] bf16
+        R = z.shape[0]
+        s1, s2 = ops.col_moments(z, z)                            # sum z, sum z^2 per channel (fp32)
+        mean = s1 / R
+        var = (s2 / R - mean * mean).clamp_min_(0.0)
+        rstd = torch.rsqrt(var + bn.eps)
+        gamma, beta = bn.weight.data.float(), bn.bias.data.float()
+        scale = (gamma * rstd).contiguous()
+        shift = (beta - mean * scale).contiguous()
+        res2 = res.reshape(R, -1) if res is not None else None
+        y = ops.channel_affine(z, scale, c0=shift, res=res2, relu=relu)
+        with torch.no_grad():                                     # nn.BatchNorm2d running statistics (unbiased variance)
+            m = self.bn_momentum
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (R / max(R - 1, 1)), alpha=m)
+            bn.num_batches_tracked += 1
+        tape.append({"conv": conv, "bn": bn, "k": k, "stride": stride, "in_shape": (B, H, W, Cin), "cols": cols, "wp": wp,
+                     "z": z, "mean": mean, "rstd": rstd, "gamma": gamma, "y": y if relu else None,
+                     "has_res": res is not None, "pad": pad_cin_to, "need_dx": need_dx})
+        return y.view(B, Ho, Wo, -1)
+
+    def _conv_bn_bwd(self, rec, dy, acc):
+        """dy: gradient w.r.t. the unit's output [R, Cout]. Returns (gradient w.r.t. the NHWC input or None, gradient
+        w.r.t. the residual input or None)."""
+        z, mean, rstd, gamma, mask = rec["z"], rec["mean"], rec["rstd"], rec["gamma"], rec["y"]
+        R, Cout = z.shape
+        s1, t = ops.col_moments(dy, z, mask)                      # sum dy', sum dy' * z   (dy' = dy * 1[y > 0])
+        s2 = rstd * (t - mean * s1)                               # sum dy' * xhat
+        self._put_grad(rec["bn"].weight, s2, acc)
+        self._put_grad(rec["bn"].bias, s1, acc)
+        a = gamma * rstd
+        k2 = a * rstd * s2 / R
+        dz = ops.channel_affine(dy, a.contiguous(), x2=z, a2=(-k2).contiguous(), c0=(k2 * mean - a * s1 / R).contiguous(),
+                                mask=mask)                        # a * (dy' - s1/R - xhat * s2/R)
+        dres = None
+        if rec["has_res"]:
+            dres = dy if mask is None else ops.channel_affine(dy, torch.ones_like(a), mask=mask)
+        conv, k, pad = rec["conv"], rec["k"], rec["pad"]
+        B, H, W, Cin = rec["in_shape"]
+        dwp = ops.gemm(dz, rec["cols"], a_mn=True, b_mn=True, out_dtype=torch.float32)   # [Cout, k*k*Cin] = dz^T cols
+        dw = dwp.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+        self._put_grad(conv.weight, dw[:, : conv.weight.shape[1]] if pad else dw, acc)
+        if not rec["need_dx"]:
+            return None, dres
+        dcols = ops.gemm(dz, rec["wp"], b_mn=True)                # [R, k*k*Cin] = dz Wp
+        dx = ops.col2im3x3(dcols, B, H, W, Cin, rec["stride"]) if k == 3 else dcols.view(B, H, W, Cin)
+        return dx, dres
+
+    def _train_forward(self, x):
+        if self._arena is not None:
+            self._arena.sync_shadow()
+        self._packed = None  # the folded (eval) weights go stale with every optimizer step
+        B = x.shape[0]
+        tape = {"stem": [], "blocks": []}
+        t = ops.nchw_to_nhwc8(x)
+        t = self._conv_bn_fwd(tape["stem"], t, self.conv1, self.bn1, 3, 2, True, pad_cin_to=8, need_dx=False)
+        t = self._conv_bn_fwd(tape["stem"], t, self.conv2, self.bn2, 3, 1, True)
+        t = self._conv_bn_fwd(tape["stem"], t, self.conv3, self.bn3, 3, 1, True)
+        tape["stem_pool_in"] = t.shape
+        t = ops.avgpool_nhwc(t, 2)
+        for blk in self.blocks():
+            rec = {"units": [], "stride": blk.stride, "in_shape": t.shape, "ds": blk.downsample is not None}
+            out = self._conv_bn_fwd(rec["units"], t, blk.conv1, blk.bn1, 1, 1, True)
+            out = self._conv_bn_fwd(rec["units"], out, blk.conv2, blk.bn2, 3, 1, True)
+            rec["pool_in"] = out.shape
+            if blk.stride > 1:
+                out = ops.avgpool_nhwc(out, blk.stride)
+            idn = t
+            if blk.downsample is not None:
+                if blk.stride > 1:
+                    idn = ops.avgpool_nhwc(t, blk.stride)
+                idn = self._conv_bn_fwd(rec["units"], idn, blk.downsample[1], blk.downsample[2], 1, 1, False)
+            t = self._conv_bn_fwd(rec["units"], out, blk.conv3, blk.bn3, 1, 1, True, res=idn)  # relu(bn3(conv3) + idn)
+            tape["blocks"].append(rec)
+        return t.reshape(B, -1, t.shape[-1]), tape
+
+    def _train_backward(self, tape, dfeats):
+        ar = self._arena
+        acc = bool(getattr(ar, "_accumulate_current", False)) if ar is not None else False
+        g = dfeats.reshape(-1, dfeats.shape[-1])                  # [B*h*w, C]: NHWC rows, like the forward reshape
+        for rec in reversed(tape["blocks"]):
+            units = rec["units"]
+            u1, u2, u3 = units[0], units[1], units[-1]
+            d_out, d_idn = self._conv_bn_bwd(u3, g, acc)
+            if rec["stride"] > 1:
+                _, H, W, _ = rec["pool_in"]
+                d_out = ops.avgpool_nhwc_bwd(d_out, H, W, rec["stride"])
+            d2, _ = self._conv_bn_bwd(u2, d_out.reshape(-1, d_out.shape[-1]), acc)
+            d1, _ = self._conv_bn_bwd(u1, d2.reshape(-1, d2.shape[-1]), acc)
+            Bx, Hx, Wx, Cx = rec["in_shape"]
+            if rec["ds"]:
+                dd, _ = self._conv_bn_bwd(units[2], d_idn, acc)
+                if rec["stride"] > 1:
+                    dd = ops.avgpool_nhwc_bwd(dd, Hx, Wx, rec["stride"])
+            else:
+                dd = d_idn
+            g = ops.add(d1.reshape(-1, Cx), dd.reshape(-1, Cx))
+        _, H, W, C = tape["stem_pool_in"]
+        g = ops.avgpool_nhwc_bwd(g.view(-1, H // 2, W // 2, C), H, W, 2)
+        for rec in reversed(tape["stem"]):
+            g, _ = self._conv_bn_bwd(rec, g.reshape(-1, g.shape[-1]), acc)
+        if ar is not None:
+            ar.publish_grads()
 
     @torch.no_grad()
     def init_weights(self, seed=0):
@@ -412,13 +591,14 @@ class B200ModifiedResNet(nn.Module):
 
     def forward(self, x):
         """[b, 3, R, R] -> [b, (R/32)^2, width*32]."""
-        if any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
-            raise MB200Error("training the image encoder (freeze_img_encoder: false) is not supported: the conv trunk "
-                             "runs with eval-mode BatchNorm folded into its weights and has no backward pass")
         B, C, R, R2 = x.shape
         if C != 3 or R != self.input_resolution or R2 != R:
             raise ValueError(f"expected [b,3,{self.input_resolution},{self.input_resolution}], got {tuple(x.shape)}")
         x = x.to(device=self._device, dtype=torch.bfloat16).contiguous()
+        if self._trainable():
+            if self.training and torch.is_grad_enabled():
+                return _ResNetTrainFn.apply(self, x, self.conv1.weight)   # BatchNorm in training mode + backward
+            return self._forward_eager(x)  # eval: running statistics, folded from the current fp32 parameters
         if os.environ.get("MB200_RESNET_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing():
             return self._forward_graphed(x)
         return self._forward_eager(x)

@@ -311,6 +311,49 @@ def avgpool_nhwc(x, k):
     return y
 
 
+def col_moments(u, v, mask=None):
+    """Per-channel (sum u', sum u' * v) over the rows of [rows, C] bf16 tensors, u' = u * 1[mask > 0]; fp32 [C] each."""
+    rows, C = u.shape
+    assert u.dtype == v.dtype == torch.bfloat16 and v.shape == u.shape and u.stride(1) == 1 and v.stride(1) == 1
+    o1 = torch.empty(C, dtype=torch.float32, device=u.device)
+    o2 = torch.empty(C, dtype=torch.float32, device=u.device)
+    check(lib().mb200_col_moments(_ptr(u), ctypes.c_int64(u.stride(0)), _ptr(v), ctypes.c_int64(v.stride(0)), _ptr(mask),
+                                  ctypes.c_int64(mask.stride(0) if mask is not None else 0), rows, C, _ptr(o1), _ptr(o2),
+                                  _stream()))
+    return o1, o2
+
+
+def channel_affine(x1, a1, x2=None, a2=None, c0=None, mask=None, res=None, relu=False):
+    """y = relu?(a1[c] * x1 * 1[mask > 0] + a2[c] * x2 + c0[c] + res) over contiguous [rows, C] bf16 tensors with fp32
+    per-channel coefficients (BatchNorm forward / backward, ReLU backward)."""
+    rows, C = x1.shape
+    for t in (x1, x2, mask, res):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == x1.shape)
+    for t in (a1, a2, c0):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == C)
+    y = torch.empty_like(x1)
+    check(lib().mb200_channel_affine(_ptr(x1), _ptr(a1), _ptr(x2), _ptr(a2), _ptr(c0), _ptr(mask), _ptr(res), int(relu),
+                                     _ptr(y), ctypes.c_int64(rows), C, _stream()))
+    return y
+
+
+def col2im3x3(dcols, B, H, W, C, stride=1):
+    """Adjoint of im2col3x3: [B*Ho*Wo, 9*C] bf16 -> [B, H, W, C] bf16."""
+    assert dcols.dtype == torch.bfloat16 and dcols.is_contiguous() and dcols.shape[1] == 9 * C
+    dx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dcols.device)
+    check(lib().mb200_col2im3x3(_ptr(dcols), _ptr(dx), B, H, W, C, stride, _stream()))
+    return dx
+
+
+def avgpool_nhwc_bwd(dy, H, W, k):
+    """Adjoint of avgpool_nhwc: [B, H//k, W//k, C] -> [B, H, W, C]."""
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and dy.ndim == 4
+    B, _, _, C = dy.shape
+    dx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dy.device)
+    check(lib().mb200_avgpool_nhwc_bwd(_ptr(dy), _ptr(dx), B, H, W, C, k, _stream()))
+    return dx
+
+
 def sample(logits, temperature, top_k=0, top_p=0.0, seed=0, offset=0, return_mask=False):
     """One token per row of `logits` [rows, V] (bf16 or fp32, unit column stride) sampled like magma/sampling.py:97-105
     (top-k filter, the reference's nucleus filter, softmax(logits / T), multinomial)."""

@@ -604,6 +604,84 @@ int mb200_avgpool_nhwc(const void* src_, void* dst_, int32_t B, int32_t H, int32
   return 0;
 }
 
+// conv-trunk training   (col_moments_kernel / channel_affine_kernel / col2im3x3_kernel / avgpool_nhwc_bwd_kernel)
+int mb200_col_moments(const void* u_, int64_t ldu, const void* v_, int64_t ldv, const void* mask_, int64_t ldm,
+                      int32_t rows, int32_t cols, float* out1, float* out2, void*) {
+  EM_REQUIRE(rows > 0 && cols > 0 && cols % 2 == 0 && ldu % 2 == 0 && ldv % 2 == 0 && (!mask_ || ldm % 2 == 0),
+             MB200_E_ALIGN, "col_moments: cols and row strides must be even");
+  const bf16_t *u = (const bf16_t*)u_, *v = (const bf16_t*)v_, *mask = (const bf16_t*)mask_;
+  for (int c = 0; c < cols; ++c) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      float x = b2f(u[(long long)r * ldu + c]);
+      if (mask && !(b2f(mask[(long long)r * ldm + c]) > 0.f)) x = 0.f;
+      s1 += x;
+      s2 += (double)x * b2f(v[(long long)r * ldv + c]);
+    }
+    out1[c] = (float)s1;
+    out2[c] = (float)s2;
+  }
+  return 0;
+}
+
+int mb200_channel_affine(const void* x1_, const float* a1, const void* x2_, const float* a2, const float* c0,
+                         const void* mask_, const void* res_, int32_t relu, void* y_, int64_t rows, int32_t C, void*) {
+  EM_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && x1_ && a1 && y_ && (!x2_ || a2), MB200_E_ARG, "channel_affine: bad args");
+  EM_REQUIRE(aligned16(x1_) && aligned16(x2_) && aligned16(mask_) && aligned16(res_) && aligned16(y_), MB200_E_ALIGN,
+             "channel_affine: alignment");
+  const bf16_t *x1 = (const bf16_t*)x1_, *x2 = (const bf16_t*)x2_, *mask = (const bf16_t*)mask_, *res = (const bf16_t*)res_;
+  bf16_t* y = (bf16_t*)y_;
+  for (int64_t r = 0; r < rows; ++r)
+    for (int c = 0; c < C; ++c) {
+      const int64_t i = r * C + c;
+      float f = b2f(x1[i]);
+      if (mask && !(b2f(mask[i]) > 0.f)) f = 0.f;
+      f = f * a1[c] + (c0 ? c0[c] : 0.f);
+      if (x2) f += b2f(x2[i]) * a2[c];
+      if (res) f += b2f(res[i]);
+      if (relu) f = fmaxf(f, 0.f);
+      y[i] = f2b(f);
+    }
+  return 0;
+}
+
+int mb200_col2im3x3(const void* dcols_, void* dx_, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, void*) {
+  EM_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2), MB200_E_SHAPE,
+             "col2im3x3: bad shape / stride");
+  const bf16_t* dcols = (const bf16_t*)dcols_;
+  bf16_t* dx = (bf16_t*)dx_;
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  std::vector<float> acc((size_t)B * H * W * C, 0.f);
+  for (long long b = 0; b < B; ++b)  // scatter form: the adjoint of the im2col loop above, tap by tap
+    for (int ho = 0; ho < Ho; ++ho)
+      for (int wo = 0; wo < Wo; ++wo)
+        for (int tap = 0; tap < 9; ++tap) {
+          const int hi = ho * stride - 1 + tap / 3, wi = wo * stride - 1 + tap % 3;
+          if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+          const bf16_t* s = dcols + ((((b * Ho + ho) * Wo + wo) * 9) + tap) * C;
+          float* d = acc.data() + ((b * H + hi) * W + wi) * C;
+          for (int c = 0; c < C; ++c) d[c] += b2f(s[c]);
+        }
+  for (size_t i = 0; i < acc.size(); ++i) dx[i] = f2b(acc[i]);
+  return 0;
+}
+
+int mb200_avgpool_nhwc_bwd(const void* dy_, void* dx_, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void*) {
+  EM_REQUIRE(B > 0 && k >= 1 && H >= k && W >= k && C > 0 && C % 8 == 0, MB200_E_SHAPE, "avgpool_nhwc_bwd: bad shape");
+  const bf16_t* dy = (const bf16_t*)dy_;
+  bf16_t* dx = (bf16_t*)dx_;
+  const int Ho = H / k, Wo = W / k;
+  for (long long b = 0; b < B; ++b)
+    for (int h = 0; h < H; ++h)
+      for (int w = 0; w < W; ++w)
+        for (int c = 0; c < C; ++c) {
+          float f = 0.f;
+          if (h / k < Ho && w / k < Wo) f = b2f(dy[((b * Ho + h / k) * Wo + w / k) * C + c]) / (float)(k * k);
+          dx[((b * H + h) * W + w) * C + c] = f2b(f);
+        }
+  return 0;
+}
+
 // images [B,3,R,R] -> patches [B*g*g][ldp], column order (c, py, px)   (patchify_kernel)
 int mb200_patchify(const void* img_, void* patches_, int64_t ldp, int32_t B, int32_t R, int32_t P, void*) {
   EM_REQUIRE(R % P == 0 && ldp >= 3 * P * P, MB200_E_SHAPE, "patchify: bad geometry");

@@ -268,8 +268,11 @@ def vit_forward(images, w, cfg: OracleConfig, pre="image_prefix.enc"):
 # with stride-2 first conv and a 2x2 average pool, anti-aliased bottlenecks where the stride is an average pool after
 # conv2 and in front of the 1x1 downsample conv, BatchNorm in eval mode) with its state-dict names.
 # ------------------------------------------------------------------------------------------------
-def _bn_eval(x, w, p, eps=1e-5):
-    return F.batch_norm(x, w[f"{p}.running_mean"], w[f"{p}.running_var"], w[f"{p}.weight"], w[f"{p}.bias"], False, 0.0, eps)
+def _bn_eval(x, w, p, eps=1e-5, train=False, momentum=0.1):
+    """nn.BatchNorm2d: eval mode (running statistics) or, with train=True, training mode — batch statistics, and the
+    running_mean / running_var tensors in `w` are updated IN PLACE with `momentum` like the module does."""
+    return F.batch_norm(x, w[f"{p}.running_mean"], w[f"{p}.running_var"], w[f"{p}.weight"], w[f"{p}.bias"], train,
+                        momentum if train else 0.0, eps)
 
 
 def resnet_block_specs(cfg: OracleConfig):
@@ -283,23 +286,38 @@ def resnet_block_specs(cfg: OracleConfig):
     return specs
 
 
-def resnet_forward(images, w, cfg: OracleConfig, pre="image_prefix.enc"):
+def resnet_forward(images, w, cfg: OracleConfig, pre="image_prefix.enc", train_bn=False, relu=F.relu, store=None):
+    """train_bn=True: BatchNorm in training mode (the reference leaves the encoder in train() when
+    freeze_img_encoder is false, magma/magma.py:98-100) — batch statistics, running statistics in `w` updated in place.
+    `relu` lets a test substitute x * given_mask for the ReLUs (called in network order). `store` (default identity) is
+    applied wherever the CUDA training path writes a tensor to HBM — convolution output, unit output, pooled tensors —
+    so a test can pass a straight-through bf16 rounding and compare like with like: through ~18 BatchNorm units with
+    batch statistics, bf16 storage alone moves the features by ~5 % relative to this function run in pure fp32."""
+    t = train_bn
+    st = store if store is not None else (lambda v: v)
     x = images
+
+    def unit(v, conv_w, bn, stride=1, padding=0, act=True, res=None):
+        z = st(F.conv2d(v, w[conv_w], stride=stride, padding=padding))
+        y = _bn_eval(z, w, bn, train=t)
+        if res is not None:
+            y = y + res
+        return st(relu(y) if act else y)
+
     for i, stride in ((1, 2), (2, 1), (3, 1)):  # stem
-        x = F.relu(_bn_eval(F.conv2d(x, w[f"{pre}.conv{i}.weight"], stride=stride, padding=1), w, f"{pre}.bn{i}"))
-    x = F.avg_pool2d(x, 2)
+        x = unit(x, f"{pre}.conv{i}.weight", f"{pre}.bn{i}", stride=stride, padding=1)
+    x = st(F.avg_pool2d(x, 2))
     for name, inpl, planes, stride in resnet_block_specs(cfg):
         p = f"{pre}.{name}"
-        out = F.relu(_bn_eval(F.conv2d(x, w[f"{p}.conv1.weight"]), w, f"{p}.bn1"))
-        out = F.relu(_bn_eval(F.conv2d(out, w[f"{p}.conv2.weight"], padding=1), w, f"{p}.bn2"))
+        out = unit(x, f"{p}.conv1.weight", f"{p}.bn1")
+        out = unit(out, f"{p}.conv2.weight", f"{p}.bn2", padding=1)
         if stride > 1:
-            out = F.avg_pool2d(out, stride)
-        out = _bn_eval(F.conv2d(out, w[f"{p}.conv3.weight"]), w, f"{p}.bn3")
+            out = st(F.avg_pool2d(out, stride))
         idn = x
         if stride > 1 or inpl != planes * 4:
-            idn = F.avg_pool2d(x, stride) if stride > 1 else x
-            idn = _bn_eval(F.conv2d(idn, w[f"{p}.downsample.0.weight"]), w, f"{p}.downsample.1")
-        x = F.relu(out + idn)
+            idn = st(F.avg_pool2d(x, stride)) if stride > 1 else x
+            idn = unit(idn, f"{p}.downsample.0.weight", f"{p}.downsample.1", act=False)
+        x = unit(out, f"{p}.conv3.weight", f"{p}.bn3", res=idn)  # relu(bn3(conv3(out)) + identity)
     B, D = x.shape[:2]
     return x.reshape(B, D, -1).permute(0, 2, 1)  # image_encoders.py:71-73
 

@@ -169,3 +169,108 @@ def test_arena_optimizer_matches_torch_adamw_with_param_groups(emul_ops):
         assert torch.allclose(p.detach(), r.detach(), rtol=2e-5, atol=2e-6), n
         assert torch.equal(arena.shadow_of(p), p.detach().to(torch.bfloat16)), n
     assert float(arena.grad.abs().sum()) == 0.0    # zero_grad folded into the kernel
+
+
+def test_conv_trunk_training_forward_and_backward(emul_ops):
+    """freeze_img_encoder: false with a CLIP conv trunk (MAGMA_v1.yml / MAGMA_v2.yml): BatchNorm in training mode and the
+    hand-scheduled backward of B200ModifiedResNet against torch autograd of the oracle — features, every conv / BN
+    parameter gradient, and the running statistics. The oracle is run like-with-like: straight-through bf16 rounding
+    wherever the CUDA path stores a tensor (`store=`), and the SAME ReLU pattern as the recorded activations (`relu=`).
+    In pure fp32 the same graph differs from the bf16 run by ~5 % in the features (18 BatchNorm units with batch
+    statistics) and ~40 % in the gradients (0.3 % of the pre-activations sit inside bf16 rounding of zero and flip their
+    mask entry) — neither says anything about the schedule."""
+    from magma_b200.image_encoders import B200ModifiedResNet
+
+    cfg = O.OracleConfig(rn_width=16, rn_layers=(1, 2, 1, 1), rn_image=64)
+    w = O.init_resnet_weights(cfg, seed=6, pre="enc")
+    # the kernels read the bf16 compute copy of the convolution weights: give both sides bf16-representable values
+    w = {k: (v.to(torch.bfloat16).float() if v.ndim == 4 else v) for k, v in w.items()}
+    enc = B200ModifiedResNet(cfg.rn_layers, cfg.rn_width, cfg.rn_image, device=torch.device("cpu"))
+    enc.load_state_dict({k[4:]: v for k, v in w.items()}, strict=False)
+    for p in enc.parameters():
+        p.requires_grad = True
+    enc.train()
+    g = torch.Generator().manual_seed(1)
+    B = 4
+    images = torch.randn(B, 3, 64, 64, generator=g).to(torch.bfloat16)
+    feats, tape = enc._train_forward(images)
+    dfeats = torch.randn(feats.shape, generator=g).to(torch.bfloat16)
+    enc._train_backward(tape, dfeats)
+    # the ReLU pattern of the bf16 run, in network order, as NCHW masks
+    units = list(tape["stem"]) + [u for blk in tape["blocks"] for u in blk["units"]]
+    masks = [(u["y"] > 0).view(B, -1, u["y"].shape[1]) for u in units if u["y"] is not None]
+    it = iter(masks)
+
+    def masked_relu(x):
+        m = next(it)                                   # [B, H*W, C] -> [B, C, H, W]
+        return x * m.permute(0, 2, 1).reshape(x.shape).to(x.dtype)
+
+    wo = {k: (v.clone().requires_grad_(True) if not k.endswith(("running_mean", "running_var")) else v.clone())
+          for k, v in w.items()}
+    def store(v):                                      # bf16 storage, identity gradient
+        return v + (v.detach().to(torch.bfloat16).float() - v.detach())
+
+    want = O.resnet_forward(images.float(), wo, cfg, pre="enc", train_bn=True, relu=masked_relu, store=store)
+    assert next(it, None) is None                      # every recorded mask was consumed: same number of ReLUs
+    want.backward(dfeats.float())
+    assert feats.shape == want.shape and rel(feats, want.detach()) < 1.5e-2
+    sd = dict(enc.named_parameters())
+    errs = {k[4:]: rel(sd[k[4:]].grad, v.grad) for k, v in wo.items() if v.requires_grad}
+    assert len(errs) == len(sd)
+    bad = {k: round(e, 3) for k, e in errs.items() if e > 3e-2}
+    assert not bad, bad
+    assert sorted(errs.values())[len(errs) // 2] < 1.5e-2   # median
+    bufs = dict(enc.named_buffers())
+    for k, v in wo.items():
+        if k.endswith(("running_mean", "running_var")):
+            assert torch.allclose(bufs[k[4:]], v, rtol=2e-2, atol=2e-3), k
+    assert int(bufs["bn1.num_batches_tracked"]) == 1
+    # through the autograd function (what ImagePrefix calls): same features, gradients land on the parameters
+    for p in enc.parameters():
+        p.grad = None
+    f2 = enc(images)
+    assert f2.requires_grad and rel(f2, want.detach()) < 3e-2
+    f2.backward(dfeats)
+    assert all(p.grad is not None for p in enc.parameters())
+    # eval mode afterwards: running statistics, folded weights rebuilt from the current parameters
+    enc.eval()
+    with torch.no_grad():
+        e1 = enc(images)
+    w_eval = {k: v.detach() for k, v in wo.items()}
+    for k, v in enc.named_buffers():                  # the module has now seen two training batches
+        if not k.endswith("num_batches_tracked"):
+            w_eval["enc." + k] = v.clone()
+    assert rel(e1, O.resnet_forward(images.float(), w_eval, cfg, pre="enc")) < 2e-2
+
+
+def test_conv_training_primitives_are_what_the_schedule_assumes(emul_ops):
+    """The emulated col2im3x3 / avgpool_nhwc_bwd are the adjoints of the forward layout operators (checked against
+    torch autograd of unfold / avg_pool2d), and col_moments / channel_affine compute the documented expressions —
+    the same reference formulas the GPU test of the real kernels uses (tests/test_zz_unverified_gpu.py)."""
+    import torch.nn.functional as F
+
+    from magma_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    for B, H, W, C, s in ((2, 6, 6, 8, 1), (2, 6, 6, 8, 2), (1, 7, 5, 16, 2)):
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        xb = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+        cols, ho, wo = ops.im2col3x3(xb, s)
+        x = xb.float().requires_grad_(True)
+        xu = F.unfold(x.permute(0, 3, 1, 2), 3, padding=1, stride=s)                       # [B, C*9, Ho*Wo], (c, kh, kw)
+        xu = xu.view(B, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 9 * C)      # (kh*3+kw, c)
+        assert (ho, wo) == (Ho, Wo) and torch.equal(cols.float(), xu.detach())
+        dcols = torch.randn(cols.shape, generator=g).to(torch.bfloat16)
+        xu.backward(dcols.float())
+        assert rel(ops.col2im3x3(dcols, B, H, W, C, s), x.grad) < 5e-3
+    dy = torch.randn(2, 3, 4, 16, generator=g).to(torch.bfloat16)
+    x = torch.zeros(2, 6, 8, 16).requires_grad_(True)
+    F.avg_pool2d(x.permute(0, 3, 1, 2), 2).backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(ops.avgpool_nhwc_bwd(dy, 6, 8, 2), x.grad) < 5e-3
+    u, v, m = (torch.randn(50, 16, generator=g).to(torch.bfloat16) for _ in range(3))
+    o1, o2 = ops.col_moments(u, v, m)
+    um = u.float() * (m.float() > 0)
+    assert rel(o1, um.sum(0)) < 1e-5 and rel(o2, (um * v.float()).sum(0)) < 1e-5
+    a1, a2, c0 = (torch.randn(16, generator=g) for _ in range(3))
+    y = ops.channel_affine(u, a1, x2=v, a2=a2, c0=c0, mask=m, res=v, relu=True)
+    assert rel(y, F.relu(um * a1 + v.float() * a2 + c0 + v.float())) < 5e-3

@@ -349,3 +349,91 @@ def test_general_schedule_agrees_with_the_fast_runtime():
     assert abs(l0 - l1) < 5e-3 and _rel(lg1, lg0) < 1e-2
     bad = {n: round(_rel(g1[n], g0[n]), 4) for n in names if _rel(g1[n], g0[n]) > 2e-2}
     assert not bad, bad
+
+
+def test_conv_trunk_training_kernels_match_torch():
+    """col_moments / channel_affine / col2im3x3 / avgpool_nhwc_bwd against torch (fp32 math on the same bf16 inputs)."""
+    import torch
+    import torch.nn.functional as F
+
+    from magma_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    R, C = 1000, 96
+    u = torch.randn(R, C, generator=g).to(torch.bfloat16).to(dev)
+    v = torch.randn(R, C, generator=g).to(torch.bfloat16).to(dev)
+    m = torch.randn(R, C, generator=g).to(torch.bfloat16).to(dev)
+    o1, o2 = ops.col_moments(u, v, m)
+    um = u.float() * (m.float() > 0)
+    assert _rel(o1, um.sum(0)) < 1e-4 and _rel(o2, (um * v.float()).sum(0)) < 1e-4
+    o1, o2 = ops.col_moments(u, u)
+    assert _rel(o1, u.float().sum(0)) < 1e-4 and _rel(o2, (u.float() ** 2).sum(0)) < 1e-4
+    a1, a2, c0 = (torch.randn(C, generator=g).to(dev) for _ in range(3))
+    y = ops.channel_affine(u, a1, x2=v, a2=a2, c0=c0, mask=m, res=v, relu=True)
+    want = F.relu(um * a1 + v.float() * a2 + c0 + v.float())
+    assert _rel(y, want) < 5e-3
+    y = ops.channel_affine(u, a1)
+    assert _rel(y, u.float() * a1) < 5e-3
+    for B, H, W, Cc, s in ((2, 12, 12, 16, 1), (2, 12, 12, 16, 2), (1, 7, 9, 8, 2)):
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        dcols = torch.randn(B * Ho * Wo, 9 * Cc, generator=g).to(torch.bfloat16).to(dev)
+        x = torch.zeros(B, H, W, Cc, dtype=torch.bfloat16, device=dev).float().requires_grad_(True)
+        cols, ho, wo = ops.im2col3x3(torch.zeros(B, H, W, Cc, dtype=torch.bfloat16, device=dev), s)
+        assert (ho, wo) == (Ho, Wo)
+        # the adjoint of im2col via autograd of the same gather written with unfold (columns ordered (kh, kw, c))
+        xu = F.unfold(x.permute(0, 3, 1, 2), 3, padding=1, stride=s)                        # [B, C*9, Ho*Wo], (c, kh, kw)
+        xu = xu.view(B, Cc, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 9 * Cc)     # (kh*3+kw, c)
+        xu.backward(dcols.float())
+        got = ops.col2im3x3(dcols, B, H, W, Cc, s)
+        assert _rel(got, x.grad) < 5e-3, (B, H, W, Cc, s)
+    dy = torch.randn(2, 3, 4, 16, generator=g).to(torch.bfloat16).to(dev)
+    x = torch.zeros(2, 6, 8, 16, device=dev).requires_grad_(True)
+    F.avg_pool2d(x.permute(0, 3, 1, 2), 2).backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(ops.avgpool_nhwc_bwd(dy, 6, 8, 2), x.grad) < 5e-3
+
+
+def test_conv_trunk_training_matches_oracle_like_with_like():
+    """freeze_img_encoder: false with a CLIP conv trunk (MAGMA_v1.yml / v2.yml): BatchNorm in training mode + backward,
+    compared the same way as tests/test_host_dryrun_cpu.py does on the CPU (bf16 store points and the recorded ReLU
+    pattern given to the oracle)."""
+    import torch
+
+    from magma_b200.image_encoders import B200ModifiedResNet
+    from oracle import magma_oracle as O
+
+    dev = torch.device("cuda:0")
+    cfg = O.OracleConfig(rn_width=16, rn_layers=(1, 2, 1, 1), rn_image=64)
+    w = O.init_resnet_weights(cfg, seed=6, pre="enc")
+    w = {k: (v.to(torch.bfloat16).float() if v.ndim == 4 else v) for k, v in w.items()}
+    enc = B200ModifiedResNet(cfg.rn_layers, cfg.rn_width, cfg.rn_image, device=dev)
+    enc.load_state_dict({k[4:]: v for k, v in w.items()}, strict=False)
+    for p in enc.parameters():
+        p.requires_grad = True
+    enc.train()
+    g = torch.Generator().manual_seed(1)
+    B = 4
+    images = torch.randn(B, 3, 64, 64, generator=g).to(torch.bfloat16)
+    feats, tape = enc._train_forward(images.to(dev))
+    dfeats = torch.randn(feats.shape, generator=g).to(torch.bfloat16)
+    enc._train_backward(tape, dfeats.to(dev))
+    units = list(tape["stem"]) + [u for blk in tape["blocks"] for u in blk["units"]]
+    masks = [(u["y"] > 0).view(B, -1, u["y"].shape[1]).cpu() for u in units if u["y"] is not None]
+    it = iter(masks)
+
+    def masked_relu(x):
+        m = next(it)
+        return x * m.permute(0, 2, 1).reshape(x.shape).to(x.dtype)
+
+    def store(v):
+        return v + (v.detach().to(torch.bfloat16).float() - v.detach())
+
+    wo = {k: (v.clone().requires_grad_(True) if not k.endswith(("running_mean", "running_var")) else v.clone())
+          for k, v in w.items()}
+    want = O.resnet_forward(images.float(), wo, cfg, pre="enc", train_bn=True, relu=masked_relu, store=store)
+    want.backward(dfeats.float())
+    assert _rel(feats, want.detach()) < 2e-2
+    sd = dict(enc.named_parameters())
+    bad = {k[4:]: round(_rel(sd[k[4:]].grad, v.grad), 4) for k, v in wo.items()
+           if v.requires_grad and _rel(sd[k[4:]].grad, v.grad) > 4e-2}
+    assert not bad, bad
