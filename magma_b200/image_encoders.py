@@ -376,7 +376,7 @@ class B200ModifiedResNet(nn.Module):
     statistics by `col_moments`, normalisation + residual + ReLU by `channel_affine`, running statistics updated with
     momentum 0.1) and a hand-scheduled backward — BatchNorm / ReLU backward from the same two kernels, convolution
     wgrad and dgrad as GEMMs over the saved im2col matrix (MN-major operands), `col2im3x3` and `avgpool_nhwc_bwd` as
-    the adjoints of the layout kernels. NOT YET RUN ON A B200 (DESIGN.md §3.11); dry-run on the CPU against the
+    the adjoints of the layout kernels. NOT YET RUN ON A B200 (DESIGN.md §3.10); dry-run on the CPU against the
     oracle's autograd in tests/test_host_dryrun_cpu.py."""
 
     supports_training = True
