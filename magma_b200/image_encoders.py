@@ -177,8 +177,8 @@ class B200VisionTransformer(nn.Module):
             if self._arena is None:
                 raise MB200Error("trainable ViT parameters need the parameter arena (Magma.finalize())")
             return self._arena.shadow_of(p)
-        if p.dtype != torch.bfloat16 or not p.is_cuda:
-            raise MB200Error(f"frozen ViT parameter {name} must be bf16 on CUDA")
+        if p.dtype != torch.bfloat16 or p.device.type != self._device.type:
+            raise MB200Error(f"frozen ViT parameter {name} must be bf16 on {self._device}")
         return p.data
 
     def _refresh_packed(self):

@@ -68,8 +68,7 @@ class Magma(nn.Module):
             assert isinstance(config, MultimodalConfig)
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda" if torch.cuda.is_available() else "cpu")
-        if self.device.type != "cuda":
-            raise RuntimeError("magma_b200 has no CPU path: construct Magma on a CUDA (sm_100) device")
+        self._require_cuda()
         self.config = config
         lm_cfg = getattr(config, "_lm_config", None)  # test hook: small architectures
         self.lm = get_gptj(config=lm_cfg, device=self.device) if lm_cfg is not None else get_gptj(device=self.device)
@@ -123,6 +122,10 @@ class Magma(nn.Module):
                 self.image_prefix.enc.init_weights(seed=init_seed + 1)
         self._arena = None
         self.finalize()
+
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("magma_b200 has no CPU path: construct Magma on a CUDA (sm_100) device")
 
     # ------------------------------------------------------------------------------------------
     def finalize(self):

@@ -1,0 +1,165 @@
+"""Whole-model dry run on the CPU: Magma.forward -> loss.backward() -> B200Engine.step() with the primitive operators
+emulated (fixture `emul_ops`) and the LM routed through the general host-only schedule (csrc/gptj_sched.cu, compiled
+into the emulation library). What runs here is the product's own Python — Magma / ImagePrefix / the trainable encoders /
+ParamArena / B200Engine / checkpointing — and the two host-only C++ schedules; what is emulated are the kernels. The
+result is held to torch autograd of the oracle (oracle/magma_oracle.py::magma_forward).
+
+Not covered: engine.cu (the fast LM runtime, frozen-ViT forward, KV-cache decoding) — it contains kernels and only
+runs on a GPU — and therefore `generate()`."""
+import pytest
+import torch
+
+from oracle import magma_oracle as O
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def tiny_cfg(**kw):
+    base = dict(d=64, n_layer=2, n_head=4, rotary_dim=8, vocab=96, image_seq_len=2, enc_out_dim=48, vit_width=64,
+                vit_layers=2, vit_heads=4, vit_patch=8, vit_image=32, vit_mlp=128, eos_token=90, image_token=91)
+    base.update(kw)
+    return O.OracleConfig(**base)
+
+
+def build(monkeypatch, cfg, w16, S, encoder="clip_vit_dry", freeze_enc=False, **mc_kw):
+    from magma_b200.config import MultimodalConfig
+    from magma_b200.image_encoders import register_vit
+    from magma_b200.language_model import GPTJConfig
+    from magma_b200.magma import Magma
+
+    monkeypatch.setattr(Magma, "_require_cuda", lambda self: None)   # test-only: kernels are emulated (emul_ops)
+    register_vit("clip_vit_dry", cfg.vit_width, cfg.vit_layers, cfg.vit_heads, cfg.vit_patch, cfg.vit_image, cfg.vit_mlp,
+                 cfg.enc_out_dim)
+    mc = MultimodalConfig(batch_size=2, train_steps=1, encoder_name=encoder,
+                          adapter_config={"mlp": dict(cfg.mlp_adapter)}, image_seq_len=cfg.image_seq_len,
+                          image_embed_dropout_prob=0.0, use_image_embed_layernorm=True, image_size=cfg.vit_image,
+                          seq_len=S, freeze_img_encoder=freeze_enc, **mc_kw)
+    mc._lm_config = GPTJConfig(vocab_size=cfg.vocab, hidden_size=cfg.d, num_layers=cfg.n_layer, num_heads=cfg.n_head,
+                               rotary_dim=cfg.rotary_dim)
+    model = Magma(mc, device=torch.device("cpu"), init_seed=None)
+    model.eos_token, model.image_token = cfg.eos_token, cfg.image_token
+    if w16 is not None:
+        missing, unexpected = model.load_state_dict(w16, strict=False)
+        missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
+        assert not missing and not unexpected, (missing, unexpected)
+    model.lm._force_general = True        # the LM through csrc/gptj_sched.cu (engine.cu has kernels: GPU only)
+    model.lm.invalidate()
+    model.lm.attach_arena(model.arena)
+    model.image_prefix.enc.invalidate()
+    return model, mc
+
+
+def oracle_weights(cfg, seed=5):
+    w = O.init_weights(cfg, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    for k in w:
+        if ".adapter." in k:  # O(0.05) adapters with decided ReLU masks (bias +-3), like tools/model_check.py
+            w[k] = torch.randn(w[k].shape, generator=g) * (0.05 if k.endswith("weight") else 0.02)
+            if k.endswith("adapter.0.bias"):
+                w[k] = torch.where(torch.rand(w[k].shape, generator=g) < 0.5, -3.0, 3.0)
+        elif k.startswith("image_prefix.enc.") and k.endswith(("in_proj_weight", "out_proj.weight", "c_fc.weight",
+                                                                "c_proj.weight", "conv1.weight", ".proj")):
+            w[k] = w[k] * 4
+        elif k.startswith("lm.") and k.endswith(("proj.weight", "fc_in.weight", "fc_out.weight")):
+            w[k] = w[k] * 3
+    return {k: v.to(torch.bfloat16).float() for k, v in w.items()}
+
+
+def test_magma_with_a_trainable_vit_end_to_end(emul_ops, monkeypatch, tmp_path):
+    """MAGMA_v1's optimizer settings on the ViT encoder: every trainable gradient (adapters, image prefix, all ViT
+    parameters) against the oracle's autograd; then engine steps with image_enc_lr and a checkpoint round trip."""
+    from magma_b200.train_loop import B200Engine
+    from magma_b200.utils import load_model, save_model
+
+    cfg = tiny_cfg()
+    S, B = 16, 3
+    w16 = oracle_weights(cfg)
+    model, mc = build(monkeypatch, cfg, w16, S, lr=1e-2, image_enc_lr=1e-4, warmup_num_steps=2)
+    model.eval()
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert any(n.startswith("image_prefix.enc.") for n in names) and model.arena.numel > 0
+    images, captions = O.synthetic_batch(cfg, B, S, seed=11)
+    images = images.to(torch.bfloat16).float()
+    params = {k: v.clone().requires_grad_(k in names) for k, v in w16.items()}
+    loss_o, logits_o, labels_o = O.magma_forward(images, captions, params, cfg)
+    loss_o.backward()
+    out = model(images, captions)
+    assert abs(float(out.loss.detach()) - float(loss_o.detach())) < 2e-2
+    assert rel(out.logits, logits_o.detach()) < 3e-2
+    out.loss.backward()
+    sd = dict(model.named_parameters())
+    bad = {k: round(rel(sd[k].grad, params[k].grad), 4) for k in names if rel(sd[k].grad, params[k].grad) > 5e-2}
+    assert not bad, bad
+    # a second identical pass accumulates (gradient accumulation: grads are live)
+    g1 = {k: sd[k].grad.clone() for k in names}
+    model(images, captions).loss.backward()
+    assert max(rel(sd[k].grad, 2 * g1[k]) for k in names) < 1e-2
+    # engine: WarmupLR gives lr = 0 at step 0; the encoder moves at image_enc_lr / lr of the others' rate
+    for p in model.parameters():
+        p.grad = None
+    model.arena.grad.zero_()
+    model.train()
+    eng = B200Engine(model, mc, n_buckets=2)
+    before = {k: sd[k].detach().clone() for k in names}
+    losses = []
+    for _ in range(4):
+        o = eng(images, captions)
+        eng.backward(o.loss)
+        eng.step()
+        losses.append(float(o.loss.detach()))
+    assert losses[-1] < losses[0] and abs(losses[1] - losses[0]) < 1e-6
+    enc_move = max(float((sd[k].detach() - before[k]).abs().max()) for k in names if k.startswith("image_prefix.enc."))
+    oth_move = max(float((sd[k].detach() - before[k]).abs().max()) for k in names if not k.startswith("image_prefix.enc."))
+    assert 0 < enc_move < 5e-2 * oth_move
+    assert len(eng._segments) == 3 and eng._segments[1][2] == pytest.approx(1e-2)
+    # checkpoint round trip through save_model / load_model (magma/utils.py:89-117)
+    save_model(eng, str(tmp_path), eng.global_step, config=mc)
+    want = []
+    for _ in range(2):
+        o = eng(images, captions)
+        eng.backward(o.loss)
+        eng.step()
+        want.append(float(o.loss.detach()))
+    model2, mc2 = build(monkeypatch, cfg, w16, S, lr=1e-2, image_enc_lr=1e-4, warmup_num_steps=2)
+    model2.train()
+    eng2 = B200Engine(model2, mc2, n_buckets=2)
+    assert load_model(eng2, str(tmp_path)) == 4 and eng2.global_step == 4
+    got = []
+    for _ in range(2):
+        o = eng2(images, captions)
+        eng2.backward(o.loss)
+        eng2.step()
+        got.append(float(o.loss.detach()))
+    assert got == pytest.approx(want, abs=1e-5)
+
+
+def test_magma_with_a_trainable_conv_trunk_trains(emul_ops, monkeypatch):
+    """MAGMA_v1.yml's encoder type (a CLIP conv trunk, freeze_img_encoder: false): the whole step runs and learns."""
+    from magma_b200.image_encoders import register_resnet
+    from magma_b200.train_loop import B200Engine
+
+    cfg = tiny_cfg(vit_image=64)
+    register_resnet("clip_resnet_dry", (1, 1, 1, 1), 16, 64)          # 4 prefix tokens of width 512
+    S, B = 16, 4
+    model, mc = build(monkeypatch, cfg, None, S, encoder="clip_resnet_dry", lr=5e-3, image_enc_lr=5e-4,
+                      warmup_num_steps=2)
+    model.lm.init_weights(seed=0)
+    model.image_prefix.enc.init_weights(seed=1)
+    model.finalize()
+    model.lm._force_general = True
+    model.train()
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert any("enc.layer4" in n for n in names) and any(n.endswith("bn1.weight") for n in names)
+    images, captions = O.synthetic_batch(cfg, B, S, seed=3, prefix_len=4)
+    eng = B200Engine(model, mc, n_buckets=2)
+    rm0 = model.image_prefix.enc.bn1.running_mean.clone()
+    losses = []
+    for _ in range(6):
+        o = eng(images.to(torch.bfloat16), captions)
+        eng.backward(o.loss)
+        eng.step()
+        losses.append(float(o.loss.detach()))
+    assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.05, losses
+    assert not torch.equal(rm0, model.image_prefix.enc.bn1.running_mean)   # BatchNorm ran in training mode
