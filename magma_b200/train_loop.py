@@ -27,7 +27,8 @@ class B200Engine:
         self.micro_step = 0
         self.global_step = 0
         self.betas, self.eps = betas, eps
-        self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
+        on_gpu = getattr(getattr(model, "device", None), "type", "cuda") == "cuda"
+        self.comm_stream = torch.cuda.Stream() if (self.world > 1 and on_gpu) else None
         # experimental data-parallel knobs (both off by default): exchange gradients as bf16, and keep a
         # few SMs out of the persistent GEMM grids so NCCL's CTAs run beside the backward GEMMs
         self.comm_dtype = torch.bfloat16 if os.environ.get("MB200_DP_BF16", "0") == "1" else None
@@ -58,6 +59,9 @@ class B200Engine:
     def _allreduce_slice(self, lo, hi):
         arena = self.module.arena
         if self.world == 1 or lo is None:
+            return
+        if self.comm_stream is None:  # host-side dry run (tests): no streams, same collective
+            dp.allreduce_slice(arena.grad, lo, hi, comm_dtype=self.comm_dtype)
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())

@@ -163,3 +163,96 @@ def test_magma_with_a_trainable_conv_trunk_trains(emul_ops, monkeypatch):
         losses.append(float(o.loss.detach()))
     assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.05, losses
     assert not torch.equal(rm0, model.image_prefix.enc.bn1.running_mean)   # BatchNorm ran in training mode
+
+
+def _dp_worker(rank, world, port, q):
+    """One data-parallel rank of the whole-model dry run (gloo): shard of the global batch -> engine step."""
+    import ctypes
+    import os
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from magma_b200 import _lib, dp, ops
+        from magma_b200.magma import Magma
+        from magma_b200.train_loop import B200Engine
+        from magma_b200.utils import reduce_losses
+        from oracle import build_emul
+
+        L = ctypes.CDLL(build_emul.build())                 # what the emul_ops fixture does, in this child process
+        L.mb200_last_error.restype = ctypes.c_char_p
+        _lib._lib, ops._stream = L, (lambda: None)
+
+        class MP:                                           # minimal monkeypatch stand-in for build()
+            @staticmethod
+            def setattr(obj, name, val):
+                setattr(obj, name, val)
+
+        cfg = tiny_cfg()
+        S, GB = 16, 4
+        w16 = oracle_weights(cfg)
+        images, captions = O.synthetic_batch(cfg, GB, S, seed=11)
+        images = images.to(torch.bfloat16)
+
+        def run(model_world, shard):
+            model, mc = build(MP, cfg, w16, S, lr=1e-2, image_enc_lr=1e-3, warmup_num_steps=2, gradient_clipping=0.0)
+            model.train()
+            eng = B200Engine(model, mc, n_buckets=2)
+            eng.world = model_world
+            lo, hi = shard
+            out = []
+            for _ in range(3):  # the body of train_step (train_loop.py:7-21) without its .cuda() copies
+                o = eng(images[lo:hi], captions[lo:hi])
+                eng.backward(o.loss)
+                eng.step()
+                out.append(float(reduce_losses(o.loss.detach())))
+            return model, out
+
+        lo, hi = dp.shard_batch(GB, rank, world)
+        model, losses = run(world, (lo, hi))
+        flat = model.arena.master.clone()
+        # every rank must hold identical parameters after the exchanged steps
+        gathered = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same = all(torch.equal(gathered[0], t) for t in gathered)
+        moved = float((flat - B200_initial(cfg, w16, S, MP)).abs().max()) > 0
+        q.put((rank, same, moved, losses))
+    except Exception as exc:  # surface the failure instead of letting the parent wait for its queue timeout
+        q.put((rank, False, False, repr(exc)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def B200_initial(cfg, w16, S, MP):
+    model, _ = build(MP, cfg, w16, S)
+    return model.arena.master.clone()
+
+
+def test_two_rank_data_parallel_engine_step(emul_ops):
+    """B200Engine over gloo, world size 2, whole model on emulated kernels: after three train_steps on different shards
+    the ranks hold bit-identical parameters (the slice-wise gradient all-reduce + 1/world in the fused optimizer), the
+    parameters moved, and train_step returned the cross-rank mean loss on every rank."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[0] for r in res] == [0, 1]
+    assert all(r[1] for r in res), "ranks diverged"
+    assert all(r[2] for r in res), "parameters did not move"
+    assert res[0][3] == pytest.approx(res[1][3], abs=1e-6)      # reduce_losses: the same mean on both ranks
