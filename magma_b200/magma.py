@@ -151,46 +151,42 @@ class Magma(nn.Module):
                      adapter_type: Literal["normal", "parallel", "scaled_parallel"] = "normal",
                      location: Literal["mlp", "attention"] = "mlp", ff_attr: str = "mlp", attn_attr: str = "attn",
                      **adapter_kwargs):
-        """magma/magma.py:102-174 — in-place rewiring of each block's `.mlp` / `.attn`."""
+        """magma/magma.py:102-174 — rewires `block.<ff_attr>` / `block.<attn_attr>` of every LM block in place:
+        mlp + "normal" -> Sequential(mlp, Adapter); mlp + parallel forms -> ParallelAdapter(module=mlp);
+        attention + "normal" -> AdapterWrapper(attn_block=attn); attention + parallel forms -> ParallelAdapterWrapper.
+        The C++ runtime re-discovers the wiring from the module tree on its next call."""
         assert adapter_type in ["normal", "parallel", "scaled_parallel"], \
             "adapter_type must be one of 'normal', 'parallel', or 'scaled_parallel'"
         assert location in ["mlp", "attention"], "location must be one of 'mlp' or 'attention'"
-        dim = self.lm.config.hidden_size
+        flag = "mlp_adapter_added" if location == "mlp" else "attn_adapter_added"
+        if getattr(self, flag):
+            raise ValueError("Adapter layer already added")
+        width = self.lm.config.hidden_size
+        is_parallel, is_scaled = adapter_type != "normal", adapter_type == "scaled_parallel"
+        attr = ff_attr if location == "mlp" else attn_attr
 
-        def own_params_to_device(mod):
+        def on_device(mod):  # only the new adapter parameters move; the wrapped (frozen) module is already in place
             for n, p in mod.named_parameters():
                 if n.startswith("adapter"):
                     p.data = p.data.to(self.device)
             return mod
 
-        for l in range(len(self.transformer)):
+        def wrap(inner):
             if location == "mlp":
-                if self.mlp_adapter_added:
-                    raise ValueError("Adapter layer already added")
-                mlp = getattr(self.transformer[l], ff_attr)
-                if adapter_type in ["parallel", "scaled_parallel"]:
-                    adapter_layer = own_params_to_device(
-                        ParallelAdapter(module=mlp, dim=dim, downsample_factor=downsample_factor,
-                                        scaled=adapter_type == "scaled_parallel", **adapter_kwargs))
-                else:
-                    adpt = own_params_to_device(Adapter(dim=dim, downsample_factor=downsample_factor, **adapter_kwargs))
-                    adapter_layer = nn.Sequential(*[mlp, adpt])
-                setattr(self.transformer[l], ff_attr, adapter_layer)
-            else:
-                if self.attn_adapter_added:
-                    raise ValueError("Adapter layer already added")
-                attn = getattr(self.transformer[l], attn_attr)
-                if adapter_type in ["parallel", "scaled_parallel"]:
-                    adapter_layer = ParallelAdapterWrapper(module=attn, dim=dim, downsample_factor=downsample_factor,
-                                                           scaled="scaled" in adapter_type, **adapter_kwargs)
-                else:
-                    adapter_layer = AdapterWrapper(attn_block=attn, dim=dim, downsample_factor=downsample_factor,
-                                                   **adapter_kwargs)
-                setattr(self.transformer[l], attn_attr, own_params_to_device(adapter_layer))
-        if location == "mlp":
-            self.mlp_adapter_added = True
-        else:
-            self.attn_adapter_added = True
+                if is_parallel:
+                    return on_device(ParallelAdapter(module=inner, dim=width, downsample_factor=downsample_factor,
+                                                     scaled=is_scaled, **adapter_kwargs))
+                return nn.Sequential(inner, on_device(Adapter(dim=width, downsample_factor=downsample_factor,
+                                                              **adapter_kwargs)))
+            if is_parallel:
+                return on_device(ParallelAdapterWrapper(module=inner, dim=width, downsample_factor=downsample_factor,
+                                                        scaled=is_scaled, **adapter_kwargs))
+            return on_device(AdapterWrapper(attn_block=inner, dim=width, downsample_factor=downsample_factor,
+                                            **adapter_kwargs))
+
+        for block in self.transformer:
+            setattr(block, attr, wrap(getattr(block, attr)))
+        setattr(self, flag, True)
         self.lm.invalidate()
 
     def preprocess_inputs(self, input_list: list, embed=True) -> List[torch.Tensor]:

@@ -23,7 +23,7 @@ def tiny_cfg(**kw):
     return O.OracleConfig(**base)
 
 
-def build(monkeypatch, cfg, w16, S, encoder="clip_vit_dry", freeze_enc=False, **mc_kw):
+def build(monkeypatch, cfg, w16, S, encoder="clip_vit_dry", freeze_enc=False, adapter_config=None, **mc_kw):
     from magma_b200.config import MultimodalConfig
     from magma_b200.image_encoders import register_vit
     from magma_b200.language_model import GPTJConfig
@@ -33,7 +33,8 @@ def build(monkeypatch, cfg, w16, S, encoder="clip_vit_dry", freeze_enc=False, **
     register_vit("clip_vit_dry", cfg.vit_width, cfg.vit_layers, cfg.vit_heads, cfg.vit_patch, cfg.vit_image, cfg.vit_mlp,
                  cfg.enc_out_dim)
     mc = MultimodalConfig(batch_size=2, train_steps=1, encoder_name=encoder,
-                          adapter_config={"mlp": dict(cfg.mlp_adapter)}, image_seq_len=cfg.image_seq_len,
+                          adapter_config=adapter_config or {"mlp": dict(cfg.mlp_adapter)},
+                          image_seq_len=cfg.image_seq_len,
                           image_embed_dropout_prob=0.0, use_image_embed_layernorm=True, image_size=cfg.vit_image,
                           seq_len=S, freeze_img_encoder=freeze_enc, **mc_kw)
     mc._lm_config = GPTJConfig(vocab_size=cfg.vocab, hidden_size=cfg.d, num_layers=cfg.n_layer, num_heads=cfg.n_head,
@@ -256,3 +257,43 @@ def test_two_rank_data_parallel_engine_step(emul_ops):
     assert all(r[1] for r in res), "ranks diverged"
     assert all(r[2] for r in res), "parameters did not move"
     assert res[0][3] == pytest.approx(res[1][3], abs=1e-6)      # reduce_losses: the same mean on both ranks
+
+
+def test_magma_with_layernorm_and_scaled_adapters_end_to_end(emul_ops, monkeypatch):
+    """adapter_config with add_layernorm (adapters.py:16-17) and scaled_parallel (adapters.py:57-61) through
+    Magma.add_adapters -> language_model._cmodel_ex -> csrc/gptj_sched.cu, against the oracle's autograd."""
+    mlp = {"adapter_type": "scaled_parallel", "downsample_factor": 4}
+    attn = {"adapter_type": "normal", "downsample_factor": 8}
+    cfg = tiny_cfg(mlp_adapter=mlp, attn_adapter=attn)
+    S, B = 16, 3
+    w = oracle_weights(cfg)
+    g = torch.Generator().manual_seed(9)
+    for l in range(cfg.n_layer):
+        for pre in (f"lm.transformer.h.{l}.mlp", f"lm.transformer.h.{l}.attn"):   # add_layernorm shifts the indices
+            for i, j in ((2, 3), (0, 1)):
+                for sfx in ("weight", "bias"):
+                    w[f"{pre}.adapter.{j}.{sfx}"] = w.pop(f"{pre}.adapter.{i}.{sfx}")
+            w[f"{pre}.adapter.0.weight"] = (1.0 + 0.1 * torch.randn(cfg.d, generator=g)).to(torch.bfloat16).float()
+            w[f"{pre}.adapter.0.bias"] = (0.1 * torch.randn(cfg.d, generator=g)).to(torch.bfloat16).float()
+        w[f"lm.transformer.h.{l}.mlp.adapter_scale"] = torch.tensor([0.75 + 0.25 * l])
+    ac = {"mlp": dict(mlp, add_layernorm=True), "attention": dict(attn, add_layernorm=True)}
+    model, mc = build(monkeypatch, cfg, w, S, freeze_enc=True, adapter_config=ac)
+    model.eval()
+    assert model.lm._general_schedule()
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert any(n.endswith("adapter_scale") for n in names) and any(n.endswith("adapter.0.weight") for n in names)
+    images, captions = O.synthetic_batch(cfg, B, S, seed=11)
+    images = images.to(torch.bfloat16).float()
+    # the frozen ViT forward lives in engine.cu (GPU only): feed the oracle's prefix embeddings instead of images
+    with torch.no_grad():
+        prefix = O.image_prefix(images, w, cfg).to(torch.bfloat16)
+    params = {k: v.clone().requires_grad_(k in names) for k, v in w.items()}
+    loss_o, logits_o, _ = O.magma_forward(None, captions, params, cfg, input_embeddings=prefix.float())
+    loss_o.backward()
+    out = model(None, captions, input_embeddings=prefix)
+    assert abs(float(out.loss.detach()) - float(loss_o.detach())) < 2e-2 and rel(out.logits, logits_o.detach()) < 3e-2
+    out.loss.backward()
+    sd = dict(model.named_parameters())
+    lm_names = [n for n in names if n.startswith("lm.")]
+    bad = {k: round(rel(sd[k].grad, params[k].grad), 4) for k in lm_names if rel(sd[k].grad, params[k].grad) > 5e-2}
+    assert not bad, bad
