@@ -12,6 +12,7 @@ All frozen weights are bf16 tensors on the GPU; parameter names follow HF GPT-J 
 28-block forward and backward run inside libmagma_b200.so (engine.cu); this file only owns tensors and plumbing.
 """
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -279,7 +280,8 @@ class B200GPTJForCausalLM(nn.Module):
         """True when an adapter uses an option the fast runtime (engine.cu) does not schedule — a leading LayerNorm
         (add_layernorm, adapters.py:16-17) or the learnable adapter_scale (scaled_parallel, adapters.py:57-61). Those
         models run through the general host-only schedule csrc/gptj_sched.cu (training / full-sequence passes only)."""
-        if getattr(self, "_force_general", False):  # test hook: cross-check the two schedules on the same model
+        # test / experiment hook: run any model through the general schedule (cross-checks the two schedules)
+        if getattr(self, "_force_general", False) or os.environ.get("MB200_FORCE_GENERAL", "0") == "1":
             return True
         for blk in self.transformer.h:
             for ad in (_split_mlp(blk.mlp)[2], _split_attn(blk.attn)[2]):
