@@ -401,8 +401,8 @@ class B200GPTJForCausalLM(nn.Module):
             raise MB200Error("all blocks must carry the same adapter configuration")
         mk, ak = kinds.pop()
         for name, p in self.named_parameters():
-            if "adapter" not in name and (p.dtype != torch.bfloat16 or not p.is_cuda):
-                raise MB200Error(f"frozen LM parameter {name} must be bf16 on CUDA (got {p.dtype}, {p.device})")
+            if "adapter" not in name and (p.dtype != torch.bfloat16 or p.device.type != self._device.type):
+                raise MB200Error(f"frozen LM parameter {name} must be bf16 on {self._device} (got {p.dtype}, {p.device})")
         m = GptjModelC()
         m.n_layer, m.d, m.n_head, m.rotary_dim = n, cfg.hidden_size, cfg.num_heads, cfg.rotary_dim
         m.vocab, m.d_ff = self.lm_head.weight.shape[0], cfg.intermediate_size

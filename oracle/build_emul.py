@@ -11,7 +11,8 @@ OUT = os.path.join(OUT_DIR, "libsched_emul.so")
 SCHEDULES = [os.path.join(ROOT, "magma_b200", "csrc", "vit_train.cu"),
              os.path.join(ROOT, "magma_b200", "csrc", "gptj_sched.cu")]
 EMUL = os.path.join(ROOT, "oracle", "cabi_emul.cpp")
-DEPS = SCHEDULES + [EMUL, os.path.join(ROOT, "magma_b200", "csrc", "sched_rt.h"),
+EMUL_MODELS = os.path.join(ROOT, "oracle", "cabi_emul_models.cpp")  # model-level entries, delegating to the schedules
+DEPS = SCHEDULES + [EMUL, EMUL_MODELS, os.path.join(ROOT, "magma_b200", "csrc", "sched_rt.h"),
                     os.path.join(ROOT, "include", "magma_b200.h")]
 
 
@@ -19,7 +20,7 @@ def build(force=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in DEPS):
         return OUT
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-o", OUT, "-x", "c++", *SCHEDULES, EMUL]
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-o", OUT, "-x", "c++", *SCHEDULES, EMUL, EMUL_MODELS]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"g++ failed:\n{r.stdout}\n{r.stderr}")

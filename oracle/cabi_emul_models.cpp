@@ -1,0 +1,121 @@
+// TEST INFRASTRUCTURE — the MODEL-LEVEL entry points of the C ABI, for the CPU emulation library only.
+//
+// In the product, mb200_gptj_forward / mb200_gptj_backward / mb200_vit_forward live in csrc/engine.cu, which contains
+// kernels and runs on a GPU only. So that the DEFAULT Python paths that call them (language_model.py::_run_forward /
+// _run_backward with chunked backward, image_encoders.py::B200VisionTransformer.forward, Magma.forward, B200Engine,
+// __graft_entry__.smoke) can be replayed on the CPU by tests, this file provides the same entry points by DELEGATING
+// to the product's host-only schedules compiled into the same library (csrc/gptj_sched.cu, csrc/vit_train.cu), which
+// compute the same arithmetic from the emulated primitives (cabi_emul.cpp). Not emulated — returns MB200_E_ARG with a
+// message: KV cache (prefill / decode), last-position logits, hidden-state output.
+//
+// What a replay through this file shows: the Python wiring of the default path (pointer tables, workspaces, autograd
+// functions, arena, engine) is intact. What it does not show: anything about engine.cu's own schedule or any kernel.
+#include <string.h>
+
+#include <vector>
+
+#include "../include/magma_b200.h"
+
+namespace mb200 {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+struct ExModel {
+  mb200_gptj_model_ex m;
+  std::vector<mb200_gptj_layer_ex> layers;
+};
+
+void to_ex(const mb200_adapter& a, mb200_adapter_ex& e) {
+  memset(&e, 0, sizeof(e));
+  e.wd = a.wd;
+  e.bd = a.bd;
+  e.wu = a.wu;
+  e.bu = a.bu;
+  e.g_wd = a.g_wd;
+  e.g_bd = a.g_bd;
+  e.g_wu = a.g_wu;
+  e.g_bu = a.g_bu;
+}
+
+void convert(const mb200_gptj_model* m, ExModel& x) {
+  x.layers.resize(m->n_layer);
+  for (int l = 0; l < m->n_layer; ++l) {
+    const mb200_gptj_layer& s = m->layers[l];
+    mb200_gptj_layer_ex& d = x.layers[l];
+    d.ln1_g = s.ln1_g;
+    d.ln1_b = s.ln1_b;
+    d.w_qkv = s.w_qkv;
+    d.w_out = s.w_out;
+    d.w_fc_in = s.w_fc_in;
+    d.b_fc_in = s.b_fc_in;
+    d.w_fc_out = s.w_fc_out;
+    d.b_fc_out = s.b_fc_out;
+    to_ex(s.mlp_ad, d.mlp_ad);
+    to_ex(s.attn_ad, d.attn_ad);
+  }
+  memset(&x.m, 0, sizeof(x.m));
+  x.m.n_layer = m->n_layer;
+  x.m.d = m->d;
+  x.m.n_head = m->n_head;
+  x.m.rotary_dim = m->rotary_dim;
+  x.m.vocab = m->vocab;
+  x.m.d_ff = m->d_ff;
+  x.m.mlp_adapter = m->mlp_adapter;
+  x.m.mlp_adapter_r = m->mlp_adapter_r;
+  x.m.attn_adapter = m->attn_adapter;
+  x.m.attn_adapter_r = m->attn_adapter_r;
+  x.m.ln_eps = m->ln_eps;
+  x.m.layers = x.layers.data();
+  x.m.lnf_g = m->lnf_g;
+  x.m.lnf_b = m->lnf_b;
+  x.m.w_lm = m->w_lm;
+  x.m.b_lm = m->b_lm;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mb200_gptj_workspace_bytes(const mb200_gptj_model* m, int32_t B, int32_t S, int32_t, int32_t) {
+  ExModel x;
+  convert(m, x);
+  return mb200_gptj_sched_workspace_bytes(&x.m, B, S);
+}
+
+int mb200_gptj_forward(const mb200_gptj_model* m, const void* xin, const int64_t* labels, void* logits, int64_t ldv,
+                       int32_t last_only, float* loss, void* hidden, void* kcache, void* vcache, int32_t, int32_t pos0,
+                       int32_t B, int32_t S, int32_t, void* ws, size_t ws_bytes, void* stream) {
+  if (kcache || vcache || last_only || hidden || pos0 != 0) {
+    mb200::set_error("emulation: KV cache / last-position logits / hidden output live in engine.cu (GPU only)");
+    return MB200_E_ARG;
+  }
+  ExModel x;
+  convert(m, x);
+  return mb200_gptj_sched_forward(&x.m, xin, labels, logits, ldv, loss, B, S, ws, ws_bytes, stream);
+}
+
+// The product processes layers [layer_lo, layer_hi) per call so the caller can overlap the gradient exchange. The
+// general schedule runs the whole backward at once: it is issued with the LAST chunk (layer_lo == 0, the call that
+// carries dx); earlier chunk calls are no-ops. Single-process replays only.
+int mb200_gptj_backward(const mb200_gptj_model* m, void* dx, float loss_scale, int32_t layer_hi, int32_t layer_lo,
+                        int32_t accumulate, int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream) {
+  if (layer_lo < 0 || layer_lo > layer_hi || layer_hi > m->n_layer) {
+    mb200::set_error("gptj_backward: bad layer range [%d,%d)", layer_lo, layer_hi);
+    return MB200_E_ARG;
+  }
+  if (layer_lo != 0) return 0;
+  ExModel x;
+  convert(m, x);
+  return mb200_gptj_sched_backward(&x.m, dx, loss_scale, accumulate, B, S, ws, ws_bytes, stream);
+}
+
+size_t mb200_vit_workspace_bytes(const mb200_vit_model* m, int32_t B) { return mb200_vit_train_workspace_bytes(m, B); }
+
+int mb200_vit_forward(const mb200_vit_model* m, const void* images, void* feats, int32_t B, void* ws, size_t ws_bytes,
+                      void* stream) {
+  return mb200_vit_forward_train(m, images, feats, B, ws, ws_bytes, stream);
+}
+
+}  // extern "C"
