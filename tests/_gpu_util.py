@@ -1,5 +1,12 @@
 """Helpers for the GPU parity tests: build the CUDA-backed Magma from oracle/reference-named weights."""
+import os
+
 import torch
+
+
+def gpu_device():
+    """cuda:0 — or the CPU when tests/test_default_path_replay_cpu.py replays a GPU test body on emulated kernels."""
+    return torch.device(os.environ.get("MB200_TEST_DEVICE", "cuda:0"))
 
 
 def build_magma_from_weights(w, cfg, adapter_config, S, dev, vit_name="clip_vit_test"):

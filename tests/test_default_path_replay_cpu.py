@@ -31,3 +31,21 @@ def test_smoke_replays_on_emulated_kernels(replay, capsys):
 
     entry.smoke(_device="cpu", _decode=False)     # KV-cache decoding lives in engine.cu (GPU only)
     assert "smoke (no decode) OK" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("tag", ["v1_mlp_normal", "v2_mlp_attn_normal", "parallel", "no_adapters"])
+def test_reference_goldens_replay_on_emulated_kernels(replay, monkeypatch, golden_dir, tag):
+    """The fixtures the REFERENCE ITSELF produced (tests/golden/magma_*.pt: loss, logits, every trainable gradient of
+    Magma.forward under four adapter wirings) against this package's Python + host-only schedules on emulated kernels —
+    the body of tests/test_model_gpu.py::test_magma_matches_reference_golden, unchanged."""
+    import test_model_gpu as G
+
+    monkeypatch.setenv("MB200_TEST_DEVICE", "cpu")
+    G.test_magma_matches_reference_golden(golden_dir, tag)
+
+
+def test_reference_assertion_behaviour_replays(replay, monkeypatch):
+    import test_model_gpu as G
+
+    monkeypatch.setenv("MB200_TEST_DEVICE", "cpu")
+    G.test_magma_forward_asserts_like_the_reference()

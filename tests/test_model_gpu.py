@@ -26,10 +26,10 @@ def test_model_group(group):
 def test_magma_matches_reference_golden(golden_dir, tag):
     import torch
 
-    from _gpu_util import build_magma_from_weights, rel
+    from _gpu_util import build_magma_from_weights, gpu_device, rel
     from conftest import oracle_cfg_from_record
 
-    dev = torch.device("cuda:0")
+    dev = gpu_device()
     rec = torch.load(os.path.join(golden_dir, f"magma_{tag}.pt"), weights_only=False)
     cfg = oracle_cfg_from_record(rec)
     # the reference ran in fp32; the CUDA path stores weights/activations in bf16
@@ -57,10 +57,10 @@ def test_magma_matches_reference_golden(golden_dir, tag):
 def test_vit_embed_generate_match_reference_golden(golden_dir):
     import torch
 
-    from _gpu_util import build_magma_from_weights, rel
+    from _gpu_util import build_magma_from_weights, gpu_device, rel
     from conftest import oracle_cfg_from_record
 
-    dev = torch.device("cuda:0")
+    dev = gpu_device()
     rec = torch.load(os.path.join(golden_dir, "magma_v1_mlp_normal.pt"), weights_only=False)
     cfg = oracle_cfg_from_record(rec)
     model = build_magma_from_weights(rec["weights"], cfg, rec["adapter_config"], rec["S"], dev, vit_name="clip_vit_golden")
@@ -81,11 +81,11 @@ def test_vit_embed_generate_match_reference_golden(golden_dir):
 def test_magma_forward_asserts_like_the_reference():
     import torch
 
-    from _gpu_util import build_magma_from_weights
+    from _gpu_util import build_magma_from_weights, gpu_device
     from oracle import magma_oracle as O
     from tools.model_check import small_cfg
 
-    dev = torch.device("cuda:0")
+    dev = gpu_device()
     cfg = small_cfg()
     w = {k: v.to(torch.bfloat16).float() for k, v in O.init_weights(cfg, seed=3).items()}
     model = build_magma_from_weights(w, cfg, {"mlp": {"adapter_type": "normal", "downsample_factor": 4}}, 32, dev)
