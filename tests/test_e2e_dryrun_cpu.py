@@ -297,3 +297,45 @@ def test_magma_with_layernorm_and_scaled_adapters_end_to_end(emul_ops, monkeypat
     lm_names = [n for n in names if n.startswith("lm.")]
     bad = {k: round(rel(sd[k].grad, params[k].grad), 4) for k in lm_names if rel(sd[k].grad, params[k].grad) > 5e-2}
     assert not bad, bad
+
+
+def test_gradient_accumulation_matches_the_mean_of_micro_batch_gradients(emul_ops, monkeypatch):
+    """gradient_accumulation_steps = 2 (MAGMA_v1.yml uses 8): engine.backward scales each micro-batch loss by 1/2 and
+    accumulates; engine.step only acts at the boundary (train_loop.py:9-19 under DeepSpeed)."""
+    from magma_b200.train_loop import B200Engine
+
+    cfg = tiny_cfg()
+    S = 16
+    w16 = oracle_weights(cfg)
+    images, captions = O.synthetic_batch(cfg, 4, S, seed=21)
+    images = images.to(torch.bfloat16)
+    model, mc = build(monkeypatch, cfg, w16, S, freeze_enc=False, gradient_accumulation_steps=2, lr=1e-2,
+                      warmup_num_steps=2)
+    model.eval()
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    sd = dict(model.named_parameters())
+
+    def grads_of(lo, hi):
+        for p in model.parameters():
+            p.grad = None
+        model.arena.grad.zero_()
+        model(images[lo:hi], captions[lo:hi]).loss.backward()
+        return {n: sd[n].grad.clone() for n in names}
+
+    ga, gb = grads_of(0, 2), grads_of(2, 4)
+    for p in model.parameters():
+        p.grad = None
+    model.arena.grad.zero_()
+    eng = B200Engine(model, mc, n_buckets=2)
+    before = model.arena.master.clone()
+    o = eng(images[0:2], captions[0:2])
+    eng.backward(o.loss)
+    eng.step()                                        # not a boundary: nothing moves, gradients stay
+    assert torch.equal(model.arena.master, before) and eng.global_step == 0
+    o = eng(images[2:4], captions[2:4])
+    eng.backward(o.loss)
+    got = {n: sd[n].grad.clone() for n in names}
+    bad = {n: round(rel(got[n], 0.5 * (ga[n] + gb[n])), 4) for n in names if rel(got[n], 0.5 * (ga[n] + gb[n])) > 1e-2}
+    assert not bad, bad
+    eng.step()                                        # boundary: WarmupLR gives lr(0) = 0, but the step is counted
+    assert eng.global_step == 1 and float(model.arena.grad.abs().sum()) == 0.0
