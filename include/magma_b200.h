@@ -431,6 +431,14 @@ int mb200_gptj_sched_forward(const mb200_gptj_model_ex* m, const void* x, const 
 int mb200_gptj_sched_backward(const mb200_gptj_model_ex* m, void* dx, float loss_scale, int32_t accumulate, int32_t B,
                               int32_t S, void* ws, size_t ws_bytes, void* stream);
 
+/* Inference pass of the general schedule (no saved activations): optional KV cache exactly as mb200_gptj_forward
+ * (prefill S > 1 at pos0, decode S == 1 through mb200_attn_decode), last_only = project the last position only
+ * (logits [B][ldv]), hidden = ln_f output or NULL. */
+size_t mb200_gptj_sched_infer_workspace_bytes(const mb200_gptj_model_ex* m, int32_t B, int32_t S, int32_t S_kv_max);
+int mb200_gptj_sched_infer(const mb200_gptj_model_ex* m, const void* x, void* logits, int64_t ldv, int32_t last_only,
+                           void* hidden, void* kcache, void* vcache, int32_t S_kv_max, int32_t pos0, int32_t B, int32_t S,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* out = s[0] * u + r1 + r2 over n bf16 elements (s: DEVICE fp32 scalar or NULL = 1; r1, r2 optional) — the
  * `* adapter_scale` of ParallelAdapter.forward (magma/adapters.py:63-66,85-92) with the residual sum folded in. */
 int mb200_scale_add(const void* u, const float* s, const void* r1, const void* r2, void* out, int64_t n, void* stream);
@@ -454,6 +462,11 @@ int mb200_attn_bwd_tile(const void* qkv, int64_t ld_qkv, const void* dO, int64_t
 
 int mb200_attn_decode(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, void* out, int64_t ld_out,
                       int32_t B, int32_t H, int32_t hd, int32_t S_kv_max, int32_t pos, void* stream);
+/* K/V of S positions (prefill) from the fused, rotated qkv rows [B*S][3][H][hd] into one layer's static cache
+ * [B][H][S_kv_max][hd] at positions [pos0, pos0 + S) — the in-place replacement of the torch.cat cache growth of
+ * hf:gptj/modeling_gptj.py:209-214 for S > 1. */
+int mb200_kv_append(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, int32_t B, int32_t S, int32_t H,
+                    int32_t hd, int32_t S_kv_max, int32_t pos0, void* stream);
 
 #ifdef __cplusplus
 }

@@ -184,6 +184,7 @@ def _setup_signatures(L):
     L.mb200_vit_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_vit_train_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_gptj_sched_workspace_bytes.restype = ctypes.c_size_t
+    L.mb200_gptj_sched_infer_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_launch_count.restype = ctypes.c_longlong
 
 
@@ -203,4 +204,5 @@ EXPORTED_SYMBOLS = [
     "mb200_layernorm_param_grad_rows", "mb200_set_gemm_sm_limit", "mb200_scale_add", "mb200_dot",
     "mb200_gptj_sched_workspace_bytes", "mb200_gptj_sched_forward", "mb200_gptj_sched_backward",
     "mb200_col_moments", "mb200_channel_affine", "mb200_col2im3x3", "mb200_avgpool_nhwc_bwd",
+    "mb200_kv_append", "mb200_gptj_sched_infer_workspace_bytes", "mb200_gptj_sched_infer",
 ]

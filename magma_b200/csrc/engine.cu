@@ -903,3 +903,21 @@ extern "C" int mb200_attn_decode(const void* qkv, int64_t ld_qkv, void* kcache, 
   MB_CUDA(cudaGetLastError());
   return 0;
 }
+
+// K/V rows of a prefill (or any S > 1 continuation) into the static cache — the launch gptj_forward issues, exposed for
+// the host-only general schedule (csrc/gptj_sched.cu).
+extern "C" int mb200_kv_append(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, int32_t B, int32_t S,
+                               int32_t H, int32_t hd, int32_t S_kv_max, int32_t pos0, void* stream) {
+  int rc = check_arch();
+  if (rc) return rc;
+  MB_REQUIRE(hd % 8 == 0 && B > 0 && S > 0 && pos0 >= 0 && pos0 + S <= S_kv_max, MB200_E_SHAPE,
+             "kv_append: bad hd=%d B=%d S=%d pos0=%d Smax=%d", hd, B, S, pos0, S_kv_max);
+  const long long tot = (long long)B * S * H * (hd / 8);
+  int grid = (int)((tot + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  kv_append_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)qkv, ld_qkv, (bf16*)kcache, (bf16*)vcache, B, S, H,
+                                                           hd, S_kv_max, pos0);
+  count_launch();
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}

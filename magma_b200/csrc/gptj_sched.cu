@@ -66,6 +66,10 @@ struct Epi {
   int rope_mode = 0, rope_S = 0, rope_hd = 0, rope_rot = 0, rope_ncols = 0;
 };
 
+// split-K scratch of the pass being issued (small-M decode GEMMs stream their weights; see gemm.cu::plan_small_m)
+thread_local void* t_splitk_ws = nullptr;
+thread_local long long t_splitk_bytes = 0;
+
 int gemm(void* st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, int c_f32, const Epi& e = Epi(),
          int nb0 = 1, int nb1 = 1, long long c_bs0 = 0, long long c_bs1 = 0) {
   mb200_gemm_args g;
@@ -106,6 +110,8 @@ int gemm(void* st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, in
   g.rope_hd = e.rope_hd;
   g.rope_rot = e.rope_rot;
   g.rope_ncols = e.rope_ncols;
+  g.splitk_ws = t_splitk_ws;
+  g.splitk_ws_bytes = t_splitk_bytes;
   return mb200_gemm(&g, st);
 }
 
@@ -466,8 +472,182 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int acc,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// inference (no saved activations): full sequence, prefill into a KV cache, or one decode step
+// ---------------------------------------------------------------------------------------------
+struct InferPlan {
+  int M, d, dff, H, hd, ldS;
+  bf16s *xa, *xb, *h, *qkv, *P, *attn_o, *hact, *ax, *a_out, *mlp_out, *xf_ln;
+  AdapterActs am, aa;
+  float *scores, *rope_tab, *splitk;
+  size_t splitk_bytes, bytes;
+};
+
+int make_infer_plan(InferPlan& P, const mb200_gptj_model_ex* m, int B, int S, int Skv, void* ws) {
+  Plan chk;  // same validation as the training plan
+  MBS_TRY(make_plan(chk, m, B, S, nullptr));
+  Carver c(ws);
+  P.M = B * S;
+  P.d = m->d;
+  P.dff = m->d_ff;
+  P.H = m->n_head;
+  P.hd = m->d / m->n_head;
+  const int Sk = Skv > S ? Skv : S;
+  P.ldS = (int)align_up(Sk, 8);
+  const size_t M = P.M, d = P.d, dff = P.dff, nP = (size_t)B * P.H * S * P.ldS;
+  P.xa = c.take<bf16s>(M * d);
+  P.xb = c.take<bf16s>(M * d);
+  P.h = c.take<bf16s>(M * d);
+  P.qkv = c.take<bf16s>(M * 3 * d);
+  P.P = c.take<bf16s>(nP);
+  P.attn_o = c.take<bf16s>(M * d);
+  P.hact = c.take<bf16s>(M * dff);
+  P.ax = c.take<bf16s>(M * d);
+  P.a_out = c.take<bf16s>(M * d);
+  P.mlp_out = c.take<bf16s>(M * d);
+  P.xf_ln = c.take<bf16s>(M * d);
+  carve_adapter(c, P.am, m->layers[0].mlp_ad, m->mlp_adapter, M, d, m->mlp_adapter_r);
+  carve_adapter(c, P.aa, m->layers[0].attn_ad, m->attn_adapter, M, d, m->attn_adapter_r);
+  P.am.mean = P.am.rstd = P.aa.mean = P.aa.rstd = nullptr;  // no backward: LayerNorm statistics are not kept
+  P.scores = c.take<float>(nP);
+  P.rope_tab = c.take<float>((size_t)S * m->rotary_dim);
+  P.splitk_bytes = M <= 128 ? (size_t)16 * M * d * sizeof(float) : 0;
+  P.splitk = P.splitk_bytes ? c.take<float>(P.splitk_bytes / sizeof(float)) : nullptr;
+  P.bytes = align_up(c.off, 256);
+  return 0;
+}
+
+int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, long long ldv, int last_only, bf16s* hidden,
+                  bf16s* kcache, bf16s* vcache, int Smax, int pos0, int B, int S, void* ws, size_t ws_bytes, void* st) {
+  InferPlan P;
+  MBS_TRY(make_infer_plan(P, m, B, S, kcache ? Smax : S, ws));
+  MBS_REQUIRE(ws != nullptr && ws_bytes >= P.bytes, MB200_E_ARG, "gptj_sched_infer: workspace too small (%zu < %zu)",
+              ws_bytes, P.bytes);
+  MBS_REQUIRE((kcache == nullptr) == (vcache == nullptr), MB200_E_ARG, "gptj_sched_infer: kcache and vcache go together");
+  MBS_REQUIRE(pos0 >= 0 && (kcache ? pos0 + S <= Smax : pos0 == 0), MB200_E_SHAPE,
+              "gptj_sched_infer: pos0=%d S=%d does not fit the cache (%d) / needs a cache", pos0, S, Smax);
+  for (int l = 1; l < m->n_layer; ++l)
+    MBS_REQUIRE(has_ln(m->layers[l].mlp_ad) == has_ln(m->layers[0].mlp_ad) &&
+                    has_scale(m->layers[l].mlp_ad) == has_scale(m->layers[0].mlp_ad) &&
+                    has_ln(m->layers[l].attn_ad) == has_ln(m->layers[0].attn_ad) &&
+                    has_scale(m->layers[l].attn_ad) == has_scale(m->layers[0].attn_ad),
+                MB200_E_ARG, "gptj_sched_infer: every layer must carry the same adapter options");
+  const int M = P.M, d = P.d, dff = P.dff, H = P.H, hd = P.hd;
+  const int Sk = kcache ? pos0 + S : S;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const size_t cache_layer = (size_t)B * H * Smax * hd;
+  struct SplitScope {
+    SplitScope(void* w, size_t b) { t_splitk_ws = w; t_splitk_bytes = (long long)b; }
+    ~SplitScope() { t_splitk_ws = nullptr; t_splitk_bytes = 0; }
+  } split_scope(P.splitk, P.splitk_bytes);
+  MBS_TRY(mb200_rope_table(P.rope_tab, S, m->rotary_dim, pos0, st));
+  const bf16s* xin = x;
+  for (int l = 0; l < m->n_layer; ++l) {
+    const mb200_gptj_layer_ex& L = m->layers[l];
+    bf16s* xout = (l & 1) ? P.xb : P.xa;
+    MBS_TRY(mb200_layernorm_fwd(xin, d, L.ln1_g, L.ln1_b, P.h, d, nullptr, nullptr, M, d, m->ln_eps, st));
+    {
+      Epi e;
+      e.rope_tab = P.rope_tab;
+      e.rope_mode = 1;
+      e.rope_S = S;
+      e.rope_hd = hd;
+      e.rope_rot = m->rotary_dim;
+      e.rope_ncols = 2 * d;
+      MBS_TRY(gemm(st, M, 3 * d, d, mat(P.h, d), mat(L.w_qkv, d), P.qkv, 3 * d, 0, e));
+    }
+    bf16s* kc = kcache ? kcache + (size_t)l * cache_layer : nullptr;
+    bf16s* vc = vcache ? vcache + (size_t)l * cache_layer : nullptr;
+    if (kcache && S == 1) {
+      MBS_TRY(mb200_attn_decode(P.qkv, 3 * d, kc, vc, P.attn_o, d, B, H, hd, Smax, pos0, st));
+    } else {
+      Mat Q = mat(P.qkv, 3 * d, 0, hd, (long long)S * 3 * d), Kk, Vv;
+      if (kcache) {
+        MBS_TRY(mb200_kv_append(P.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0, st));
+        Kk = mat(kc, hd, 0, (long long)Smax * hd, (long long)H * Smax * hd);
+        Vv = mat(vc, hd, 1, (long long)Smax * hd, (long long)H * Smax * hd);
+      } else {
+        Kk = mat(P.qkv + d, 3 * d, 0, hd, (long long)S * 3 * d);
+        Vv = mat(P.qkv + 2 * d, 3 * d, 1, hd, (long long)S * 3 * d);
+      }
+      const long long pb0 = (long long)S * P.ldS, pb1 = (long long)H * S * P.ldS;
+      MBS_TRY(gemm(st, S, Sk, hd, Q, Kk, P.scores, P.ldS, 1, Epi(), H, B, pb0, pb1));
+      MBS_TRY(mb200_softmax_fwd(P.scores, P.ldS, pb0, P.P, P.ldS, pb0, B * H, S, Sk, scale, 1, Sk - S, st));
+      MBS_TRY(gemm(st, S, hd, Sk, mat(P.P, P.ldS, 0, pb0, pb1), Vv, P.attn_o, d, 0, Epi(), H, B, hd, (long long)S * d));
+    }
+    if (m->attn_adapter == MB200_ADAPTER_NONE) {
+      Epi e;
+      e.res1 = xin;
+      e.ld_res = d;
+      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), mat(L.w_out, d), P.ax, d, 0, e));
+    } else if (m->attn_adapter == MB200_ADAPTER_NORMAL) {
+      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), mat(L.w_out, d), P.a_out, d, 0));
+      MBS_TRY(adapter_fwd(st, L.attn_ad, P.aa, M, d, m->attn_adapter_r, m->ln_eps, P.a_out, P.ax, P.a_out, xin));
+    } else {
+      Epi e;
+      e.res1 = xin;
+      e.ld_res = d;
+      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), mat(L.w_out, d), P.a_out, d, 0, e));
+      MBS_TRY(adapter_fwd(st, L.attn_ad, P.aa, M, d, m->attn_adapter_r, m->ln_eps, P.h, P.ax, P.a_out, nullptr));
+    }
+    {
+      Epi e;
+      e.bias = L.b_fc_in;
+      e.act = MB200_ACT_GELU_NEW;
+      MBS_TRY(gemm(st, M, dff, d, mat(P.h, d), mat(L.w_fc_in, d), P.hact, dff, 0, e));
+    }
+    Epi eo;
+    eo.bias = L.b_fc_out;
+    if (m->mlp_adapter == MB200_ADAPTER_NONE) {
+      eo.res1 = P.ax;
+      eo.ld_res = d;
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), xout, d, 0, eo));
+    } else if (m->mlp_adapter == MB200_ADAPTER_NORMAL) {
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), P.mlp_out, d, 0, eo));
+      MBS_TRY(adapter_fwd(st, L.mlp_ad, P.am, M, d, m->mlp_adapter_r, m->ln_eps, P.mlp_out, xout, P.mlp_out, P.ax));
+    } else {
+      eo.res1 = P.ax;
+      eo.ld_res = d;
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), P.mlp_out, d, 0, eo));
+      MBS_TRY(adapter_fwd(st, L.mlp_ad, P.am, M, d, m->mlp_adapter_r, m->ln_eps, P.h, xout, P.mlp_out, nullptr));
+    }
+    xin = xout;
+  }
+  if (!logits && !hidden) return 0;
+  const int rows = last_only ? B : M;
+  if (last_only)
+    MBS_TRY(mb200_layernorm_fwd(xin + (size_t)(S - 1) * d, (long long)S * d, m->lnf_g, m->lnf_b, P.xf_ln, d, nullptr, nullptr,
+                                B, d, m->ln_eps, st));
+  else
+    MBS_TRY(mb200_layernorm_fwd(xin, d, m->lnf_g, m->lnf_b, P.xf_ln, d, nullptr, nullptr, M, d, m->ln_eps, st));
+  if (hidden) MBS_TRY(rt_copy(hidden, P.xf_ln, (size_t)rows * d * sizeof(bf16s), st));
+  if (logits) {
+    MBS_REQUIRE(ldv % 8 == 0 && ldv >= m->vocab, MB200_E_ALIGN, "gptj_sched_infer: ldv=%lld must be >= vocab and %%8", ldv);
+    Epi e;
+    e.bias = m->b_lm;
+    MBS_TRY(gemm(st, rows, m->vocab, d, mat(P.xf_ln, d), mat(m->w_lm, d), logits, ldv, 0, e));
+  }
+  return 0;
+}
+
 }  // namespace
 }  // namespace mb200
+
+extern "C" size_t mb200_gptj_sched_infer_workspace_bytes(const mb200_gptj_model_ex* m, int32_t B, int32_t S,
+                                                         int32_t S_kv_max) {
+  mb200::InferPlan P;
+  if (mb200::make_infer_plan(P, m, B, S, S_kv_max, nullptr)) return 0;
+  return P.bytes;
+}
+
+extern "C" int mb200_gptj_sched_infer(const mb200_gptj_model_ex* m, const void* x, void* logits, int64_t ldv,
+                                      int32_t last_only, void* hidden, void* kcache, void* vcache, int32_t S_kv_max,
+                                      int32_t pos0, int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream) {
+  int rc = mb200::rt_check_arch();
+  if (rc) return rc;
+  return mb200::forward_infer(m, (const mb200::bf16s*)x, (mb200::bf16s*)logits, ldv, last_only, (mb200::bf16s*)hidden,
+                              (mb200::bf16s*)kcache, (mb200::bf16s*)vcache, S_kv_max, pos0, B, S, ws, ws_bytes, stream);
+}
 
 extern "C" size_t mb200_gptj_sched_workspace_bytes(const mb200_gptj_model_ex* m, int32_t B, int32_t S) {
   mb200::Plan P;

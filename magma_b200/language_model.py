@@ -473,25 +473,48 @@ class B200GPTJForCausalLM(nn.Module):
         return (loss.squeeze(0) if loss is not None else None), lg
 
     def _run_forward_general(self, x, labels, training, cache, last_only, want_hidden, want_logits):
-        """Full-sequence pass through csrc/gptj_sched.cu (adapters with add_layernorm / adapter_scale)."""
-        if cache is not None or last_only or want_hidden:
-            raise MB200Error("adapters with add_layernorm / scaled_parallel run through the general schedule, which has "
-                             "no KV-cache, last-position or hidden-state output (generate() is not supported for them)")
-        B, S, _ = x.shape
+        """csrc/gptj_sched.cu (adapters with add_layernorm / adapter_scale, or MB200_FORCE_GENERAL): the training pass
+        (activations saved for backward) when a loss is asked for, else the inference pass — full sequence, KV-cache
+        prefill / decode step, last-position logits, ln_f output."""
+        B, S, d = x.shape
         m = self._cmodel_ex()[0]
         V, ldv = self.lm_head.weight.shape[0], self.ldv
-        ws = self._workspace_ex(B, S)
-        logits = torch.empty(B * S, ldv, dtype=torch.bfloat16, device=x.device) if want_logits else None
-        loss = torch.zeros(1, dtype=torch.float32, device=x.device) if labels is not None else None
-        if labels is not None:
-            labels = labels.to(device=x.device, dtype=torch.int64).contiguous()
-        self._generation += 1  # this schedule always records its activations in the workspace
-        check(lib().mb200_gptj_sched_forward(ctypes.byref(m), ops._ptr(x), ops._ptr(labels), ops._ptr(logits),
-                                             ctypes.c_int64(ldv), ops._ptr(loss), B, S, ops._ptr(ws),
-                                             ctypes.c_size_t(ws.numel()), ops._stream()))
-        self._last_hidden = None
-        lg = logits.view(B, S, ldv)[..., :V] if logits is not None else None
-        return (loss.squeeze(0) if loss is not None else None), lg
+        if labels is not None or training:
+            if cache is not None or last_only or want_hidden:
+                raise MB200Error("a loss together with a KV cache / last-position logits / hidden states is not supported")
+            ws = self._workspace_ex(B, S)
+            logits = torch.empty(B * S, ldv, dtype=torch.bfloat16, device=x.device) if want_logits else None
+            loss = torch.zeros(1, dtype=torch.float32, device=x.device) if labels is not None else None
+            if labels is not None:
+                labels = labels.to(device=x.device, dtype=torch.int64).contiguous()
+            self._generation += 1  # this pass records its activations in the workspace
+            check(lib().mb200_gptj_sched_forward(ctypes.byref(m), ops._ptr(x), ops._ptr(labels), ops._ptr(logits),
+                                                 ctypes.c_int64(ldv), ops._ptr(loss), B, S, ops._ptr(ws),
+                                                 ctypes.c_size_t(ws.numel()), ops._stream()))
+            self._last_hidden = None
+            lg = logits.view(B, S, ldv)[..., :V] if logits is not None else None
+            return (loss.squeeze(0) if loss is not None else None), lg
+        S_kv = cache.S_max if cache is not None else S
+        key = ("ex_infer", B, S, S_kv)
+        if key not in self._ws:
+            nbytes = lib().mb200_gptj_sched_infer_workspace_bytes(ctypes.byref(m), B, S, S_kv)
+            if nbytes == 0:
+                raise MB200Error(lib().mb200_last_error().decode())
+            self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+        ws = self._ws[key]
+        rows = B if last_only else B * S
+        logits = torch.empty(rows, ldv, dtype=torch.bfloat16, device=x.device) if want_logits else None
+        hidden = torch.empty(rows, d, dtype=torch.bfloat16, device=x.device) if want_hidden else None
+        check(lib().mb200_gptj_sched_infer(
+            ctypes.byref(m), ops._ptr(x), ops._ptr(logits), ctypes.c_int64(ldv), int(last_only), ops._ptr(hidden),
+            ops._ptr(cache.k) if cache is not None else None, ops._ptr(cache.v) if cache is not None else None,
+            S_kv if cache is not None else 0, cache.pos if cache is not None else 0, B, S, ops._ptr(ws),
+            ctypes.c_size_t(ws.numel()), ops._stream()))
+        if cache is not None:
+            cache.pos += S
+        self._last_hidden = hidden
+        lg = logits.view(B, 1 if last_only else S, ldv)[..., :V] if logits is not None else None
+        return None, lg
 
     def _run_backward(self, shape, loss_scale):
         B, S, d = shape

@@ -604,6 +604,59 @@ int mb200_avgpool_nhwc(const void* src_, void* dst_, int32_t B, int32_t H, int32
   return 0;
 }
 
+// KV cache   (engine.cu: kv_append_kernel / attn_decode_kernel)
+int mb200_kv_append(const void* qkv_, int64_t ld, void* kc_, void* vc_, int32_t B, int32_t S, int32_t H, int32_t hd,
+                    int32_t Smax, int32_t pos0, void*) {
+  EM_REQUIRE(hd % 8 == 0 && B > 0 && S > 0 && pos0 >= 0 && pos0 + S <= Smax, MB200_E_SHAPE, "kv_append: bad shape");
+  const bf16_t* qkv = (const bf16_t*)qkv_;
+  bf16_t *kc = (bf16_t*)kc_, *vc = (bf16_t*)vc_;
+  for (long long b = 0; b < B; ++b)
+    for (int s = 0; s < S; ++s)
+      for (int h = 0; h < H; ++h) {
+        const bf16_t* src = qkv + (b * S + s) * ld + (long long)h * hd;
+        const long long dst = ((b * H + h) * Smax + (pos0 + s)) * hd;
+        memcpy(kc + dst, src + (long long)H * hd, (size_t)hd * 2);
+        memcpy(vc + dst, src + 2LL * H * hd, (size_t)hd * 2);
+      }
+  return 0;
+}
+
+// one decode step: append this step's k, v at `pos`, then softmax(q K^T / sqrt(hd)) V over [0, pos], probabilities
+// rounded to bf16 before P*V like the prefill path
+int mb200_attn_decode(const void* qkv_, int64_t ld_qkv, void* kc_, void* vc_, void* out_, int64_t ld_out, int32_t B,
+                      int32_t H, int32_t hd, int32_t Smax, int32_t pos, void*) {
+  EM_REQUIRE(hd % 8 == 0 && pos >= 0 && pos < Smax, MB200_E_SHAPE, "attn_decode: bad hd / pos");
+  const bf16_t* qkv = (const bf16_t*)qkv_;
+  bf16_t *kc = (bf16_t*)kc_, *vc = (bf16_t*)vc_, *out = (bf16_t*)out_;
+  const float scale = 1.f / sqrtf((float)hd);
+  std::vector<float> sc(pos + 1);
+  for (long long b = 0; b < B; ++b)
+    for (int h = 0; h < H; ++h) {
+      const bf16_t* q = qkv + b * ld_qkv + (long long)h * hd;
+      bf16_t* kb = kc + ((b * H + h) * (long long)Smax) * hd;
+      bf16_t* vb = vc + ((b * H + h) * (long long)Smax) * hd;
+      memcpy(kb + (long long)pos * hd, q + (long long)H * hd, (size_t)hd * 2);
+      memcpy(vb + (long long)pos * hd, q + 2LL * H * hd, (size_t)hd * 2);
+      float m = -INFINITY, sum = 0.f;
+      for (int j = 0; j <= pos; ++j) {
+        float acc = 0.f;
+        for (int c = 0; c < hd; ++c) acc += b2f(kb[(long long)j * hd + c]) * b2f(q[c]);
+        sc[j] = acc * scale;
+        m = fmaxf(m, sc[j]);
+      }
+      for (int j = 0; j <= pos; ++j) {
+        sc[j] = expf(sc[j] - m);
+        sum += sc[j];
+      }
+      for (int c = 0; c < hd; ++c) {
+        float acc = 0.f;
+        for (int j = 0; j <= pos; ++j) acc += b2f(f2b(sc[j] / sum)) * b2f(vb[(long long)j * hd + c]);
+        out[b * ld_out + (long long)h * hd + c] = f2b(acc);
+      }
+    }
+  return 0;
+}
+
 // conv-trunk training   (col_moments_kernel / channel_affine_kernel / col2im3x3_kernel / avgpool_nhwc_bwd_kernel)
 int mb200_col_moments(const void* u_, int64_t ldu, const void* v_, int64_t ldv, const void* mask_, int64_t ldm,
                       int32_t rows, int32_t cols, float* out1, float* out2, void*) {

@@ -5,8 +5,7 @@
 // _run_backward with chunked backward, image_encoders.py::B200VisionTransformer.forward, Magma.forward, B200Engine,
 // __graft_entry__.smoke) can be replayed on the CPU by tests, this file provides the same entry points by DELEGATING
 // to the product's host-only schedules compiled into the same library (csrc/gptj_sched.cu, csrc/vit_train.cu), which
-// compute the same arithmetic from the emulated primitives (cabi_emul.cpp). Not emulated — returns MB200_E_ARG with a
-// message: KV cache (prefill / decode), last-position logits, hidden-state output.
+// compute the same arithmetic from the emulated primitives (cabi_emul.cpp), including KV-cache prefill / decode.
 //
 // What a replay through this file shows: the Python wiring of the default path (pointer tables, workspaces, autograd
 // functions, arena, engine) is intact. What it does not show: anything about engine.cu's own schedule or any kernel.
@@ -78,22 +77,30 @@ void convert(const mb200_gptj_model* m, ExModel& x) {
 
 extern "C" {
 
-size_t mb200_gptj_workspace_bytes(const mb200_gptj_model* m, int32_t B, int32_t S, int32_t, int32_t) {
+size_t mb200_gptj_workspace_bytes(const mb200_gptj_model* m, int32_t B, int32_t S, int32_t S_kv_max, int32_t) {
   ExModel x;
   convert(m, x);
-  return mb200_gptj_sched_workspace_bytes(&x.m, B, S);
+  const size_t a = mb200_gptj_sched_workspace_bytes(&x.m, B, S);
+  const size_t b = mb200_gptj_sched_infer_workspace_bytes(&x.m, B, S, S_kv_max);
+  return a > b ? a : b;
 }
 
+// labels (a loss, and possibly a backward pass afterwards) -> the training pass of the general schedule; everything
+// else (plain logits, KV-cache prefill / decode, last-position logits, hidden output) -> its inference pass
 int mb200_gptj_forward(const mb200_gptj_model* m, const void* xin, const int64_t* labels, void* logits, int64_t ldv,
-                       int32_t last_only, float* loss, void* hidden, void* kcache, void* vcache, int32_t, int32_t pos0,
-                       int32_t B, int32_t S, int32_t, void* ws, size_t ws_bytes, void* stream) {
-  if (kcache || vcache || last_only || hidden || pos0 != 0) {
-    mb200::set_error("emulation: KV cache / last-position logits / hidden output live in engine.cu (GPU only)");
-    return MB200_E_ARG;
-  }
+                       int32_t last_only, float* loss, void* hidden, void* kcache, void* vcache, int32_t S_kv_max,
+                       int32_t pos0, int32_t B, int32_t S, int32_t training, void* ws, size_t ws_bytes, void* stream) {
   ExModel x;
   convert(m, x);
-  return mb200_gptj_sched_forward(&x.m, xin, labels, logits, ldv, loss, B, S, ws, ws_bytes, stream);
+  if (labels || training) {
+    if (kcache || vcache || last_only || hidden || pos0 != 0) {
+      mb200::set_error("emulation: a loss together with a KV cache / last-position / hidden output is not a path of the product");
+      return MB200_E_ARG;
+    }
+    return mb200_gptj_sched_forward(&x.m, xin, labels, logits, ldv, loss, B, S, ws, ws_bytes, stream);
+  }
+  return mb200_gptj_sched_infer(&x.m, xin, logits, ldv, last_only, hidden, kcache, vcache, S_kv_max, pos0, B, S, ws,
+                                ws_bytes, stream);
 }
 
 // The product processes layers [layer_lo, layer_hi) per call so the caller can overlap the gradient exchange. The

@@ -26,11 +26,6 @@ def test_gpu_parity_harness_replays_on_emulated_kernels(replay, group, capsys):
     assert "[FAIL]" not in capsys.readouterr().out
 
 
-def test_smoke_replays_on_emulated_kernels(replay, capsys):
-    import __graft_entry__ as entry
-
-    entry.smoke(_device="cpu", _decode=False)     # KV-cache decoding lives in engine.cu (GPU only)
-    assert "smoke (no decode) OK" in capsys.readouterr().out
 
 
 @pytest.mark.parametrize("tag", ["v1_mlp_normal", "v2_mlp_attn_normal", "parallel", "no_adapters"])
@@ -49,3 +44,56 @@ def test_reference_assertion_behaviour_replays(replay, monkeypatch):
 
     monkeypatch.setenv("MB200_TEST_DEVICE", "cpu")
     G.test_magma_forward_asserts_like_the_reference()
+
+
+def test_generate_harness_and_reference_greedy_golden_replay(replay, monkeypatch, golden_dir, capsys):
+    """KV-cache decoding on the CPU: the generate group of the GPU harness (greedy tokens identical to the oracle's, a
+    decode step equal to the full forward) and the reference's own greedy-token golden
+    (tests/test_model_gpu.py::test_vit_embed_generate_match_reference_golden), through sampling.generate ->
+    decode_logits -> the emulated entry points (prefill + per-token decode of the general schedule)."""
+    import test_model_gpu as G
+    from tools import model_check
+
+    assert model_check.group_generate(replay)
+    assert "[FAIL]" not in capsys.readouterr().out
+    monkeypatch.setenv("MB200_TEST_DEVICE", "cpu")
+    G.test_vit_embed_generate_match_reference_golden(golden_dir)
+
+
+def test_full_smoke_replays_with_decode(replay, capsys):
+    import __graft_entry__ as entry
+
+    entry.smoke(_device="cpu")
+    assert "smoke OK" in capsys.readouterr().out
+
+
+def test_generate_works_for_layernorm_and_scaled_adapters(replay, monkeypatch):
+    """language_model routes adapters with add_layernorm / adapter_scale through the general schedule for decoding too:
+    greedy tokens of the KV-cache loop equal an argmax over full re-forwards of the growing sequence."""
+    import test_e2e_dryrun_cpu as E
+    from oracle import magma_oracle as O
+
+    mlp = {"adapter_type": "scaled_parallel", "downsample_factor": 4}
+    cfg = E.tiny_cfg(mlp_adapter=mlp)
+    w = E.oracle_weights(cfg)
+    g = torch.Generator().manual_seed(2)
+    for l in range(cfg.n_layer):
+        pre = f"lm.transformer.h.{l}.mlp"
+        for i, j in ((2, 3), (0, 1)):
+            for sfx in ("weight", "bias"):
+                w[f"{pre}.adapter.{j}.{sfx}"] = w.pop(f"{pre}.adapter.{i}.{sfx}")
+        w[f"{pre}.adapter.0.weight"] = (1.0 + 0.1 * torch.randn(cfg.d, generator=g)).to(torch.bfloat16).float()
+        w[f"{pre}.adapter.0.bias"] = (0.1 * torch.randn(cfg.d, generator=g)).to(torch.bfloat16).float()
+        w[f"{pre}.adapter_scale"] = torch.tensor([0.5 + 0.25 * l])
+    model, _ = E.build(monkeypatch, cfg, w, 16, freeze_enc=True, adapter_config={"mlp": dict(mlp, add_layernorm=True)})
+    model.lm._force_general = False
+    assert model.lm._general_schedule()          # selected by the adapter options themselves
+    model.eval()
+    emb = (torch.randn(2, 5, cfg.d, generator=g) * 0.5).to(torch.bfloat16)
+    toks = model.generate(emb, max_steps=6, temperature=0.0, decode=False)
+    x = emb
+    for i in range(6):   # reference loop without a cache: re-run the whole sequence, take the last position's argmax
+        logits = model.lm(inputs_embeds=x).logits[:, -1, :].float()
+        nxt = logits.argmax(-1)
+        assert torch.equal(toks[:, 5 + i], nxt), i
+        x = torch.cat([x, model.lm.transformer.wte(nxt[:, None])], 1)

@@ -358,6 +358,16 @@ def test_general_schedule_agrees_with_the_fast_runtime():
     assert abs(l0 - l1) < 5e-3 and _rel(lg1, lg0) < 1e-2
     bad = {n: round(_rel(g1[n], g0[n]), 4) for n in names if _rel(g1[n], g0[n]) > 2e-2}
     assert not bad, bad
+    # KV-cache decoding through the general schedule (prefill + mb200_attn_decode steps) against the fast runtime's
+    emb = model.embed([x])
+    t_general = model.generate(emb, max_steps=8, temperature=0.0, decode=False)
+    model.lm._force_general = False
+    model.lm.invalidate()
+    model.lm.attach_arena(model.arena)
+    t_fast = model.generate(emb, max_steps=8, temperature=0.0, decode=False)
+    n = min(t_general.shape[1], t_fast.shape[1])
+    assert torch.equal(t_general[:, : emb.shape[1] + 1], t_fast[:, : emb.shape[1] + 1])      # first token: same logits
+    assert (t_general[:, :n] == t_fast[:, :n]).float().mean().item() > 0.8               # later: up to bf16 near-ties
 
 
 def test_conv_trunk_training_kernels_match_torch():
