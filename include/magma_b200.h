@@ -431,6 +431,11 @@ int mb200_gptj_sched_forward(const mb200_gptj_model_ex* m, const void* x, const 
 int mb200_gptj_sched_backward(const mb200_gptj_model_ex* m, void* dx, float loss_scale, int32_t accumulate, int32_t B,
                               int32_t S, void* ws, size_t ws_bytes, void* stream);
 
+/* As mb200_gptj_backward: layers layer_hi-1 .. layer_lo per call (LM head / CE backward when layer_hi == n_layer), so
+ * the caller can exchange the gradients of finished layers while the rest runs. dx is written when layer_lo == 0. */
+int mb200_gptj_sched_backward_range(const mb200_gptj_model_ex* m, void* dx, float loss_scale, int32_t layer_hi,
+                                    int32_t layer_lo, int32_t accumulate, int32_t B, int32_t S, void* ws,
+                                    size_t ws_bytes, void* stream);
 /* Inference pass of the general schedule (no saved activations): optional KV cache exactly as mb200_gptj_forward
  * (prefill S > 1 at pos0, decode S == 1 through mb200_attn_decode), last_only = project the last position only
  * (logits [B][ldv]), hidden = ln_f output or NULL. */

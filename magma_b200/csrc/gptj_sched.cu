@@ -21,6 +21,7 @@
 #include "sched_rt.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mb200 {
@@ -150,6 +151,17 @@ struct Plan {
   bf16s *g0, *g1, *gs, *dt, *dzn, *dm, *dhact, *dh_mlp, *dattn_o, *dqkv, *dS, *dh, *da, *dhp;
   size_t bytes;
 };
+
+// the fused single-tile attention kernels (csrc/attention.cu) cover S <= 128 with head_dim in {64, 128, 192, 256};
+// MB200_ATTN_TILE=0 forces the batched-GEMM path (same switch as engine.cu)
+inline bool tile_ok(int S, int hd) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB200_ATTN_TILE");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0 && S >= 1 && S <= 128 && hd >= 64 && hd <= 256 && hd % 64 == 0;
+}
 
 inline bool has_ln(const mb200_adapter_ex& a) { return a.ln_g != nullptr; }
 inline bool has_scale(const mb200_adapter_ex& a) { return a.scale != nullptr; }
@@ -326,12 +338,16 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
       e.rope_ncols = 2 * d;
       MBS_TRY(gemm(st, M, 3 * d, d, mat(a.h, d), mat(L.w_qkv, d), a.qkv, 3 * d, 0, e));
     }
-    // scores = Q K^T (fp32), P = softmax(scores / sqrt(hd) + causal mask), O = P V
-    MBS_TRY(gemm(st, S, S, hd, mat(a.qkv, 3 * d, 0, qb0, qb1), mat(a.qkv + d, 3 * d, 0, qb0, qb1), P.scores, P.ldP, 1,
-                 Epi(), H, B, pb0, pb1));
-    MBS_TRY(mb200_softmax_fwd(P.scores, P.ldP, pb0, a.P, P.ldP, pb0, B * H, S, S, scale, 1, 0, st));
-    MBS_TRY(gemm(st, S, hd, S, mat(a.P, P.ldP, 0, pb0, pb1), mat(a.qkv + 2 * d, 3 * d, 1, qb0, qb1), a.attn_o, d, 0, Epi(),
-                 H, B, hd, (long long)S * d));
+    if (tile_ok(S, hd)) {  // whole sequence in one tile: fused QK^T / softmax / PV, one CTA per (batch, head)
+      MBS_TRY(mb200_attn_fwd_tile(a.qkv, 3 * d, a.P, P.ldP, a.attn_o, d, B, S, H, hd, st));
+    } else {
+      // scores = Q K^T (fp32), P = softmax(scores / sqrt(hd) + causal mask), O = P V
+      MBS_TRY(gemm(st, S, S, hd, mat(a.qkv, 3 * d, 0, qb0, qb1), mat(a.qkv + d, 3 * d, 0, qb0, qb1), P.scores, P.ldP, 1,
+                   Epi(), H, B, pb0, pb1));
+      MBS_TRY(mb200_softmax_fwd(P.scores, P.ldP, pb0, a.P, P.ldP, pb0, B * H, S, S, scale, 1, 0, st));
+      MBS_TRY(gemm(st, S, hd, S, mat(a.P, P.ldP, 0, pb0, pb1), mat(a.qkv + 2 * d, 3 * d, 1, qb0, qb1), a.attn_o, d, 0,
+                   Epi(), H, B, hd, (long long)S * d));
+    }
     // out_proj; ax = attention branch + residual x
     if (m->attn_adapter == MB200_ADAPTER_NONE) {
       Epi e;
@@ -389,25 +405,30 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
   return 0;
 }
 
-int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int acc, int B, int S, void* ws, size_t ws_bytes,
-             void* st) {
+// Layers are processed from layer_hi-1 down to layer_lo; the LM-head / CE backward runs when layer_hi == n_layer. The
+// residual-stream gradient lives in the workspace between calls, so a caller can split the range and exchange the
+// gradients of finished layers while the rest runs (B200Engine.backward).
+int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int layer_hi, int layer_lo, int acc, int B, int S,
+             void* ws, size_t ws_bytes, void* st) {
   Plan P;
   MBS_TRY(make_plan(P, m, B, S, ws));
   MBS_REQUIRE(ws != nullptr && ws_bytes >= P.bytes, MB200_E_ARG, "gptj_sched_backward: workspace too small");
+  MBS_REQUIRE(0 <= layer_lo && layer_lo <= layer_hi && layer_hi <= m->n_layer, MB200_E_ARG,
+              "gptj_sched_backward: bad layer range [%d,%d)", layer_lo, layer_hi);
   const int M = P.M, d = P.d, dff = P.dff, H = P.H, hd = P.hd;
   const float scale = 1.0f / sqrtf((float)hd);
   const long long qb0 = hd, qb1 = (long long)S * 3 * d;
   const long long pb0 = (long long)S * P.ldP, pb1 = (long long)H * S * P.ldP;
   // gradient w.r.t. the residual stream entering layer l lives in g[(l) & 1]
   bf16s* gb[2] = {P.g0, P.g1};
-  {  // dxf = loss_scale * dlogits Wlm ; g = LN_f backward
+  if (layer_hi == m->n_layer) {  // dxf = loss_scale * dlogits Wlm ; g = LN_f backward
     Epi e;
     e.alpha = loss_scale;
     MBS_TRY(gemm(st, M, d, m->vocab, mat(P.dlogits, P.ldv), mat(m->w_lm, d, 1), P.dh, d, 0, e));
     MBS_TRY(mb200_layernorm_bwd(P.dh, d, P.x_final, d, m->lnf_g, P.lnf_mean, P.lnf_rstd, nullptr, 0, gb[m->n_layer & 1], d,
                                 M, d, st));
   }
-  for (int l = m->n_layer - 1; l >= 0; --l) {
+  for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const mb200_gptj_layer_ex& L = m->layers[l];
     LayerActs& a = P.acts[l];
     const bf16s* g = gb[(l + 1) & 1];
@@ -443,7 +464,10 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int acc,
       dh_acc = P.dhp;
     }
     MBS_TRY(gemm(st, M, d, d, mat(da, d), mat(L.w_out, d, 1), P.dattn_o, d, 0));  // d(attn_o) = da Wo
-    {
+    if (tile_ok(S, hd)) {
+      MBS_TRY(mb200_attn_bwd_tile(a.qkv, 3 * d, P.dattn_o, d, a.P, P.ldP, P.dqkv, 3 * d, P.rope_tab, m->rotary_dim, B, S, H,
+                                  hd, st));
+    } else {
       Mat dO = mat(P.dattn_o, d, 0, hd, (long long)S * d);
       Mat dO_mn = mat(P.dattn_o, d, 1, hd, (long long)S * d);
       MBS_TRY(gemm(st, S, S, hd, dO, mat(a.qkv + 2 * d, 3 * d, 0, qb0, qb1), P.scores, P.ldP, 1, Epi(), H, B, pb0, pb1));
@@ -560,6 +584,9 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
     bf16s* vc = vcache ? vcache + (size_t)l * cache_layer : nullptr;
     if (kcache && S == 1) {
       MBS_TRY(mb200_attn_decode(P.qkv, 3 * d, kc, vc, P.attn_o, d, B, H, hd, Smax, pos0, st));
+    } else if (pos0 == 0 && tile_ok(S, hd)) {
+      if (kcache) MBS_TRY(mb200_kv_append(P.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0, st));
+      MBS_TRY(mb200_attn_fwd_tile(P.qkv, 3 * d, P.P, P.ldS, P.attn_o, d, B, S, H, hd, st));
     } else {
       Mat Q = mat(P.qkv, 3 * d, 0, hd, (long long)S * 3 * d), Kk, Vv;
       if (kcache) {
@@ -667,5 +694,13 @@ extern "C" int mb200_gptj_sched_backward(const mb200_gptj_model_ex* m, void* dx,
                                          int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream) {
   int rc = mb200::rt_check_arch();
   if (rc) return rc;
-  return mb200::backward(m, (mb200::bf16s*)dx, loss_scale, accumulate, B, S, ws, ws_bytes, stream);
+  return mb200::backward(m, (mb200::bf16s*)dx, loss_scale, m ? m->n_layer : 0, 0, accumulate, B, S, ws, ws_bytes, stream);
+}
+
+extern "C" int mb200_gptj_sched_backward_range(const mb200_gptj_model_ex* m, void* dx, float loss_scale, int32_t layer_hi,
+                                               int32_t layer_lo, int32_t accumulate, int32_t B, int32_t S, void* ws,
+                                               size_t ws_bytes, void* stream) {
+  int rc = mb200::rt_check_arch();
+  if (rc) return rc;
+  return mb200::backward(m, (mb200::bf16s*)dx, loss_scale, layer_hi, layer_lo, accumulate, B, S, ws, ws_bytes, stream);
 }

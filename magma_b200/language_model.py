@@ -522,11 +522,13 @@ class B200GPTJForCausalLM(nn.Module):
             arena = self._arena
             dx = torch.empty(B, S, d, dtype=torch.bfloat16, device=self._device)
             ws = self._workspace_ex(B, S)
-            check(lib().mb200_gptj_sched_backward(ctypes.byref(self._cmodel_ex()[0]), ops._ptr(dx),
-                                                  ctypes.c_float(loss_scale), int(arena.grads_live()), B, S,
-                                                  ops._ptr(ws), ctypes.c_size_t(ws.numel()), ops._stream()))
-            if self._after_chunk is not None:  # one backward call: the gradient slices are exchanged afterwards
-                for hi, lo in (self._bwd_chunks or [(len(self.transformer.h), 0)]):
+            accumulate = int(arena.grads_live())
+            for hi, lo in (self._bwd_chunks or [(len(self.transformer.h), 0)]):
+                check(lib().mb200_gptj_sched_backward_range(ctypes.byref(self._cmodel_ex()[0]),
+                                                            ops._ptr(dx) if lo == 0 else None, ctypes.c_float(loss_scale),
+                                                            hi, lo, accumulate, B, S, ops._ptr(ws),
+                                                            ctypes.c_size_t(ws.numel()), ops._stream()))
+                if self._after_chunk is not None:
                     self._after_chunk(hi, lo)
             if self._own_arena:
                 arena.publish_grads()

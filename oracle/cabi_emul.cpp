@@ -604,6 +604,106 @@ int mb200_avgpool_nhwc(const void* src_, void* dst_, int32_t B, int32_t H, int32
   return 0;
 }
 
+// fused causal self-attention of one tile (csrc/attention.cu: attn_fwd_tile_kernel / attn_bwd_tile_kernel): per
+// (batch, head) S = Q K^T / sqrt(hd), causal softmax in fp32, P rounded to bf16 (saved, [B,H,S,ldP]), O = P V; backward
+// dP = dO V^T, dV = P^T dO, dS = P * (dP - sum(dP * P)) / sqrt(hd), dQ = dS K, dK = dS^T Q with the inverse rotary
+// rotation applied to dQ / dK on the way out (rope_tab [S][rot/2] (cos, sin), may be NULL)
+static bool tile_supported(int S, int hd) { return S >= 1 && S <= 128 && hd >= 64 && hd <= 256 && hd % 64 == 0; }
+
+int mb200_attn_fwd_tile(const void* qkv_, int64_t ld, void* P_, int64_t ldP, void* O_, int64_t ldo, int32_t B, int32_t S,
+                        int32_t H, int32_t hd, void*) {
+  EM_REQUIRE(tile_supported(S, hd) && ldP % 8 == 0, MB200_E_SHAPE, "attn_fwd_tile: unsupported S=%d hd=%d", S, hd);
+  const bf16_t* qkv = (const bf16_t*)qkv_;
+  bf16_t *P = (bf16_t*)P_, *O = (bf16_t*)O_;
+  const long long d = (long long)H * hd;
+  const float scale = 1.f / sqrtf((float)hd);
+  std::vector<float> sc(S);
+  for (long long b = 0; b < B; ++b)
+    for (int h = 0; h < H; ++h)
+      for (int i = 0; i < S; ++i) {
+        const bf16_t* q = qkv + (b * S + i) * ld + (long long)h * hd;
+        float m = -INFINITY, sum = 0.f;
+        for (int j = 0; j <= i; ++j) {
+          const bf16_t* k = qkv + (b * S + j) * ld + d + (long long)h * hd;
+          float acc = 0.f;
+          for (int c = 0; c < hd; ++c) acc += b2f(q[c]) * b2f(k[c]);
+          sc[j] = acc * scale;
+          m = fmaxf(m, sc[j]);
+        }
+        for (int j = 0; j <= i; ++j) sum += expf(sc[j] - m);
+        bf16_t* pr = P + ((b * H + h) * S + i) * ldP;
+        for (int j = 0; j < S; ++j) pr[j] = f2b(j <= i ? expf(sc[j] - m) / sum : 0.f);
+        bf16_t* o = O + (b * S + i) * ldo + (long long)h * hd;
+        for (int c = 0; c < hd; ++c) {
+          float acc = 0.f;
+          for (int j = 0; j <= i; ++j) acc += b2f(pr[j]) * b2f(qkv[(b * S + j) * ld + 2 * d + (long long)h * hd + c]);
+          o[c] = f2b(acc);
+        }
+      }
+  return 0;
+}
+
+int mb200_attn_bwd_tile(const void* qkv_, int64_t ld, const void* dO_, int64_t ld_do, const void* P_, int64_t ldP,
+                        void* dqkv_, int64_t ldd, const float* rope_tab, int32_t rot, int32_t B, int32_t S, int32_t H,
+                        int32_t hd, void*) {
+  EM_REQUIRE(tile_supported(S, hd) && ldP % 8 == 0, MB200_E_SHAPE, "attn_bwd_tile: unsupported S=%d hd=%d", S, hd);
+  const bf16_t *qkv = (const bf16_t*)qkv_, *dO = (const bf16_t*)dO_, *P = (const bf16_t*)P_;
+  bf16_t* dqkv = (bf16_t*)dqkv_;
+  const long long d = (long long)H * hd;
+  const float scale = 1.f / sqrtf((float)hd);
+  std::vector<float> dS((size_t)S * S), dq((size_t)S * hd), dk((size_t)S * hd), dv((size_t)S * hd);
+  for (long long b = 0; b < B; ++b)
+    for (int h = 0; h < H; ++h) {
+      auto Q = [&](int i, int c) { return b2f(qkv[(b * S + i) * ld + (long long)h * hd + c]); };
+      auto K = [&](int i, int c) { return b2f(qkv[(b * S + i) * ld + d + (long long)h * hd + c]); };
+      auto V = [&](int i, int c) { return b2f(qkv[(b * S + i) * ld + 2 * d + (long long)h * hd + c]); };
+      auto G = [&](int i, int c) { return b2f(dO[(b * S + i) * ld_do + (long long)h * hd + c]); };
+      auto Pr = [&](int i, int j) { return b2f(P[((b * H + h) * S + i) * ldP + j]); };
+      for (int i = 0; i < S; ++i) {
+        float dot = 0.f;
+        for (int j = 0; j < S; ++j) {
+          float dp = 0.f;
+          for (int c = 0; c < hd; ++c) dp += G(i, c) * V(j, c);
+          dS[(size_t)i * S + j] = dp;
+          dot += dp * Pr(i, j);
+        }
+        for (int j = 0; j < S; ++j)  // bf16 like the kernel's dS operand
+          dS[(size_t)i * S + j] = b2f(f2b(Pr(i, j) * (dS[(size_t)i * S + j] - dot) * scale));
+      }
+      for (int i = 0; i < S; ++i)
+        for (int c = 0; c < hd; ++c) {
+          float aq = 0.f, ak = 0.f, av = 0.f;
+          for (int j = 0; j < S; ++j) {
+            aq += dS[(size_t)i * S + j] * K(j, c);
+            ak += dS[(size_t)j * S + i] * Q(j, c);
+            av += Pr(j, i) * G(j, c);
+          }
+          dq[(size_t)i * hd + c] = aq;
+          dk[(size_t)i * hd + c] = ak;
+          dv[(size_t)i * hd + c] = av;
+        }
+      for (int i = 0; i < S; ++i) {
+        if (rope_tab)  // inverse rotation (transpose of rotate_every_two) on the first `rot` dims of dQ, dK
+          for (int p = 0; p < rot / 2; ++p) {
+            const float cs = rope_tab[((long long)i * (rot / 2) + p) * 2], sn = rope_tab[((long long)i * (rot / 2) + p) * 2 + 1];
+            for (std::vector<float>* t : {&dq, &dk}) {
+              float& x0 = (*t)[(size_t)i * hd + 2 * p];
+              float& x1 = (*t)[(size_t)i * hd + 2 * p + 1];
+              const float a = x0, c2 = x1;
+              x0 = a * cs + c2 * sn;
+              x1 = c2 * cs - a * sn;
+            }
+          }
+        for (int c = 0; c < hd; ++c) {
+          dqkv[(b * S + i) * ldd + (long long)h * hd + c] = f2b(dq[(size_t)i * hd + c]);
+          dqkv[(b * S + i) * ldd + d + (long long)h * hd + c] = f2b(dk[(size_t)i * hd + c]);
+          dqkv[(b * S + i) * ldd + 2 * d + (long long)h * hd + c] = f2b(dv[(size_t)i * hd + c]);
+        }
+      }
+    }
+  return 0;
+}
+
 // KV cache   (engine.cu: kv_append_kernel / attn_decode_kernel)
 int mb200_kv_append(const void* qkv_, int64_t ld, void* kc_, void* vc_, int32_t B, int32_t S, int32_t H, int32_t hd,
                     int32_t Smax, int32_t pos0, void*) {

@@ -103,19 +103,11 @@ int mb200_gptj_forward(const mb200_gptj_model* m, const void* xin, const int64_t
                                 ws_bytes, stream);
 }
 
-// The product processes layers [layer_lo, layer_hi) per call so the caller can overlap the gradient exchange. The
-// general schedule runs the whole backward at once: it is issued with the LAST chunk (layer_lo == 0, the call that
-// carries dx); earlier chunk calls are no-ops. Single-process replays only.
 int mb200_gptj_backward(const mb200_gptj_model* m, void* dx, float loss_scale, int32_t layer_hi, int32_t layer_lo,
                         int32_t accumulate, int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream) {
-  if (layer_lo < 0 || layer_lo > layer_hi || layer_hi > m->n_layer) {
-    mb200::set_error("gptj_backward: bad layer range [%d,%d)", layer_lo, layer_hi);
-    return MB200_E_ARG;
-  }
-  if (layer_lo != 0) return 0;
   ExModel x;
   convert(m, x);
-  return mb200_gptj_sched_backward(&x.m, dx, loss_scale, accumulate, B, S, ws, ws_bytes, stream);
+  return mb200_gptj_sched_backward_range(&x.m, dx, loss_scale, layer_hi, layer_lo, accumulate, B, S, ws, ws_bytes, stream);
 }
 
 size_t mb200_vit_workspace_bytes(const mb200_vit_model* m, int32_t B) { return mb200_vit_train_workspace_bytes(m, B); }
