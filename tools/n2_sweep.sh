@@ -4,3 +4,9 @@ run ch8 NCCL_MAX_NCHANNELS=8
 run ch4 NCCL_MAX_NCHANNELS=4
 run ch8_b7 NCCL_MAX_NCHANNELS=8 MB200_DP_BUCKETS=7
 run b7 MB200_DP_BUCKETS=7
+# knobs added after the round-1 GPU budget was spent: keep SMs free for NCCL, bf16 gradient exchange
+run gemm140 MB200_DP_GEMM_SMS=140
+run gemm132 MB200_DP_GEMM_SMS=132
+run bf16 MB200_DP_BF16=1
+run gemm140_bf16 MB200_DP_GEMM_SMS=140 MB200_DP_BF16=1
+run gemm140_b7 MB200_DP_GEMM_SMS=140 MB200_DP_BUCKETS=7

@@ -18,6 +18,12 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1.json.
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   --profile-from-start off --csv --log-file gpurun_out/r2_launches_step.csv python tools/profile_step.py \
   > gpurun_out/r2_profile_step.log 2>&1
+# 3b. the same bench line with the LM on the general host-only schedule (candidate replacement of engine.cu's host code)
+MB200_FORCE_GENERAL=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline \
+  > gpurun_out/r2_bench_n1_general_schedule.json.log 2>&1
 # 4. trainable-encoder step time (freeze_img_encoder: false) ----------------------------------------------------------
 timeout 600 python tools/encoder_train_bench.py > gpurun_out/r2_encoder_train_bench.log 2>&1
 echo done
+
+# A second call, on 2 GPUs, for the data-parallel knobs (each line: samples/s at N = 2):
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/n2_sweep.sh'
