@@ -1,5 +1,5 @@
 """Replay of the DEFAULT Python paths on the CPU. The GPU parity harness itself (tools/model_check.py groups lm,
-lm_variants, vit, magma — what tests/test_model_gpu.py runs on a B200) and __graft_entry__.smoke() are executed here on
+lm_variants, vit, resnet, magma — what tests/test_model_gpu.py runs on a B200) and __graft_entry__.smoke() are executed here on
 CPU tensors: primitive operators emulated (oracle/cabi_emul.cpp), and the model-level entry points of engine.cu
 (mb200_gptj_forward / backward, mb200_vit_forward) provided by oracle/cabi_emul_models.cpp, which delegates to the
 product's host-only schedules. This shows that the Python of the default path — Magma.forward, _EmbedLMFn, the pointer
@@ -15,10 +15,12 @@ def replay(emul_ops, monkeypatch):
 
     monkeypatch.setattr(Magma, "_require_cuda", lambda self: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    # the frozen conv trunk replays ~300 launches as one CUDA graph per batch size; "already capturing" = eager launches
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: True)
     return torch.device("cpu")
 
 
-@pytest.mark.parametrize("group", ["lm", "lm_variants", "vit", "magma"])
+@pytest.mark.parametrize("group", ["lm", "lm_variants", "vit", "resnet", "magma"])
 def test_gpu_parity_harness_replays_on_emulated_kernels(replay, group, capsys):
     from tools import model_check
 
