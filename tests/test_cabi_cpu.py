@@ -128,3 +128,15 @@ def test_shipped_and_reference_configs_load():
         r = MultimodalConfig.from_yml(ref)
         assert r.encoder_name == "clip_resnet_large" and not r.freeze_img_encoder and r.image_enc_lr == 2.0e-6
         assert r.adapter_config == {"mlp": {"adapter_type": "normal", "downsample_factor": 4}}
+
+
+def test_top_level_exports_mirror_the_reference_package():
+    """`from magma import Magma, MultimodalConfig, get_gptj, ...` (magma/__init__.py) works with the package name swapped."""
+    import magma_b200
+    from magma_b200 import ImageInput, Magma, MultimodalConfig, collate_fn, get_gptj, get_transforms, train_step  # noqa: F401
+
+    for name in ("count_parameters", "is_main", "cycle", "get_tokenizer", "save_model", "load_model", "print_main",
+                 "configure_param_groups", "eval_step"):
+        assert callable(getattr(magma_b200, name)), name
+    with pytest.raises(AttributeError):
+        magma_b200.wandb_log  # logging glue is out of scope
