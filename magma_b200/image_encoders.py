@@ -595,10 +595,10 @@ class B200ModifiedResNet(nn.Module):
         if C != 3 or R != self.input_resolution or R2 != R:
             raise ValueError(f"expected [b,3,{self.input_resolution},{self.input_resolution}], got {tuple(x.shape)}")
         x = x.to(device=self._device, dtype=torch.bfloat16).contiguous()
-        if self._trainable():
-            if self.training and torch.is_grad_enabled():
-                return _ResNetTrainFn.apply(self, x, self.conv1.weight)   # BatchNorm in training mode + backward
-            return self._forward_eager(x)  # eval: running statistics, folded from the current fp32 parameters
+        if self._trainable() and self.training and torch.is_grad_enabled():
+            return _ResNetTrainFn.apply(self, x, self.conv1.weight)       # BatchNorm in training mode + backward
+        # frozen, or a trainable trunk in eval mode: running statistics folded into the weights (re-packed from the
+        # current fp32 parameters after every training forward, which resets self._packed)
         if os.environ.get("MB200_RESNET_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing():
             return self._forward_graphed(x)
         return self._forward_eager(x)
