@@ -386,6 +386,31 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
 
+    # ---- gradient exchange in isolation (N > 1): bytes, time and bus bandwidth of the arena all-reduce;
+    # measured AFTER the timed regions, never part of `value`. Any failure here leaves the field null.
+    allreduce = None
+    if world > 1:
+        try:
+            g = model.arena.grad
+            for _ in range(2):
+                dist.all_reduce(g)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(5):
+                dist.all_reduce(g)
+            a1.record()
+            torch.cuda.synchronize()
+            ar_ms = max_over_ranks(a0.elapsed_time(a1) / 5)
+            nbytes = g.numel() * g.element_size()
+            allreduce = {"bytes": nbytes, "ms_isolated": ar_ms,
+                         "busbw_gbs": 2 * (world - 1) / world * nbytes / (ar_ms / 1e3) / 1e9,
+                         "note": "fp32 gradient arena, one NCCL all-reduce, nothing else running; in the step it is issued in "
+                                 "slices overlapped with backward"}
+            g.zero_()
+        except Exception as exc:  # diagnostics only
+            allreduce = {"error": repr(exc)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=1, warmup=0, budget_s=40.0)
@@ -396,7 +421,7 @@ def run_b200(args):
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "loss": last_loss,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "allreduce": allreduce, "loss": last_loss,
                 "trainable_params": int(model.arena.numel)}
         print(json.dumps(line), flush=True)
     if world > 1:
