@@ -305,6 +305,7 @@ static int gemm(cudaStream_t st, int M, int N, int K, Mat A, Mat B, void* C, lon
 // ---------------------------------------------------------------------------------------------
 // KV-cache append (prefill and decode): cache[b][h][pos0+s][:] = qkv[b*S+s][which][h][:]
 // ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__  // device code; the host schedule below also compiles as plain C++ for the CPU dry run (oracle/)
 __global__ void kv_append_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict__ kc,
                                  bf16* __restrict__ vc, int B, int S, int H, int hd, int Smax, int pos0) {
   const int vec = hd >> 3;
@@ -398,6 +399,8 @@ attn_decode_kernel(const bf16* __restrict__ qkv, long long ld_qkv, bf16* __restr
     out[(long long)b * ld_out + (long long)h * hd + c] = __float2bfloat16(acc);
   }
 }
+
+#endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------------
 // adapter bottleneck forward: out = [alpha](relu(X Wd^T + bd) Wu^T + bu) + res1 + res2 ; saves t = relu(...)
@@ -498,21 +501,29 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
     if (kcache && S == 1) {
       bf16* kc = kcache + (size_t)l * cache_layer;
       bf16* vc = vcache + (size_t)l * cache_layer;
+#ifdef __CUDACC__
       const size_t smem = (((size_t)(pos0 + 1) + 31) & ~(size_t)31) * 4 + 32 * 4;
       attn_decode_kernel<<<B * H, kDecThreads, smem, sa>>>(a.qkv, 3 * d, kc, vc, a.attn_o, d, H, hd, Smax, pos0);
       count_launch();
       MB_CUDA(cudaGetLastError());
+#else
+      MB_TRY(mb200_attn_decode(a.qkv, 3 * d, kc, vc, a.attn_o, d, B, H, hd, Smax, pos0, sa));
+#endif
     } else if (use_attn_tile() && attn_tile_supported(S, hd) && pos0 == 0) {
       // whole sequence in one tile: fused QK^T / softmax / PV kernel, one CTA per (batch, head)
       if (kcache) {
         bf16* kc = kcache + (size_t)l * cache_layer;
         bf16* vc = vcache + (size_t)l * cache_layer;
+#ifdef __CUDACC__
         const long long tot = (long long)B * S * H * (hd / 8);
         int grid = (int)((tot + 255) / 256);
         if (grid > num_sms() * 8) grid = num_sms() * 8;
         kv_append_kernel<<<grid, 256, 0, sa>>>(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0);
         count_launch();
         MB_CUDA(cudaGetLastError());
+#else
+        MB_TRY(mb200_kv_append(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0, sa));
+#endif
       }
       MB_TRY(attn_fwd_tile(a.qkv, 3 * d, a.P, P.ldP, a.attn_o, d, B, S, H, hd, sa));
     } else {
@@ -521,12 +532,16 @@ static int gptj_forward(const mb200_gptj_model* m, const bf16* x, const int64_t*
       if (kcache) {
         bf16* kc = kcache + (size_t)l * cache_layer;
         bf16* vc = vcache + (size_t)l * cache_layer;
+#ifdef __CUDACC__
         const long long tot = (long long)B * S * H * (hd / 8);
         int grid = (int)((tot + 255) / 256);
         if (grid > num_sms() * 8) grid = num_sms() * 8;
         kv_append_kernel<<<grid, 256, 0, sa>>>(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0);
         count_launch();
       MB_CUDA(cudaGetLastError());
+#else
+        MB_TRY(mb200_kv_append(a.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0, sa));
+#endif
         Kk = mat(kc, hd, 0, (long long)Smax * hd, (long long)H * Smax * hd);
         Vv = mat(vc, hd, 1, (long long)Smax * hd, (long long)H * Smax * hd);
       } else {
@@ -888,6 +903,7 @@ extern "C" int mb200_vit_forward(const mb200_vit_model* m, const void* images, v
   return vit_forward(m, (const bf16*)images, (bf16*)feats, B, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+#ifdef __CUDACC__  // kernel wrappers (the CPU dry-run build takes these two from oracle/cabi_emul.cpp)
 extern "C" int mb200_attn_decode(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, void* out,
                                  int64_t ld_out, int32_t B, int32_t H, int32_t hd, int32_t S_kv_max, int32_t pos,
                                  void* stream) {
@@ -921,3 +937,4 @@ extern "C" int mb200_kv_append(const void* qkv, int64_t ld_qkv, void* kcache, vo
   MB_CUDA(cudaGetLastError());
   return 0;
 }
+#endif  // __CUDACC__

@@ -1,10 +1,11 @@
-"""Replay of the DEFAULT Python paths on the CPU. The GPU parity harness itself (tools/model_check.py groups lm,
-lm_variants, vit, resnet, magma — what tests/test_model_gpu.py runs on a B200) and __graft_entry__.smoke() are executed here on
-CPU tensors: primitive operators emulated (oracle/cabi_emul.cpp), and the model-level entry points of engine.cu
-(mb200_gptj_forward / backward, mb200_vit_forward) provided by oracle/cabi_emul_models.cpp, which delegates to the
-product's host-only schedules. This shows that the Python of the default path — Magma.forward, _EmbedLMFn, the pointer
-tables of language_model.py / image_encoders.py, chunked backward, ParamArena, B200Engine — still works after a change,
-without a GPU. It says nothing about engine.cu's own schedule or about any kernel: those are GPU-tested only."""
+"""Replay of the DEFAULT paths on the CPU. The GPU parity harness itself (tools/model_check.py groups lm, lm_variants,
+vit, resnet, magma, generate — what tests/test_model_gpu.py runs on a B200), the reference-golden tests of that file and
+__graft_entry__.smoke() are executed here on CPU tensors. What runs is the product's own code: its Python, and the HOST
+SCHEDULE of csrc/engine.cu itself — compiled as plain C++ into the emulation library (its kernels sit behind
+#ifdef __CUDACC__; the nvcc-preprocessed file is byte-identical to the version without those guards) — issuing the
+primitive operators, which are what is emulated (oracle/cabi_emul.cpp). So a change to anything but a kernel — pointer
+tables, workspace carving, operand majors and strides, chunked backward, KV-cache prefill / decode, arena, engine — is
+caught without a GPU; the kernels themselves are verified by the `-m gpu` tests only."""
 import pytest
 import torch
 

@@ -4,8 +4,8 @@ into the emulation library). What runs here is the product's own Python — Magm
 ParamArena / B200Engine / checkpointing — and the two host-only C++ schedules; what is emulated are the kernels. The
 result is held to torch autograd of the oracle (oracle/magma_oracle.py::magma_forward).
 
-Not covered: engine.cu (the fast LM runtime, frozen-ViT forward, KV-cache decoding) — it contains kernels and only
-runs on a GPU — and therefore `generate()`."""
+The LM goes through the general schedule here (`_force_general`); the fast runtime's own host schedule (engine.cu) is
+replayed in tests/test_default_path_replay_cpu.py."""
 import pytest
 import torch
 
@@ -45,7 +45,7 @@ def build(monkeypatch, cfg, w16, S, encoder="clip_vit_dry", freeze_enc=False, ad
         missing, unexpected = model.load_state_dict(w16, strict=False)
         missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
         assert not missing and not unexpected, (missing, unexpected)
-    model.lm._force_general = True        # the LM through csrc/gptj_sched.cu (engine.cu has kernels: GPU only)
+    model.lm._force_general = True        # the LM through csrc/gptj_sched.cu (the general schedule)
     model.lm.invalidate()
     model.lm.attach_arena(model.arena)
     model.image_prefix.enc.invalidate()

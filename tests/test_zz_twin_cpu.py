@@ -1,5 +1,5 @@
-"""CPU replay of the test BODIES in tests/test_zz_unverified_gpu.py that do not need engine.cu: the same functions, run
-on CPU tensors with the kernels emulated (fixture `emul_ops`) and the LM on the general schedule. This does not verify
+"""CPU replay of test BODIES in tests/test_zz_unverified_gpu.py: the same functions, run on CPU tensors with the kernels
+emulated (fixture `emul_ops`). This does not verify
 any kernel; it makes sure that when those GPU tests run for the first time, a failure is about the kernels and not about
 a typo in the test."""
 import pytest
@@ -13,7 +13,16 @@ REPLAYABLE = [
     "test_conv_trunk_training_matches_oracle_like_with_like",
     "test_trainable_vit_gradients_match_oracle_autograd",
     "test_encoder_learning_rate_group_and_weight_decay_exemptions",
+    "test_frozen_vit_is_unchanged_by_the_training_path",
+    "test_engine_checkpoint_resume_continues_the_same_trajectory",
+    "test_general_schedule_agrees_with_the_fast_runtime",
 ]
+
+REPLAYABLE_WITH_ARGS = {
+    "test_adapter_forms_with_layernorm_and_scale_match_oracle": [("normal", "normal", True, True),
+                                                                 ("scaled_parallel", "scaled_parallel", False, False),
+                                                                 ("scaled_parallel", "normal", True, True)],
+}
 
 
 @pytest.mark.parametrize("name", REPLAYABLE)
@@ -21,6 +30,24 @@ def test_replay_on_emulated_kernels(emul_ops, monkeypatch, name):
     from magma_b200.magma import Magma
 
     monkeypatch.setenv("MB200_TEST_DEVICE", "cpu")
-    monkeypatch.setenv("MB200_FORCE_GENERAL", "1")      # the LM through csrc/gptj_sched.cu (engine.cu is GPU only)
     monkeypatch.setattr(Magma, "_require_cuda", lambda self: None)
-    getattr(Z, name)()
+    fn = getattr(Z, name)
+    import inspect
+
+    if "tmp_path" in inspect.signature(fn).parameters:
+        import pathlib
+        import tempfile
+
+        with tempfile.TemporaryDirectory() as d:
+            fn(pathlib.Path(d))
+    else:
+        fn()
+
+
+@pytest.mark.parametrize("args", REPLAYABLE_WITH_ARGS["test_adapter_forms_with_layernorm_and_scale_match_oracle"])
+def test_replay_adapter_forms(emul_ops, monkeypatch, args):
+    from magma_b200.magma import Magma
+
+    monkeypatch.setenv("MB200_TEST_DEVICE", "cpu")
+    monkeypatch.setattr(Magma, "_require_cuda", lambda self: None)
+    Z.test_adapter_forms_with_layernorm_and_scale_match_oracle(*args)

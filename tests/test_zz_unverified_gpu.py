@@ -82,6 +82,7 @@ def _build(dev, freeze_enc, S=32, image_enc_lr=None, weight_decay=0.0):
     from tools.model_check import boost_adapters, small_cfg
 
     cfg = small_cfg()
+    torch.manual_seed(5)  # boost_adapters draws from the global generator
     w = boost_adapters(O.init_weights(cfg, seed=5), True)
     for k in w:  # larger encoder weights than the 0.02 init: encoder gradients well above bf16 noise
         if k.startswith("image_prefix.enc.") and k.endswith(("in_proj_weight", "out_proj.weight", "c_fc.weight",
@@ -231,7 +232,7 @@ def test_engine_checkpoint_resume_continues_the_same_trajectory(tmp_path):
             o = engine(x, c)
             engine.backward(o.loss)
             engine.step()
-            out.append(float(o.loss))
+            out.append(float(o.loss.detach()))
         return out
 
     eng = B200Engine(model, mc, n_buckets=2)
@@ -255,6 +256,7 @@ def _variant_weights(cfg, mlp, attn, mlp_ln, attn_ln, seed=5):
     from oracle import magma_oracle as O
     from tools.model_check import boost_adapters
 
+    torch.manual_seed(seed)  # boost_adapters draws from the global generator
     w = boost_adapters(O.init_weights(cfg, seed=seed), True)
     g = torch.Generator().manual_seed(seed + 7)
     for l in range(cfg.n_layer):
@@ -322,8 +324,10 @@ def test_adapter_forms_with_layernorm_and_scale_match_oracle(mlp, attn, mlp_ln, 
     assert _rel(out.logits, logits_o.detach()) < 3e-2
     out.loss.backward()
     sd = dict(model.named_parameters())
+    # d loss / d adapter_scale is ONE number, <g, u> summed over B*S*d products of both signs: its relative error is
+    # the bf16 noise of those products divided by whatever survives the cancellation, so it gets a looser bound
     bad = {k: round(_rel(sd[k].grad, params[k].grad), 4) for k in trainable
-           if _rel(sd[k].grad, params[k].grad) > 5e-2}
+           if _rel(sd[k].grad, params[k].grad) > (2.5e-1 if k.endswith("adapter_scale") else 5e-2)}
     assert not bad, bad
 
 
