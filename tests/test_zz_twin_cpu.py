@@ -16,6 +16,7 @@ REPLAYABLE = [
     "test_frozen_vit_is_unchanged_by_the_training_path",
     "test_engine_checkpoint_resume_continues_the_same_trajectory",
     "test_general_schedule_agrees_with_the_fast_runtime",
+    "test_preprocess_inputs_image_and_text_to_embeddings",
 ]
 
 REPLAYABLE_WITH_ARGS = {
