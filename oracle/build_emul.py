@@ -40,5 +40,26 @@ def build(force=False):
     return OUT
 
 
+KX_OUT = os.path.join(OUT_DIR, "libkernel_host_exec.so")
+KX_SRC = os.path.join(ROOT, "oracle", "kernel_host_exec.cpp")
+KX_DEPS = [KX_SRC] + [os.path.join(ROOT, "magma_b200", "csrc", f) for f in ("warp_helpers.cuh", "elt_helpers.cuh",
+                                                                          "train_kernels.cuh")]
+
+
+def build_kernel_exec(force=False):
+    """oracle/_build/libkernel_host_exec.so: the product's kernel SOURCE (csrc/train_kernels.cuh and the helper fragments it
+    uses) compiled as host C++ and executed with the CUDA thread model emulated (oracle/kernel_host_exec.cpp)."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    if not force and os.path.exists(KX_OUT) and os.path.getmtime(KX_OUT) >= max(os.path.getmtime(d) for d in KX_DEPS):
+        return KX_OUT
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-I", CUDA_INC, "-o", KX_OUT,
+           KX_SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for {KX_SRC}:\n{r.stdout}\n{r.stderr}")
+    return KX_OUT
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_kernel_exec(force=True))

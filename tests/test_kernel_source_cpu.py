@@ -1,0 +1,123 @@
+"""The SOURCE of the kernels that have not run on a B200 yet (magma_b200/csrc/train_kernels.cuh), executed on the CPU.
+
+oracle/kernel_host_exec.cpp compiles those kernels unchanged as host C++ and runs them with the CUDA execution model
+emulated (threads of a block = OS threads, __syncthreads = barrier, warp shuffles and atomicAdd emulated, blocks in
+sequence). Here each kernel is held to the torch formula its GPU test uses (tests/test_zz_unverified_gpu.py): this checks
+what a kernel COMPUTES — indexing, 8-wide vector handling, masks, smem reductions, row-chunk accumulation through atomics —
+not what the hardware does with it."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+@pytest.fixture(scope="module")
+def kx():
+    from oracle import build_emul
+
+    return ctypes.CDLL(build_emul.build_kernel_exec())
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def bf(g, *shape, scale=1.0):
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16)
+
+
+LL = ctypes.c_longlong
+
+
+def test_quick_gelu_bwd_kernel_source(kx):
+    g = torch.Generator().manual_seed(0)
+    pre, dy = bf(g, 37, 64, scale=2.0), bf(g, 37, 64)
+    x = pre.float().requires_grad_(True)
+    (x * torch.sigmoid(1.702 * x)).backward(dy.float())
+    out = torch.empty_like(dy)
+    kx.hx_quick_gelu_bwd(P(dy), P(pre), P(out), LL(dy.numel()))
+    assert rel(out, x.grad) < 5e-3
+    buf = dy.clone()
+    kx.hx_quick_gelu_bwd(P(buf), P(pre), P(buf), LL(buf.numel()))   # in place
+    assert torch.equal(buf, out)
+
+
+def test_scale_add_and_dot_kernel_source(kx):
+    g = torch.Generator().manual_seed(1)
+    u, r1, r2 = bf(g, 20, 48), bf(g, 20, 48), bf(g, 20, 48)
+    s = torch.tensor([0.625])
+    out = torch.empty_like(u)
+    kx.hx_scale_add(P(u), P(s), P(r1), P(r2), P(out), LL(u.numel()))
+    assert rel(out, 0.625 * u.float() + r1.float() + r2.float()) < 5e-3
+    kx.hx_scale_add(P(u), None, None, None, P(out), LL(u.numel()))
+    assert torch.equal(out, u)
+    a, b = bf(g, 4096 + 64), bf(g, 4096 + 64)
+    acc = torch.tensor([3.0])
+    kx.hx_dot(P(a), P(b), LL(a.numel()), P(acc), 0)
+    want = float((a.float() * b.float()).sum())
+    assert abs(float(acc) - want) < 1e-3 * (a.float().norm() * b.float().norm()).item()
+    kx.hx_dot(P(a), P(b), LL(a.numel()), P(acc), 1)
+    assert abs(float(acc) - 2 * want) < 2e-3 * (a.float().norm() * b.float().norm()).item()
+
+
+def test_layernorm_param_grad_rows_kernel_source(kx):
+    g = torch.Generator().manual_seed(2)
+    rows, d, ld = 150, 96, 104                      # ragged rows (3 chunks of 64), d not a multiple of 64, padded rows
+    xs, dys = bf(g, rows, ld), bf(g, rows, ld)
+    x, dy = xs[:, :d], dys[:, :d]
+    mean = x.float().mean(1).contiguous()
+    rstd = torch.rsqrt(x.float().var(1, unbiased=False) + 1e-5).contiguous()
+    xh = (x.float() - mean[:, None]) * rstd[:, None]
+    dg, db = torch.full((d,), 9.0), torch.full((d,), 9.0)
+    kx.hx_layernorm_param_grad_rows(P(dys), LL(ld), P(xs), LL(ld), P(mean), P(rstd), P(dg), P(db), rows, d, 0)
+    assert rel(dg, (dy.float() * xh).sum(0)) < 1e-5 and rel(db, dy.float().sum(0)) < 1e-5
+    kx.hx_layernorm_param_grad_rows(P(dys), LL(ld), P(xs), LL(ld), P(mean), P(rstd), P(dg), P(db), rows, d, 1)
+    assert rel(dg, 2 * (dy.float() * xh).sum(0)) < 1e-5 and rel(db, 2 * dy.float().sum(0)) < 1e-5
+
+
+def test_col_moments_and_channel_affine_kernel_source(kx):
+    g = torch.Generator().manual_seed(3)
+    R, C = 300, 96                                   # 3 row chunks of 128, 2 column strips
+    u, v, m = bf(g, R, C), bf(g, R, C), bf(g, R, C)
+    o1, o2 = torch.empty(C), torch.empty(C)
+    kx.hx_col_moments(P(u), LL(C), P(v), LL(C), P(m), LL(C), R, C, P(o1), P(o2))
+    um = u.float() * (m.float() > 0)
+    assert rel(o1, um.sum(0)) < 1e-5 and rel(o2, (um * v.float()).sum(0)) < 1e-5
+    kx.hx_col_moments(P(u), LL(C), P(u), LL(C), None, LL(0), R, C, P(o1), P(o2))
+    assert rel(o1, u.float().sum(0)) < 1e-5 and rel(o2, (u.float() ** 2).sum(0)) < 1e-5
+    a1, a2, c0 = torch.randn(C, generator=g), torch.randn(C, generator=g), torch.randn(C, generator=g)
+    y = torch.empty_like(u)
+    kx.hx_channel_affine(P(u), P(a1), P(v), P(a2), P(c0), P(m), P(v), 1, P(y), LL(R), C)
+    assert rel(y, F.relu(um * a1 + v.float() * a2 + c0 + v.float())) < 5e-3
+    kx.hx_channel_affine(P(u), P(a1), None, None, None, None, None, 0, P(y), LL(R), C)
+    assert rel(y, u.float() * a1) < 5e-3
+
+
+@pytest.mark.parametrize("B,H,W,C,s", [(2, 6, 6, 8, 1), (2, 6, 6, 16, 2), (1, 7, 5, 8, 2), (1, 5, 9, 8, 1)])
+def test_col2im3x3_kernel_source_is_the_adjoint_of_im2col(kx, B, H, W, C, s):
+    g = torch.Generator().manual_seed(4)
+    Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+    dcols = bf(g, B * Ho * Wo, 9 * C)
+    x = torch.zeros(B, H, W, C, requires_grad=True)
+    xu = F.unfold(x.permute(0, 3, 1, 2), 3, padding=1, stride=s)
+    xu = xu.view(B, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 9 * C)
+    xu.backward(dcols.float())
+    dx = torch.empty(B, H, W, C, dtype=torch.bfloat16)
+    kx.hx_col2im3x3(P(dcols), P(dx), B, H, W, C, s)
+    assert rel(dx, x.grad) < 5e-3
+
+
+def test_avgpool_nhwc_bwd_kernel_source(kx):
+    g = torch.Generator().manual_seed(5)
+    for (B, H, W, C, k) in ((2, 6, 8, 16, 2), (1, 7, 9, 8, 3)):          # 7x9 with k = 3: the last row / columns get no gradient
+        dy = bf(g, B, H // k, W // k, C)
+        x = torch.zeros(B, H, W, C, requires_grad=True)
+        F.avg_pool2d(x.permute(0, 3, 1, 2), k).backward(dy.float().permute(0, 3, 1, 2))
+        dx = torch.empty(B, H, W, C, dtype=torch.bfloat16)
+        kx.hx_avgpool_nhwc_bwd(P(dy), P(dx), B, H, W, C, k)
+        assert rel(dx, x.grad) < 5e-3
