@@ -381,6 +381,11 @@ class B200ModifiedResNet(nn.Module):
 
     supports_training = True
     bn_momentum = 0.1
+    # The reference never puts a frozen encoder in eval(): under model.train() its BatchNorm layers use batch statistics
+    # and keep updating their running statistics even when freeze_img_encoder is true (magma/magma.py:98-100 only clears
+    # requires_grad). Setting this to True reproduces that (forward through the training-mode schedule, no backward);
+    # the default keeps the frozen trunk on the GPU-verified folded path until the training kernels have run on a B200.
+    bn_batch_stats_when_frozen = False
 
     def __init__(self, layers, width, input_resolution, device=None):
         super().__init__()
@@ -597,6 +602,9 @@ class B200ModifiedResNet(nn.Module):
         x = x.to(device=self._device, dtype=torch.bfloat16).contiguous()
         if self._trainable() and self.training and torch.is_grad_enabled():
             return _ResNetTrainFn.apply(self, x, self.conv1.weight)       # BatchNorm in training mode + backward
+        if self.training and self.bn_batch_stats_when_frozen and not self._trainable():
+            with torch.no_grad():
+                return self._train_forward(x)[0]                          # reference-literal frozen trunk under train()
         # frozen, or a trainable trunk in eval mode: running statistics folded into the weights (re-packed from the
         # current fp32 parameters after every training forward, which resets self._packed)
         if os.environ.get("MB200_RESNET_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing():

@@ -275,3 +275,31 @@ def test_conv_training_primitives_are_what_the_schedule_assumes(emul_ops):
     a1, a2, c0 = (torch.randn(16, generator=g) for _ in range(3))
     y = ops.channel_affine(u, a1, x2=v, a2=a2, c0=c0, mask=m, res=v, relu=True)
     assert rel(y, F.relu(um * a1 + v.float() * a2 + c0 + v.float())) < 5e-3
+
+
+def test_frozen_conv_trunk_can_follow_the_reference_train_mode_batchnorm(emul_ops, monkeypatch):
+    """Reference-literal option: a FROZEN trunk under train() still normalises with batch statistics and updates its
+    running statistics (magma/magma.py:98-100 only clears requires_grad). Off by default (GPU-verified folded path)."""
+    from magma_b200.image_encoders import B200ModifiedResNet
+
+    monkeypatch.setenv("MB200_RESNET_GRAPH", "0")
+    cfg = O.OracleConfig(rn_width=16, rn_layers=(1, 1, 1, 1), rn_image=64)
+    w = O.init_resnet_weights(cfg, seed=8, pre="enc")
+    w = {k: (v.to(torch.bfloat16).float() if v.ndim == 4 else v) for k, v in w.items()}
+    enc = B200ModifiedResNet(cfg.rn_layers, cfg.rn_width, cfg.rn_image, device=torch.device("cpu"))
+    enc.load_state_dict({k[4:]: v for k, v in w.items()}, strict=False)
+    enc.train()
+    g = torch.Generator().manual_seed(0)
+    images = torch.randn(4, 3, 64, 64, generator=g).to(torch.bfloat16)
+    folded = enc(images)                                           # default: eval statistics even under train()
+    assert rel(folded, O.resnet_forward(images.float(), {k: v.clone() for k, v in w.items()}, cfg, pre="enc")) < 2e-2
+    rm0 = enc.bn1.running_mean.clone()
+    enc.bn_batch_stats_when_frozen = True
+    got = enc(images)
+    assert not got.requires_grad and not torch.equal(rm0, enc.bn1.running_mean)
+
+    def store(v):
+        return v.to(torch.bfloat16).float()
+
+    want = O.resnet_forward(images.float(), {k: v.clone() for k, v in w.items()}, cfg, pre="enc", train_bn=True, store=store)
+    assert rel(got, want) < 1.5e-2 and rel(got, folded) > 5e-2     # batch statistics, not the running ones
