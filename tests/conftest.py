@@ -54,3 +54,21 @@ def emul_ops(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", L)
     monkeypatch.setattr(ops, "_stream", lambda: None)
     return L
+
+
+@pytest.fixture
+def kernel_ops(monkeypatch):
+    """magma_b200/ops.py driven by KERNEL SOURCE executed on the CPU (oracle/kernel_host_exec.cpp: the product's .cuh kernel
+    fragments compiled as host C++, CUDA thread model emulated) — for the elementwise / reduction operators only; there is
+    no GEMM or attention here (tcgen05 / TMA code cannot run on a CPU)."""
+    import ctypes
+
+    from magma_b200 import _lib, ops
+    from oracle import build_emul
+
+    L = ctypes.CDLL(build_emul.build_kernel_exec())
+    L.mb200_last_error.restype = ctypes.c_char_p
+    L.mb200_version.restype = ctypes.c_int
+    monkeypatch.setattr(_lib, "_lib", L)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    return L

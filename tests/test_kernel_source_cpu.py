@@ -121,3 +121,101 @@ def test_avgpool_nhwc_bwd_kernel_source(kx):
         dx = torch.empty(B, H, W, C, dtype=torch.bfloat16)
         kx.hx_avgpool_nhwc_bwd(P(dy), P(dx), B, H, W, C, k)
         assert rel(dx, x.grad) < 5e-3
+
+
+def test_gpu_verified_kernel_source_passes_the_gpu_ops_harness(kernel_ops, monkeypatch, capsys):
+    """Calibration of the executor itself: the kernels of csrc/elt_kernels.cuh ARE verified on a B200
+    (tests/test_ops_gpu.py); executed on the CPU under the emulated thread model, their source passes the very same
+    harness (LayerNorm fwd / bwd / parameter gradients, rotary, softmax fwd / bwd, build_labels bit-exact, cross-entropy,
+    gathers, colsum, argmax tie rule, fused AdamW against torch.optim.AdamW, dropout) — so a pass of the NEW kernels under
+    this executor means what it would mean for these."""
+    from tools import model_check
+
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    assert model_check.group_ops(torch.device("cpu"))
+    assert "[FAIL]" not in capsys.readouterr().out
+
+
+def _both(monkeypatch, fn):
+    """Run fn() once on the kernel-source executor and once on the operator emulation; returns the two results."""
+    import ctypes as C
+
+    from magma_b200 import _lib, ops
+    from oracle import build_emul
+
+    out = []
+    for path in (build_emul.build_kernel_exec(), build_emul.build()):
+        L = C.CDLL(path)
+        L.mb200_last_error.restype = C.c_char_p
+        monkeypatch.setattr(_lib, "_lib", L)
+        monkeypatch.setattr(ops, "_stream", lambda: None)
+        out.append(fn())
+    return out
+
+
+def test_operator_emulation_agrees_with_the_kernel_source(monkeypatch):
+    """Every dry run in this suite goes through oracle/cabi_emul.cpp, a RESTATEMENT of the operators. Here that
+    restatement is compared, operator by operator on the same inputs, with the kernel source itself executed on the CPU:
+    identical integers / bf16 values for the layout and gather kernels, fp32-reassociation-level agreement for reductions."""
+    from magma_b200 import ops
+
+    g = torch.Generator().manual_seed(7)
+
+    def close(a, b, tol=2e-3):
+        assert a.shape == b.shape and rel(a, b) < tol, rel(a, b)
+
+    # LayerNorm forward / backward / parameter gradients
+    x, dy, res = bf(g, 9, 64), bf(g, 9, 64), bf(g, 9, 64)
+    gam, bet = (1 + 0.1 * torch.randn(64, generator=g)).to(torch.bfloat16), bf(g, 64, scale=0.1)
+    (yk, mk, rk), (ye, me, re_) = _both(monkeypatch, lambda: ops.layernorm_fwd(x, gam, bet, 1e-5))
+    close(yk, ye), close(mk, me, 1e-5), close(rk, re_, 1e-5)
+    dk, de = _both(monkeypatch, lambda: ops.layernorm_bwd(dy, x, gam, mk, rk, res=res))
+    close(dk, de)
+    def pg():
+        a, b = torch.zeros(64), torch.zeros(64)
+        ops.layernorm_param_grad(dy, x, mk, rk, a, b)
+        return torch.stack([a, b])
+    close(*_both(monkeypatch, pg), tol=1e-5)
+    # softmax forward (causal with offset) / backward
+    s = torch.randn(3, 5, 16, generator=g)
+    pk, pe = _both(monkeypatch, lambda: ops.softmax_fwd(s, 0.25, True, koff=3))
+    close(pk, pe)
+    dp = torch.randn(3, 5, 16, generator=g)
+    close(*_both(monkeypatch, lambda: ops.softmax_bwd(dp, pk.contiguous(), 0.25)))
+    # shifted cross-entropy: loss and gradient (V = 70 columns of a 72-wide row)
+    logits = bf(g, 2, 3, 72)
+    labels = torch.randint(0, 70, (2, 3), generator=g)
+    labels[0, 2] = -100
+    (lk, gk), (le, ge) = _both(monkeypatch, lambda: ops.cross_entropy(logits, labels, 70, write_grad=True))
+    assert abs(float(lk) - float(le)) < 1e-5
+    close(gk[..., :70], ge[..., :70])
+    # integer / layout kernels: identical
+    caps = torch.randint(0, 50, (3, 12), generator=g)
+    caps[1, 4:] = 49
+    a, b = _both(monkeypatch, lambda: ops.build_labels(caps, 3, 49))
+    assert torch.equal(a, b)
+    img = bf(g, 2, 3, 16, 16)
+    a, b = _both(monkeypatch, lambda: ops.nchw_to_nhwc8(img))
+    assert torch.equal(a, b)
+    t = bf(g, 2, 6, 6, 8)
+    for st in (1, 2):
+        (ca, _, _), (cb, _, _) = _both(monkeypatch, lambda: ops.im2col3x3(t, st))
+        assert torch.equal(ca, cb)
+    a, b = _both(monkeypatch, lambda: ops.avgpool_nhwc(t, 2))
+    close(a, b)
+    rows = bf(g, 5, 96)
+    a, b = _both(monkeypatch, lambda: ops.argmax(rows, 90))
+    assert torch.equal(a, b)
+    a, b = _both(monkeypatch, lambda: ops.colsum(rows))
+    close(a, b, 1e-6)
+    (ya, ma), (yb, mb) = _both(monkeypatch, lambda: ops.dropout_fwd(rows, 0.3, 11))
+    assert torch.equal(ma, mb) and torch.equal(ya, yb)       # same counter-based hash, same mask
+    # the training kernels: emulation vs source
+    u, v, m = bf(g, 40, 16), bf(g, 40, 16), bf(g, 40, 16)
+    (a1, a2), (b1, b2) = _both(monkeypatch, lambda: ops.col_moments(u, v, m))
+    close(a1, b1, 1e-5), close(a2, b2, 1e-5)
+    co = torch.randn(16, generator=g)
+    close(*_both(monkeypatch, lambda: ops.channel_affine(u, co, x2=v, a2=co, c0=co, mask=m, res=v, relu=True)))
+    dcols = bf(g, 2 * 3 * 3, 9 * 8)
+    close(*_both(monkeypatch, lambda: ops.col2im3x3(dcols, 2, 6, 6, 8, 2)))
+    close(*_both(monkeypatch, lambda: ops.quick_gelu_bwd(u, v)))
