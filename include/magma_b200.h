@@ -205,6 +205,17 @@ int mb200_col_moments(const void* u, int64_t ldu, const void* v, int64_t ldv, co
                       int32_t cols, float* out1, float* out2, void* stream);
 int mb200_channel_affine(const void* x1, const float* a1, const void* x2, const float* a2, const float* c0,
                          const void* mask, const void* res, int32_t relu, void* y, int64_t rows, int32_t C, void* stream);
+/* Per-channel BatchNorm bookkeeping (one thread per channel; all arrays fp32 [C]).
+ *   bn_finalize_fwd  (s1 = sum z, s2 = sum z^2 over `rows`) -> mean, rstd, scale = gamma * rstd, shift = beta - mean * scale,
+ *                    and nn.BatchNorm2d's running statistics (momentum, unbiased variance; both NULL = no update).
+ *   bn_bwd_coeffs    (s1 = sum dy', t = sum dy' * z) -> dgamma, dbeta (written, or added when accumulate != 0) and the
+ *                    coefficients of dz = A * dy' + Bc * z + Cc for mb200_channel_affine. */
+int mb200_bn_finalize_fwd(const float* s1, const float* s2, const float* gamma, const float* beta, int64_t rows, float eps,
+                          float momentum, float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
+                          float* shift, int32_t C, void* stream);
+int mb200_bn_bwd_coeffs(const float* s1, const float* t, const float* mean, const float* rstd, const float* gamma,
+                        int64_t rows, float* dgamma, float* dbeta, int32_t accumulate, float* A, float* Bc, float* Cc,
+                        int32_t C, void* stream);
 int mb200_col2im3x3(const void* dcols, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, void* stream);
 int mb200_avgpool_nhwc_bwd(const void* dy, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* stream);
 /* torch.argmax(logits.float(), -1) (magma/sampling.py:92,97): lowest index wins ties. */

@@ -143,6 +143,33 @@ extern "C" int mb200_avgpool_nhwc_bwd(const void* dy, void* dx, int32_t B, int32
   return 0;
 }
 
+extern "C" int mb200_bn_finalize_fwd(const float* s1, const float* s2, const float* gamma, const float* beta, int64_t rows,
+                                     float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                                     float* rstd, float* scale, float* shift, int32_t C, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(rows > 0 && C > 0 && s1 && s2 && gamma && beta && mean && rstd && scale && shift &&
+                 ((running_mean == nullptr) == (running_var == nullptr)),
+             MB200_E_ARG, "bn_finalize_fwd: bad arguments");
+  const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
+  bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(s1, s2, gamma, beta, (float)(1.0 / (double)rows), unbias, eps,
+                                                                momentum, running_mean, running_var, mean, rstd, scale,
+                                                                shift, C);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_bn_bwd_coeffs(const float* s1, const float* t, const float* mean, const float* rstd, const float* gamma,
+                                   int64_t rows, float* dgamma, float* dbeta, int32_t accumulate, float* A, float* Bc,
+                                   float* Cc, int32_t C, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(rows > 0 && C > 0 && s1 && t && mean && rstd && gamma && dgamma && dbeta && A && Bc && Cc, MB200_E_ARG,
+             "bn_bwd_coeffs: bad arguments");
+  bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(s1, t, mean, rstd, gamma, (float)(1.0 / (double)rows), dgamma,
+                                                              dbeta, accumulate, A, Bc, Cc, C);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mb200_scale_add(const void* u, const float* s, const void* r1, const void* r2, void* out, int64_t n,
                                void* stream) {
   MB_ENTER();

@@ -209,6 +209,51 @@ __global__ void avgpool_nhwc_bwd_kernel(const bf16* __restrict__ dy, bf16* __res
   }
 }
 
+// Per-channel BatchNorm bookkeeping, one thread per channel (C is a few thousand at most): these replace ~16 C-element
+// framework launches per conv-BN unit and pass.
+//   forward : batch statistics from (sum z, sum z^2), the normalisation coefficients channel_affine consumes
+//             (scale = gamma * rstd, shift = beta - mean * scale), and nn.BatchNorm2d's running-statistics update
+//             (momentum, unbiased variance)
+//   backward: dgamma = sum dy' * xhat, dbeta = sum dy' (written or accumulated), and the coefficients of
+//             dz = A * dy' + Bc * z + Cc  ==  gamma * rstd * (dy' - mean(dy') - xhat * mean(dy' * xhat))
+__global__ void bn_finalize_fwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float inv_rows,
+                                       float unbias, float eps, float momentum, float* __restrict__ running_mean,
+                                       float* __restrict__ running_var, float* __restrict__ mean, float* __restrict__ rstd,
+                                       float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = s1[c] * inv_rows;
+  const float var = fmaxf(s2[c] * inv_rows - m * m, 0.f);
+  const float rs = rsqrtf(var + eps);
+  const float sc = gamma[c] * rs;
+  mean[c] = m;
+  rstd[c] = rs;
+  scale[c] = sc;
+  shift[c] = beta[c] - m * sc;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+  }
+}
+
+__global__ void bn_bwd_coeffs_kernel(const float* __restrict__ s1, const float* __restrict__ t,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, float inv_rows, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int accumulate, float* __restrict__ A,
+                                     float* __restrict__ Bc, float* __restrict__ Cc, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s2 = rstd[c] * (t[c] - mean[c] * s1[c]);  // sum dy' * xhat
+  dgamma[c] = accumulate ? dgamma[c] + s2 : s2;
+  dbeta[c] = accumulate ? dbeta[c] + s1[c] : s1[c];
+  const float a = gamma[c] * rstd[c];
+  const float k2 = a * rstd[c] * s2 * inv_rows;
+  A[c] = a;
+  Bc[c] = -k2;
+  Cc[c] = k2 * mean[c] - a * s1[c] * inv_rows;
+}
+
 // out = s[0] * u + r1 + r2 (r1 / r2 optional; s == nullptr means 1): the `* adapter_scale` of ParallelAdapter.forward
 // (magma/adapters.py:63-66,85-92) with the block's residual sum folded in. s is a DEVICE scalar (a trainable parameter).
 __global__ void scale_add_kernel(const bf16* __restrict__ u, const float* __restrict__ s, const bf16* __restrict__ r1,

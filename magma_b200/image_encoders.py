@@ -455,19 +455,15 @@ class B200ModifiedResNet(nn.Module):
         z = ops.gemm(cols, wp)                                    # conv output, [R, Cout] bf16
         R = z.shape[0]
         s1, s2 = ops.col_moments(z, z)                            # sum z, sum z^2 per channel (fp32)
-        mean = s1 / R
-        var = (s2 / R - mean * mean).clamp_min_(0.0)
-        rstd = torch.rsqrt(var + bn.eps)
-        gamma, beta = bn.weight.data.float(), bn.bias.data.float()
-        scale = (gamma * rstd).contiguous()
-        shift = (beta - mean * scale).contiguous()
+        gamma = bn.weight.data if bn.weight.dtype == torch.float32 else bn.weight.data.float()
+        beta = bn.bias.data if bn.bias.dtype == torch.float32 else bn.bias.data.float()
+        # one launch: batch statistics, scale = gamma * rstd, shift = beta - mean * scale, and nn.BatchNorm2d's
+        # running statistics (momentum 0.1, unbiased variance)
+        mean, rstd, scale, shift = ops.bn_finalize_fwd(s1, s2, gamma.contiguous(), beta.contiguous(), R, bn.eps,
+                                                       self.bn_momentum, bn.running_mean, bn.running_var)
         res2 = res.reshape(R, -1) if res is not None else None
         y = ops.channel_affine(z, scale, c0=shift, res=res2, relu=relu)
-        with torch.no_grad():                                     # nn.BatchNorm2d running statistics (unbiased variance)
-            m = self.bn_momentum
-            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-            bn.running_var.mul_(1 - m).add_(var * (R / max(R - 1, 1)), alpha=m)
-            bn.num_batches_tracked += 1
+        bn.num_batches_tracked += 1
         tape.append({"conv": conv, "bn": bn, "k": k, "stride": stride, "in_shape": (B, H, W, Cin), "cols": cols, "wp": wp,
                      "z": z, "mean": mean, "rstd": rstd, "gamma": gamma, "y": y if relu else None,
                      "has_res": res is not None, "pad": pad_cin_to, "need_dx": need_dx})
@@ -479,16 +475,20 @@ class B200ModifiedResNet(nn.Module):
         z, mean, rstd, gamma, mask = rec["z"], rec["mean"], rec["rstd"], rec["gamma"], rec["y"]
         R, Cout = z.shape
         s1, t = ops.col_moments(dy, z, mask)                      # sum dy', sum dy' * z   (dy' = dy * 1[y > 0])
-        s2 = rstd * (t - mean * s1)                               # sum dy' * xhat
-        self._put_grad(rec["bn"].weight, s2, acc)
-        self._put_grad(rec["bn"].bias, s1, acc)
-        a = gamma * rstd
-        k2 = a * rstd * s2 / R
-        dz = ops.channel_affine(dy, a.contiguous(), x2=z, a2=(-k2).contiguous(), c0=(k2 * mean - a * s1 / R).contiguous(),
-                                mask=mask)                        # a * (dy' - s1/R - xhat * s2/R)
+        bn = rec["bn"]
+        if self._arena is not None:                               # dgamma / dbeta straight into the arena's gradient views
+            dg, db, bn_acc = self._arena.grad_of(bn.weight), self._arena.grad_of(bn.bias), acc
+        else:
+            dg, db, bn_acc = torch.empty_like(s1), torch.empty_like(s1), False
+        # one launch: dgamma = sum dy' * xhat, dbeta = sum dy', and the coefficients of dz = A dy' + Bc z + Cc
+        A, Bc, Cc = ops.bn_bwd_coeffs(s1, t, mean, rstd, gamma.contiguous(), R, dg, db, accumulate=bn_acc)
+        if self._arena is None:
+            self._put_grad(bn.weight, dg, acc)
+            self._put_grad(bn.bias, db, acc)
+        dz = ops.channel_affine(dy, A, x2=z, a2=Bc, c0=Cc, mask=mask)   # gamma * rstd * (dy' - s1/R - xhat * s2/R)
         dres = None
         if rec["has_res"]:
-            dres = dy if mask is None else ops.channel_affine(dy, torch.ones_like(a), mask=mask)
+            dres = dy if mask is None else ops.channel_affine(dy, torch.ones_like(A), mask=mask)
         conv, k, pad = rec["conv"], rec["k"], rec["pad"]
         B, H, W, Cin = rec["in_shape"]
         dwp = ops.gemm(dz, rec["cols"], a_mn=True, b_mn=True, out_dtype=torch.float32)   # [Cout, k*k*Cin] = dz^T cols

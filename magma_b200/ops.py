@@ -337,6 +337,31 @@ def channel_affine(x1, a1, x2=None, a2=None, c0=None, mask=None, res=None, relu=
     return y
 
 
+def bn_finalize_fwd(s1, s2, gamma, beta, rows, eps, momentum, running_mean=None, running_var=None):
+    """(sum z, sum z^2) -> (mean, rstd, scale, shift) fp32 [C]; updates the running statistics in place when given."""
+    C = s1.numel()
+    for t in (s1, s2, gamma, beta, running_mean, running_var):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == C)
+    out = torch.empty(4, C, dtype=torch.float32, device=s1.device)
+    check(lib().mb200_bn_finalize_fwd(_ptr(s1), _ptr(s2), _ptr(gamma), _ptr(beta), ctypes.c_int64(rows), ctypes.c_float(eps),
+                                      ctypes.c_float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(out[0]),
+                                      _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), C, _stream()))
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_bwd_coeffs(s1, t, mean, rstd, gamma, rows, dgamma, dbeta, accumulate=False):
+    """(sum dy', sum dy' * z) -> dgamma / dbeta (written or accumulated in place) and the coefficients (A, Bc, Cc) of
+    dz = A * dy' + Bc * z + Cc."""
+    C = s1.numel()
+    for x in (s1, t, mean, rstd, gamma, dgamma, dbeta):
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == C
+    out = torch.empty(3, C, dtype=torch.float32, device=s1.device)
+    check(lib().mb200_bn_bwd_coeffs(_ptr(s1), _ptr(t), _ptr(mean), _ptr(rstd), _ptr(gamma), ctypes.c_int64(rows),
+                                    _ptr(dgamma), _ptr(dbeta), int(accumulate), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), C,
+                                    _stream()))
+    return out[0], out[1], out[2]
+
+
 def col2im3x3(dcols, B, H, W, C, stride=1):
     """Adjoint of im2col3x3: [B*Ho*Wo, 9*C] bf16 -> [B, H, W, C] bf16."""
     assert dcols.dtype == torch.bfloat16 and dcols.is_contiguous() and dcols.shape[1] == 9 * C

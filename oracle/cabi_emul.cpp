@@ -798,6 +798,45 @@ int mb200_channel_affine(const void* x1_, const float* a1, const void* x2_, cons
   return 0;
 }
 
+int mb200_bn_finalize_fwd(const float* s1, const float* s2, const float* gamma, const float* beta, int64_t rows, float eps,
+                          float momentum, float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
+                          float* shift, int32_t C, void*) {
+  EM_REQUIRE(rows > 0 && C > 0 && ((running_mean == nullptr) == (running_var == nullptr)), MB200_E_ARG, "bn_finalize_fwd");
+  const double unbias = rows > 1 ? (double)rows / (double)(rows - 1) : 1.0;
+  for (int c = 0; c < C; ++c) {
+    const double m = (double)s1[c] / rows;
+    double var = (double)s2[c] / rows - m * m;
+    if (var < 0) var = 0;
+    const double rs = 1.0 / sqrt(var + eps);
+    mean[c] = (float)m;
+    rstd[c] = (float)rs;
+    scale[c] = (float)(gamma[c] * rs);
+    shift[c] = (float)(beta[c] - m * gamma[c] * rs);
+    if (running_mean) {
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * var * unbias);
+    }
+  }
+  return 0;
+}
+
+int mb200_bn_bwd_coeffs(const float* s1, const float* t, const float* mean, const float* rstd, const float* gamma,
+                        int64_t rows, float* dgamma, float* dbeta, int32_t accumulate, float* A, float* Bc, float* Cc,
+                        int32_t C, void*) {
+  EM_REQUIRE(rows > 0 && C > 0, MB200_E_ARG, "bn_bwd_coeffs");
+  for (int c = 0; c < C; ++c) {
+    const double s2 = (double)rstd[c] * ((double)t[c] - (double)mean[c] * s1[c]);
+    dgamma[c] = (float)((accumulate ? dgamma[c] : 0.f) + s2);
+    dbeta[c] = (accumulate ? dbeta[c] : 0.f) + s1[c];
+    const double a = (double)gamma[c] * rstd[c];
+    const double k2 = a * rstd[c] * s2 / rows;
+    A[c] = (float)a;
+    Bc[c] = (float)(-k2);
+    Cc[c] = (float)(k2 * mean[c] - a * s1[c] / rows);
+  }
+  return 0;
+}
+
 int mb200_col2im3x3(const void* dcols_, void* dx_, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride, void*) {
   EM_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2), MB200_E_SHAPE,
              "col2im3x3: bad shape / stride");

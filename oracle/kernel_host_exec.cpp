@@ -414,6 +414,24 @@ int mb200_avgpool_nhwc_bwd(const void* dy, void* dx, int32_t B, int32_t H, int32
   hx_avgpool_nhwc_bwd(dy, dx, B, H, W, C, k);
   return 0;
 }
+int mb200_bn_finalize_fwd(const float* s1, const float* s2, const float* gamma, const float* beta, int64_t rows, float eps,
+                          float momentum, float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
+                          float* shift, int32_t C, void*) {
+  const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
+  run_grid(Dim3{(unsigned)((C + 127) / 128), 1, 1}, 128, [&] {
+    bn_finalize_fwd_kernel(s1, s2, gamma, beta, (float)(1.0 / (double)rows), unbias, eps, momentum, running_mean, running_var,
+                           mean, rstd, scale, shift, C);
+  });
+  return 0;
+}
+int mb200_bn_bwd_coeffs(const float* s1, const float* t, const float* mean, const float* rstd, const float* gamma,
+                        int64_t rows, float* dgamma, float* dbeta, int32_t accumulate, float* A, float* Bc, float* Cc,
+                        int32_t C, void*) {
+  run_grid(Dim3{(unsigned)((C + 127) / 128), 1, 1}, 128, [&] {
+    bn_bwd_coeffs_kernel(s1, t, mean, rstd, gamma, (float)(1.0 / (double)rows), dgamma, dbeta, accumulate, A, Bc, Cc, C);
+  });
+  return 0;
+}
 const char* mb200_last_error(void) { return ""; }
 int mb200_version(void) { return 100; }
 

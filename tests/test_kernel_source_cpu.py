@@ -219,3 +219,39 @@ def test_operator_emulation_agrees_with_the_kernel_source(monkeypatch):
     dcols = bf(g, 2 * 3 * 3, 9 * 8)
     close(*_both(monkeypatch, lambda: ops.col2im3x3(dcols, 2, 6, 6, 8, 2)))
     close(*_both(monkeypatch, lambda: ops.quick_gelu_bwd(u, v)))
+
+
+def test_batchnorm_bookkeeping_kernel_source(kx):
+    """bn_finalize_fwd / bn_bwd_coeffs (one thread per channel) against nn.BatchNorm2d semantics and autograd."""
+    g = torch.Generator().manual_seed(9)
+    R, C = 200, 40
+    z = torch.randn(R, C, generator=g) * 2 + 0.5
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    rm, rv = torch.randn(C, generator=g) * 0.1, 1 + 0.2 * torch.rand(C, generator=g)
+    s1, s2 = z.sum(0).contiguous(), (z * z).sum(0).contiguous()
+    bn = torch.nn.BatchNorm2d(C, momentum=0.1)
+    with torch.no_grad():
+        bn.weight.copy_(gamma), bn.bias.copy_(beta), bn.running_mean.copy_(rm), bn.running_var.copy_(rv)
+    zz = z.clone().requires_grad_(True)
+    y = bn(zz.t().reshape(1, C, R, 1))                       # training mode: batch statistics over the R positions
+    rm_k, rv_k = rm.clone(), rv.clone()
+    out = [torch.empty(C) for _ in range(4)]
+    F32 = ctypes.c_float
+    rc = kx.mb200_bn_finalize_fwd(P(s1), P(s2), P(gamma), P(beta), LL(R), F32(1e-5), F32(0.1), P(rm_k), P(rv_k),
+                                  P(out[0]), P(out[1]), P(out[2]), P(out[3]), C, None)
+    assert rc == 0
+    mean, rstd, scale, shift = out
+    assert torch.allclose(z * scale + shift, y.reshape(C, R).t(), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(rm_k, bn.running_mean, rtol=1e-5, atol=1e-6) and torch.allclose(rv_k, bn.running_var, rtol=1e-4, atol=1e-5)
+    dy = torch.randn(R, C, generator=g)
+    y.backward(dy.t().reshape(1, C, R, 1))
+    t = (dy * z).sum(0).contiguous()
+    d1 = dy.sum(0).contiguous()
+    dg, db = torch.full((C,), 2.0), torch.full((C,), 2.0)
+    co = [torch.empty(C) for _ in range(3)]
+    rc = kx.mb200_bn_bwd_coeffs(P(d1), P(t), P(mean), P(rstd), P(gamma), LL(R), P(dg), P(db), 1, P(co[0]), P(co[1]), P(co[2]),
+                                C, None)
+    assert rc == 0
+    assert torch.allclose(dg, 2.0 + bn.weight.grad, rtol=1e-3, atol=1e-3) and torch.allclose(db, 2.0 + bn.bias.grad, rtol=1e-4, atol=1e-4)
+    dz = dy * co[0] + z * co[1] + co[2]
+    assert torch.allclose(dz, zz.grad, rtol=1e-3, atol=1e-4)
