@@ -339,3 +339,36 @@ def test_gradient_accumulation_matches_the_mean_of_micro_batch_gradients(emul_op
     assert not bad, bad
     eng.step()                                        # boundary: WarmupLR gives lr(0) = 0, but the step is counted
     assert eng.global_step == 1 and float(model.arena.grad.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("reference_names", [False, True])
+def test_from_checkpoint_round_trip(emul_ops, monkeypatch, tmp_path, reference_names):
+    """Magma.from_checkpoint (magma/magma.py:278-301) on a full state dict written in DeepSpeed's file layout — with this
+    package's parameter names, and with the reference fork's names (attn.attention.*, mlp.c_fc / c_proj), which
+    checkpoint.convert_reference_state_dict maps back: the loaded model reproduces the logits of the one that was saved."""
+    from magma_b200 import checkpoint as ck
+    from magma_b200.magma import Magma
+
+    cfg = tiny_cfg()
+    S = 16
+    w16 = oracle_weights(cfg)
+    model, mc = build(monkeypatch, cfg, w16, S, freeze_enc=True)
+    model.eval()
+    images, captions = O.synthetic_batch(cfg, 2, S, seed=5)
+    images = images.to(torch.bfloat16)
+    with torch.no_grad():
+        want = model(images, captions).logits.float().clone()
+    sd = {k: v for k, v in model.state_dict().items() if not k.startswith(("word_embedding.", "transformer."))}
+    d = ck.save_training_checkpoint(tmp_path, "global_step0", sd, ck.arena_optimizer_state(model.arena), {"global_step": 0},
+                                    reference_names=reference_names)
+    path = str(tmp_path / "global_step0" / "mp_rank_00_model_states.pt")
+    if reference_names:
+        keys = torch.load(path, weights_only=False)["module"].keys()
+        assert any(".attention.q_proj." in k for k in keys) and any(".c_fc." in k and k.startswith("lm.") for k in keys)
+    loaded = Magma.from_checkpoint(mc, path, device="cpu")
+    loaded.eos_token, loaded.image_token = cfg.eos_token, cfg.image_token
+    with torch.no_grad():
+        got = loaded(images, captions).logits.float()
+    assert torch.equal(got, want)
+    with pytest.raises(FileNotFoundError):
+        Magma.from_checkpoint(mc, str(tmp_path / "nope.pt"), device="cpu")
