@@ -21,6 +21,8 @@
 
 #include "../include/magma_b200.h"
 
+extern "C" int mb200_emul_tracing(void);
+
 namespace mb200 {
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
@@ -31,10 +33,12 @@ void set_error(const char* fmt, ...) {
 }
 int rt_check_arch() { return 0; }
 int rt_copy(void* dst, const void* src, size_t bytes, void*) {
+  if (mb200_emul_tracing()) return 0;
   memmove(dst, src, bytes);
   return 0;
 }
 int rt_zero(void* dst, size_t bytes, void*) {
+  if (mb200_emul_tracing()) return 0;
   memset(dst, 0, bytes);
   return 0;
 }
@@ -46,6 +50,24 @@ int rt_zero(void* dst, size_t bytes, void*) {
       mb200::set_error(__VA_ARGS__);  \
       return (code);                  \
     }                                 \
+  } while (0)
+
+// ---- launch-plan trace (tools/plan_trace.py): with a trace file open every primitive logs one line — operator, shape,
+// algorithmic FLOPs and bytes — and returns WITHOUT touching memory, so a full-size pass (GPT-J-6B at B = 8, S = 128) can be
+// "issued" with placeholder pointers in milliseconds and the product's own schedule code writes out its launch plan.
+static FILE* g_trace = nullptr;
+extern "C" void mb200_emul_trace(const char* path) {
+  if (g_trace) fclose(g_trace);
+  g_trace = path ? fopen(path, "w") : nullptr;
+}
+extern "C" int mb200_emul_tracing(void) { return g_trace != nullptr; }
+#define EM_TRACE(flops, bytes, ...)                                   \
+  do {                                                                \
+    if (g_trace) {                                                    \
+      fprintf(g_trace, __VA_ARGS__);                                  \
+      fprintf(g_trace, "\tflops=%.0f\tbytes=%.0f\n", (double)(flops), (double)(bytes)); \
+      return 0;                                                       \
+    }                                                                 \
   } while (0)
 
 typedef uint16_t bf16_t;
@@ -112,6 +134,18 @@ int mb200_gemm(const mb200_gemm_args* a, void*) {
     EM_REQUIRE(a->rope_S > 0 && a->rope_hd > 0 && a->rope_rot % 4 == 0 && a->rope_rot <= a->rope_hd &&
                    a->rope_hd % 4 == 0 && a->rope_ncols % 4 == 0,
                MB200_E_ARG, "gemm: bad rope epilogue parameters");
+  {
+    const double nb = (double)a->nb0 * a->nb1, csz = a->c_dtype == MB200_F32 ? 4.0 : 2.0;
+    const double MN = (double)a->M * a->N;
+    double bytes = nb * (2.0 * ((double)a->M * a->K + (double)a->N * a->K) + csz * MN);
+    bytes += nb * 2.0 * MN * ((a->res1 ? 1 : 0) + (a->res2 ? 1 : 0) + (a->aux_in ? 1 : 0) + (a->aux_out ? 1 : 0));
+    if (a->accumulate) bytes += nb * 4.0 * MN;
+    EM_TRACE(2.0 * MN * a->K * nb, bytes,
+             "gemm\tM=%d N=%d K=%d nb=%d a_mn=%d b_mn=%d c=%s bias=%d act=%d dact=%d res=%d aux=%d acc=%d rope=%d", a->M,
+             a->N, a->K, a->nb0 * a->nb1, a->A.mn_major, a->B.mn_major, a->c_dtype == MB200_F32 ? "f32" : "bf16",
+             a->bias != nullptr, a->act, a->dact, (a->res1 ? 1 : 0) + (a->res2 ? 1 : 0),
+             (a->aux_in ? 1 : 0) + (a->aux_out ? 1 : 0), a->accumulate, rope ? a->rope_mode : 0);
+  }
   const bf16_t* bias = (const bf16_t*)a->bias;
   const bf16_t* aux_in = (const bf16_t*)a->aux_in;
   bf16_t* aux_out = (bf16_t*)a->aux_out;
@@ -175,6 +209,7 @@ int mb200_gemm(const mb200_gemm_args* a, void*) {
 // ---- LayerNorm (elementwise.cu: layernorm_fwd_kernel / layernorm_bwd_kernel / layernorm_param_grad*_kernel) ----
 int mb200_layernorm_fwd(const void* x_, int64_t ldx, const void* gamma_, const void* beta_, void* y_, int64_t ldy,
                         float* mean, float* rstd, int32_t rows, int32_t d, float eps, void*) {
+  EM_TRACE(8.0 * rows * d, (double)rows * d * 4 + (mean ? rows * 8.0 : 0), "layernorm_fwd\trows=%d d=%d", rows, d);
   EM_REQUIRE(rows > 0 && d > 0 && d % 8 == 0 && d <= 8192, MB200_E_SHAPE, "layernorm: bad d=%d", d);
   EM_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, MB200_E_ALIGN, "layernorm: row strides must be multiples of 8");
   const bf16_t *x = (const bf16_t*)x_, *g = (const bf16_t*)gamma_, *b = (const bf16_t*)beta_;
@@ -200,6 +235,7 @@ int mb200_layernorm_fwd(const void* x_, int64_t ldx, const void* gamma_, const v
 int mb200_layernorm_bwd(const void* dy_, int64_t lddy, const void* x_, int64_t ldx, const void* gamma_,
                         const float* mean, const float* rstd, const void* res_, int64_t ldres, void* dx_, int64_t lddx,
                         int32_t rows, int32_t d, void*) {
+  EM_TRACE(12.0 * rows * d, (double)rows * d * (res_ ? 8 : 6), "layernorm_bwd\trows=%d d=%d res=%d", rows, d, res_ != nullptr);
   EM_REQUIRE(rows > 0 && d > 0 && d % 8 == 0 && d <= 8192, MB200_E_SHAPE, "layernorm_bwd: bad d=%d", d);
   EM_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && (!res_ || ldres % 8 == 0), MB200_E_ALIGN,
              "layernorm_bwd: row strides must be multiples of 8");
@@ -223,6 +259,7 @@ int mb200_layernorm_bwd(const void* dy_, int64_t lddy, const void* x_, int64_t l
 
 static int ln_param_grad(const void* dy_, int64_t lddy, const void* x_, int64_t ldx, const float* mean,
                          const float* rstd, float* dgamma, float* dbeta, int32_t rows, int32_t d, int32_t accumulate) {
+  EM_TRACE(4.0 * rows * d, (double)rows * d * 4, "layernorm_param_grad\trows=%d d=%d", rows, d);
   const bf16_t *dy = (const bf16_t*)dy_, *x = (const bf16_t*)x_;
   for (int c = 0; c < d; ++c) {
     float sg = 0.f, sb = 0.f;
@@ -244,6 +281,7 @@ int mb200_layernorm_param_grad(const void* dy, int64_t lddy, const void* x, int6
 int mb200_layernorm_param_grad_rows(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
                                     const float* rstd, float* dgamma, float* dbeta, int32_t rows, int32_t d,
                                     int32_t accumulate, void*) {
+  /* traced in ln_param_grad */
   EM_REQUIRE(rows > 0 && d > 0 && d % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0, MB200_E_ALIGN,
              "layernorm_param_grad_rows: d and row strides must be even");
   return ln_param_grad(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, d, accumulate);
@@ -252,6 +290,7 @@ int mb200_layernorm_param_grad_rows(const void* dy, int64_t lddy, const void* x,
 // ---- softmax (elementwise.cu: softmax_fwd_kernel / softmax_bwd_kernel) ----
 int mb200_softmax_fwd(const float* s, int64_t lds, int64_t s_bs, void* p_, int64_t ldp, int64_t p_bs, int32_t nz,
                       int32_t Sq, int32_t Sk, float scale, int32_t causal, int32_t koff, void*) {
+  EM_TRACE(5.0 * nz * Sq * Sk, (double)nz * Sq * Sk * 6, "softmax_fwd\tnz=%d Sq=%d Sk=%d causal=%d", nz, Sq, Sk, causal);
   bf16_t* p = (bf16_t*)p_;
   for (int z = 0; z < nz; ++z)
     for (int i = 0; i < Sq; ++i) {
@@ -269,6 +308,7 @@ int mb200_softmax_fwd(const float* s, int64_t lds, int64_t s_bs, void* p_, int64
 
 int mb200_softmax_bwd(const float* dp, int64_t lddp, int64_t dp_bs, const void* p_, int64_t ldp, int64_t p_bs,
                       void* ds_, int64_t ldds, int64_t ds_bs, int32_t nz, int32_t Sq, int32_t Sk, float scale, void*) {
+  EM_TRACE(4.0 * nz * Sq * Sk, (double)nz * Sq * Sk * 8, "softmax_bwd\tnz=%d Sq=%d Sk=%d", nz, Sq, Sk);
   const bf16_t* p = (const bf16_t*)p_;
   bf16_t* ds = (bf16_t*)ds_;
   for (int z = 0; z < nz; ++z)
@@ -285,6 +325,7 @@ int mb200_softmax_bwd(const float* dp, int64_t lddp, int64_t dp_bs, const void* 
 
 // ---- reductions / elementwise / ViT front end ----
 int mb200_colsum(const void* x_, int64_t ldx, int32_t rows, int32_t cols, float* out, int32_t accumulate, void*) {
+  EM_TRACE((double)rows * cols, (double)rows * cols * 2, "colsum\trows=%d cols=%d", rows, cols);
   EM_REQUIRE(cols % 2 == 0 && ldx % 2 == 0, MB200_E_ALIGN, "colsum: cols and ldx must be even");
   const bf16_t* x = (const bf16_t*)x_;
   for (int c = 0; c < cols; ++c) {
@@ -296,6 +337,7 @@ int mb200_colsum(const void* x_, int64_t ldx, int32_t rows, int32_t cols, float*
 }
 
 int mb200_quick_gelu_bwd(const void* dy_, const void* pre_, void* dx_, int64_t n, void*) {
+  EM_TRACE(8.0 * n, (double)n * 6, "quick_gelu_bwd\tn=%lld", (long long)n);
   EM_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "quick_gelu_bwd: n must be a positive multiple of 8");
   EM_REQUIRE(aligned16(dy_) && aligned16(pre_) && aligned16(dx_), MB200_E_ALIGN, "quick_gelu_bwd: 16B alignment");
   const bf16_t *dy = (const bf16_t*)dy_, *pre = (const bf16_t*)pre_;
@@ -309,6 +351,7 @@ int mb200_quick_gelu_bwd(const void* dy_, const void* pre_, void* dx_, int64_t n
 
 // out = s[0] * u + r1 + r2   (scale_add_kernel)
 int mb200_scale_add(const void* u_, const float* s, const void* r1_, const void* r2_, void* out_, int64_t n, void*) {
+  EM_TRACE(3.0 * n, (double)n * (4 + (r1_ ? 2 : 0) + (r2_ ? 2 : 0)), "scale_add\tn=%lld", (long long)n);
   EM_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "scale_add: n must be a positive multiple of 8");
   EM_REQUIRE(aligned16(u_) && aligned16(r1_) && aligned16(r2_) && aligned16(out_), MB200_E_ALIGN, "scale_add: alignment");
   const bf16_t *u = (const bf16_t*)u_, *r1 = (const bf16_t*)r1_, *r2 = (const bf16_t*)r2_;
@@ -320,6 +363,7 @@ int mb200_scale_add(const void* u_, const float* s, const void* r1_, const void*
 
 // out[0] (+)= <a, b>   (dot_kernel)
 int mb200_dot(const void* a_, const void* b_, int64_t n, float* out, int32_t accumulate, void*) {
+  EM_TRACE(2.0 * n, (double)n * 4, "dot\tn=%lld", (long long)n);
   EM_REQUIRE(n > 0 && n % 8 == 0, MB200_E_SHAPE, "dot: n must be a positive multiple of 8");
   EM_REQUIRE(aligned16(a_) && aligned16(b_), MB200_E_ALIGN, "dot: alignment");
   const bf16_t *a = (const bf16_t*)a_, *b = (const bf16_t*)b_;
@@ -331,6 +375,7 @@ int mb200_dot(const void* a_, const void* b_, int64_t n, float* out, int32_t acc
 
 // (cos, sin) fp32 [S][rot/2][2]   (rope_table_kernel)
 int mb200_rope_table(float* tab, int32_t S, int32_t rot, int32_t pos0, void*) {
+  EM_TRACE(0, (double)S * rot * 4, "rope_table\tS=%d rot=%d", S, rot);
   EM_REQUIRE(S > 0 && rot > 0 && rot % 2 == 0, MB200_E_SHAPE, "rope_table: bad S / rot");
   const int half = rot / 2;
   for (int s = 0; s < S; ++s)
@@ -347,6 +392,7 @@ int mb200_rope_table(float* tab, int32_t S, int32_t rot, int32_t pos0, void*) {
 // zero rows where the target is ignored; dlogits may alias logits   (ce_count / ce_row / ce_reduce kernels)
 int mb200_cross_entropy(const void* logits_, int64_t ldv, const int64_t* labels, int32_t B, int32_t S, int32_t V,
                         float* row_loss, int32_t* n_valid, float* loss, void* dlogits_, float grad_scale, void*) {
+  EM_TRACE(6.0 * B * S * V, (double)B * S * V * (dlogits_ ? 4 : 2), "cross_entropy\trows=%d V=%d grad=%d", B * S, V, dlogits_ != nullptr);
   EM_REQUIRE(ldv % 8 == 0 && V <= ldv, MB200_E_ALIGN, "cross_entropy: ldv must be a multiple of 8 and >= V");
   const bf16_t* logits = (const bf16_t*)logits_;
   bf16_t* dlogits = (bf16_t*)dlogits_;
@@ -612,6 +658,7 @@ static bool tile_supported(int S, int hd) { return S >= 1 && S <= 128 && hd >= 6
 
 int mb200_attn_fwd_tile(const void* qkv_, int64_t ld, void* P_, int64_t ldP, void* O_, int64_t ldo, int32_t B, int32_t S,
                         int32_t H, int32_t hd, void*) {
+  EM_TRACE(4.0 * B * H * S * (double)S * hd, (double)B * S * H * hd * 8 + (double)B * H * S * ldP * 2, "attn_fwd_tile\tB=%d S=%d H=%d hd=%d", B, S, H, hd);
   EM_REQUIRE(tile_supported(S, hd) && ldP % 8 == 0, MB200_E_SHAPE, "attn_fwd_tile: unsupported S=%d hd=%d", S, hd);
   const bf16_t* qkv = (const bf16_t*)qkv_;
   bf16_t *P = (bf16_t*)P_, *O = (bf16_t*)O_;
@@ -646,6 +693,7 @@ int mb200_attn_fwd_tile(const void* qkv_, int64_t ld, void* P_, int64_t ldP, voi
 int mb200_attn_bwd_tile(const void* qkv_, int64_t ld, const void* dO_, int64_t ld_do, const void* P_, int64_t ldP,
                         void* dqkv_, int64_t ldd, const float* rope_tab, int32_t rot, int32_t B, int32_t S, int32_t H,
                         int32_t hd, void*) {
+  EM_TRACE(10.0 * B * H * S * (double)S * hd, (double)B * S * H * hd * 14 + (double)B * H * S * ldP * 2, "attn_bwd_tile\tB=%d S=%d H=%d hd=%d", B, S, H, hd);
   EM_REQUIRE(tile_supported(S, hd) && ldP % 8 == 0, MB200_E_SHAPE, "attn_bwd_tile: unsupported S=%d hd=%d", S, hd);
   const bf16_t *qkv = (const bf16_t*)qkv_, *dO = (const bf16_t*)dO_, *P = (const bf16_t*)P_;
   bf16_t* dqkv = (bf16_t*)dqkv_;
@@ -707,6 +755,7 @@ int mb200_attn_bwd_tile(const void* qkv_, int64_t ld, const void* dO_, int64_t l
 // KV cache   (engine.cu: kv_append_kernel / attn_decode_kernel)
 int mb200_kv_append(const void* qkv_, int64_t ld, void* kc_, void* vc_, int32_t B, int32_t S, int32_t H, int32_t hd,
                     int32_t Smax, int32_t pos0, void*) {
+  EM_TRACE(0, (double)B * S * H * hd * 8, "kv_append\tB=%d S=%d H=%d hd=%d", B, S, H, hd);
   EM_REQUIRE(hd % 8 == 0 && B > 0 && S > 0 && pos0 >= 0 && pos0 + S <= Smax, MB200_E_SHAPE, "kv_append: bad shape");
   const bf16_t* qkv = (const bf16_t*)qkv_;
   bf16_t *kc = (bf16_t*)kc_, *vc = (bf16_t*)vc_;
@@ -725,6 +774,7 @@ int mb200_kv_append(const void* qkv_, int64_t ld, void* kc_, void* vc_, int32_t 
 // rounded to bf16 before P*V like the prefill path
 int mb200_attn_decode(const void* qkv_, int64_t ld_qkv, void* kc_, void* vc_, void* out_, int64_t ld_out, int32_t B,
                       int32_t H, int32_t hd, int32_t Smax, int32_t pos, void*) {
+  EM_TRACE(4.0 * B * H * (double)(pos + 1) * hd, (double)B * H * (pos + 1) * hd * 4, "attn_decode\tB=%d H=%d hd=%d pos=%d", B, H, hd, pos);
   EM_REQUIRE(hd % 8 == 0 && pos >= 0 && pos < Smax, MB200_E_SHAPE, "attn_decode: bad hd / pos");
   const bf16_t* qkv = (const bf16_t*)qkv_;
   bf16_t *kc = (bf16_t*)kc_, *vc = (bf16_t*)vc_, *out = (bf16_t*)out_;
@@ -876,6 +926,7 @@ int mb200_avgpool_nhwc_bwd(const void* dy_, void* dx_, int32_t B, int32_t H, int
 
 // images [B,3,R,R] -> patches [B*g*g][ldp], column order (c, py, px)   (patchify_kernel)
 int mb200_patchify(const void* img_, void* patches_, int64_t ldp, int32_t B, int32_t R, int32_t P, void*) {
+  EM_TRACE(0, (double)B * 3 * R * R * 4, "patchify\tB=%d R=%d P=%d", B, R, P);
   EM_REQUIRE(R % P == 0 && ldp >= 3 * P * P, MB200_E_SHAPE, "patchify: bad geometry");
   const bf16_t* img = (const bf16_t*)img_;
   bf16_t* patches = (bf16_t*)patches_;
@@ -894,6 +945,7 @@ int mb200_patchify(const void* img_, void* patches_, int64_t ldp, int32_t B, int
 // x[b,0] = cls + pos[0]; x[b,1+p] = pe[b,p] + pos[1+p]   (vit_assemble_kernel)
 int mb200_vit_assemble(void* x_, const void* pe_, const void* cls_, const void* pos_, int32_t B, int32_t T, int32_t w,
                        void*) {
+  EM_TRACE((double)B * T * w, (double)B * T * w * 4, "vit_assemble\tB=%d T=%d w=%d", B, T, w);
   bf16_t* x = (bf16_t*)x_;
   const bf16_t *pe = (const bf16_t*)pe_, *cls = (const bf16_t*)cls_, *pos = (const bf16_t*)pos_;
   for (long long b = 0; b < B; ++b)

@@ -361,3 +361,24 @@ def test_gptj_schedule_fused_attention_tile_and_chunked_backward(emul):
                                                   lo, 0, B, S, wsp, ctypes.c_size_t(n), None)
         assert rc == 0, emul.mb200_last_error()
     assert torch.equal(dx2, dx) and all(torch.equal(grads2[k], grads[k]) for k in grads)
+
+
+def test_launch_plan_trace_of_a_full_size_step():
+    """tools/plan_trace.py: the product's own schedules issue a full-size training step (GPT-J-6B + ViT-L/14, B = 8,
+    S = 128) on the emulation in trace mode — placeholder pointers, nothing touches memory — and the launch list carries the
+    algorithmic FLOPs of BASELINE.md §4 (LM forward + backward, frozen: 2 x 1.5635 + 0.0601 TFLOP/sample + ViT 0.162)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import plan_trace
+
+    rows = plan_trace.train_step_plan(8, 128)
+    gemms = [r for r in rows if r["op"] == "gemm"]
+    assert 700 < len(rows) < 900 and len(gemms) > 500
+    tflop = sum(r["flops"] for r in rows) / 1e12
+    want = 8 * (2 * 1.5635 + 0.0601 + 0.1620)          # SURVEY.md §8d, per sample -> per step of 8
+    assert abs(tflop - want) / want < 0.03, (tflop, want)
+    # the frozen-weight GEMMs of one block, forward: qkv, out, fc_in, fc_out at M = B*S = 1024
+    shapes = {(int(r["args"]["M"]), int(r["args"]["N"]), int(r["args"]["K"])) for r in gemms}
+    assert {(1024, 12288, 4096), (1024, 4096, 4096), (1024, 16384, 4096), (1024, 4096, 16384), (1024, 50258, 4096)} <= shapes
