@@ -108,6 +108,19 @@ def train_step_plan(B, S):
     return trace(issue)
 
 
+def decode_step_plan(B, pos, S_max=264):
+    """One KV-cache decode step (BASELINE config 5: B = 32) at cache position `pos`: S = 1, last-position logits."""
+    gm, keep = gptj_model(None, 4096, 16, 64, 50258, 1024)
+
+    def issue(L):
+        ws = ctypes.c_void_p(FAKE)
+        n = L.mb200_gptj_workspace_bytes(ctypes.byref(gm), B, 1, S_max, 0)
+        check(L, L.mb200_gptj_forward(ctypes.byref(gm), FAKE, None, FAKE, ctypes.c_int64(50304), 1, None, None, FAKE, FAKE,
+                                      S_max, pos, B, 1, 0, ws, ctypes.c_size_t(n), None))
+
+    return trace(issue)
+
+
 def gemm_tiles(a):
     """Tile counts of one GEMM launch under the dispatch rules of csrc/gemm.cu (CTA-pair 256x256 tiles when M > 128,
     N >= 256, K >= 512; else 128 x BN tiles with BN = 256 unless N is small)."""
@@ -137,18 +150,20 @@ def summarise(rows, B, S, peaks, out):
         g["flops"] += r["flops"]
         g["bytes"] += r["bytes"]
         g["t"] += t
-    lines = [f"launch plan of one training step (ViT-L/14 forward + GPT-J-6B forward + backward, B={B}, S={S}, MLP adapters f=4),",
+    title = (f"launch plan of one training step (ViT-L/14 forward + GPT-J-6B forward + backward, B={B}, S={S}, MLP adapters f=4),"
+             if S else f"launch plan of one KV-cache decode step (GPT-J-6B + MLP adapters, B={B}, S=1, last-position logits),")
+    lines = [title,
              "issued by the product's own host schedules on the CPU emulation in trace mode - analytic, not measured.",
              f"peaks: {peaks['bf16_tflops']:.1f} TFLOP/s (burst bf16), {peaks['hbm_gbs']:.1f} GB/s (MEASURED_PEAKS.json)", "",
              f"{len(rows)} launches, {sum(r['flops'] for r in rows) / 1e12:.2f} TFLOP, {sum(r['bytes'] for r in rows) / 1e9:.2f} GB "
              f"algorithmic; sum of per-launch roofline times {total_t * 1e3:.2f} ms "
-             f"(= {B / total_t:.0f} samples/s if every launch ran at its roofline with no gaps)", "",
+             f"(= {B / total_t:.0f} {'samples' if S else 'tokens'}/s if every launch ran at its roofline with no gaps)", "",
              f"{'n':>4} {'roofline us':>11} {'each us':>8} {'bound':>6} {'tiles':>6} {'last wave':>9}  launch"]
     for key, g in sorted(groups.items(), key=lambda kv: -kv[1]["t"]):
         r = g["row"]
         bound = "tensor" if r["flops"] / tf >= r["bytes"] / gbs else "hbm"
         tiles = wave = ""
-        if r["op"] == "gemm":
+        if r["op"] == "gemm" and int(r["args"]["M"]) > 128:  # small-M GEMMs are tiled by plan_small_m (tile width x split-K)
             kind, t, slots = gemm_tiles(r["args"])
             waves = t / slots
             wave = f"{(t % slots or slots) / slots:.2f}"
@@ -166,9 +181,15 @@ def main():
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--S", type=int, default=128)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--decode", action="store_true", help="plan of one decode step (B defaults to 32, --pos the cache position)")
+    ap.add_argument("--pos", type=int, default=136)
     a = ap.parse_args()
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(p)) if os.path.exists(p) else {"bf16_tflops": 1684.7, "hbm_gbs": 6575.1}
+    if a.decode:
+        B = a.B if a.B != 8 else 32
+        summarise(decode_step_plan(B, a.pos), B, 0, peaks, a.out)
+        return
     rows = train_step_plan(a.B, a.S)
     summarise(rows, a.B, a.S, peaks, a.out)
 
