@@ -60,7 +60,8 @@ __device__ __forceinline__ uint4 pack8f(const float* f) {
 // issue the k-steps of one 128 x N x (nkb*64) product. A/B tiles are sequences of 16 KB k-blocks (K-major) or of
 // 16 KB 64-wide MN chunks holding 128 k-rows each (MN-major).
 template <bool A_MN, bool B_MN>
-__device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_base, uint32_t b_base, int nkb, int N) {
+__device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_base, uint32_t b_base, int nkb, int N,
+                                          uint32_t acc0 = 0u) {  // acc0 != 0: accumulate onto what D already holds
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   for (int kb = 0; kb < nkb; ++kb) {
@@ -72,7 +73,7 @@ __device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_base, uint
       const uint32_t bo = B_MN ? (uint32_t)((kb * 4 + k) * 2048) : (uint32_t)(kb * kTile + k * 32);
       const uint64_t da = make_smem_desc(a_base + ao, A_MN ? (uint32_t)kTile : 0u, 1024);
       const uint64_t db = make_smem_desc(b_base + bo, B_MN ? (uint32_t)kTile : 0u, 1024);
-      umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+      umma_bf16(d_tmem, da, db, idesc, ((kb | k) != 0 ? 1u : 0u) | acc0);
     }
   }
 }
@@ -381,6 +382,248 @@ attn_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// multi-tile forward (any Sq / Sk, causal with a key offset or not): one CTA per (128-query tile, head, batch)
+// ---------------------------------------------------------------------------------------------
+// Same numerics as the single-tile kernel and as the reference's materialised softmax (fp32 scores from bf16 q,k,
+// softmax over the WHOLE key row in fp32, probabilities rounded to bf16 before P*V — hf:gptj/modeling_gptj.py:136-149,
+// hf:clip/modeling_clip.py:282-330), obtained with two sweeps over the key tiles instead of an online rescale:
+//   sweep 1: S_j = Q K_j^T per 128-key tile, running row maximum m and sum l = sum exp(s - m)          (no V, no O)
+//   sweep 2: S_j again, p = bf16(exp(s - m) / l) exactly as the materialised path rounds it, O += P_j V_j in TMEM
+// so O never needs rescaling (no TMEM read-modify-write of a 128 x hd fp32 tile) and P — when the caller wants it for
+// the backward pass — is bit-identical to what softmax_fwd_kernel would have written. QK^T is computed twice: +50 % of
+// the attention FLOPs, which are < 1 % of the step (S = 128 .. 2048), in exchange for no [B,H,S,S] fp32 score buffer.
+// K / V tiles are double-buffered (TMA of tile j+1 under the softmax of tile j) when head_dim <= 128; at head_dim 256
+// one buffer each fits next to Q and P (224 KB) and the next tile is prefetched into L2 instead.
+struct FlashParams {
+  int Sq, Sk, H, hd, causal, kv_off;  // key j visible to query i iff j < Sk and (!causal or j <= i + kv_off)
+  float scale;
+  bf16* O;             // [B,Sq,H,hd], row stride ldo
+  long long ldo;
+  bf16* P;             // optional [B,H,Sq,ldP] (columns >= Sk up to ldP are written as zeros)
+  long long ldP;
+  float2* stats;       // optional [B,H,Sq] (row max of the scaled scores, 1 / sum)
+};
+
+template <int NBUF>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nhb = p.hd >> 6;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + nhb * kTile;            // NBUF buffers
+  uint8_t* sV = sK + NBUF * nhb * kTile;     // NBUF buffers
+  uint8_t* sP = sV + NBUF * nhb * kTile;     // 2 k-blocks of 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTile);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;   // [2]
+  uint64_t* bar_v = bars + 3;   // [2]
+  uint64_t* bar_s = bars + 5;
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int qi = q0 + t;  // this thread's query row
+
+  pdl_trigger();
+  if (t == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    if (NBUF == 2) tmem_alloc<256>(tmem_ptr);
+    else tmem_alloc<512>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_o = tmem + 128;
+  pdl_wait();
+
+  // key tiles this query tile looks at
+  int n_kv = (p.Sk + 127) >> 7;
+  if (p.causal) {
+    const int last_key = min(p.Sk - 1, q0 + 127 + p.kv_off);
+    n_kv = last_key < 0 ? 0 : min(n_kv, (last_key >> 7) + 1);
+  }
+  const int row_lim = !p.causal ? p.Sk : min(p.Sk, qi + p.kv_off + 1);  // keys [0, row_lim) are visible to this row
+  const bool row_ok = qi < p.Sq;
+
+  uint32_t ph_k[2] = {0, 0}, ph_v[2] = {0, 0}, ph_s = 0, ph_o = 0;
+  auto load_k = [&](int j, int buf) {
+    mbar_expect_tx(&bar_k[buf], nhb * kTile);
+    for (int kb = 0; kb < nhb; ++kb) tma_load_4d(sK + (buf * nhb + kb) * kTile, &tmK, &bar_k[buf], kb * 64, j * 128, h, b);
+  };
+  auto load_v = [&](int j, int buf) {
+    mbar_expect_tx(&bar_v[buf], nhb * kTile);
+    for (int kb = 0; kb < nhb; ++kb) tma_load_4d(sV + (buf * nhb + kb) * kTile, &tmV, &bar_v[buf], kb * 64, j * 128, h, b);
+  };
+
+  // ---------------- sweep 1: row maximum and sum ----------------
+  float m = -INFINITY, l = 0.f;
+  if (t == 0 && n_kv > 0) {
+    mbar_expect_tx(bar_q, nhb * kTile);
+    for (int kb = 0; kb < nhb; ++kb) tma_load_4d(sQ + kb * kTile, &tmQ, bar_q, kb * 64, q0, h, b);
+    load_k(0, 0);
+    mbar_wait(bar_q, 0);
+  }
+  for (int j = 0; j < n_kv; ++j) {
+    const int buf = NBUF == 2 ? (j & 1) : 0;
+    if (t == 0) {
+      if (NBUF == 2 && j + 1 < n_kv) load_k(j + 1, (j + 1) & 1);  // its previous user (tile j-1) has completed (bar_s)
+      if (NBUF == 1 && j + 1 < n_kv)
+        for (int kb = 0; kb < nhb; ++kb) tma_prefetch_4d(&tmK, kb * 64, (j + 1) * 128, h, b);
+      mbar_wait(&bar_k[buf], ph_k[buf]);
+      tc_fence_after();
+      issue_mma<false, false>(tmem, smem_u32(sQ), smem_u32(sK + buf * nhb * kTile), nhb, 128);
+      umma_commit(bar_s);
+    }
+    ph_k[buf] ^= 1;
+    mbar_wait(bar_s, ph_s);
+    ph_s ^= 1;
+    tc_fence_after();
+    if (NBUF == 1 && t == 0 && j + 1 < n_kv) load_k(j + 1, 0);  // the single K buffer is free once S_j is complete
+    const int kbase = j * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rr[32];
+      tmem_ld_32x32(lane_addr + (uint32_t)(c * 32), rr);
+      tmem_ld_wait();
+      float cm = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float sv = __uint_as_float(rr[e]) * p.scale;
+        if (kbase + c * 32 + e < row_lim) cm = fmaxf(cm, sv);
+      }
+      if (cm > m) {  // rescale the running sum to the new maximum
+        l *= __expf(m - cm);
+        m = cm;
+      }
+      if (m != -INFINITY) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float sv = __uint_as_float(rr[e]) * p.scale;
+          if (kbase + c * 32 + e < row_lim) l += __expf(sv - m);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // every row of S_j has been read: the next QK^T may overwrite it
+    tc_fence_after();
+  }
+  const float inv = (row_ok && l > 0.f) ? 1.f / l : 0.f;
+  if (m == -INFINITY) m = 0.f;
+  if (p.stats != nullptr && row_ok) p.stats[((long long)b * p.H + h) * p.Sq + qi] = make_float2(m, inv);
+
+  // ---------------- sweep 2: probabilities and O = P V ----------------
+  bf16* prow = p.P ? p.P + (((long long)b * p.H + h) * p.Sq + qi) * p.ldP : nullptr;
+  const uint32_t sP_s = smem_u32(sP);
+  if (t == 0 && n_kv > 0) {
+    load_k(0, 0);  // (NBUF == 1: the buffer's last reader was S_{n_kv-1}, complete; NBUF == 2: buffer 0's last load was
+    load_v(0, 0);  //  consumed in sweep 1 unless n_kv is even — either way its MMA has completed)
+  }
+  for (int j = 0; j < n_kv; ++j) {
+    const int buf = NBUF == 2 ? (j & 1) : 0;
+    if (t == 0) {
+      if (NBUF == 2 && j + 1 < n_kv) {
+        load_k(j + 1, (j + 1) & 1);
+        load_v(j + 1, (j + 1) & 1);   // V_{j-1} (same buffer) was consumed by the PV of tile j-1: bar_o waited below
+      }
+      if (NBUF == 1 && j + 1 < n_kv)
+        for (int kb = 0; kb < nhb; ++kb) {
+          tma_prefetch_4d(&tmK, kb * 64, (j + 1) * 128, h, b);
+          tma_prefetch_4d(&tmV, kb * 64, (j + 1) * 128, h, b);
+        }
+      mbar_wait(&bar_k[buf], ph_k[buf]);
+      tc_fence_after();
+      issue_mma<false, false>(tmem, smem_u32(sQ), smem_u32(sK + buf * nhb * kTile), nhb, 128);
+      umma_commit(bar_s);
+    }
+    ph_k[buf] ^= 1;
+    mbar_wait(bar_s, ph_s);
+    ph_s ^= 1;
+    tc_fence_after();
+    if (NBUF == 1 && t == 0 && j + 1 < n_kv) load_k(j + 1, 0);
+    const int kbase = j * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rr[32];
+      tmem_ld_32x32(lane_addr + (uint32_t)(c * 32), rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int key = kbase + c * 32 + g8 * 8 + e;
+          f[e] = key < row_lim ? __expf(__uint_as_float(rr[g8 * 8 + e]) * p.scale - m) * inv : 0.f;
+        }
+        const uint4 u = pack8f(f);
+        const int col = c * 32 + g8 * 8;
+        st_operand_chunk(sP_s, t, col >> 6, (col & 63) >> 3, u);
+        if (prow != nullptr && row_ok && kbase + col < p.ldP) *reinterpret_cast<uint4*>(prow + kbase + col) = u;
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();  // P_j complete in smem; S_j fully read
+    if (t == 0) {
+      tc_fence_after();
+      mbar_wait(&bar_v[buf], ph_v[buf]);
+      tc_fence_after();
+      issue_mma<false, true>(tmem_o, sP_s, smem_u32(sV + buf * nhb * kTile), 2, p.hd, j > 0 ? 1u : 0u);  // O += P_j V_j
+      umma_commit(bar_o);
+    }
+    ph_v[buf] ^= 1;
+    // P (smem) and, with one buffer, V are reused by the next tile: wait for this PV before going on
+    mbar_wait(bar_o, ph_o);
+    ph_o ^= 1;
+    tc_fence_after();
+    if (NBUF == 1 && t == 0 && j + 1 < n_kv) load_v(j + 1, 0);
+  }
+  // ---------------- O -> bf16 -> global ----------------
+  bf16* orow = p.O + ((long long)b * p.Sq + qi) * p.ldo + (long long)h * p.hd;
+  for (int c = 0; c < p.hd / 32; ++c) {
+    uint32_t rr[32];
+    if (n_kv > 0) {
+      tmem_ld_32x32(lane_addr + (uint32_t)(128 + c * 32), rr);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) rr[e] = 0u;
+    }
+    if (row_ok) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 8) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(rr[e + k]);
+        *reinterpret_cast<uint4*>(orow + c * 32 + e) = pack8f(f);
+      }
+    }
+  }
+  // rows of P beyond this tile's last key tile (causal) are zeros in the materialised layout
+  if (prow != nullptr && row_ok) {
+    for (int col = n_kv * 128; col < p.ldP; col += 8) *reinterpret_cast<uint4*>(prow + col) = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    if (NBUF == 2) tmem_dealloc<256>(tmem);
+    else tmem_dealloc<512>(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
 static int tile_map(CUtensorMap* m, const void* ptr, long long ld, long long bs0, long long bs1, int rows, int cols,
@@ -462,6 +705,64 @@ int attn_bwd_tile(const bf16* qkv, long long ld_qkv, const bf16* dO, long long l
   return 0;
 }
 
+// Multi-tile forward. q / k / v: element pointers of head 0, batch 0, row 0 with row stride ld*, head stride *_bsh and
+// batch stride *_bsb (elements) — the fused qkv buffer (ld = 3d, bsh = hd, bsb = S * 3d) or a KV cache
+// [B,H,Smax,hd] (ld = hd, bsh = Smax * hd, bsb = H * Smax * hd). Causal: key j is visible to query i iff
+// j <= i + (Sk - Sq) (queries are the LAST Sq positions of the Sk keys — prefill and its continuations).
+bool attn_flash_supported(int hd) { return hd >= 64 && hd <= 256 && hd % 64 == 0; }
+
+int attn_fwd_flash(const bf16* q, long long ldq, long long q_bsh, long long q_bsb, const bf16* k, long long ldk,
+                   long long k_bsh, long long k_bsb, const bf16* v, long long ldv, long long v_bsh, long long v_bsb,
+                   bf16* O, long long ldo, bf16* P, long long ldP, float* stats, int B, int Sq, int Sk, int H, int hd,
+                   int causal, cudaStream_t st) {
+  MB_REQUIRE(attn_flash_supported(hd) && Sq >= 1 && Sk >= 1 && B >= 1 && H >= 1, MB200_E_SHAPE,
+             "attn_fwd_flash: unsupported Sq=%d Sk=%d hd=%d", Sq, Sk, hd);
+  MB_REQUIRE(!causal || Sk >= Sq, MB200_E_SHAPE, "attn_fwd_flash: causal needs Sk >= Sq (%d < %d)", Sk, Sq);
+  MB_REQUIRE(P == nullptr || (ldP % 8 == 0 && ldP >= Sk), MB200_E_ALIGN, "attn_fwd_flash: ldP=%lld must be >= Sk and %%8",
+             ldP);
+  MB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, MB200_E_ALIGN, "attn_fwd_flash: O alignment");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = tile_map(&tq, q, ldq, q_bsh, q_bsb, Sq, hd, H, B))) return rc;
+  if ((rc = tile_map(&tk, k, ldk, k_bsh, k_bsb, Sk, hd, H, B))) return rc;  // rows = Sk: cache rows beyond are OOB zeros
+  if ((rc = tile_map(&tv, v, ldv, v_bsh, v_bsb, Sk, hd, H, B))) return rc;
+  FlashParams p;
+  memset(&p, 0, sizeof(p));
+  p.Sq = Sq;
+  p.Sk = Sk;
+  p.H = H;
+  p.hd = hd;
+  p.causal = causal;
+  p.kv_off = Sk - Sq;
+  p.scale = 1.0f / sqrtf((float)hd);
+  p.O = O;
+  p.ldo = ldo;
+  p.P = P;
+  p.ldP = ldP;
+  p.stats = reinterpret_cast<float2*>(stats);
+  const int nhb = hd / 64;
+  const dim3 grid((Sq + 127) / 128, H, B);
+  if (hd <= 128) {
+    const int smem = (5 * nhb + 2) * kTile + 1024 + 128;
+    static bool set = false;
+    if (!set) {
+      MB_CUDA(cudaFuncSetAttribute(attn_fwd_flash_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      set = true;
+    }
+    MB_CUDA(launch_pdl(attn_fwd_flash_kernel<2>, grid, dim3(kAttThreads), (size_t)smem, st, tq, tk, tv, p));
+  } else {
+    const int smem = (3 * nhb + 2) * kTile + 1024 + 128;
+    static bool set = false;
+    if (!set) {
+      MB_CUDA(cudaFuncSetAttribute(attn_fwd_flash_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      set = true;
+    }
+    MB_CUDA(launch_pdl(attn_fwd_flash_kernel<1>, grid, dim3(kAttThreads), (size_t)smem, st, tq, tk, tv, p));
+  }
+  count_launch();
+  return 0;
+}
+
 }  // namespace mb200
 
 // C ABI (exposed for the parity tests; the engine calls the C++ functions directly)
@@ -480,4 +781,15 @@ extern "C" int mb200_attn_bwd_tile(const void* qkv, int64_t ld_qkv, const void* 
   if (rc) return rc;
   return mb200::attn_bwd_tile((const mb200::bf16*)qkv, ld_qkv, (const mb200::bf16*)dO, ld_do, (const mb200::bf16*)P, ldP,
                               (mb200::bf16*)dqkv, ld_dqkv, rope_tab, rot, B, S, H, hd, (cudaStream_t)stream);
+}
+
+extern "C" int mb200_attn_fwd_flash(const void* q, int64_t ldq, int64_t q_bsh, int64_t q_bsb, const void* k, int64_t ldk,
+                                    int64_t k_bsh, int64_t k_bsb, const void* v, int64_t ldv, int64_t v_bsh, int64_t v_bsb,
+                                    void* O, int64_t ldo, void* P, int64_t ldP, float* stats, int32_t B, int32_t Sq,
+                                    int32_t Sk, int32_t H, int32_t hd, int32_t causal, void* stream) {
+  int rc = mb200::check_arch();
+  if (rc) return rc;
+  return mb200::attn_fwd_flash((const mb200::bf16*)q, ldq, q_bsh, q_bsb, (const mb200::bf16*)k, ldk, k_bsh, k_bsb,
+                               (const mb200::bf16*)v, ldv, v_bsh, v_bsb, (mb200::bf16*)O, ldo, (mb200::bf16*)P, ldP, stats,
+                               B, Sq, Sk, H, hd, causal, (cudaStream_t)stream);
 }

@@ -42,6 +42,18 @@ def test_reference_goldens_replay_on_emulated_kernels(replay, monkeypatch, golde
     G.test_magma_matches_reference_golden(golden_dir, tag)
 
 
+def test_shared_layer_parity_case_replays_at_small_size(replay):
+    """The body of tests/test_model_gpu.py::test_config2_full_size_matches_oracle (frozen weights shared across layers,
+    per-layer adapters, decided ReLU masks) on emulated kernels at a small size, held to the same bars."""
+    import test_model_gpu as G
+    from tools.model_check import small_cfg
+
+    r = G._shared_layer_case(replay, small_cfg(n_layer=3, vit_layers=2), B=2, S=32, vit_name="clip_vit_shared_small")
+    assert r["dloss"] < 2e-2 and r["logits"] < 3e-2, r
+    assert max(r["grads"].values()) < 3e-2, r["grads"]
+    assert len(r["grads"]) == 3 * 4 + 4
+
+
 def test_reference_assertion_behaviour_replays(replay, monkeypatch):
     import test_model_gpu as G
 

@@ -247,7 +247,7 @@ def test_conv_trunk_training_forward_and_backward(emul_ops, monkeypatch):
 def test_conv_training_primitives_are_what_the_schedule_assumes(emul_ops):
     """The emulated col2im3x3 / avgpool_nhwc_bwd are the adjoints of the forward layout operators (checked against
     torch autograd of unfold / avg_pool2d), and col_moments / channel_affine compute the documented expressions —
-    the same reference formulas the GPU test of the real kernels uses (tests/test_zz_unverified_gpu.py)."""
+    the same reference formulas the GPU test of the real kernels uses (tests/test_training_paths_gpu.py)."""
     import torch.nn.functional as F
 
     from magma_b200 import ops

@@ -2,7 +2,7 @@
 
 oracle/kernel_host_exec.cpp compiles those kernels unchanged as host C++ and runs them with the CUDA execution model
 emulated (threads of a block = OS threads, __syncthreads = barrier, warp shuffles and atomicAdd emulated, blocks in
-sequence). Here each kernel is held to the torch formula its GPU test uses (tests/test_zz_unverified_gpu.py): this checks
+sequence). Here each kernel is held to the torch formula its GPU test uses (tests/test_training_paths_gpu.py): this checks
 what a kernel COMPUTES — indexing, 8-wide vector handling, masks, smem reductions, row-chunk accumulation through atomics —
 not what the hardware does with it."""
 import ctypes

@@ -3,9 +3,10 @@ the drop-in Python API (Magma.forward / embed / generate, B200Engine) against th
 inputs, and against the golden fixtures produced by the REFERENCE ITSELF (tests/golden/, oracle/make_golden.py).
 
 Tolerances (bf16 kernels vs fp32 oracle): |dloss| < 2e-2; logits rel-Frobenius < 3e-2; gradients
-rel-Frobenius < 3e-2 when every adapter ReLU is decided away from zero, < 1.5e-1 with free ReLU masks (a flipped mask
-entry is an O(1) relative error in that entry; the flip rate is ~2^-8, so ~sqrt(2^-8) relative Frobenius error is the
-expected bf16-vs-fp32 disagreement, not a kernel defect). Integer results (labels, greedy token ids) are exact."""
+rel-Frobenius < 3e-2 — the reference-made fixtures and the full-size case use adapters whose ReLU masks are decided away
+from zero (down-projection biases of +-3), so that bf16 and fp32 agree on the mask; only tools/model_check.py's
+"free relu mask" case (a flipped mask entry is an O(1) relative error in that entry) uses a wider bound. Integer results
+(labels, greedy token ids up to the reference's first top-1/top-2 near-tie) are exact."""
 import os
 
 import pytest
@@ -41,15 +42,14 @@ def test_magma_matches_reference_golden(golden_dir, tag):
     if rec["grads"]:
         out.loss.backward()
         sd = dict(model.named_parameters())
-        # Down-projection (adapter.0) gradients pass through the ReLU mask of the bottleneck: where a pre-activation is
-        # within the bf16 error of zero the mask differs from the fp32 reference's, and in the tiny golden configuration
-        # (8-16 hidden units x 64 tokens) a handful of flipped (token, unit) entries is 10-20 % of the tensor. The same
-        # kernels are held to 5e-3 with decided masks in tools/model_check.py::group_lm (test_model_group[lm]).
+        # The fixtures are generated with DECIDED ReLU masks (adapter down-projection biases of +-3,
+        # oracle/make_golden.py): bf16 and the reference's fp32 take the same mask, so every trainable gradient —
+        # including the down-projection ones that pass through the mask — is held to the tight bar.
         bad = {}
         for k, gref in rec["grads"].items():
             assert sd[k].grad is not None, k
             err = rel(sd[k].grad, gref)
-            if err >= (3e-1 if ".adapter.0." in k else 1.5e-1):
+            if err >= 3e-2:
                 bad[k] = round(err, 4)
         assert not bad, bad
 
@@ -71,11 +71,20 @@ def test_vit_embed_generate_match_reference_golden(golden_dir):
     assert emb.shape == rec["embeddings"].shape and rel(emb, rec["embeddings"]) < 3e-2
     toks = model.generate(rec["embeddings"].to(dev).to(torch.bfloat16), max_steps=10, temperature=0.0, decode=False).cpu()
     ref = rec["greedy_tokens"]
-    n = min(toks.shape[1], ref.shape[1])
-    agree = (toks[:, :n] == ref[:, :n]).float().mean().item()
-    # token ids are exact up to the first bf16 near-tie between the top two logits
-    assert torch.equal(toks[:, : rec["embeddings"].shape[1] + 1], ref[:, : rec["embeddings"].shape[1] + 1])
-    assert agree > 0.85, agree
+    # Token ids are exact up to (not including) the first greedy step at which the reference's own top-1 / top-2 logit
+    # margin is a bf16 near-tie; logits here are O(1), one bf16 ulp of them is ~8e-3, and the
+    # accumulated bf16 error of the tiny model's logits is held to 3e-2 relative above.
+    s0, tau = rec["embeddings"].shape[1], 0.05
+    assert torch.equal(toks[:, :s0], ref[:, :s0])
+    margin = rec["greedy_margin"]
+    n_exact = 0
+    for b in range(ref.shape[0]):
+        tied = (margin[b] < tau).nonzero()
+        first_tie = int(tied[0]) if len(tied) else margin.shape[1]
+        n = min(first_tie, toks.shape[1] - s0)
+        assert torch.equal(toks[b, s0:s0 + n], ref[b, s0:s0 + n]), (b, toks[b, s0:], ref[b, s0:], margin[b])
+        n_exact += n
+    assert n_exact >= ref.shape[0] * 3, (n_exact, margin)  # the fixture must actually pin several steps per row
 
 
 def test_magma_forward_asserts_like_the_reference():
@@ -153,3 +162,75 @@ def test_full_size_step_properties():
         losses.append(float(o.loss))
     assert losses[-1] < losses[0], losses
     assert torch.equal(frozen_before, model.lm.transformer.h[5].attn.out_proj.weight)
+
+
+def _shared_layer_case(dev, cfg, B, S, seed=0, vit_name="clip_vit_shared_case"):
+    """Magma.forward + backward against the oracle on a model whose FROZEN per-layer weights are one set of random
+    tensors shared by every GPT-J / ViT layer (the host-memory trick of bench.py's CPU arm: identical shapes, FLOPs
+    and kernels per layer, 1/28 of the fp32 host weights), while every layer keeps its OWN adapter parameters, so the
+    per-layer trainable gradients are compared one by one. Adapter weights are O(0.05) with down-projection biases of
+    +-3 (tools/model_check.py::boost_adapters): every bottleneck ReLU is decided away from zero and bf16 / fp32 agree
+    on the mask. Returns the measured errors."""
+    import torch
+
+    from _gpu_util import build_magma_from_weights, rel
+    from oracle import magma_oracle as O
+    from tools.model_check import boost_adapters
+
+    import dataclasses
+
+    one = dataclasses.replace(cfg, n_layer=1, vit_layers=1)
+    w1 = O.init_weights(one, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    w = {}
+    for k, v in w1.items():
+        v = v.to(torch.bfloat16).float()  # the oracle sees the bf16-representable values the device stores
+        if ".transformer.h.0." in k:
+            for l in range(cfg.n_layer):
+                kk = k.replace(".transformer.h.0.", f".transformer.h.{l}.")
+                w[kk] = torch.randn(v.shape, generator=g) if ".adapter." in k else v
+        elif ".resblocks.0." in k:
+            for l in range(cfg.vit_layers):
+                w[k.replace(".resblocks.0.", f".resblocks.{l}.")] = v
+        else:
+            w[k] = v
+    torch.manual_seed(seed + 2)
+    w = boost_adapters(w, True)
+    w = {k: (v.to(torch.bfloat16).float() if ".adapter." in k else v) for k, v in w.items()}
+    model = build_magma_from_weights(w, cfg, {"mlp": cfg.mlp_adapter}, S, dev, vit_name=vit_name)
+    model.eval()
+    images, captions = O.synthetic_batch(cfg, B, S, seed=seed + 3)
+    images = images.to(torch.bfloat16).float()
+    trainable = [k for k in w if ".adapter." in k or k.startswith(("image_prefix.proj", "image_prefix.ln"))]
+    params = {k: (v.clone().requires_grad_(True) if k in trainable else v) for k, v in w.items()}
+    loss_o, logits_o, labels_o = O.magma_forward(images, captions, params, cfg)
+    loss_o.backward()
+    out = model(images.to(dev), captions.to(dev))
+    out.loss.backward()
+    sd = dict(model.named_parameters())
+    errs = {k: rel(sd[k].grad, params[k].grad) for k in trainable}
+    return {"dloss": abs(float(out.loss.detach()) - float(loss_o.detach())), "logits": rel(out.logits, logits_o.detach()),
+            "grads": errs, "n_trainable": sum(sd[k].numel() for k in trainable), "loss": float(loss_o.detach())}
+
+
+def test_config2_full_size_matches_oracle():
+    """BASELINE.json config 2 at FULL SIZE against the oracle: GPT-J-6B (28 layers, d = 4096, 16 heads of 256, V = 50258
+    with the ragged LM head) + CLIP ViT-L/14 (24 layers, T = 257) + MLP adapters f = 4, 224 x 224 images, seq_len 128,
+    batch 2 (the oracle's fp32 forward + backward of 2 samples takes seconds on the host; the kernels, tile shapes and
+    launch paths are those of the B = 8 benchmark step except for M = 256 instead of 1024 — the CTA-pair GEMM with
+    K = 4096 / 16384, head_dim-256 fused attention, the 50258-wide LM head and cross-entropy).
+    Bars: |dloss| < 2e-2, logits rel-Frobenius < 3e-2, every trainable gradient < 3e-2."""
+    import torch
+
+    from oracle import magma_oracle as O
+
+    r = _shared_layer_case(torch.device(os.environ.get("MB200_TEST_DEVICE", "cuda:0")), O.OracleConfig(), B=2, S=128,
+                           vit_name="clip_vit_large_fullsize_case")
+    worst = max(r["grads"], key=r["grads"].get)
+    print(f"full-size config 2 vs oracle: loss {r['loss']:.4f} |dloss| {r['dloss']:.2e}, logits rel {r['logits']:.2e}, "
+          f"worst gradient rel {r['grads'][worst]:.2e} ({worst}) over {len(r['grads'])} tensors / {r['n_trainable']} parameters")
+    assert r["n_trainable"] == 28 * 8_393_728 + 768 * 8192 + 8192 + 2 * 4096
+    assert r["dloss"] < 2e-2
+    assert r["logits"] < 3e-2
+    bad = {k: round(e, 4) for k, e in r["grads"].items() if e >= 3e-2}
+    assert not bad, bad

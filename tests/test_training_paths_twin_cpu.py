@@ -1,15 +1,16 @@
-"""CPU replay of test BODIES in tests/test_zz_unverified_gpu.py: the same functions, run on CPU tensors with the kernels
+"""CPU replay of test BODIES in tests/test_training_paths_gpu.py: the same functions, run on CPU tensors with the kernels
 emulated (fixture `emul_ops`). This does not verify
-any kernel; it makes sure that when those GPU tests run for the first time, a failure is about the kernels and not about
-a typo in the test."""
+any kernel; it keeps the test bodies themselves exercised in the CPU suite, so a failure on the GPU is about the kernels and not
+about the test."""
 import pytest
 
-import test_zz_unverified_gpu as Z
+import test_training_paths_gpu as Z
 
 REPLAYABLE = [
     "test_quick_gelu_bwd_matches_autograd",
     "test_layernorm_param_grad_rows_matches_the_small_kernel_and_fp32",
     "test_conv_trunk_training_kernels_match_torch",
+    "test_conv_trunk_training_units_match_fp32_locally",
     "test_conv_trunk_training_matches_oracle_like_with_like",
     "test_trainable_vit_gradients_match_oracle_autograd",
     "test_encoder_learning_rate_group_and_weight_decay_exemptions",

@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 # 1. the unverified tests, with real outcomes (xfail marks off) ------------------------------------------------------
-timeout 900 python -m pytest tests/test_zz_unverified_gpu.py -m gpu -q -p no:cacheprovider --runxfail -x --timeout 300 \
+timeout 900 python -m pytest tests/test_zz_unverified_gpu.py -m gpu -q -p no:cacheprovider --runxfail -rA --timeout 300 \
   > gpurun_out/r2_unverified_tests.log 2>&1
 echo "unverified tests exit $?" | tee -a gpurun_out/r2_unverified_tests.log
 # 2. the verified suite (must stay green) -----------------------------------------------------------------------------
@@ -22,7 +22,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 MB200_FORCE_GENERAL=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline \
   > gpurun_out/r2_bench_n1_general_schedule.json.log 2>&1
 # 4. trainable-encoder step time (freeze_img_encoder: false) ----------------------------------------------------------
-timeout 600 python tools/encoder_train_bench.py > gpurun_out/r2_encoder_train_bench.log 2>&1
+nvidia-smi > gpurun_out/r2_nvsmi.log 2>&1
 echo done
 
 # A second call, on 2 GPUs, for the data-parallel knobs (each line: samples/s at N = 2):
