@@ -240,81 +240,11 @@ int mb200_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream)
 int mb200_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
 
 /* -------------------------------------------------------------------------------------------
- * Model-level runtime (engine.cu): the whole GPT-J / CLIP-ViT / ImagePrefix forward and backward
- * scheduled in C++ (one C call per pass instead of ~1000 Python-level op calls).
+ * Model-level runtime: the whole GPT-J / CLIP-ViT forward and backward scheduled in C++ (one C call per pass
+ * instead of ~1000 Python-level op calls; host-only schedule files csrc/gptj_sched.cu, csrc/vit_sched.cu).
  * All weights bf16; trainable-parameter gradients fp32. Pointers not used by a configuration are NULL.
  * ------------------------------------------------------------------------------------------- */
 enum { MB200_ADAPTER_NONE = 0, MB200_ADAPTER_NORMAL = 1, MB200_ADAPTER_PARALLEL = 2 };
-
-/* Adapter bottleneck (magma/adapters.py:6-39): Linear(d,r) -> ReLU -> Linear(r,d). */
-typedef struct {
-  const void* wd; /* [r, d] */
-  const void* bd; /* [r]    */
-  const void* wu; /* [d, r] */
-  const void* bu; /* [d]    */
-  float* g_wd;    /* fp32 grads, same shapes; NULL => adapter frozen / inference */
-  float* g_bd;
-  float* g_wu;
-  float* g_bu;
-} mb200_adapter;
-
-/* One GPT-J block (hf:gptj/modeling_gptj.py:400-413; fork GPTNeoBlock with jax=True). */
-typedef struct {
-  const void* ln1_g;
-  const void* ln1_b;
-  const void* w_qkv;    /* [3d, d] = cat(q_proj, k_proj, v_proj).weight */
-  const void* w_out;    /* [d, d]  */
-  const void* w_fc_in;  /* [4d, d] */
-  const void* b_fc_in;  /* [4d]    */
-  const void* w_fc_out; /* [d, 4d] */
-  const void* b_fc_out; /* [d]     */
-  mb200_adapter mlp_ad;
-  mb200_adapter attn_ad;
-} mb200_gptj_layer;
-
-typedef struct {
-  int32_t n_layer, d, n_head, rotary_dim;
-  int32_t vocab;           /* logits width V (50258 after resize_token_embeddings, magma/magma.py:50) */
-  int32_t d_ff;            /* 4d */
-  int32_t mlp_adapter;     /* MB200_ADAPTER_* (magma/magma.py:128-149) */
-  int32_t mlp_adapter_r;
-  int32_t attn_adapter;    /* MB200_ADAPTER_* (magma/magma.py:150-169) */
-  int32_t attn_adapter_r;
-  float ln_eps;
-  int32_t _pad;
-  const mb200_gptj_layer* layers; /* host array [n_layer] */
-  const void* lnf_g;
-  const void* lnf_b;
-  const void* w_lm; /* [V, d] */
-  const void* b_lm; /* [V]    */
-} mb200_gptj_model;
-
-/* bytes of caller-provided workspace for a [B,S] pass. training != 0 keeps per-layer activations. */
-size_t mb200_gptj_workspace_bytes(const mb200_gptj_model* m, int32_t B, int32_t S, int32_t S_kv_max,
-                                  int32_t training);
-
-/* GPTJForCausalLM.forward(inputs_embeds=x, labels=labels) as called from magma/magma.py:270-274.
- *   x      : bf16 [B,S,d] input embeddings
- *   labels : int64 [B,S] or NULL (no loss)
- *   logits : bf16 [B*S][ldv] or NULL. With last_only != 0 only the last position of each row is projected
- *            (logits is then [B][ldv]) — the decode path of magma/sampling.py:92.
- *   loss   : fp32 [1] device (mean CE) when labels != NULL
- *   hidden : bf16 [B,S,d] ln_f output or NULL
- *   kcache/vcache : bf16 [n_layer][B][H][S_kv_max][hd] or NULL; the K/V of this call are written at positions
- *            [pos0, pos0+S) and attention runs over [0, pos0+S) (use_cache=True, magma/sampling.py:81-90).
- * training != 0 saves activations in `ws` for mb200_gptj_backward. */
-int mb200_gptj_forward(const mb200_gptj_model* m, const void* x, const int64_t* labels, void* logits, int64_t ldv,
-                       int32_t last_only, float* loss, void* hidden, void* kcache, void* vcache, int32_t S_kv_max,
-                       int32_t pos0, int32_t B, int32_t S, int32_t training, void* ws, size_t ws_bytes,
-                       void* stream);
-
-/* Backward of the pass recorded in `ws` (loss.backward() of magma/train_loop.py:18 with the LM frozen:
- * dgrad through every GEMM, wgrad only for adapters). dx: bf16 [B,S,d] gradient w.r.t. inputs_embeds.
- * Layers are processed from layer_hi-1 down to layer_lo; the LM-head/CE backward runs when layer_hi == n_layer.
- * Splitting the range lets the caller overlap the gradient all-reduce of finished layers with the rest.
- * accumulate != 0 adds into the fp32 gradient buffers (gradient accumulation), else overwrites. */
-int mb200_gptj_backward(const mb200_gptj_model* m, void* dx, float loss_scale, int32_t layer_hi, int32_t layer_lo,
-                        int32_t accumulate, int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream);
 
 /* CLIP VisionTransformer (openai/CLIP model.py; hf:clip/modeling_clip.py:138-219,282-386,647-694). */
 typedef struct {
@@ -349,7 +279,7 @@ int mb200_vit_forward(const mb200_vit_model* m, const void* images, void* feats,
 
 /* ---- CLIP-ViT training (freeze_img_encoder: false — MAGMA_v1.yml:5; magma/magma.py:98-100 leaves the encoder
  * trainable, and the optimizer gives it its own learning rate, magma/utils.py:173-177). Host-only schedule in
- * csrc/vit_train.cu over the same primitives as the inference pass; activations of every layer are kept in `ws`
+ * csrc/vit_sched.cu over the same primitives as the inference pass; activations of every layer are kept in `ws`
  * (no recomputation: ~85 MB per ViT-L/14 layer at B = 8). Gradient buffers are fp32 with the parameter's own shape. */
 typedef struct {
   float *ln1_g, *ln1_b;
@@ -384,12 +314,13 @@ int mb200_vit_backward(const mb200_vit_model* m, const mb200_vit_grads* g, const
 /* dx = dy * d/dx[x * sigmoid(1.702 x)] at x = pre (CLIP QuickGELU, backward). dx may alias dy. */
 int mb200_quick_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream);
 
-/* ---- GPT-J + adapters, general training schedule (csrc/gptj_sched.cu, host-only). Same arithmetic as
- * mb200_gptj_forward/backward (training, no KV cache) for EVERY adapter form of the reference: normal / parallel /
- * scaled_parallel (learnable scalar adapter_scale, magma/adapters.py:57-61), each with or without the leading
- * LayerNorm (add_layernorm, adapters.py:16-17), on the MLP and / or the attention branch (magma/magma.py:102-174).
- * Attention runs as batched GEMMs + softmax kernels. The fast runtime above covers the forms the shipped configs use;
- * this one is what language_model.py selects for the others. */
+/* ---- GPT-J + adapters (csrc/gptj_sched.cu, host-only): GPTJForCausalLM as magma/magma.py:270-274 and
+ * magma/sampling.py:81-93 call it, for EVERY adapter form of the reference: normal / parallel / scaled_parallel
+ * (learnable scalar adapter_scale, magma/adapters.py:57-61), each with or without the leading LayerNorm
+ * (add_layernorm, adapters.py:16-17), on the MLP and / or the attention branch (magma/magma.py:102-174).
+ * Block math: hf:gptj/modeling_gptj.py:400-413 (fork GPTNeoBlock with jax=True); LM head + shifted CE:
+ * hf:gptj/modeling_gptj.py:573,623, hf:loss/loss_utils.py:28-67. */
+/* Adapter bottleneck (magma/adapters.py:6-39): [LayerNorm ->] Linear(d,r) -> ReLU -> Linear(r,d) [* scale]. */
 typedef struct {
   const void* wd; /* [r, d] bf16 */
   const void* bd;
@@ -433,23 +364,31 @@ typedef struct {
   const void* b_lm;
 } mb200_gptj_model_ex;
 
+/* bytes of caller-provided workspace for a [B,S] training pass (per-layer activations are kept: 122 MB per GPT-J-6B
+ * layer at B = 8, S = 128; nothing is recomputed — the reference uses gradient checkpointing, language_model.py:23). */
 size_t mb200_gptj_sched_workspace_bytes(const mb200_gptj_model_ex* m, int32_t B, int32_t S);
-/* x bf16 [B,S,d]; labels int64 [B,S] or NULL; logits bf16 [B*S][ldv] or NULL (kept in the workspace then);
- * loss fp32 [1] (device) when labels != NULL. Activations are saved in `ws` for the backward pass. */
+/* GPTJForCausalLM.forward(inputs_embeds=x, labels=labels) as called from magma/magma.py:270-274.
+ * x bf16 [B,S,d]; labels int64 [B,S] or NULL; logits bf16 [B*S][ldv] or NULL (kept in the workspace then);
+ * loss fp32 [1] (device, mean CE over the valid shifted labels) when labels != NULL. Activations are saved in `ws`
+ * for the backward pass. */
 int mb200_gptj_sched_forward(const mb200_gptj_model_ex* m, const void* x, const int64_t* labels, void* logits,
                              int64_t ldv, float* loss, int32_t B, int32_t S, void* ws, size_t ws_bytes, void* stream);
-/* dx: bf16 [B,S,d] gradient w.r.t. x (or NULL). accumulate != 0 adds into the fp32 gradient buffers. */
+/* Backward of the pass recorded in `ws` (loss.backward() of magma/train_loop.py:18 with the LM frozen: dgrad through
+ * every GEMM, wgrad only for adapters). dx: bf16 [B,S,d] gradient w.r.t. x (or NULL). accumulate != 0 adds into the
+ * fp32 gradient buffers (gradient accumulation), else overwrites. */
 int mb200_gptj_sched_backward(const mb200_gptj_model_ex* m, void* dx, float loss_scale, int32_t accumulate, int32_t B,
                               int32_t S, void* ws, size_t ws_bytes, void* stream);
 
-/* As mb200_gptj_backward: layers layer_hi-1 .. layer_lo per call (LM head / CE backward when layer_hi == n_layer), so
- * the caller can exchange the gradients of finished layers while the rest runs. dx is written when layer_lo == 0. */
+/* The same in layer ranges: layers layer_hi-1 .. layer_lo per call (LM head / CE backward when layer_hi == n_layer),
+ * so the caller can exchange the gradients of finished layers while the rest runs. dx is written when layer_lo == 0. */
 int mb200_gptj_sched_backward_range(const mb200_gptj_model_ex* m, void* dx, float loss_scale, int32_t layer_hi,
                                     int32_t layer_lo, int32_t accumulate, int32_t B, int32_t S, void* ws,
                                     size_t ws_bytes, void* stream);
-/* Inference pass of the general schedule (no saved activations): optional KV cache exactly as mb200_gptj_forward
- * (prefill S > 1 at pos0, decode S == 1 through mb200_attn_decode), last_only = project the last position only
- * (logits [B][ldv]), hidden = ln_f output or NULL. */
+/* Inference pass (no saved activations) — use_cache=True of magma/sampling.py:81-90: kcache / vcache bf16
+ * [n_layer][B][H][S_kv_max][hd] or NULL; the K / V of this call are written at positions [pos0, pos0 + S) and attention
+ * runs over [0, pos0 + S) (prefill S > 1 through mb200_attn_fwd_flash, decode S == 1 through mb200_attn_decode).
+ * last_only != 0 projects the last position only (logits [B][ldv] — what magma/sampling.py:92 consumes); hidden = ln_f
+ * output (bf16 [rows, d]) or NULL. */
 size_t mb200_gptj_sched_infer_workspace_bytes(const mb200_gptj_model_ex* m, int32_t B, int32_t S, int32_t S_kv_max);
 int mb200_gptj_sched_infer(const mb200_gptj_model_ex* m, const void* x, void* logits, int64_t ldv, int32_t last_only,
                            void* hidden, void* kcache, void* vcache, int32_t S_kv_max, int32_t pos0, int32_t B, int32_t S,
@@ -461,9 +400,6 @@ int mb200_scale_add(const void* u, const float* s, const void* r1, const void* r
 /* out[0] (+)= sum_i a_i * b_i (fp32) over n bf16 elements — d loss / d adapter_scale. */
 int mb200_dot(const void* a, const void* b, int64_t n, float* out, int32_t accumulate, void* stream);
 
-/* Fused KV-cache attention for one decode step (Sq = 1): q/k/v come from the fused qkv row [B][3][H][hd] (already
- * rotated); k,v are appended to the cache at position `pos`, then softmax(q K^T / sqrt(hd)) V over [0, pos].
- * Replaces the torch.cat cache growth + _attn of hf:gptj/modeling_gptj.py:209-214,136-149 per step. */
 /* Fused causal self-attention for sequences that fit one tile (S <= 128, head_dim a multiple of 64, <= 256): one CTA
  * per (batch, head), S = QK^T / softmax / PV entirely on-chip (TMEM + smem). qkv is the fused, already-rotated
  * [B*S][3][H][hd] buffer; P (bf16 [B,H,S,ldP]) is saved for the backward pass; O is [B,S,H,hd] with row stride ldo.
@@ -475,7 +411,24 @@ int mb200_attn_fwd_tile(const void* qkv, int64_t ld_qkv, void* P, int64_t ldP, v
 int mb200_attn_bwd_tile(const void* qkv, int64_t ld_qkv, const void* dO, int64_t ld_do, const void* P, int64_t ldP,
                         void* dqkv, int64_t ld_dqkv, const float* rope_tab, int32_t rot, int32_t B, int32_t S, int32_t H,
                         int32_t hd, void* stream);
+/* The forward attention for ANY sequence length (multi-tile): one CTA per (128-query tile, head, batch) sweeps the key
+ * tiles twice (row max / sum, then bf16 probabilities and O += P V in TMEM), so no [B,H,S,S] fp32 score buffer exists
+ * and the probabilities are rounded exactly where the materialised softmax rounds them. q / k / v point at head 0,
+ * batch 0, row 0 with row stride ld*, head stride *_bsh and batch stride *_bsb in elements: the fused qkv buffer
+ * (ld = 3d, bsh = hd, bsb = S * 3d) or a KV cache [B,H,Smax,hd] (ld = hd, bsh = Smax * hd, bsb = H * Smax * hd).
+ * causal != 0: key j is visible to query i iff j <= i + (Sk - Sq) (prefill and its continuations). P (optional, bf16
+ * [B,H,Sq,ldP], ldP >= Sk and % 8) is written for a materialised backward; stats (optional, [B,H,Sq][2]) receives the
+ * row maximum of the scaled scores and 1 / sum. Replaces, for S > 128 and for the ViT (T = 257), the QK^T GEMM + softmax
+ * kernel + PV GEMM of hf:gptj/modeling_gptj.py:136-149 / hf:clip/modeling_clip.py:282-330 (magma/magma.py:44: the
+ * reference runs at seq_len 2048). */
+int mb200_attn_fwd_flash(const void* q, int64_t ldq, int64_t q_bsh, int64_t q_bsb, const void* k, int64_t ldk,
+                         int64_t k_bsh, int64_t k_bsb, const void* v, int64_t ldv, int64_t v_bsh, int64_t v_bsb, void* O,
+                         int64_t ldo, void* P, int64_t ldP, float* stats, int32_t B, int32_t Sq, int32_t Sk, int32_t H,
+                         int32_t hd, int32_t causal, void* stream);
 
+/* Fused KV-cache attention for one decode step (Sq = 1): q/k/v come from the fused qkv row [B][3][H][hd] (already
+ * rotated); k,v are appended to the cache at position `pos`, then softmax(q K^T / sqrt(hd)) V over [0, pos].
+ * Replaces the torch.cat cache growth + _attn of hf:gptj/modeling_gptj.py:209-214,136-149 per step. */
 int mb200_attn_decode(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, void* out, int64_t ld_out,
                       int32_t B, int32_t H, int32_t hd, int32_t S_kv_max, int32_t pos, void* stream);
 /* K/V of S positions (prefill) from the fused, rotated qkv rows [B*S][3][H][hd] into one layer's static cache

@@ -86,39 +86,6 @@ def check(rc):
 
 
 # ---- model-level runtime structs (include/magma_b200.h) ----
-class AdapterC(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ("wd", "bd", "wu", "bu", "g_wd", "g_bd", "g_wu", "g_bu")]
-
-
-class GptjLayerC(ctypes.Structure):
-    _fields_ = [
-        (n, ctypes.c_void_p)
-        for n in ("ln1_g", "ln1_b", "w_qkv", "w_out", "w_fc_in", "b_fc_in", "w_fc_out", "b_fc_out")
-    ] + [("mlp_ad", AdapterC), ("attn_ad", AdapterC)]
-
-
-class GptjModelC(ctypes.Structure):
-    _fields_ = [
-        ("n_layer", ctypes.c_int32),
-        ("d", ctypes.c_int32),
-        ("n_head", ctypes.c_int32),
-        ("rotary_dim", ctypes.c_int32),
-        ("vocab", ctypes.c_int32),
-        ("d_ff", ctypes.c_int32),
-        ("mlp_adapter", ctypes.c_int32),
-        ("mlp_adapter_r", ctypes.c_int32),
-        ("attn_adapter", ctypes.c_int32),
-        ("attn_adapter_r", ctypes.c_int32),
-        ("ln_eps", ctypes.c_float),
-        ("_pad", ctypes.c_int32),
-        ("layers", ctypes.POINTER(GptjLayerC)),
-        ("lnf_g", ctypes.c_void_p),
-        ("lnf_b", ctypes.c_void_p),
-        ("w_lm", ctypes.c_void_p),
-        ("b_lm", ctypes.c_void_p),
-    ]
-
-
 class VitLayerC(ctypes.Structure):
     _fields_ = [
         (n, ctypes.c_void_p)
@@ -152,7 +119,7 @@ class VitModelC(ctypes.Structure):
 
 
 class AdapterExC(ctypes.Structure):
-    """mb200_adapter_ex: adapter with the optional leading LayerNorm and the learnable scale (general schedule)."""
+    """mb200_adapter_ex: adapter bottleneck with the optional leading LayerNorm and the learnable scale."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("wd", "bd", "wu", "bu", "ln_g", "ln_b", "scale", "g_wd", "g_bd", "g_wu",
                                                "g_bu", "g_ln_g", "g_ln_b", "g_scale")]
 
@@ -165,8 +132,26 @@ class GptjLayerExC(ctypes.Structure):
 
 
 class GptjModelExC(ctypes.Structure):
-    _fields_ = [(n, t) for n, t in GptjModelC._fields_ if n != "layers"]
-    _fields_.insert(12, ("layers", ctypes.POINTER(GptjLayerExC)))
+    """mb200_gptj_model_ex (include/magma_b200.h)."""
+    _fields_ = [
+        ("n_layer", ctypes.c_int32),
+        ("d", ctypes.c_int32),
+        ("n_head", ctypes.c_int32),
+        ("rotary_dim", ctypes.c_int32),
+        ("vocab", ctypes.c_int32),
+        ("d_ff", ctypes.c_int32),
+        ("mlp_adapter", ctypes.c_int32),
+        ("mlp_adapter_r", ctypes.c_int32),
+        ("attn_adapter", ctypes.c_int32),
+        ("attn_adapter_r", ctypes.c_int32),
+        ("ln_eps", ctypes.c_float),
+        ("_pad", ctypes.c_int32),
+        ("layers", ctypes.POINTER(GptjLayerExC)),
+        ("lnf_g", ctypes.c_void_p),
+        ("lnf_b", ctypes.c_void_p),
+        ("w_lm", ctypes.c_void_p),
+        ("b_lm", ctypes.c_void_p),
+    ]
 
 
 class VitLayerGradsC(ctypes.Structure):
@@ -180,7 +165,6 @@ class VitGradsC(ctypes.Structure):
 
 
 def _setup_signatures(L):
-    L.mb200_gptj_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_vit_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_vit_train_workspace_bytes.restype = ctypes.c_size_t
     L.mb200_gptj_sched_workspace_bytes.restype = ctypes.c_size_t
@@ -197,8 +181,7 @@ EXPORTED_SYMBOLS = [
     "mb200_nchw_to_nhwc8", "mb200_im2col3x3", "mb200_avgpool_nhwc",
     "mb200_vit_assemble", "mb200_argmax", "mb200_sample", "mb200_add", "mb200_sumsq", "mb200_adamw_step",
     "mb200_cast_f32_to_bf16", "mb200_cast_bf16_to_f32",
-    "mb200_gptj_workspace_bytes", "mb200_gptj_forward", "mb200_gptj_backward",
-    "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode", "mb200_attn_fwd_tile",
+    "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode", "mb200_attn_fwd_tile", "mb200_attn_fwd_flash",
     "mb200_attn_bwd_tile",
     "mb200_vit_train_workspace_bytes", "mb200_vit_forward_train", "mb200_vit_backward", "mb200_quick_gelu_bwd",
     "mb200_layernorm_param_grad_rows", "mb200_set_gemm_sm_limit", "mb200_scale_add", "mb200_dot",

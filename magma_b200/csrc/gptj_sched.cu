@@ -1,10 +1,11 @@
-// magma_b200 — GPT-J + adapters, general training schedule (forward with saved activations + backward), host-only.
+// magma_b200 — GPT-J + adapters: THE language-model runtime (training forward with saved activations + backward,
+// full-sequence inference, KV-cache prefill and decode steps), host-only.
 //
-// engine.cu's runtime covers the adapter forms the reference's shipped configurations use (plain bottleneck, "normal"
-// and "parallel" wiring). The reference's Adapter classes have two more options — a leading LayerNorm
-// (`add_layernorm`, magma/adapters.py:16-17) and a learnable scalar on the parallel forms (`scaled_parallel`,
-// adapters.py:57-66,85-92) — and this file schedules the whole LM pass for ANY combination of them, on the MLP and / or
-// the attention branch (magma/magma.py:102-174), from the primitive operators of the C ABI only:
+// One C call per pass instead of ~1000 Python-level op calls: this file carves the workspace and issues the kernels of a
+// pass on one stream. It schedules every adapter form of the reference — plain bottleneck in "normal" or "parallel"
+// wiring (what the shipped configurations use), with or without a leading LayerNorm (`add_layernorm`,
+// magma/adapters.py:16-17) and the learnable scalar of the parallel forms (`scaled_parallel`, adapters.py:57-66,85-92) —
+// on the MLP and / or the attention branch (magma/magma.py:102-174), from the primitive operators of the C ABI only:
 //
 //   block (hf:gptj/modeling_gptj.py:400-413, parallel residual):  h = ln_1(x);  x' = attn(h) + mlp(h) + x
 //   Adapter.forward            adapters.py:38-39    y = A(z) + z            A(z) = Wu relu(Wd LN?(z) + bd) + bu
@@ -12,12 +13,16 @@
 //   AdapterWrapper / ParallelAdapterWrapper         the same two on the attention output / input (:85-92,:109-116)
 //   LM head + shifted CE       hf:gptj/modeling_gptj.py:573,623 ; hf:loss/loss_utils.py:28-67
 //
-// Attention runs as strided batched GEMMs on the fused qkv buffer + the softmax kernels (the path engine.cu uses when
-// the fused single-tile kernel does not apply). The LM is frozen: dgrad through every GEMM, wgrad only for adapters.
+// Attention: the fused single-tile kernels when the sequence fits one tile (S <= 128: BASELINE config 2), the fused
+// multi-tile forward (mb200_attn_fwd_flash) for longer sequences / prefill over a KV cache — in training it also writes
+// the probabilities, and the backward then runs as strided batched GEMMs on the fused qkv buffer + softmax_bwd — and
+// batched GEMMs + softmax kernels for head dims the fused kernels do not take. The LM is frozen: dgrad through every
+// GEMM, wgrad only for adapters.
 //
 // No kernels and no CUDA calls here (sched_rt.h): tests/test_sched_emul_cpu.py compiles this file as plain C++ against
-// oracle/cabi_emul.cpp and checks every adapter form against torch autograd of the oracle on the CPU.
-// Written after the round's GPU budget was spent: NOT YET RUN ON A B200.
+// oracle/cabi_emul.cpp and checks every adapter form against torch autograd of the oracle on the CPU; on the B200 it is
+// the path every LM test and the benchmark run (measured equal to the round-1 engine.cu schedule it replaced:
+// profiles/r02_bench_n1_general_schedule.json.log).
 #include "sched_rt.h"
 
 #include <math.h>
@@ -153,7 +158,7 @@ struct Plan {
 };
 
 // the fused single-tile attention kernels (csrc/attention.cu) cover S <= 128 with head_dim in {64, 128, 192, 256};
-// MB200_ATTN_TILE=0 forces the batched-GEMM path (same switch as engine.cu)
+// MB200_ATTN_TILE=0 skips them
 inline bool tile_ok(int S, int hd) {
   static int on = -1;
   if (on < 0) {
@@ -161,6 +166,16 @@ inline bool tile_ok(int S, int hd) {
     on = e ? atoi(e) : 1;
   }
   return on != 0 && S >= 1 && S <= 128 && hd >= 64 && hd <= 256 && hd % 64 == 0;
+}
+
+// the fused multi-tile forward takes any sequence length at those head dims; MB200_ATTN_FLASH=0 forces batched GEMMs
+inline bool flash_ok(int hd) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB200_ATTN_FLASH");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0 && hd >= 64 && hd <= 256 && hd % 64 == 0;
 }
 
 inline bool has_ln(const mb200_adapter_ex& a) { return a.ln_g != nullptr; }
@@ -340,6 +355,9 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
     }
     if (tile_ok(S, hd)) {  // whole sequence in one tile: fused QK^T / softmax / PV, one CTA per (batch, head)
       MBS_TRY(mb200_attn_fwd_tile(a.qkv, 3 * d, a.P, P.ldP, a.attn_o, d, B, S, H, hd, st));
+    } else if (flash_ok(hd)) {  // any S: fused multi-tile forward; P is written for the materialised backward
+      MBS_TRY(mb200_attn_fwd_flash(a.qkv, 3 * d, qb0, qb1, a.qkv + d, 3 * d, qb0, qb1, a.qkv + 2 * d, 3 * d, qb0, qb1,
+                                   a.attn_o, d, a.P, P.ldP, nullptr, B, S, S, H, hd, 1, st));
     } else {
       // scores = Q K^T (fp32), P = softmax(scores / sqrt(hd) + causal mask), O = P V
       MBS_TRY(gemm(st, S, S, hd, mat(a.qkv, 3 * d, 0, qb0, qb1), mat(a.qkv + d, 3 * d, 0, qb0, qb1), P.scores, P.ldP, 1,
@@ -518,7 +536,8 @@ int make_infer_plan(InferPlan& P, const mb200_gptj_model_ex* m, int B, int S, in
   P.hd = m->d / m->n_head;
   const int Sk = Skv > S ? Skv : S;
   P.ldS = (int)align_up(Sk, 8);
-  const size_t M = P.M, d = P.d, dff = P.dff, nP = (size_t)B * P.H * S * P.ldS;
+  // the fp32 score / bf16 probability buffers only exist for head dims the fused attention kernels do not take
+  const size_t M = P.M, d = P.d, dff = P.dff, nP = flash_ok(P.hd) ? 8 : (size_t)B * P.H * S * P.ldS;
   P.xa = c.take<bf16s>(M * d);
   P.xb = c.take<bf16s>(M * d);
   P.h = c.take<bf16s>(M * d);
@@ -584,9 +603,17 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
     bf16s* vc = vcache ? vcache + (size_t)l * cache_layer : nullptr;
     if (kcache && S == 1) {
       MBS_TRY(mb200_attn_decode(P.qkv, 3 * d, kc, vc, P.attn_o, d, B, H, hd, Smax, pos0, st));
-    } else if (pos0 == 0 && tile_ok(S, hd)) {
-      if (kcache) MBS_TRY(mb200_kv_append(P.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0, st));
-      MBS_TRY(mb200_attn_fwd_tile(P.qkv, 3 * d, P.P, P.ldS, P.attn_o, d, B, S, H, hd, st));
+    } else if (flash_ok(hd)) {  // prompts of any length and prefill continuations: fused forward over qkv or the cache
+      const long long qb0 = hd, qb1 = (long long)S * 3 * d;
+      if (kcache) {
+        MBS_TRY(mb200_kv_append(P.qkv, 3 * d, kc, vc, B, S, H, hd, Smax, pos0, st));
+        const long long cb0 = (long long)Smax * hd, cb1 = (long long)H * Smax * hd;
+        MBS_TRY(mb200_attn_fwd_flash(P.qkv, 3 * d, qb0, qb1, kc, hd, cb0, cb1, vc, hd, cb0, cb1, P.attn_o, d, nullptr, 0,
+                                     nullptr, B, S, Sk, H, hd, 1, st));
+      } else {
+        MBS_TRY(mb200_attn_fwd_flash(P.qkv, 3 * d, qb0, qb1, P.qkv + d, 3 * d, qb0, qb1, P.qkv + 2 * d, 3 * d, qb0, qb1,
+                                     P.attn_o, d, nullptr, 0, nullptr, B, S, S, H, hd, 1, st));
+      }
     } else {
       Mat Q = mat(P.qkv, 3 * d, 0, hd, (long long)S * 3 * d), Kk, Vv;
       if (kcache) {

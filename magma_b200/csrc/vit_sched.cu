@@ -1,9 +1,10 @@
-// magma_b200 — CLIP-ViT training schedule (forward with saved activations + backward), host-only.
+// magma_b200 — CLIP-ViT schedules, host-only: the inference forward (frozen image encoder: the measured path,
+// mb200_vit_forward) and the training schedule (forward with saved activations + backward).
 //
 // `freeze_img_encoder: false` (MAGMA_v1.yml:5; magma/magma.py:98-100 only freezes the encoder when asked to) puts the
 // image encoder on the training path: loss.backward() (magma/train_loop.py:18) then runs through
 // ImagePrefix.proj into the encoder, and the optimizer gives the encoder its own learning rate
-// (magma/utils.py:173-177). This file is the ViT half of that: the forward of engine.cu::vit_forward with every
+// (magma/utils.py:173-177). The training schedule is the ViT half of that: the inference forward below with every
 // layer's activations kept, and the matching backward — dgrad and wgrad of every linear on the tcgen05 GEMM core with
 // MN-major operands (no transposed copies), attention backward as strided batched GEMMs on the fused qkv buffer,
 // LayerNorm / softmax / QuickGELU backward and the bias / LN-parameter / positional reductions as HBM-bound kernels.
@@ -12,10 +13,13 @@
 // SURVEY.md §8c); the backward is the autograd of that forward and is checked against torch autograd of the oracle.
 //
 // This file contains no kernels and no CUDA calls (see sched_rt.h): tests/ dry-run it on the CPU against
-// oracle/cabi_emul.cpp. Written after the round's GPU budget was spent: NOT YET RUN ON A B200.
+// oracle/cabi_emul.cpp. Attention (T = 257 for ViT-L/14, head_dim 64, no mask) runs in the fused multi-tile kernel
+// (mb200_attn_fwd_flash) whenever head_dim is a multiple of 64 — the training forward asks it for the probabilities
+// the materialised backward consumes — and as batched GEMMs + softmax otherwise.
 #include "sched_rt.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mb200 {
@@ -179,6 +183,115 @@ int make_plan(Plan& P, const mb200_vit_model* m, int B, void* ws) {
 
 const float kEps = 1e-5f;  // CLIP LayerNorm eps
 
+// head dims the fused multi-tile attention kernel takes (csrc/attention.cu); MB200_ATTN_FLASH=0 forces the GEMM path
+inline bool flash_ok(int hd) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB200_ATTN_FLASH");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0 && hd >= 64 && hd <= 256 && hd % 64 == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// inference forward (the image encoder is frozen on the measured path, magma/magma.py:98-100): one set of activation
+// buffers reused by every layer. Arithmetic: hf:clip/modeling_clip.py:138-219 (patch + class + position embeddings),
+// :647-694 (pre / post LayerNorm, class-token pooling), :282-386 (blocks), :1015-1069 (projection).
+// ---------------------------------------------------------------------------------------------
+struct InferPlan {
+  int T, M, ldS, ldpatch;
+  bf16s *x, *h, *qkv, *P, *attn_o, *hact, *patches, *pooled;
+  float* scores;
+  size_t bytes;
+};
+
+int make_infer_plan(InferPlan& P, const mb200_vit_model* m, int B, void* ws) {
+  MBS_REQUIRE(m && m->layers && m->n_layer > 0 && B > 0 && m->patch > 0 && m->image % m->patch == 0 && m->n_head > 0 &&
+                  m->width % m->n_head == 0,
+              MB200_E_SHAPE, "vit: bad geometry");
+  const int g = m->image / m->patch;
+  Carver c(ws);
+  P.T = g * g + 1;
+  P.M = B * P.T;
+  P.ldS = (int)align_up(P.T, 8);
+  P.ldpatch = (int)align_up(3 * m->patch * m->patch, 8);
+  const size_t M = P.M, w = m->width;
+  const bool fl = flash_ok(m->width / m->n_head);
+  const size_t nP = fl ? 8 : (size_t)B * m->n_head * P.T * P.ldS;  // no score / probability buffers with fused attention
+  P.x = c.take<bf16s>(M * w);
+  P.h = c.take<bf16s>(M * w);
+  P.qkv = c.take<bf16s>(M * 3 * w);
+  P.scores = c.take<float>(nP);
+  P.P = c.take<bf16s>(nP);
+  P.attn_o = c.take<bf16s>(M * w);
+  P.hact = c.take<bf16s>(M * (size_t)m->mlp);
+  P.patches = c.take<bf16s>((size_t)B * g * g * P.ldpatch);
+  P.pooled = c.take<bf16s>((size_t)B * w);
+  P.bytes = align_up(c.off, 256);
+  return 0;
+}
+
+int forward_infer(const mb200_vit_model* m, const bf16s* images, bf16s* feats, int B, void* ws, size_t ws_bytes, void* st) {
+  InferPlan P;
+  MBS_TRY(make_infer_plan(P, m, B, ws));
+  MBS_REQUIRE(ws != nullptr && ws_bytes >= P.bytes, MB200_E_ARG, "vit_forward: workspace too small (%zu < %zu)", ws_bytes,
+              P.bytes);
+  const int w = m->width, H = m->n_head, hd = w / H, T = P.T, M = P.M, g = m->image / m->patch;
+  const int Kp = 3 * m->patch * m->patch;
+  const float scale = 1.0f / sqrtf((float)hd);
+  // conv1 as im2col + GEMM (patch embeddings staged in h), then [cls; patches] + positional embedding
+  MBS_TRY(rt_zero(P.patches, (size_t)B * g * g * P.ldpatch * sizeof(bf16s), st));
+  MBS_TRY(mb200_patchify(images, P.patches, P.ldpatch, B, m->image, m->patch, st));
+  MBS_TRY(gemm(st, B * g * g, w, Kp, mat(P.patches, P.ldpatch), mat(m->w_conv, m->ld_conv), P.h, w, 0));
+  MBS_TRY(mb200_vit_assemble(P.x, P.h, m->cls, m->pos, B, T, w, st));
+  // ln_pre (in place: each row is cached in registers before it is rewritten)
+  MBS_TRY(mb200_layernorm_fwd(P.x, w, m->ln_pre_g, m->ln_pre_b, P.x, w, nullptr, nullptr, M, w, kEps, st));
+  const long long qb0 = hd, qb1 = (long long)T * 3 * w;
+  const long long pb0 = (long long)T * P.ldS, pb1 = (long long)H * T * P.ldS;
+  for (int l = 0; l < m->n_layer; ++l) {
+    const mb200_vit_layer& L = m->layers[l];
+    MBS_TRY(mb200_layernorm_fwd(P.x, w, L.ln1_g, L.ln1_b, P.h, w, nullptr, nullptr, M, w, kEps, st));
+    {
+      Epi e;
+      e.bias = L.b_qkv;
+      MBS_TRY(gemm(st, M, 3 * w, w, mat(P.h, w), mat(L.w_qkv, w), P.qkv, 3 * w, 0, e));
+    }
+    if (flash_ok(hd)) {
+      MBS_TRY(mb200_attn_fwd_flash(P.qkv, 3 * w, qb0, qb1, P.qkv + w, 3 * w, qb0, qb1, P.qkv + 2 * w, 3 * w, qb0, qb1,
+                                   P.attn_o, w, nullptr, 0, nullptr, B, T, T, H, hd, 0, st));
+    } else {
+      MBS_TRY(gemm(st, T, T, hd, mat(P.qkv, 3 * w, 0, qb0, qb1), mat(P.qkv + w, 3 * w, 0, qb0, qb1), P.scores, P.ldS, 1,
+                   Epi(), H, B, pb0, pb1));
+      MBS_TRY(mb200_softmax_fwd(P.scores, P.ldS, pb0, P.P, P.ldS, pb0, B * H, T, T, scale, 0, 0, st));
+      MBS_TRY(gemm(st, T, hd, T, mat(P.P, P.ldS, 0, pb0, pb1), mat(P.qkv + 2 * w, 3 * w, 1, qb0, qb1), P.attn_o, w, 0,
+                   Epi(), H, B, hd, (long long)T * w));
+    }
+    {
+      Epi e;
+      e.bias = L.b_out;
+      e.res1 = P.x;
+      e.ld_res = w;
+      MBS_TRY(gemm(st, M, w, w, mat(P.attn_o, w), mat(L.w_out, w), P.x, w, 0, e));  // x += out_proj(attn)
+    }
+    MBS_TRY(mb200_layernorm_fwd(P.x, w, L.ln2_g, L.ln2_b, P.h, w, nullptr, nullptr, M, w, kEps, st));
+    {
+      Epi e;
+      e.bias = L.b_fc;
+      e.act = MB200_ACT_QUICK_GELU;
+      MBS_TRY(gemm(st, M, m->mlp, w, mat(P.h, w), mat(L.w_fc, w), P.hact, m->mlp, 0, e));
+      Epi e2;
+      e2.bias = L.b_proj;
+      e2.res1 = P.x;
+      e2.ld_res = w;
+      MBS_TRY(gemm(st, M, w, m->mlp, mat(P.hact, m->mlp), mat(L.w_proj, m->mlp), P.x, w, 0, e2));  // x += mlp
+    }
+  }
+  // ln_post on the class token, then the visual projection
+  MBS_TRY(mb200_layernorm_fwd(P.x, (long long)T * w, m->ln_post_g, m->ln_post_b, P.pooled, w, nullptr, nullptr, B, w, kEps,
+                              st));
+  return gemm(st, B, m->out_dim, w, mat(P.pooled, w), mat(m->proj_t, w), feats, m->out_dim, 0);
+}
+
 int forward_train(const mb200_vit_model* m, const bf16s* images, bf16s* feats, int B, void* ws, size_t ws_bytes,
                   void* st) {
   Plan P;
@@ -207,11 +320,16 @@ int forward_train(const mb200_vit_model* m, const bf16s* images, bf16s* feats, i
       MBS_TRY(gemm(st, M, 3 * w, w, mat(a.h1, w), mat(L.w_qkv, w), a.qkv, 3 * w, 0, e));
     }
     // scores = Q K^T (fp32), P = softmax(scores / sqrt(hd)), O = P V   (no mask: CLIP's image tower attends fully)
-    MBS_TRY(gemm(st, T, T, hd, mat(a.qkv, 3 * w, 0, qb0, qb1), mat(a.qkv + w, 3 * w, 0, qb0, qb1), P.scores, P.ldS, 1,
-                 Epi(), H, B, pb0, pb1));
-    MBS_TRY(mb200_softmax_fwd(P.scores, P.ldS, pb0, a.P, P.ldS, pb0, B * H, T, T, scale, 0, 0, st));
-    MBS_TRY(gemm(st, T, hd, T, mat(a.P, P.ldS, 0, pb0, pb1), mat(a.qkv + 2 * w, 3 * w, 1, qb0, qb1), a.attn_o, w, 0,
-                 Epi(), H, B, hd, (long long)T * w));
+    if (flash_ok(hd)) {
+      MBS_TRY(mb200_attn_fwd_flash(a.qkv, 3 * w, qb0, qb1, a.qkv + w, 3 * w, qb0, qb1, a.qkv + 2 * w, 3 * w, qb0, qb1,
+                                   a.attn_o, w, a.P, P.ldS, nullptr, B, T, T, H, hd, 0, st));
+    } else {
+      MBS_TRY(gemm(st, T, T, hd, mat(a.qkv, 3 * w, 0, qb0, qb1), mat(a.qkv + w, 3 * w, 0, qb0, qb1), P.scores, P.ldS, 1,
+                   Epi(), H, B, pb0, pb1));
+      MBS_TRY(mb200_softmax_fwd(P.scores, P.ldS, pb0, a.P, P.ldS, pb0, B * H, T, T, scale, 0, 0, st));
+      MBS_TRY(gemm(st, T, hd, T, mat(a.P, P.ldS, 0, pb0, pb1), mat(a.qkv + 2 * w, 3 * w, 1, qb0, qb1), a.attn_o, w, 0,
+                   Epi(), H, B, hd, (long long)T * w));
+    }
     {
       Epi e;
       e.bias = L.b_out;
@@ -324,6 +442,19 @@ int backward(const mb200_vit_model* m, const mb200_vit_grads* G, const bf16s* df
 
 }  // namespace
 }  // namespace mb200
+
+extern "C" size_t mb200_vit_workspace_bytes(const mb200_vit_model* m, int32_t B) {
+  mb200::InferPlan P;
+  if (mb200::make_infer_plan(P, m, B, nullptr)) return 0;
+  return P.bytes;
+}
+
+extern "C" int mb200_vit_forward(const mb200_vit_model* m, const void* images, void* feats, int32_t B, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  int rc = mb200::rt_check_arch();
+  if (rc) return rc;
+  return mb200::forward_infer(m, (const mb200::bf16s*)images, (mb200::bf16s*)feats, B, ws, ws_bytes, stream);
+}
 
 extern "C" size_t mb200_vit_train_workspace_bytes(const mb200_vit_model* m, int32_t B) {
   mb200::Plan P;

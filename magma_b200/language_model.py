@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import (AdapterC, AdapterExC, GptjLayerC, GptjLayerExC, GptjModelC, GptjModelExC, MB200Error, check,
+from ._lib import (AdapterExC, GptjLayerExC, GptjModelExC, MB200Error, check,
                    lib)
 from .adapters import Adapter, AdapterWrapper, ParallelAdapter, ParallelAdapterWrapper
 from .arena import ParamArena
@@ -219,7 +219,6 @@ class B200GPTJForCausalLM(nn.Module):
         self.lm_head = Linear(self.config.hidden_size, self.config.vocab_size, True, dev)
         self._arena = None
         self._own_arena = False
-        self._cmodel_cache = None
         self._cmodel_ex_cache = None
         self._ws = {}
         self._generation = 0
@@ -239,7 +238,7 @@ class B200GPTJForCausalLM(nn.Module):
                 p.data.copy_(1.0 + std * torch.randn(p.shape, generator=g, device=self._device))
             else:
                 p.data.copy_(std * torch.randn(p.shape, generator=g, device=self._device))
-        self._cmodel_cache = None
+        self._cmodel_ex_cache = None
         return self
 
     def resize_token_embeddings(self, n):
@@ -254,7 +253,7 @@ class B200GPTJForCausalLM(nn.Module):
                 setattr(mod, nm, nn.Parameter(new, requires_grad=False))
         self.lm_head.out_features = n
         self.config.vocab_size = n
-        self._cmodel_cache = None
+        self._cmodel_ex_cache = None
         return self.transformer.wte
 
     def adapter_parameters(self):
@@ -263,7 +262,6 @@ class B200GPTJForCausalLM(nn.Module):
     def attach_arena(self, arena: ParamArena):
         self._arena = arena
         self._own_arena = False
-        self._cmodel_cache = None
         self._cmodel_ex_cache = None
 
     def _ensure_arena(self):
@@ -276,19 +274,6 @@ class B200GPTJForCausalLM(nn.Module):
         return self._arena
 
     # ---- C model struct ---------------------------------------------------------------------
-    def _general_schedule(self):
-        """True when an adapter uses an option the fast runtime (engine.cu) does not schedule — a leading LayerNorm
-        (add_layernorm, adapters.py:16-17) or the learnable adapter_scale (scaled_parallel, adapters.py:57-61). Those
-        models run through the general host-only schedule csrc/gptj_sched.cu (training / full-sequence passes only)."""
-        # test / experiment hook: run any model through the general schedule (cross-checks the two schedules)
-        if getattr(self, "_force_general", False) or os.environ.get("MB200_FORCE_GENERAL", "0") == "1":
-            return True
-        for blk in self.transformer.h:
-            for ad in (_split_mlp(blk.mlp)[2], _split_attn(blk.attn)[2]):
-                if ad is not None and (ad.add_layernorm or isinstance(getattr(ad, "adapter_scale", 1), nn.Parameter)):
-                    return True
-        return False
-
     def _adapter_struct_ex(self, ad):
         c = AdapterExC()
         if ad is None:
@@ -352,87 +337,16 @@ class B200GPTJForCausalLM(nn.Module):
             nbytes = lib().mb200_gptj_sched_workspace_bytes(ctypes.byref(self._cmodel_ex()[0]), B, S)
             if nbytes == 0:
                 raise MB200Error(lib().mb200_last_error().decode())
-            for k in [k for k in self._ws if k[0] == "ex"]:
+            for k in [k for k in self._ws if isinstance(k, tuple) and k[0] == "ex"]:
                 del self._ws[k]
             self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
         return self._ws[key]
 
-    def _adapter_struct(self, ad, with_grad):
-        c = AdapterC()
-        if ad is None:
-            return c
-        if ad.add_layernorm:
-            raise MB200Error("add_layernorm adapters are not supported by the fused runtime")
-        if isinstance(getattr(ad, "adapter_scale", 1), nn.Parameter):
-            raise MB200Error("scaled_parallel adapters are not supported by the fused runtime yet")
-        ar = self._arena
-        for cname, p in (("wd", ad.down.weight), ("bd", ad.down.bias), ("wu", ad.up.weight), ("bu", ad.up.bias)):
-            setattr(c, cname, ar.shadow_of(p).data_ptr())
-            if with_grad and p.requires_grad:
-                setattr(c, "g_" + cname, ar.grad_of(p).data_ptr())
-        return c
-
-    def _cmodel(self):
-        self._ensure_arena()
-        if self._cmodel_cache is not None:
-            return self._cmodel_cache
-        cfg = self.config
-        n = len(self.transformer.h)
-        layers = (GptjLayerC * n)()
-        kinds = set()
-        rm = ra = 0
-        for l, blk in enumerate(self.transformer.h):
-            mk, mlp, mad = _split_mlp(blk.mlp)
-            ak, attn, aad = _split_attn(blk.attn)
-            kinds.add((mk, ak))
-            L = layers[l]
-            L.ln1_g, L.ln1_b = blk.ln_1.weight.data_ptr(), blk.ln_1.bias.data_ptr()
-            L.w_qkv = attn.fused_qkv().data_ptr()
-            L.w_out = attn.out_proj.weight.data_ptr()
-            L.w_fc_in, L.b_fc_in = mlp.fc_in.weight.data_ptr(), mlp.fc_in.bias.data_ptr()
-            L.w_fc_out, L.b_fc_out = mlp.fc_out.weight.data_ptr(), mlp.fc_out.bias.data_ptr()
-            L.mlp_ad = self._adapter_struct(mad, True)
-            L.attn_ad = self._adapter_struct(aad, True)
-            if mad is not None:
-                rm = mad.bottleneck
-            if aad is not None:
-                ra = aad.bottleneck
-        if len(kinds) != 1:
-            raise MB200Error("all blocks must carry the same adapter configuration")
-        mk, ak = kinds.pop()
-        for name, p in self.named_parameters():
-            if "adapter" not in name and (p.dtype != torch.bfloat16 or p.device.type != self._device.type):
-                raise MB200Error(f"frozen LM parameter {name} must be bf16 on {self._device} (got {p.dtype}, {p.device})")
-        m = GptjModelC()
-        m.n_layer, m.d, m.n_head, m.rotary_dim = n, cfg.hidden_size, cfg.num_heads, cfg.rotary_dim
-        m.vocab, m.d_ff = self.lm_head.weight.shape[0], cfg.intermediate_size
-        m.mlp_adapter, m.mlp_adapter_r, m.attn_adapter, m.attn_adapter_r = mk, rm, ak, ra
-        m.ln_eps = cfg.layer_norm_epsilon
-        m.layers = ctypes.cast(layers, ctypes.POINTER(GptjLayerC))
-        m.lnf_g, m.lnf_b = self.transformer.ln_f.weight.data_ptr(), self.transformer.ln_f.bias.data_ptr()
-        m.w_lm, m.b_lm = self.lm_head.weight.data_ptr(), self.lm_head.bias.data_ptr()
-        self._cmodel_cache = (m, layers)
-        return self._cmodel_cache
-
     def invalidate(self):
         """Call after replacing parameters/modules (e.g. add_adapters) so the C model struct is rebuilt."""
-        self._cmodel_cache = None
         self._cmodel_ex_cache = None
         if self._own_arena:
             self._arena = None
-
-    def _workspace(self, B, S, S_kv, training):
-        key = (B, S, S_kv, int(training))
-        if key not in self._ws:
-            m, _ = self._cmodel()
-            nbytes = lib().mb200_gptj_workspace_bytes(ctypes.byref(m), B, S, S_kv, int(training))
-            if nbytes == 0:
-                raise MB200Error(lib().mb200_last_error().decode())
-            if training:  # only one training workspace is kept alive
-                for k in [k for k in self._ws if k[3] == 1]:
-                    del self._ws[k]
-            self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
-        return self._ws[key]
 
     @property
     def ldv(self):
@@ -444,38 +358,11 @@ class B200GPTJForCausalLM(nn.Module):
         x = x.to(torch.bfloat16).contiguous()
         if self._arena is not None or self.adapter_parameters():
             self._ensure_arena().sync_shadow()
-        if self._general_schedule():
-            return self._run_forward_general(x, labels, training, cache, last_only, want_hidden, want_logits)
-        m, _ = self._cmodel()
-        V, ldv = self.lm_head.weight.shape[0], self.ldv
-        S_kv = cache.S_max if cache is not None else S
-        ws = self._workspace(B, S, S_kv, training)
-        rows = B if last_only else B * S
-        logits = torch.empty(rows, ldv, dtype=torch.bfloat16, device=x.device) if want_logits else None
-        loss = torch.zeros(1, dtype=torch.float32, device=x.device) if labels is not None else None
-        hidden = torch.empty(rows, d, dtype=torch.bfloat16, device=x.device) if want_hidden else None
-        if labels is not None:
-            labels = labels.to(device=x.device, dtype=torch.int64).contiguous()
-        if training:
-            self._generation += 1
-        check(lib().mb200_gptj_forward(
-            ctypes.byref(m), ops._ptr(x), ops._ptr(labels), ops._ptr(logits), ctypes.c_int64(ldv), int(last_only),
-            ops._ptr(loss), ops._ptr(hidden), ops._ptr(cache.k) if cache is not None else None,
-            ops._ptr(cache.v) if cache is not None else None, S_kv if cache is not None else 0,
-            cache.pos if cache is not None else 0, B, S, int(training), ops._ptr(ws), ctypes.c_size_t(ws.numel()),
-            ops._stream()))
-        if cache is not None:
-            cache.pos += S
-        self._last_hidden = hidden
-        lg = None
-        if logits is not None:
-            lg = logits.view(B, 1 if last_only else S, ldv)[..., :V]
-        return (loss.squeeze(0) if loss is not None else None), lg
+        return self._run_pass(x, labels, training, cache, last_only, want_hidden, want_logits)
 
-    def _run_forward_general(self, x, labels, training, cache, last_only, want_hidden, want_logits):
-        """csrc/gptj_sched.cu (adapters with add_layernorm / adapter_scale, or MB200_FORCE_GENERAL): the training pass
-        (activations saved for backward) when a loss is asked for, else the inference pass — full sequence, KV-cache
-        prefill / decode step, last-position logits, ln_f output."""
+    def _run_pass(self, x, labels, training, cache, last_only, want_hidden, want_logits):
+        """csrc/gptj_sched.cu: the training pass (activations saved for backward) when a loss is asked for, else the
+        inference pass — full sequence, KV-cache prefill / decode step, last-position logits, ln_f output."""
         B, S, d = x.shape
         m = self._cmodel_ex()[0]
         V, ldv = self.lm_head.weight.shape[0], self.ldv
@@ -495,13 +382,15 @@ class B200GPTJForCausalLM(nn.Module):
             lg = logits.view(B, S, ldv)[..., :V] if logits is not None else None
             return (loss.squeeze(0) if loss is not None else None), lg
         S_kv = cache.S_max if cache is not None else S
-        key = ("ex_infer", B, S, S_kv)
-        if key not in self._ws:
-            nbytes = lib().mb200_gptj_sched_infer_workspace_bytes(ctypes.byref(m), B, S, S_kv)
-            if nbytes == 0:
-                raise MB200Error(lib().mb200_last_error().decode())
-            self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
-        ws = self._ws[key]
+        # ONE grow-only inference workspace: a serving process sees many (B, prompt length, cache length) combinations,
+        # and the C side only needs `nbytes` of scratch for the pass at hand (nothing survives between calls)
+        nbytes = lib().mb200_gptj_sched_infer_workspace_bytes(ctypes.byref(m), B, S, S_kv)
+        if nbytes == 0:
+            raise MB200Error(lib().mb200_last_error().decode())
+        ws = self._ws.get("infer")
+        if ws is None or ws.numel() < nbytes:
+            self._ws.pop("infer", None)
+            ws = self._ws["infer"] = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
         rows = B if last_only else B * S
         logits = torch.empty(rows, ldv, dtype=torch.bfloat16, device=x.device) if want_logits else None
         hidden = torch.empty(rows, d, dtype=torch.bfloat16, device=x.device) if want_hidden else None
@@ -518,32 +407,15 @@ class B200GPTJForCausalLM(nn.Module):
 
     def _run_backward(self, shape, loss_scale):
         B, S, d = shape
-        if self._general_schedule():
-            arena = self._arena
-            dx = torch.empty(B, S, d, dtype=torch.bfloat16, device=self._device)
-            ws = self._workspace_ex(B, S)
-            accumulate = int(arena.grads_live())
-            for hi, lo in (self._bwd_chunks or [(len(self.transformer.h), 0)]):
-                check(lib().mb200_gptj_sched_backward_range(ctypes.byref(self._cmodel_ex()[0]),
-                                                            ops._ptr(dx) if lo == 0 else None, ctypes.c_float(loss_scale),
-                                                            hi, lo, accumulate, B, S, ops._ptr(ws),
-                                                            ctypes.c_size_t(ws.numel()), ops._stream()))
-                if self._after_chunk is not None:
-                    self._after_chunk(hi, lo)
-            if self._own_arena:
-                arena.publish_grads()
-            return dx
-        m, _ = self._cmodel()
-        ws = self._workspace(B, S, S, True)
         arena = self._arena
-        accumulate = int(arena.grads_live()) if arena is not None else 0
         dx = torch.empty(B, S, d, dtype=torch.bfloat16, device=self._device)
-        n = len(self.transformer.h)
-        chunks = self._bwd_chunks or [(n, 0)]
-        for hi, lo in chunks:
-            check(lib().mb200_gptj_backward(ctypes.byref(m), ops._ptr(dx) if lo == 0 else None,
-                                            ctypes.c_float(loss_scale), hi, lo, accumulate, B, S, ops._ptr(ws),
-                                            ctypes.c_size_t(ws.numel()), ops._stream()))
+        ws = self._workspace_ex(B, S)
+        accumulate = int(arena.grads_live()) if arena is not None else 0
+        for hi, lo in (self._bwd_chunks or [(len(self.transformer.h), 0)]):
+            check(lib().mb200_gptj_sched_backward_range(ctypes.byref(self._cmodel_ex()[0]),
+                                                        ops._ptr(dx) if lo == 0 else None, ctypes.c_float(loss_scale),
+                                                        hi, lo, accumulate, B, S, ops._ptr(ws),
+                                                        ctypes.c_size_t(ws.numel()), ops._stream()))
             if self._after_chunk is not None:
                 self._after_chunk(hi, lo)
         if arena is not None and self._own_arena:

@@ -426,6 +426,35 @@ def attn_fwd_tile(qkv, B, S, H, hd):
     return O, P
 
 
+def attn_fwd_flash(qkv, B, S, H, hd, causal=True, want_p=False, want_stats=False, kcache=None, vcache=None, pos0=0):
+    """Multi-tile attention forward for any sequence length (mb200_attn_fwd_flash). qkv: bf16 [B*S, 3*H*hd] (already
+    rotated) supplies the queries and — without a cache — the keys / values. With kcache / vcache ([B, H, Smax, hd],
+    positions [0, pos0 + S) valid) the keys / values come from the cache (prefill continuation: queries are the last S
+    of the pos0 + S positions). Returns O [B*S, H*hd] (+ P [B, H, S, ldP]) (+ stats [B, H, S, 2])."""
+    d = H * hd
+    Sk = pos0 + S if kcache is not None else S
+    O = torch.empty(B * S, d, dtype=torch.bfloat16, device=qkv.device)
+    ldP = (Sk + 7) // 8 * 8
+    P = torch.empty(B, H, S, ldP, dtype=torch.bfloat16, device=qkv.device) if want_p else None
+    stats = torch.empty(B, H, S, 2, dtype=torch.float32, device=qkv.device) if want_stats else None
+    ld = qkv.stride(0)
+    if kcache is not None:
+        Smax = kcache.shape[2]
+        kk, vv, ldk, bsh, bsb = kcache.data_ptr(), vcache.data_ptr(), hd, Smax * hd, H * Smax * hd
+    else:
+        kk, vv, ldk, bsh, bsb = qkv.data_ptr() + 2 * d, qkv.data_ptr() + 4 * d, ld, hd, S * ld
+    c64, vp = ctypes.c_int64, ctypes.c_void_p
+    check(lib().mb200_attn_fwd_flash(_ptr(qkv), c64(ld), c64(hd), c64(S * ld), vp(kk), c64(ldk), c64(bsh), c64(bsb),
+                                     vp(vv), c64(ldk), c64(bsh), c64(bsb), _ptr(O), c64(d), _ptr(P), c64(ldP),
+                                     _ptr(stats), B, S, Sk, H, hd, int(bool(causal)), _stream()))
+    out = (O,)
+    if want_p:
+        out += (P,)
+    if want_stats:
+        out += (stats,)
+    return out if len(out) > 1 else O
+
+
 def attn_bwd_tile(qkv, dO, P, B, S, H, hd, rope_tab=None, rot=0):
     """Backward of attn_fwd_tile -> dqkv [B*S, 3*H*hd] (inverse rotary applied to dq, dk when rope_tab is given)."""
     dqkv = torch.empty_like(qkv)

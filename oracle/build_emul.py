@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — builds oracle/_build/libsched_emul.so: the product's host-only schedule files
-(magma_b200/csrc/vit_train.cu and gptj_sched.cu — no kernels, no CUDA calls, see magma_b200/csrc/sched_rt.h — and the host
-schedule of engine.cu, whose kernels sit behind #ifdef __CUDACC__), compiled as plain C++ and linked against oracle/cabi_emul.cpp, the CPU emulation of the primitive C-ABI operators.
+(magma_b200/csrc/vit_sched.cu and gptj_sched.cu — no kernels, no CUDA calls, see magma_b200/csrc/sched_rt.h), compiled as
+plain C++ and linked against oracle/cabi_emul.cpp, the CPU emulation of the primitive C-ABI operators.
 tests/test_sched_emul_cpu.py loads it to dry-run the schedules against the oracle. Nothing in magma_b200/ uses it."""
 import os
 import subprocess
@@ -8,17 +8,12 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT_DIR = os.path.join(ROOT, "oracle", "_build")
 OUT = os.path.join(OUT_DIR, "libsched_emul.so")
-SCHEDULES = [os.path.join(ROOT, "magma_b200", "csrc", "vit_train.cu"),
+SCHEDULES = [os.path.join(ROOT, "magma_b200", "csrc", "vit_sched.cu"),
              os.path.join(ROOT, "magma_b200", "csrc", "gptj_sched.cu")]
-# engine.cu (the fast runtime) has kernels, but they sit behind #ifdef __CUDACC__: its HOST schedule compiles as plain
-# C++ too, with the few CUDA runtime calls it makes mapped onto host memory operations (emul_cuda_shim.h)
-ENGINE = os.path.join(ROOT, "magma_b200", "csrc", "engine.cu")
-SHIM = os.path.join(ROOT, "oracle", "emul_cuda_shim.h")
 EMUL = os.path.join(ROOT, "oracle", "cabi_emul.cpp")
-EMUL_ENGINE = os.path.join(ROOT, "oracle", "cabi_emul_engine.cpp")  # internal symbols engine.cu links against
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"   # headers only (types, cudaStream_t)
-DEPS = SCHEDULES + [ENGINE, SHIM, EMUL, EMUL_ENGINE, os.path.join(ROOT, "magma_b200", "csrc", "sched_rt.h"),
-                    os.path.join(ROOT, "magma_b200", "csrc", "common.cuh"), os.path.join(ROOT, "include", "magma_b200.h")]
+DEPS = SCHEDULES + [EMUL, os.path.join(ROOT, "magma_b200", "csrc", "sched_rt.h"),
+                    os.path.join(ROOT, "include", "magma_b200.h")]
 
 
 def build(force=False):
@@ -27,7 +22,7 @@ def build(force=False):
         return OUT
     objs = []
     common = ["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-I", CUDA_INC, "-c"]
-    jobs = [(src, []) for src in SCHEDULES + [EMUL, EMUL_ENGINE]] + [(ENGINE, ["-include", SHIM])]
+    jobs = [(src, []) for src in SCHEDULES + [EMUL]]
     for src, extra in jobs:
         obj = os.path.join(OUT_DIR, os.path.basename(src).rsplit(".", 1)[0] + ".o")
         r = subprocess.run(common + extra + ["-x", "c++", src, "-o", obj], capture_output=True, text=True)

@@ -690,6 +690,60 @@ int mb200_attn_fwd_tile(const void* qkv_, int64_t ld, void* P_, int64_t ldP, voi
   return 0;
 }
 
+// multi-tile forward (csrc/attention.cu: attn_fwd_flash_kernel): any Sq / Sk, causal with key offset Sk - Sq or not;
+// fp32 scores, softmax over the whole key row, probabilities rounded to bf16 before P V; optional saved P [B,H,Sq,ldP]
+// (columns Sk..ldP zero) and per-row (max, 1 / sum) statistics
+int mb200_attn_fwd_flash(const void* q_, int64_t ldq, int64_t q_bsh, int64_t q_bsb, const void* k_, int64_t ldk,
+                         int64_t k_bsh, int64_t k_bsb, const void* v_, int64_t ldv, int64_t v_bsh, int64_t v_bsb, void* O_,
+                         int64_t ldo, void* P_, int64_t ldP, float* stats, int32_t B, int32_t Sq, int32_t Sk, int32_t H,
+                         int32_t hd, int32_t causal, void*) {
+  EM_TRACE(4.0 * B * H * Sq * (double)Sk * hd,  // algorithmic count (QK^T once, full rectangle), like attn_fwd_tile
+           (double)B * H * (2.0 * Sq + 2.0 * Sk) * hd * 2 + (P_ ? (double)B * H * Sq * ldP * 2 : 0.0),
+           "attn_fwd_flash\tB=%d Sq=%d Sk=%d H=%d hd=%d causal=%d", B, Sq, Sk, H, hd, causal);
+  EM_REQUIRE(hd >= 64 && hd <= 256 && hd % 64 == 0 && Sq >= 1 && Sk >= 1, MB200_E_SHAPE,
+             "attn_fwd_flash: unsupported Sq=%d Sk=%d hd=%d", Sq, Sk, hd);
+  EM_REQUIRE(!causal || Sk >= Sq, MB200_E_SHAPE, "attn_fwd_flash: causal needs Sk >= Sq");
+  EM_REQUIRE(P_ == nullptr || (ldP % 8 == 0 && ldP >= Sk), MB200_E_ALIGN, "attn_fwd_flash: ldP must be >= Sk and %%8");
+  const bf16_t *Q = (const bf16_t*)q_, *K = (const bf16_t*)k_, *V = (const bf16_t*)v_;
+  bf16_t *O = (bf16_t*)O_, *P = (bf16_t*)P_;
+  const float scale = 1.f / sqrtf((float)hd);
+  const int off = Sk - Sq;
+  std::vector<float> sc(Sk);
+  std::vector<bf16_t> pr(Sk);
+  for (long long b = 0; b < B; ++b)
+    for (long long h = 0; h < H; ++h)
+      for (int i = 0; i < Sq; ++i) {
+        const bf16_t* q = Q + b * q_bsb + h * q_bsh + (long long)i * ldq;
+        const int lim = causal ? (i + off + 1 < Sk ? i + off + 1 : Sk) : Sk;
+        float m = -INFINITY, sum = 0.f;
+        for (int j = 0; j < lim; ++j) {
+          const bf16_t* k = K + b * k_bsb + h * k_bsh + (long long)j * ldk;
+          float acc = 0.f;
+          for (int c = 0; c < hd; ++c) acc += b2f(q[c]) * b2f(k[c]);
+          sc[j] = acc * scale;
+          m = fmaxf(m, sc[j]);
+        }
+        for (int j = 0; j < lim; ++j) sum += expf(sc[j] - m);
+        const float inv = 1.f / sum;
+        for (int j = 0; j < Sk; ++j) pr[j] = f2b(j < lim ? expf(sc[j] - m) * inv : 0.f);
+        if (P) {
+          bf16_t* prow = P + ((b * H + h) * Sq + i) * ldP;
+          for (int j = 0; j < ldP; ++j) prow[j] = j < Sk ? pr[j] : f2b(0.f);
+        }
+        if (stats) {
+          stats[2 * ((b * H + h) * Sq + i)] = m;
+          stats[2 * ((b * H + h) * Sq + i) + 1] = inv;
+        }
+        bf16_t* o = O + (b * Sq + i) * ldo + h * hd;
+        for (int c = 0; c < hd; ++c) {
+          float acc = 0.f;
+          for (int j = 0; j < lim; ++j) acc += b2f(pr[j]) * b2f(V[b * v_bsb + h * v_bsh + (long long)j * ldv + c]);
+          o[c] = f2b(acc);
+        }
+      }
+  return 0;
+}
+
 int mb200_attn_bwd_tile(const void* qkv_, int64_t ld, const void* dO_, int64_t ld_do, const void* P_, int64_t ldP,
                         void* dqkv_, int64_t ldd, const float* rope_tab, int32_t rot, int32_t B, int32_t S, int32_t H,
                         int32_t hd, void*) {

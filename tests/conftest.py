@@ -48,7 +48,7 @@ def emul_ops(monkeypatch):
     L.mb200_last_error.restype = ctypes.c_char_p
     L.mb200_version.restype = ctypes.c_int
     L.mb200_launch_count.restype = ctypes.c_longlong
-    for fn in ("mb200_gptj_workspace_bytes", "mb200_vit_workspace_bytes", "mb200_vit_train_workspace_bytes",
+    for fn in ("mb200_vit_workspace_bytes", "mb200_vit_train_workspace_bytes", "mb200_gptj_sched_infer_workspace_bytes",
                "mb200_gptj_sched_workspace_bytes"):
         getattr(L, fn).restype = ctypes.c_size_t
     monkeypatch.setattr(_lib, "_lib", L)

@@ -1,11 +1,11 @@
 """Replay of the DEFAULT paths on the CPU. The GPU parity harness itself (tools/model_check.py groups lm, lm_variants,
 vit, resnet, magma, generate — what tests/test_model_gpu.py runs on a B200), the reference-golden tests of that file and
-__graft_entry__.smoke() are executed here on CPU tensors. What runs is the product's own code: its Python, and the HOST
-SCHEDULE of csrc/engine.cu itself — compiled as plain C++ into the emulation library (its kernels sit behind
-#ifdef __CUDACC__; the nvcc-preprocessed file is byte-identical to the version without those guards) — issuing the
-primitive operators, which are what is emulated (oracle/cabi_emul.cpp). So a change to anything but a kernel — pointer
-tables, workspace carving, operand majors and strides, chunked backward, KV-cache prefill / decode, arena, engine — is
-caught without a GPU; the kernels themselves are verified by the `-m gpu` tests only."""
+__graft_entry__.smoke() are executed here on CPU tensors. What runs is the product's own code: its Python, and its
+HOST-ONLY C++ schedules (csrc/gptj_sched.cu, csrc/vit_sched.cu — no kernels, no CUDA calls) compiled as plain C++ into
+the emulation library, issuing the primitive operators, which are what is emulated (oracle/cabi_emul.cpp). So a change
+to anything but a kernel — pointer tables, workspace carving, operand majors and strides, chunked backward, KV-cache
+prefill / decode, arena, engine — is caught without a GPU; the kernels themselves are verified by the `-m gpu` tests
+only."""
 import pytest
 import torch
 
@@ -101,8 +101,6 @@ def test_generate_works_for_layernorm_and_scaled_adapters(replay, monkeypatch):
         w[f"{pre}.adapter.0.bias"] = (0.1 * torch.randn(cfg.d, generator=g)).to(torch.bfloat16).float()
         w[f"{pre}.adapter_scale"] = torch.tensor([0.5 + 0.25 * l])
     model, _ = E.build(monkeypatch, cfg, w, 16, freeze_enc=True, adapter_config={"mlp": dict(mlp, add_layernorm=True)})
-    model.lm._force_general = False
-    assert model.lm._general_schedule()          # selected by the adapter options themselves
     model.eval()
     emb = (torch.randn(2, 5, cfg.d, generator=g) * 0.5).to(torch.bfloat16)
     toks = model.generate(emb, max_steps=6, temperature=0.0, decode=False)

@@ -1,11 +1,8 @@
 """Whole-model dry run on the CPU: Magma.forward -> loss.backward() -> B200Engine.step() with the primitive operators
-emulated (fixture `emul_ops`) and the LM routed through the general host-only schedule (csrc/gptj_sched.cu, compiled
-into the emulation library). What runs here is the product's own Python — Magma / ImagePrefix / the trainable encoders /
+emulated (fixture `emul_ops`) and the LM running through its host-only schedule (csrc/gptj_sched.cu, compiled into the
+emulation library). What runs here is the product's own Python — Magma / ImagePrefix / the trainable encoders /
 ParamArena / B200Engine / checkpointing — and the two host-only C++ schedules; what is emulated are the kernels. The
-result is held to torch autograd of the oracle (oracle/magma_oracle.py::magma_forward).
-
-The LM goes through the general schedule here (`_force_general`); the fast runtime's own host schedule (engine.cu) is
-replayed in tests/test_default_path_replay_cpu.py."""
+result is held to torch autograd of the oracle (oracle/magma_oracle.py::magma_forward)."""
 import pytest
 import torch
 
@@ -45,7 +42,6 @@ def build(monkeypatch, cfg, w16, S, encoder="clip_vit_dry", freeze_enc=False, ad
         missing, unexpected = model.load_state_dict(w16, strict=False)
         missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
         assert not missing and not unexpected, (missing, unexpected)
-    model.lm._force_general = True        # the LM through csrc/gptj_sched.cu (the general schedule)
     model.lm.invalidate()
     model.lm.attach_arena(model.arena)
     model.image_prefix.enc.invalidate()
@@ -149,7 +145,6 @@ def test_magma_with_a_trainable_conv_trunk_trains(emul_ops, monkeypatch):
     model.lm.init_weights(seed=0)
     model.image_prefix.enc.init_weights(seed=1)
     model.finalize()
-    model.lm._force_general = True
     model.train()
     names = [n for n, p in model.named_parameters() if p.requires_grad]
     assert any("enc.layer4" in n for n in names) and any(n.endswith("bn1.weight") for n in names)
@@ -279,12 +274,11 @@ def test_magma_with_layernorm_and_scaled_adapters_end_to_end(emul_ops, monkeypat
     ac = {"mlp": dict(mlp, add_layernorm=True), "attention": dict(attn, add_layernorm=True)}
     model, mc = build(monkeypatch, cfg, w, S, freeze_enc=True, adapter_config=ac)
     model.eval()
-    assert model.lm._general_schedule()
     names = [n for n, p in model.named_parameters() if p.requires_grad]
     assert any(n.endswith("adapter_scale") for n in names) and any(n.endswith("adapter.0.weight") for n in names)
     images, captions = O.synthetic_batch(cfg, B, S, seed=11)
     images = images.to(torch.bfloat16).float()
-    # the frozen ViT forward lives in engine.cu (GPU only): feed the oracle's prefix embeddings instead of images
+    # the LM is what this test is about: feed the oracle's prefix embeddings instead of images
     with torch.no_grad():
         prefix = O.image_prefix(images, w, cfg).to(torch.bfloat16)
     params = {k: v.clone().requires_grad_(k in names) for k, v in w.items()}

@@ -375,7 +375,7 @@ def test_launch_plan_trace_of_a_full_size_step():
 
     rows = plan_trace.train_step_plan(8, 128)
     gemms = [r for r in rows if r["op"] == "gemm"]
-    assert 700 < len(rows) < 900 and len(gemms) > 500
+    assert 650 < len(rows) < 900 and len(gemms) > 450
     tflop = sum(r["flops"] for r in rows) / 1e12
     want = 8 * (2 * 1.5635 + 0.0601 + 0.1620)          # SURVEY.md §8d, per sample -> per step of 8
     assert abs(tflop - want) / want < 0.03, (tflop, want)

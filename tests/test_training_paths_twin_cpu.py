@@ -16,7 +16,7 @@ REPLAYABLE = [
     "test_encoder_learning_rate_group_and_weight_decay_exemptions",
     "test_frozen_vit_is_unchanged_by_the_training_path",
     "test_engine_checkpoint_resume_continues_the_same_trajectory",
-    "test_general_schedule_agrees_with_the_fast_runtime",
+    "test_fused_attention_paths_agree_with_the_batched_gemm_path",
     "test_preprocess_inputs_image_and_text_to_embeddings",
 ]
 

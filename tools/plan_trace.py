@@ -1,6 +1,6 @@
 """Launch plan of a full-size pass, produced WITHOUT a GPU by the product's own schedule code.
 
-The host schedules (csrc/engine.cu, gptj_sched.cu, vit_train.cu) are compiled as plain C++ into the CPU emulation library
+The host schedules (csrc/gptj_sched.cu, vit_sched.cu) are compiled as plain C++ into the CPU emulation library
 (oracle/build_emul.py). With the emulation's trace mode on, every primitive logs (operator, shape, algorithmic FLOPs and
 bytes) and returns without touching memory, so the schedule can be "issued" at BASELINE.json's sizes — GPT-J-6B, B = 8,
 S = 128 — with placeholder pointers in milliseconds. The result is the exact list of launches a step makes, which this
@@ -27,7 +27,7 @@ FAKE = 0x10000000  # placeholder "device pointer": never dereferenced while the 
 
 
 def gptj_model(L, d, H, rot, V, r, n_layer=28):
-    from magma_b200._lib import GptjLayerC, GptjModelC
+    from magma_b200._lib import GptjLayerExC as GptjLayerC, GptjModelExC as GptjModelC
 
     layers = (GptjLayerC * n_layer)()
     for l in range(n_layer):
@@ -68,7 +68,7 @@ def trace(fn):
 
     L = ctypes.CDLL(build_emul.build())
     L.mb200_last_error.restype = ctypes.c_char_p
-    for f in ("mb200_gptj_workspace_bytes", "mb200_vit_workspace_bytes"):
+    for f in ("mb200_gptj_sched_workspace_bytes", "mb200_gptj_sched_infer_workspace_bytes", "mb200_vit_workspace_bytes"):
         getattr(L, f).restype = ctypes.c_size_t
     with tempfile.NamedTemporaryFile("r", suffix=".trace", delete=False) as t:
         path = t.name
@@ -99,11 +99,11 @@ def train_step_plan(B, S):
         ws = ctypes.c_void_p(FAKE)
         n = L.mb200_vit_workspace_bytes(ctypes.byref(vm), B)
         check(L, L.mb200_vit_forward(ctypes.byref(vm), FAKE, FAKE, B, ws, ctypes.c_size_t(n), None))
-        n = L.mb200_gptj_workspace_bytes(ctypes.byref(gm), B, S, S, 1)
-        check(L, L.mb200_gptj_forward(ctypes.byref(gm), FAKE, FAKE, None, ctypes.c_int64(0), 0, FAKE, None, None, None, 0, 0,
-                                      B, S, 1, ws, ctypes.c_size_t(n), None))
-        check(L, L.mb200_gptj_backward(ctypes.byref(gm), FAKE, ctypes.c_float(1.0), 28, 0, 0, B, S, ws, ctypes.c_size_t(n),
-                                       None))
+        n = L.mb200_gptj_sched_workspace_bytes(ctypes.byref(gm), B, S)
+        check(L, L.mb200_gptj_sched_forward(ctypes.byref(gm), FAKE, FAKE, None, ctypes.c_int64(0), FAKE, B, S, ws,
+                                            ctypes.c_size_t(n), None))
+        check(L, L.mb200_gptj_sched_backward(ctypes.byref(gm), FAKE, ctypes.c_float(1.0), 0, B, S, ws, ctypes.c_size_t(n),
+                                             None))
 
     return trace(issue)
 
@@ -114,9 +114,9 @@ def decode_step_plan(B, pos, S_max=264):
 
     def issue(L):
         ws = ctypes.c_void_p(FAKE)
-        n = L.mb200_gptj_workspace_bytes(ctypes.byref(gm), B, 1, S_max, 0)
-        check(L, L.mb200_gptj_forward(ctypes.byref(gm), FAKE, None, FAKE, ctypes.c_int64(50304), 1, None, None, FAKE, FAKE,
-                                      S_max, pos, B, 1, 0, ws, ctypes.c_size_t(n), None))
+        n = L.mb200_gptj_sched_infer_workspace_bytes(ctypes.byref(gm), B, 1, S_max)
+        check(L, L.mb200_gptj_sched_infer(ctypes.byref(gm), FAKE, FAKE, ctypes.c_int64(50304), 1, None, FAKE, FAKE, S_max,
+                                          pos, B, 1, ws, ctypes.c_size_t(n), None))
 
     return trace(issue)
 
