@@ -92,7 +92,9 @@ typedef struct {
   int64_t ld;
   int64_t bs0, bs1;
   int32_t mn_major;
-  int32_t _pad;
+  int32_t static_data; /* != 0: no kernel of the surrounding stream writes this operand's memory (frozen weights).
+                        * A B operand so marked has its first tiles fetched while the launch is still waiting for its
+                        * programmatic dependency (PDL), i.e. under the tail of the previous kernel. 0 is always safe. */
 } mb200_operand;
 
 typedef struct {

@@ -23,7 +23,7 @@ class Operand(ctypes.Structure):
         ("bs0", ctypes.c_int64),
         ("bs1", ctypes.c_int64),
         ("mn_major", ctypes.c_int32),
-        ("_pad", ctypes.c_int32),
+        ("static_data", ctypes.c_int32),
     ]
 
 

@@ -634,7 +634,7 @@ static int tile_map(CUtensorMap* m, const void* ptr, long long ld, long long bs0
   op.bs0 = bs0;
   op.bs1 = bs1;
   op.mn_major = 0;
-  op._pad = 0;
+  op.static_data = 0;
   return make_operand_map(m, op, rows, cols, H, B, 128);
 }
 

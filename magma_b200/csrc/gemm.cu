@@ -24,7 +24,7 @@ namespace mb200 {
 template <int BN, bool A_MN, bool B_MN, typename OutT, int AROWS = BM>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmKernelParams p) {
+                    const __grid_constant__ GemmKernelParams p) {
   static_assert(AROWS == BM || !A_MN, "the 32-row A ring is only implemented for K-major A");
   using C_ = Cfg<BN, AROWS>;
   constexpr int kStages = C_::kStages;
@@ -352,6 +352,29 @@ int make_operand_map(CUtensorMap* out, const mb200_operand& op, int rows, int K,
   return 0;
 }
 
+// rank-4 tensor map over an output (C / aux_out) for the TMA-store epilogue: dims (N, M, nb0, nb1), box = one
+// [128 rows x 128 bytes] SWIZZLE_128B staging slot (64 bf16 or 32 fp32 columns). Stores are clipped at N and M.
+int make_store_map(CUtensorMap* out, const void* ptr, bool f32, int N, int M, int nb0, int nb1, long long ld,
+                   long long bs0, long long bs1) {
+  PFN_encodeTiled enc = get_encode_fn();
+  MB_REQUIRE(enc != nullptr, MB200_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const long long esz = f32 ? 4 : 2;
+  MB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0 &&
+                 (nb0 == 1 || (bs0 * esz) % 16 == 0) && (nb1 == 1 || (bs1 * esz) % 16 == 0),
+             MB200_E_ALIGN, "gemm output must be 16B aligned in pointer, row stride and batch strides");
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)nb0, (cuuint64_t)nb1};
+  cuuint64_t strides[3] = {(cuuint64_t)(ld * esz), (cuuint64_t)((nb0 > 1 ? bs0 : ld) * esz),
+                           (cuuint64_t)((nb1 > 1 ? bs1 : ld) * esz)};
+  cuuint32_t box[4] = {(cuuint32_t)(f32 ? 32 : 64), 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MB_REQUIRE(r == CUDA_SUCCESS, MB200_E_CUDA, "cuTensorMapEncodeTiled (output) failed (%d): N=%d M=%d ld=%lld", (int)r, N, M,
+             ld);
+  return 0;
+}
+
 template <int BN, bool A_MN, bool B_MN, typename OutT, int AROWS = BM>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& kp,
                        cudaStream_t stream) {
@@ -578,6 +601,14 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
 
   const bool amn = a->A.mn_major != 0, bmn = a->B.mn_major != 0;
   const bool f32 = a->c_dtype == MB200_F32;
+  {
+    static int preload = -1;
+    if (preload < 0) {
+      const char* e = getenv("MB200_B_PRELOAD");  // 0 = never fetch weight tiles ahead of the PDL wait (A/B switch)
+      preload = e ? atoi(e) : 1;
+    }
+    kp.b_static = (a->B.static_data != 0 && preload) ? 1 : 0;
+  }
   kp.split_k = 1;
   kp.kb_per_split = (a->K + BK - 1) / BK;
   kp.splitk_ws = nullptr;
@@ -652,7 +683,19 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
     if (rc) return rc;
     kp.tiles_m = (a->M + 255) / 256;  // cluster tiles along M
     kp.total_tiles = kp.tiles_m * kp.tiles_n * a->nb0 * a->nb1;
-    return launch_gemm2(tmA, tmB, kp, amn, bmn, f32, stream);
+    // the rotary epilogue of the row-per-thread path works on whole 32-column chunks
+    if (kp.epi_kind == EK_ROPE && (a->rope_hd % 32 != 0 || a->rope_rot % 32 != 0 || a->rope_ncols % 32 != 0))
+      kp.epi_kind = EK_GENERIC;
+    CUtensorMap tmC, tmAux;
+    rc = make_store_map(&tmC, a->C, f32, a->N, a->M, a->nb0, a->nb1, a->ldc, a->c_bs0, a->c_bs1);
+    if (rc) return rc;
+    if (a->aux_out) {
+      rc = make_store_map(&tmAux, a->aux_out, false, a->N, a->M, a->nb0, a->nb1, a->ldc, a->c_bs0, a->c_bs1);
+      if (rc) return rc;
+    } else {
+      tmAux = tmC;
+    }
+    return launch_gemm2(tmA, tmB, tmC, tmAux, kp, amn, bmn, f32, stream);
   }
   if (small_m) {
     switch (bn) {

@@ -12,8 +12,9 @@
 //     expect_tx for the bytes of both CTAs;
 //   * only the leader issues MMAs; tcgen05.commit .multicast::cluster releases the smem slot in BOTH CTAs and
 //     publishes the accumulator to BOTH CTAs' epilogue warps;
-//   * each CTA's epilogue drains its own 128 TMEM lanes (same fused epilogue as the 1-CTA kernel) and arrives on the
-//     leader's tmem_empty barrier (the peer through mapa / mbarrier.arrive.shared::cluster).
+//   * each CTA's epilogue drains its own 128 TMEM lanes — epilogue v3 (gemm_common.cuh): row-per-thread fused
+//     arithmetic, SWIZZLE_128B staging, output by TMA store / reduce-add — and arrives on the leader's tmem_empty
+//     barrier (the peer through mapa / mbarrier.arrive.shared::cluster).
 #include "gemm_common.cuh"
 
 namespace mb200 {
@@ -30,7 +31,8 @@ static constexpr int kSmem2 = kStages2 * kStage2 + kEpi2 + 1024 + 256;
 template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const GemmKernelParams p) {
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
+                     const __grid_constant__ GemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -53,6 +55,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmC);
+    if (p.aux_out) tma_prefetch_desc(&tmAux);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's: one arrive.expect_tx by the leader's producer (+ tx bytes of both CTAs)
@@ -69,13 +75,39 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_wait();
+  // PDL: every thread that touches global memory written by earlier kernels waits for them (griddepcontrol.wait) —
+  // the producer before its first A load, the epilogue warps before their first residual load / store. The MMA
+  // issuer only reads shared memory and TMEM.
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // Frozen weights are not produced by any kernel of the stream: the B halves of the first ring stages are requested
+      // NOW, while this launch still waits for its predecessor, so the first HBM round trip (~1.5 us of weights the L2
+      // has never seen) is not added to the exposed start-up of every GEMM.
+      int npre = 0;
+      if (p.b_static && cid < p.total_tiles) {
+        const int tpb = p.tiles_m * p.tiles_n;
+        const int z = cid / tpb;
+        const int r = cid - z * tpb;
+        const int n_row = (r / p.tiles_m) * BN2 + (int)rank * HB;
+        const int z0 = z % p.nb0, z1 = z / p.nb0;
+        npre = num_kb < kStages2 ? num_kb : kStages2;
+        for (int kb = 0; kb < npre; ++kb) {
+          if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * kStage2);
+          uint8_t* sb = smem_b + kb * kB2;
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int i = 0; i < HB / 64; ++i)
+              tma_load_4d_2sm(sb + i * 8192, &tmB, &full_bar[kb], n_row + i * 64, kb * BK, z0, z1);
+          } else {
+            tma_load_4d_2sm(sb, &tmB, &full_bar[kb], kb * BK, n_row, z0, z1);
+          }
+        }
+      }
+      pdl_wait();
       for (int t = cid; t < p.total_tiles; t += ncl) {
         const int tpb = p.tiles_m * p.tiles_n;
         const int z = t / tpb;
@@ -84,8 +116,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int n_row = (r / p.tiles_m) * BN2 + (int)rank * HB;
         const int z0 = z % p.nb0, z1 = z / p.nb0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStage2);
+          const bool preloaded = t == cid && kb < npre;  // slot known free, expect_tx posted, B already in flight
+          if (!preloaded) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStage2);
+          }
           uint8_t* sa = smem_a + stage * kA2;
           uint8_t* sb = smem_b + stage * kB2;
           if constexpr (A_MN) {
@@ -95,12 +130,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           } else {
             tma_load_4d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM, z0, z1);
           }
-          if constexpr (B_MN) {
+          if (!preloaded) {
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int i = 0; i < HB / 64; ++i)
-              tma_load_4d_2sm(sb + i * 8192, &tmB, &full_bar[stage], n_row + i * 64, kb * BK, z0, z1);
-          } else {
-            tma_load_4d_2sm(sb, &tmB, &full_bar[stage], kb * BK, n_row, z0, z1);
+              for (int i = 0; i < HB / 64; ++i)
+                tma_load_4d_2sm(sb + i * 8192, &tmB, &full_bar[stage], n_row + i * 64, kb * BK, z0, z1);
+            } else {
+              tma_load_4d_2sm(sb, &tmB, &full_bar[stage], kb * BK, n_row, z0, z1);
+            }
           }
           if (++stage == kStages2) {
             stage = 0;
@@ -147,8 +184,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    pdl_wait();
     const int q = warp & 3;
     int it = 0;
+    uint32_t box = 0;  // boxes published so far (staging slot = box & 1)
     for (int t = cid; t < p.total_tiles; t += ncl, ++it) {
       const int tpb = p.tiles_m * p.tiles_n;
       const int z = t / tpb;
@@ -158,29 +197,48 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int z0 = z % p.nb0, z1 = z / p.nb0;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      EpiCtx c;
+      if (p.epi_kind == EK_GENERIC) {
+        // option combinations without a specialised instantiation: the v2 per-lane path (fp32 staging in the same pool)
+        EpiCtx c;
+        c.tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2);
+        c.stg_s = smem_u32(epi_stage + q * (32 * 64));
+        c.tmem_full = &tmem_full[acc];
+        c.tmem_empty = &tmem_empty[acc];
+        c.empty_remote = rank != 0;
+        c.ks = 0;
+        c.full_phase = acc_phase;
+        c.boff = (long long)z0 * p.c_bs0 + (long long)z1 * p.c_bs1;
+        c.row0 = m_blk * BM + q * 32;
+        c.nrows = max(0, min(32, p.M - c.row0));
+        c.n_blk = n_blk;
+        c.lane = lane;
+        epi_tile<BN2, 0, 0, 0, false, false, false, true, OutT>(p, c);
+        continue;
+      }
+      Epi3Ctx c;
       c.tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2);
-      c.stg_s = smem_u32(epi_stage + q * (32 * 64));
+      c.pool_s = smem_u32(epi_stage);
       c.tmem_full = &tmem_full[acc];
       c.tmem_empty = &tmem_empty[acc];
       c.empty_remote = rank != 0;
-      c.ks = 0;
       c.full_phase = acc_phase;
       c.boff = (long long)z0 * p.c_bs0 + (long long)z1 * p.c_bs1;
-      c.row0 = m_blk * BM + q * 32;
-      c.nrows = max(0, min(32, p.M - c.row0));
-      c.n_blk = n_blk;
+      c.row_cta0 = m_blk * BM;
+      c.q = q;
       c.lane = lane;
-#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM) epi_tile<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, false, OutT>(p, c)
+      c.n_blk = n_blk;
+      c.z0 = z0;
+      c.z1 = z1;
+      c.tmC = &tmC;
+      c.tmAux = &tmAux;
+#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM) epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT>(p, c, box)
       if constexpr (sizeof(OutT) == 4) {
         switch (p.epi_kind) {
-          case EK_PLAIN: MB_EPI(0, 0, 0, false, false, false); break;
           case EK_ACCUM: MB_EPI(0, 0, 0, false, false, true); break;
-          default: epi_tile<BN2, 0, 0, 0, false, false, false, true, OutT>(p, c); break;
+          default: MB_EPI(0, 0, 0, false, false, false); break;  // EK_PLAIN
         }
       } else {
         switch (p.epi_kind) {
-          case EK_PLAIN: MB_EPI(0, 0, 0, false, false, false); break;
           case EK_ROPE: MB_EPI(0, 0, 0, false, true, false); break;
           case EK_GELU: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, false, false, false); break;
           case EK_GELU_AUX: MB_EPI(MB200_ACT_GELU_NEW, 0, 0, true, false, false); break;
@@ -190,11 +248,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           case EK_DRELU: MB_EPI(0, MB200_DACT_RELU, 0, false, false, false); break;
           case EK_RES1: MB_EPI(0, 0, 1, false, false, false); break;
           case EK_RES2: MB_EPI(0, 0, 2, false, false, false); break;
-          default: epi_tile<BN2, 0, 0, 0, false, false, false, true, OutT>(p, c); break;
+          default: MB_EPI(0, 0, 0, false, false, false); break;  // EK_PLAIN
         }
       }
 #undef MB_EPI
     }
+    // the staging slots must outlive the bulk stores that read them, and the stores must have landed before the grid
+    // counts as complete for its dependents
+    if (q == 0 && lane == 0) tma_store_wait_all();
   }
 
   // neither CTA may exit (or free TMEM) while the pair still reads its shared memory / TMEM
@@ -207,7 +268,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <bool A_MN, bool B_MN, typename OutT>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& kp, cudaStream_t stream) {
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
+                   const GemmKernelParams& kp, cudaStream_t stream) {
   auto kern = gemm2_tcgen05_kernel<A_MN, B_MN, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -221,25 +283,25 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKer
     const double flops = 2.0 * kp.M * (double)kp.N * kp.K * nb;
     const double bytes = nb * (2.0 * ((double)kp.M * kp.K + (double)kp.N * kp.K) + (double)sizeof(OutT) * kp.M * kp.N);
     GemmProfScope prof(stream, flops, bytes);
-    MB_CUDA(launch_pdl(kern, dim3(clusters * 2), dim3(kThreads), kSmem2, stream, tmA, tmB, kp));
+    MB_CUDA(launch_pdl(kern, dim3(clusters * 2), dim3(kThreads), kSmem2, stream, tmA, tmB, tmC, tmAux, kp));
   }
   count_launch();
   MB_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& kp, bool a_mn, bool b_mn,
-                 bool f32, cudaStream_t stream) {
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
+                 const GemmKernelParams& kp, bool a_mn, bool b_mn, bool f32, cudaStream_t stream) {
   if (f32) {
-    if (!a_mn && !b_mn) return launch2<false, false, float>(tmA, tmB, kp, stream);
-    if (!a_mn && b_mn) return launch2<false, true, float>(tmA, tmB, kp, stream);
-    if (a_mn && !b_mn) return launch2<true, false, float>(tmA, tmB, kp, stream);
-    return launch2<true, true, float>(tmA, tmB, kp, stream);
+    if (!a_mn && !b_mn) return launch2<false, false, float>(tmA, tmB, tmC, tmAux, kp, stream);
+    if (!a_mn && b_mn) return launch2<false, true, float>(tmA, tmB, tmC, tmAux, kp, stream);
+    if (a_mn && !b_mn) return launch2<true, false, float>(tmA, tmB, tmC, tmAux, kp, stream);
+    return launch2<true, true, float>(tmA, tmB, tmC, tmAux, kp, stream);
   }
-  if (!a_mn && !b_mn) return launch2<false, false, bf16>(tmA, tmB, kp, stream);
-  if (!a_mn && b_mn) return launch2<false, true, bf16>(tmA, tmB, kp, stream);
-  if (a_mn && !b_mn) return launch2<true, false, bf16>(tmA, tmB, kp, stream);
-  return launch2<true, true, bf16>(tmA, tmB, kp, stream);
+  if (!a_mn && !b_mn) return launch2<false, false, bf16>(tmA, tmB, tmC, tmAux, kp, stream);
+  if (!a_mn && b_mn) return launch2<false, true, bf16>(tmA, tmB, tmC, tmAux, kp, stream);
+  if (a_mn && !b_mn) return launch2<true, false, bf16>(tmA, tmB, tmC, tmAux, kp, stream);
+  return launch2<true, true, bf16>(tmA, tmB, tmC, tmAux, kp, stream);
 }
 
 }  // namespace mb200

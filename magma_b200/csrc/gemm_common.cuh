@@ -62,6 +62,7 @@ struct GemmKernelParams {
   int split_k, kb_per_split;
   float* splitk_ws;
   long long ld_ws;
+  int b_static;  // B is never written by a kernel of this stream (frozen weights): its first tiles load before the PDL wait
 };
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, SWIZZLE_128B, version 1)
@@ -378,9 +379,311 @@ __device__ __forceinline__ void epi_tile(const GemmKernelParams& p, const EpiCtx
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Epilogue v3 (CTA-pair kernel): row-per-thread all the way, output through TMA.
+//
+// Measured on the v2 epilogue above (tools/epi_bench.py, profiles/r02_epi_bench_before.log): 6.7 us per 128x256 tile for
+// a plain bf16 store and 17-18 us with a residual or GELU + saved pre-activation — its phase 2 re-reads the tile from
+// shared memory transposed, one row pair per iteration behind a per-row branch, with generic-address global loads and
+// stores on the threads' critical path. A single-wave GEMM (64 tiles on 74 clusters: every N = 4096 shape of the GPT-J
+// block) pays all of that after its last MMA, and a short-K GEMM (ViT K = 1024, adapter up-projection) is bound by it.
+//
+// Here every epilogue thread keeps the accumulator row TMEM gave it: 32 columns at a time it applies
+// alpha / bias / rotary / activation / activation-derivative / residuals in registers, packs, and writes 16-byte chunks
+// into a SWIZZLE_128B staging slot (conflict-free: the 8 lanes of a quarter-warp hold 8 consecutive rows, whose XOR
+// patterns differ). When a slot holds a [128 rows x 128 bytes] box, one thread hands it to the TMA unit
+// (cp.async.bulk.tensor store; fp32 accumulate = cp.reduce ... add) and the threads move on — no global store, no
+// transposition, no per-row control flow. Inputs that are row-shaped (residuals, saved pre-activations) are read by the
+// owning thread as 64 contiguous bytes per 32 columns, issued one chunk ahead. Two 16 KB slots alternate; the only
+// synchronisation is one 128-thread named barrier per box.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+__device__ __forceinline__ uint4 ldg128(const void* ptr) {
+  uint4 u;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(ptr));
+  return u;
+}
+__device__ __forceinline__ void sts128u(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __bfloat1622float2(h[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f32x8_to_bf16(const float* v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+
+struct Epi3Ctx {
+  uint32_t tmem_acc;   // TMEM address of this warp's lanes, column 0 of the accumulator buffer
+  uint32_t pool_s;     // smem address of the CTA's 32 KB staging pool (1024-byte aligned): two 16 KB slots
+  uint64_t* tmem_full;
+  uint64_t* tmem_empty;
+  int empty_remote;
+  uint32_t full_phase;
+  long long boff;      // batch offset of this tile in C / aux / residuals (elements)
+  int row_cta0;        // first global row (within the batch) of this CTA's 128-row block
+  int q, lane;         // epilogue warp 0..3 (TMEM lane quarter), lane
+  int n_blk, z0, z1;
+  const CUtensorMap* tmC;
+  const CUtensorMap* tmAux;
+};
+
+// one [128 x 128-byte] box of the CTA's tile is complete in `slot`: make the generic-proxy writes visible to the TMA
+// unit, wait until the box stored TWO boxes ago has been read out (so that the other slot is free for the next writer),
+// meet, and let one thread issue the store
+template <bool ACCUM>
+__device__ __forceinline__ void epi3_publish(const Epi3Ctx& c, const CUtensorMap* tm, uint32_t slot_s, int col0,
+                                             bool elected) {
+  fence_proxy_async_smem();
+  if (elected) tma_store_wait_read0();
+  epi_bar_sync();
+  if (elected) {
+    if constexpr (ACCUM) tma_reduce_add_4d(tm, slot_s, col0, c.row_cta0, c.z0, c.z1);
+    else tma_store_4d(tm, slot_s, col0, c.row_cta0, c.z0, c.z1);
+    tma_store_commit();
+  }
+}
+
+// `box` counts the boxes this CTA has published so far (slot = box & 1); it lives across tiles.
+template <int BN, int ACT, int DACT, int NRES, bool AUX, bool ROPE, bool ACCUM, typename OutT>
+__device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi3Ctx& c, uint32_t& box) {
+  constexpr bool F32 = sizeof(OutT) == 4;
+  static_assert(!F32 || (!AUX && !ROPE && ACT == 0 && DACT == 0 && NRES == 0), "fp32 output: plain / accumulate only");
+  static_assert(!ACCUM || F32, "accumulate needs fp32 output");
+  constexpr int NIN = (DACT != 0 ? 1 : 0) + NRES;  // row-shaped bf16 inputs read by the owning thread
+  constexpr int NCH = BN / 32;
+  const int lane = c.lane;
+  const int r_cta = c.q * 32 + lane;
+  const int grow = c.row_cta0 + r_cta;
+  const bool row_ok = grow < p.M;
+  const bool elected = c.q == 0 && lane == 0;
+  const int n_tile0 = c.n_blk * BN;
+  const uint32_t row_s = (uint32_t)(r_cta * 128);
+  const uint32_t sw = (uint32_t)(r_cta & 7);
+  const long long in_row = c.boff + (long long)grow * (DACT != 0 ? p.ldc : p.ld_res);  // aux_in shares C's geometry
+  const bf16* in_ptr[NIN > 0 ? NIN : 1];
+  if constexpr (DACT != 0) in_ptr[0] = p.aux_in + c.boff + (long long)grow * p.ldc;
+  if constexpr (NRES >= 1) in_ptr[DACT != 0 ? 1 : 0] = p.res1 + c.boff + (long long)grow * p.ld_res;
+  if constexpr (NRES >= 2) in_ptr[(DACT != 0 ? 1 : 0) + 1] = p.res2 + c.boff + (long long)grow * p.ld_res;
+  (void)in_row;
+  int rope_pos = 0;
+  if constexpr (ROPE) rope_pos = grow % p.rope_S;
+
+  uint4 cur[NIN > 0 ? NIN : 1][4], nxt[NIN > 0 ? NIN : 1][4];
+  auto load_inputs = [&](int ch, uint4 (&dst)[NIN > 0 ? NIN : 1][4]) {
+    if constexpr (NIN > 0) {
+      const int n0 = n_tile0 + ch * 32;
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) {
+        if (row_ok && n0 + 32 <= p.N) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dst[i][k] = ldg128(in_ptr[i] + n0 + k * 8);
+        } else {
+          // N edge (or a padding row): element-wise, zero beyond the matrix
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            __nv_bfloat16 t[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              t[e] = (row_ok && n0 + k * 8 + e < p.N) ? in_ptr[i][n0 + k * 8 + e] : __float2bfloat16(0.f);
+            dst[i][k] = *reinterpret_cast<uint4*>(t);
+          }
+        }
+      }
+    }
+  };
+  load_inputs(0, cur);  // overlaps the accumulator wait
+  mbar_wait(c.tmem_full, c.full_phase);
+  tc_fence_after();
+  const int n_valid_ch = min(NCH, (p.N - n_tile0 + 31) / 32);  // chunks of this tile that start inside the matrix
+
+#pragma unroll 1
+  for (int ch = 0; ch < n_valid_ch; ++ch) {
+    const int n0 = n_tile0 + ch * 32;
+    if (ch + 1 < n_valid_ch) load_inputs(ch + 1, nxt);
+    uint32_t rr[32];
+    tmem_ld_32x32(c.tmem_acc + (uint32_t)(ch * 32), rr);
+    tmem_ld_wait();
+    if (ch + 1 == n_valid_ch) {
+      // the accumulator has been fully read: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (c.empty_remote) mbar_arrive_remote(c.tmem_empty, 0);
+        else mbar_arrive(c.tmem_empty);
+      }
+    }
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+    if (p.bias) {
+      if (n0 + 32 <= p.N) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float b8[8];
+          bf16x8_to_f32(ldg128(p.bias + n0 + k * 8), b8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[k * 8 + e] += b8[e];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.N) v[j] += __bfloat162float(p.bias[n0 + j]);
+      }
+    }
+    if constexpr (ROPE) {
+      // rope_hd % 32 == 0 and rope_rot % 32 == 0 (host-checked for this path): a 32-column chunk is rotary or not
+      if (n0 < p.rope_ncols && (n0 % p.rope_hd) < p.rope_rot) {
+        const float4* tp = reinterpret_cast<const float4*>(p.rope_tab + (long long)rope_pos * (p.rope_rot >> 1) +
+                                                           ((n0 % p.rope_hd) >> 1));
+        const float sg = p.rope_mode > 0 ? 1.f : -1.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 cs = __ldg(tp + k);  // (cos, sin) of two adjacent pairs
+          const float a0 = v[4 * k], a1 = v[4 * k + 1], a2 = v[4 * k + 2], a3 = v[4 * k + 3];
+          v[4 * k] = a0 * cs.x - a1 * cs.y * sg;
+          v[4 * k + 1] = a1 * cs.x + a0 * cs.y * sg;
+          v[4 * k + 2] = a2 * cs.z - a3 * cs.w * sg;
+          v[4 * k + 3] = a3 * cs.z + a2 * cs.w * sg;
+        }
+      }
+    }
+    if constexpr (F32) {
+      // one 32-column chunk = one [128 x 32] fp32 box
+      const uint32_t slot_s = c.pool_s + (box & 1u) * 16384u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        sts128(slot_s + row_s + (((uint32_t)k ^ sw) << 4), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      epi3_publish<ACCUM>(c, c.tmC, slot_s, n0, elected);
+      ++box;
+    } else {
+      const int half = ch & 1;
+      uint32_t slot_out, slot_aux = 0;
+      if constexpr (AUX) {
+        // two outputs: slot 0 = C, slot 1 = aux, both single-buffered -> the previous pair must have been read out
+        // before the first write of a new 64-column group
+        if (half == 0) {
+          if (elected) tma_store_wait_read0();
+          epi_bar_sync();
+        }
+        slot_out = c.pool_s;
+        slot_aux = c.pool_s + 16384u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sts128u(slot_aux + row_s + (((uint32_t)(half * 4 + k) ^ sw) << 4), f32x8_to_bf16(v + 8 * k));
+      } else {
+        slot_out = c.pool_s + (box & 1u) * 16384u;
+      }
+      if constexpr (ACT == MB200_ACT_GELU_NEW) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
+      } else if constexpr (ACT == MB200_ACT_QUICK_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu_f(v[j]);
+      } else if constexpr (ACT == MB200_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if constexpr (DACT != 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a8[8];
+          bf16x8_to_f32(cur[0][k], a8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if constexpr (DACT == MB200_DACT_GELU_NEW) v[k * 8 + e] *= gelu_new_grad_f(a8[e]);
+            else v[k * 8 + e] = a8[e] > 0.f ? v[k * 8 + e] : 0.f;
+          }
+        }
+      }
+      if constexpr (NRES >= 1) {
+        constexpr int r0 = DACT != 0 ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < NRES; ++i) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float a8[8];
+            bf16x8_to_f32(cur[r0 + i][k], a8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[k * 8 + e] += a8[e];
+          }
+        }
+        if (p.act == MB200_ACT_RELU_POST) {  // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        sts128u(slot_out + row_s + (((uint32_t)(half * 4 + k) ^ sw) << 4), f32x8_to_bf16(v + 8 * k));
+      if (half == 1 || ch + 1 == n_valid_ch) {
+        const int col0 = n0 - half * 32;
+        if constexpr (AUX) {
+          fence_proxy_async_smem();
+          epi_bar_sync();
+          if (elected) {
+            tma_store_4d(c.tmC, slot_out, col0, c.row_cta0, c.z0, c.z1);
+            tma_store_4d(c.tmAux, slot_aux, col0, c.row_cta0, c.z0, c.z1);
+            tma_store_commit();
+          }
+        } else {
+          epi3_publish<false>(c, c.tmC, slot_out, col0, elected);
+        }
+        ++box;
+      }
+    }
+    if constexpr (NIN > 0) {
+#pragma unroll
+      for (int i = 0; i < NIN; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cur[i][k] = nxt[i][k];
+    }
+  }
+  if (n_valid_ch <= 0) {  // (cannot happen: tiles start inside the matrix) keep the TMEM protocol intact regardless
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (c.empty_remote) mbar_arrive_remote(c.tmem_empty, 0);
+      else mbar_arrive(c.tmem_empty);
+    }
+  }
+}
+
 // host helpers shared by gemm.cu / gemm2.cu
 int make_operand_map(CUtensorMap* out, const mb200_operand& op, int rows, int K, int nb0, int nb1, int box_rows);
-int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& kp, bool a_mn, bool b_mn,
-                 bool f32, cudaStream_t stream);
+int make_store_map(CUtensorMap* out, const void* ptr, bool f32, int N, int M, int nb0, int nb1, long long ld,
+                   long long bs0, long long bs1);
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
+                 const GemmKernelParams& kp, bool a_mn, bool b_mn, bool f32, cudaStream_t stream);
 
 }  // namespace mb200

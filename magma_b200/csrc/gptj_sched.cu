@@ -52,11 +52,14 @@ struct Carver {
 struct Mat {
   const void* p;
   long long ld, bs0, bs1;
-  int mn;
+  int mn, frozen;
 };
 inline Mat mat(const void* p, long long ld, int mn = 0, long long bs0 = 0, long long bs1 = 0) {
-  return Mat{p, ld, bs0, bs1, mn};
+  return Mat{p, ld, bs0, bs1, mn, 0};
 }
+// a frozen weight matrix (never written by a kernel of the stream): the GEMM may fetch its first tiles ahead of the
+// programmatic dependency on the previous kernel (mb200_operand.static_data)
+inline Mat wmat(const void* p, long long ld, int mn = 0) { return Mat{p, ld, 0, 0, mn, 1}; }
 struct Epi {
   float alpha = 1.f;
   const void* bias = nullptr;
@@ -96,6 +99,7 @@ int gemm(void* st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, in
   g.B.bs0 = B.bs0;
   g.B.bs1 = B.bs1;
   g.B.mn_major = B.mn;
+  g.B.static_data = B.frozen;
   g.C = C;
   g.ldc = ldc;
   g.c_bs0 = c_bs0;
@@ -351,7 +355,7 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
       e.rope_hd = hd;
       e.rope_rot = m->rotary_dim;
       e.rope_ncols = 2 * d;
-      MBS_TRY(gemm(st, M, 3 * d, d, mat(a.h, d), mat(L.w_qkv, d), a.qkv, 3 * d, 0, e));
+      MBS_TRY(gemm(st, M, 3 * d, d, mat(a.h, d), wmat(L.w_qkv, d), a.qkv, 3 * d, 0, e));
     }
     if (tile_ok(S, hd)) {  // whole sequence in one tile: fused QK^T / softmax / PV, one CTA per (batch, head)
       MBS_TRY(mb200_attn_fwd_tile(a.qkv, 3 * d, a.P, P.ldP, a.attn_o, d, B, S, H, hd, st));
@@ -371,15 +375,15 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
       Epi e;
       e.res1 = xin;
       e.ld_res = d;
-      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), P.ax, d, 0, e));
+      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), wmat(L.w_out, d), P.ax, d, 0, e));
     } else if (m->attn_adapter == MB200_ADAPTER_NORMAL) {  // AdapterWrapper: A(attn_out) + attn_out
-      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), a.a_out, d, 0));
+      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), wmat(L.w_out, d), a.a_out, d, 0));
       MBS_TRY(adapter_fwd(st, L.attn_ad, a.aa, M, d, m->attn_adapter_r, m->ln_eps, a.a_out, P.ax, a.a_out, xin));
     } else {  // ParallelAdapterWrapper: attn(h) + s * A(h)
       Epi e;
       e.res1 = xin;
       e.ld_res = d;
-      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), mat(L.w_out, d), a.a_out, d, 0, e));
+      MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), wmat(L.w_out, d), a.a_out, d, 0, e));
       MBS_TRY(adapter_fwd(st, L.attn_ad, a.aa, M, d, m->attn_adapter_r, m->ln_eps, a.h, P.ax, a.a_out, nullptr));
     }
     {  // fc_in + bias + gelu_new, pre-activation kept
@@ -387,21 +391,21 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
       e.bias = L.b_fc_in;
       e.act = MB200_ACT_GELU_NEW;
       e.aux_out = a.pre;
-      MBS_TRY(gemm(st, M, dff, d, mat(a.h, d), mat(L.w_fc_in, d), P.hact, dff, 0, e));
+      MBS_TRY(gemm(st, M, dff, d, mat(a.h, d), wmat(L.w_fc_in, d), P.hact, dff, 0, e));
     }
     Epi eo;
     eo.bias = L.b_fc_out;
     if (m->mlp_adapter == MB200_ADAPTER_NONE) {
       eo.res1 = P.ax;
       eo.ld_res = d;
-      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), xout, d, 0, eo));
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), xout, d, 0, eo));
     } else if (m->mlp_adapter == MB200_ADAPTER_NORMAL) {  // Sequential(mlp, Adapter): A(mlp(h)) + mlp(h)
-      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), a.mlp_out, d, 0, eo));
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), a.mlp_out, d, 0, eo));
       MBS_TRY(adapter_fwd(st, L.mlp_ad, a.am, M, d, m->mlp_adapter_r, m->ln_eps, a.mlp_out, xout, a.mlp_out, P.ax));
     } else {  // ParallelAdapter: mlp(h) + s * A(h)
       eo.res1 = P.ax;
       eo.ld_res = d;
-      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), a.mlp_out, d, 0, eo));
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), a.mlp_out, d, 0, eo));
       MBS_TRY(adapter_fwd(st, L.mlp_ad, a.am, M, d, m->mlp_adapter_r, m->ln_eps, a.h, xout, a.mlp_out, nullptr));
     }
   }
@@ -413,7 +417,7 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
   {
     Epi e;
     e.bias = m->b_lm;
-    MBS_TRY(gemm(st, M, m->vocab, d, mat(P.xf_ln, d), mat(m->w_lm, d), lg, ldl, 0, e));
+    MBS_TRY(gemm(st, M, m->vocab, d, mat(P.xf_ln, d), wmat(m->w_lm, d), lg, ldl, 0, e));
   }
   if (labels) {
     MBS_REQUIRE(loss != nullptr, MB200_E_ARG, "gptj_sched_forward: labels given but loss pointer is NULL");
@@ -442,7 +446,7 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int laye
   if (layer_hi == m->n_layer) {  // dxf = loss_scale * dlogits Wlm ; g = LN_f backward
     Epi e;
     e.alpha = loss_scale;
-    MBS_TRY(gemm(st, M, d, m->vocab, mat(P.dlogits, P.ldv), mat(m->w_lm, d, 1), P.dh, d, 0, e));
+    MBS_TRY(gemm(st, M, d, m->vocab, mat(P.dlogits, P.ldv), wmat(m->w_lm, d, 1), P.dh, d, 0, e));
     MBS_TRY(mb200_layernorm_bwd(P.dh, d, P.x_final, d, m->lnf_g, P.lnf_mean, P.lnf_rstd, nullptr, 0, gb[m->n_layer & 1], d,
                                 M, d, st));
   }
@@ -465,11 +469,11 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int laye
       Epi e;
       e.dact = MB200_DACT_GELU_NEW;
       e.aux_in = a.pre;
-      MBS_TRY(gemm(st, M, dff, d, mat(dm, d), mat(L.w_fc_out, dff, 1), P.dhact, dff, 0, e));
+      MBS_TRY(gemm(st, M, dff, d, mat(dm, d), wmat(L.w_fc_out, dff, 1), P.dhact, dff, 0, e));
       Epi e2;
       e2.res1 = dh_acc;
       e2.ld_res = d;
-      MBS_TRY(gemm(st, M, d, dff, mat(P.dhact, dff), mat(L.w_fc_in, d, 1), P.dh_mlp, d, 0, e2));
+      MBS_TRY(gemm(st, M, d, dff, mat(P.dhact, dff), wmat(L.w_fc_in, d, 1), P.dh_mlp, d, 0, e2));
       dh_acc = P.dh_mlp;
     }
     // ---- attention branch ----
@@ -481,7 +485,7 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int laye
       MBS_TRY(adapter_bwd(st, L.attn_ad, a.aa, P, M, d, m->attn_adapter_r, g, a.h, P.dhp, dh_acc, acc));
       dh_acc = P.dhp;
     }
-    MBS_TRY(gemm(st, M, d, d, mat(da, d), mat(L.w_out, d, 1), P.dattn_o, d, 0));  // d(attn_o) = da Wo
+    MBS_TRY(gemm(st, M, d, d, mat(da, d), wmat(L.w_out, d, 1), P.dattn_o, d, 0));  // d(attn_o) = da Wo
     if (tile_ok(S, hd)) {
       MBS_TRY(mb200_attn_bwd_tile(a.qkv, 3 * d, P.dattn_o, d, a.P, P.ldP, P.dqkv, 3 * d, P.rope_tab, m->rotary_dim, B, S, H,
                                   hd, st));
@@ -507,7 +511,7 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int laye
       Epi e;
       e.res1 = dh_acc;
       e.ld_res = d;
-      MBS_TRY(gemm(st, M, d, 3 * d, mat(P.dqkv, 3 * d), mat(L.w_qkv, d, 1), P.dh, d, 0, e));  // dh = dqkv Wqkv + ...
+      MBS_TRY(gemm(st, M, d, 3 * d, mat(P.dqkv, 3 * d), wmat(L.w_qkv, d, 1), P.dh, d, 0, e));  // dh = dqkv Wqkv + ...
     }
     MBS_TRY(mb200_layernorm_bwd(P.dh, d, a.x_in, d, L.ln1_g, a.mean, a.rstd, g, d, gout, d, M, d, st));
   }
@@ -597,7 +601,7 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
       e.rope_hd = hd;
       e.rope_rot = m->rotary_dim;
       e.rope_ncols = 2 * d;
-      MBS_TRY(gemm(st, M, 3 * d, d, mat(P.h, d), mat(L.w_qkv, d), P.qkv, 3 * d, 0, e));
+      MBS_TRY(gemm(st, M, 3 * d, d, mat(P.h, d), wmat(L.w_qkv, d), P.qkv, 3 * d, 0, e));
     }
     bf16s* kc = kcache ? kcache + (size_t)l * cache_layer : nullptr;
     bf16s* vc = vcache ? vcache + (size_t)l * cache_layer : nullptr;
@@ -633,36 +637,36 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
       Epi e;
       e.res1 = xin;
       e.ld_res = d;
-      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), mat(L.w_out, d), P.ax, d, 0, e));
+      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), wmat(L.w_out, d), P.ax, d, 0, e));
     } else if (m->attn_adapter == MB200_ADAPTER_NORMAL) {
-      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), mat(L.w_out, d), P.a_out, d, 0));
+      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), wmat(L.w_out, d), P.a_out, d, 0));
       MBS_TRY(adapter_fwd(st, L.attn_ad, P.aa, M, d, m->attn_adapter_r, m->ln_eps, P.a_out, P.ax, P.a_out, xin));
     } else {
       Epi e;
       e.res1 = xin;
       e.ld_res = d;
-      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), mat(L.w_out, d), P.a_out, d, 0, e));
+      MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), wmat(L.w_out, d), P.a_out, d, 0, e));
       MBS_TRY(adapter_fwd(st, L.attn_ad, P.aa, M, d, m->attn_adapter_r, m->ln_eps, P.h, P.ax, P.a_out, nullptr));
     }
     {
       Epi e;
       e.bias = L.b_fc_in;
       e.act = MB200_ACT_GELU_NEW;
-      MBS_TRY(gemm(st, M, dff, d, mat(P.h, d), mat(L.w_fc_in, d), P.hact, dff, 0, e));
+      MBS_TRY(gemm(st, M, dff, d, mat(P.h, d), wmat(L.w_fc_in, d), P.hact, dff, 0, e));
     }
     Epi eo;
     eo.bias = L.b_fc_out;
     if (m->mlp_adapter == MB200_ADAPTER_NONE) {
       eo.res1 = P.ax;
       eo.ld_res = d;
-      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), xout, d, 0, eo));
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), xout, d, 0, eo));
     } else if (m->mlp_adapter == MB200_ADAPTER_NORMAL) {
-      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), P.mlp_out, d, 0, eo));
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), P.mlp_out, d, 0, eo));
       MBS_TRY(adapter_fwd(st, L.mlp_ad, P.am, M, d, m->mlp_adapter_r, m->ln_eps, P.mlp_out, xout, P.mlp_out, P.ax));
     } else {
       eo.res1 = P.ax;
       eo.ld_res = d;
-      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), mat(L.w_fc_out, dff), P.mlp_out, d, 0, eo));
+      MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), P.mlp_out, d, 0, eo));
       MBS_TRY(adapter_fwd(st, L.mlp_ad, P.am, M, d, m->mlp_adapter_r, m->ln_eps, P.h, xout, P.mlp_out, nullptr));
     }
     xin = xout;
@@ -679,7 +683,7 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
     MBS_REQUIRE(ldv % 8 == 0 && ldv >= m->vocab, MB200_E_ALIGN, "gptj_sched_infer: ldv=%lld must be >= vocab and %%8", ldv);
     Epi e;
     e.bias = m->b_lm;
-    MBS_TRY(gemm(st, rows, m->vocab, d, mat(P.xf_ln, d), mat(m->w_lm, d), logits, ldv, 0, e));
+    MBS_TRY(gemm(st, rows, m->vocab, d, mat(P.xf_ln, d), wmat(m->w_lm, d), logits, ldv, 0, e));
   }
   return 0;
 }

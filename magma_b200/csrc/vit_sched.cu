@@ -45,11 +45,14 @@ struct Carver {
 struct Mat {
   const void* p;
   long long ld, bs0, bs1;
-  int mn;
+  int mn, frozen;
 };
 inline Mat mat(const void* p, long long ld, int mn = 0, long long bs0 = 0, long long bs1 = 0) {
-  return Mat{p, ld, bs0, bs1, mn};
+  return Mat{p, ld, bs0, bs1, mn, 0};
 }
+// a frozen weight matrix (never written by a kernel of the stream): the GEMM may fetch its first tiles ahead of the
+// programmatic dependency on the previous kernel (mb200_operand.static_data)
+inline Mat wmat(const void* p, long long ld, int mn = 0) { return Mat{p, ld, 0, 0, mn, 1}; }
 struct Epi {
   const void* bias = nullptr;
   int act = 0;
@@ -79,6 +82,7 @@ int gemm(void* st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, in
   g.B.bs0 = B.bs0;
   g.B.bs1 = B.bs1;
   g.B.mn_major = B.mn;
+  g.B.static_data = B.frozen;
   g.C = C;
   g.ldc = ldc;
   g.c_bs0 = c_bs0;
@@ -242,7 +246,7 @@ int forward_infer(const mb200_vit_model* m, const bf16s* images, bf16s* feats, i
   // conv1 as im2col + GEMM (patch embeddings staged in h), then [cls; patches] + positional embedding
   MBS_TRY(rt_zero(P.patches, (size_t)B * g * g * P.ldpatch * sizeof(bf16s), st));
   MBS_TRY(mb200_patchify(images, P.patches, P.ldpatch, B, m->image, m->patch, st));
-  MBS_TRY(gemm(st, B * g * g, w, Kp, mat(P.patches, P.ldpatch), mat(m->w_conv, m->ld_conv), P.h, w, 0));
+  MBS_TRY(gemm(st, B * g * g, w, Kp, mat(P.patches, P.ldpatch), wmat(m->w_conv, m->ld_conv), P.h, w, 0));
   MBS_TRY(mb200_vit_assemble(P.x, P.h, m->cls, m->pos, B, T, w, st));
   // ln_pre (in place: each row is cached in registers before it is rewritten)
   MBS_TRY(mb200_layernorm_fwd(P.x, w, m->ln_pre_g, m->ln_pre_b, P.x, w, nullptr, nullptr, M, w, kEps, st));
@@ -254,7 +258,7 @@ int forward_infer(const mb200_vit_model* m, const bf16s* images, bf16s* feats, i
     {
       Epi e;
       e.bias = L.b_qkv;
-      MBS_TRY(gemm(st, M, 3 * w, w, mat(P.h, w), mat(L.w_qkv, w), P.qkv, 3 * w, 0, e));
+      MBS_TRY(gemm(st, M, 3 * w, w, mat(P.h, w), wmat(L.w_qkv, w), P.qkv, 3 * w, 0, e));
     }
     if (flash_ok(hd)) {
       MBS_TRY(mb200_attn_fwd_flash(P.qkv, 3 * w, qb0, qb1, P.qkv + w, 3 * w, qb0, qb1, P.qkv + 2 * w, 3 * w, qb0, qb1,
@@ -271,25 +275,25 @@ int forward_infer(const mb200_vit_model* m, const bf16s* images, bf16s* feats, i
       e.bias = L.b_out;
       e.res1 = P.x;
       e.ld_res = w;
-      MBS_TRY(gemm(st, M, w, w, mat(P.attn_o, w), mat(L.w_out, w), P.x, w, 0, e));  // x += out_proj(attn)
+      MBS_TRY(gemm(st, M, w, w, mat(P.attn_o, w), wmat(L.w_out, w), P.x, w, 0, e));  // x += out_proj(attn)
     }
     MBS_TRY(mb200_layernorm_fwd(P.x, w, L.ln2_g, L.ln2_b, P.h, w, nullptr, nullptr, M, w, kEps, st));
     {
       Epi e;
       e.bias = L.b_fc;
       e.act = MB200_ACT_QUICK_GELU;
-      MBS_TRY(gemm(st, M, m->mlp, w, mat(P.h, w), mat(L.w_fc, w), P.hact, m->mlp, 0, e));
+      MBS_TRY(gemm(st, M, m->mlp, w, mat(P.h, w), wmat(L.w_fc, w), P.hact, m->mlp, 0, e));
       Epi e2;
       e2.bias = L.b_proj;
       e2.res1 = P.x;
       e2.ld_res = w;
-      MBS_TRY(gemm(st, M, w, m->mlp, mat(P.hact, m->mlp), mat(L.w_proj, m->mlp), P.x, w, 0, e2));  // x += mlp
+      MBS_TRY(gemm(st, M, w, m->mlp, mat(P.hact, m->mlp), wmat(L.w_proj, m->mlp), P.x, w, 0, e2));  // x += mlp
     }
   }
   // ln_post on the class token, then the visual projection
   MBS_TRY(mb200_layernorm_fwd(P.x, (long long)T * w, m->ln_post_g, m->ln_post_b, P.pooled, w, nullptr, nullptr, B, w, kEps,
                               st));
-  return gemm(st, B, m->out_dim, w, mat(P.pooled, w), mat(m->proj_t, w), feats, m->out_dim, 0);
+  return gemm(st, B, m->out_dim, w, mat(P.pooled, w), wmat(m->proj_t, w), feats, m->out_dim, 0);
 }
 
 int forward_train(const mb200_vit_model* m, const bf16s* images, bf16s* feats, int B, void* ws, size_t ws_bytes,

@@ -59,6 +59,7 @@ def gemm(
     rope_rot=0,
     rope_ncols=0,
     splitk_ws=None,
+    b_static=False,
 ):
     """C[..., M, N] = epilogue(alpha * A @ B^T) on the tcgen05 GEMM core.
 
@@ -90,6 +91,7 @@ def gemm(
         raise TypeError("gemm out must be bf16 or f32")
     g.A.ptr, g.A.ld, g.A.bs0, g.A.bs1, g.A.mn_major = A.data_ptr(), lda, abs0, abs1, int(a_mn)
     g.B.ptr, g.B.ld, g.B.bs0, g.B.bs1, g.B.mn_major = B.data_ptr(), ldb, bbs0, bbs1, int(b_mn)
+    g.B.static_data = int(bool(b_static))  # frozen weights: first tiles may load ahead of the PDL dependency
     g.C, g.ldc, g.c_bs0, g.c_bs1 = out.data_ptr(), ldc, cbs0, cbs1
     g.alpha, g.act, g.dact, g.accumulate = float(alpha), int(act), int(dact), int(bool(accumulate))
     for name, t in (("bias", bias), ("aux_out", aux_out), ("aux_in", aux_in), ("res1", res1), ("res2", res2)):

@@ -25,17 +25,24 @@ class Adapter(nn.Module):
         return self.adapter(x) + x
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--checkpointing", action="store_true", help="gradient checkpointing like language_model.py:23")
-    a = ap.parse_args()
+def run(steps=10, warmup=3, checkpointing=False, device="cuda:0"):
+    """One process-local run of the eager step; returns the result dict (bench.py calls this for its `gpu_eager` key)."""
+    import types
+
+    a = types.SimpleNamespace(steps=steps, warmup=warmup, checkpointing=checkpointing)
     from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection, GPTJConfig, GPTJForCausalLM
 
-    dev = torch.device("cuda:0")
+    dev = torch.device(device)
     B, S, L, V = 8, 128, 2, 50258
+    prev_dtype = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
+    try:
+        return _run(a, dev, B, S, L, V, CLIPVisionConfig, CLIPVisionModelWithProjection, GPTJConfig, GPTJForCausalLM)
+    finally:
+        torch.set_default_dtype(prev_dtype)
+
+
+def _run(a, dev, B, S, L, V, CLIPVisionConfig, CLIPVisionModelWithProjection, GPTJConfig, GPTJForCausalLM):
     t0 = time.time()
     with torch.device(dev):
         cfg = GPTJConfig(vocab_size=V, n_positions=2048, n_embd=4096, n_layer=28, n_head=16, rotary_dim=64,
@@ -96,10 +103,19 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    print(json.dumps({"impl": "gpu-eager (HF GPT-J eager + reference adapter wiring, bf16, LM frozen)",
-                      "value": B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "steps": a.steps,
-                      "checkpointing": a.checkpointing, "loss": float(loss.detach()), "build_s": build_s,
-                      "max_mem_gib": torch.cuda.max_memory_allocated() / 2**30}))
+    return {"impl": "gpu-eager (HF GPT-J eager + reference adapter wiring, bf16, LM frozen)",
+            "value": B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "steps": a.steps,
+            "checkpointing": a.checkpointing, "loss": float(loss.detach()), "build_s": build_s,
+            "max_mem_gib": torch.cuda.max_memory_allocated() / 2**30}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--checkpointing", action="store_true", help="gradient checkpointing like language_model.py:23")
+    a = ap.parse_args()
+    print(json.dumps(run(a.steps, a.warmup, a.checkpointing)))
 
 
 if __name__ == "__main__":

@@ -54,7 +54,7 @@ def main():
         Bs = [rnd(K, N) if b_mn else rnd(N, K) for _ in range(nbuf)]
         A = rnd(K, M, scale=1.0) if a_mn else rnd(M, K, scale=1.0)
         C = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-        kw = dict(a_mn=a_mn, b_mn=b_mn, force_bn=force_bn)
+        kw = dict(a_mn=a_mn, b_mn=b_mn, force_bn=force_bn, b_static=not a_mn)  # K-major-A cases are weight GEMMs
         if bias:
             kw["bias"] = rnd(N)
         if act:

@@ -225,6 +225,68 @@ def run_group(g):
         Cb = ops.gemm(Ab, Bb, force_bn=512)
         torch.cuda.synchronize()
         ok &= report("pair batched", Cb, Ab.float() @ Bb.float().transpose(-1, -2))
+        # every specialised epilogue of the row-per-thread / TMA-store path (epilogue v3)
+        C = ops.gemm(A, B, bias=bias, act=ops.ACT_RELU, force_bn=512)
+        ok &= report("pair bias+relu", C, F.relu(pre))
+        C = ops.gemm(A, B, bias=bias, act=ops.ACT_QUICK_GELU, force_bn=512)
+        ok &= report("pair bias+quick_gelu", C, pre * torch.sigmoid(1.702 * pre))
+        C = ops.gemm(A, B, bias=bias, act=ops.ACT_GELU_NEW, force_bn=512)
+        ok &= report("pair bias+gelu_new (no aux)", C, F.gelu(pre, approximate="tanh"))
+        xf = x.float().requires_grad_(True)
+        F.gelu(xf, approximate="tanh").sum().backward()
+        C = ops.gemm(A, B, aux_in=x, dact=ops.DACT_GELU_NEW, force_bn=512)
+        ok &= report("pair dact gelu_new", C, base * xf.grad)
+        C = ops.gemm(A, B, bias=bias, res1=r1, alpha=0.5, force_bn=512)
+        ok &= report("pair alpha+bias+res1", C, 0.5 * base + bias.float() + r1.float())
+        C = ops.gemm(A, B, bias=bias, res1=r1, act=ops.ACT_RELU_POST, force_bn=512)
+        ok &= report("pair bias+res1+relu_post", C, F.relu(pre + r1.float()))
+        Cf = torch.full((M, N), 3.0, device=dev, dtype=torch.float32)
+        ops.gemm(A, B, out=Cf, force_bn=512)
+        ok &= report("pair f32 plain (overwrites)", Cf, base, tol=5e-3)
+        # ragged N (not a multiple of 8, like the 50258-wide LM head) and ragged M, with bias / residual / aux / f32
+        Mr, Nr, Kr = 520, 1002, 320
+        Ar, Br = mk((Mr, Kr), False, dev, 0.5), mk((Nr, Kr), False, dev, 0.125)
+        br = torch.randn(Nr, device=dev).to(torch.bfloat16)
+        rr_ = torch.full((Mr, 1008), 0.0, device=dev, dtype=torch.bfloat16)
+        rr_[:, :Nr] = mk((Mr, Nr), False, dev)
+        baser = ref_gemm(Ar, Br, False, False) + br.float()
+        buf = torch.full((Mr, 1008), 7.0, device=dev, dtype=torch.bfloat16)
+        ops.gemm(Ar, Br, out=buf[:, :Nr], bias=br, res1=rr_[:, :Nr], force_bn=512)
+        ok &= report("pair ragged M=520 N=1002 bias+res1", buf[:, :Nr], baser + rr_[:, :Nr].float())
+        ok &= bool((buf[:, Nr:] == 7.0).all().item())
+        auxr = torch.full((Mr, 1008), 5.0, device=dev, dtype=torch.bfloat16)
+        buf.fill_(7.0)
+        ops.gemm(Ar, Br, out=buf[:, :Nr], bias=br, act=ops.ACT_GELU_NEW, aux_out=auxr[:, :Nr], force_bn=512)
+        ok &= report("pair ragged gelu+aux: C", buf[:, :Nr], F.gelu(baser, approximate="tanh"))
+        ok &= report("pair ragged gelu+aux: aux", auxr[:, :Nr], baser)
+        ok &= bool((buf[:, Nr:] == 7.0).all().item()) and bool((auxr[:, Nr:] == 5.0).all().item())
+        buff = torch.full((Mr, 1004), 2.0, device=dev, dtype=torch.float32)
+        ops.gemm(Ar, Br, out=buff[:, :Nr], accumulate=True, force_bn=512)
+        ok &= report("pair ragged f32 accumulate", buff[:, :Nr], baser - br.float() + 2.0, tol=5e-3)
+        ok &= bool((buff[:, Nr:] == 2.0).all().item())
+        # fused rotary epilogue (forward and inverse) on the pair kernel == rotation of the plain fp32 product
+        Sx, H, hd, rot = 64, 2, 128, 64
+        Mx = 4 * Sx
+        A2, B2 = mk((Mx, 512), False, dev, 0.5), mk((3 * H * hd, 512), False, dev, 0.125)
+        tab = ops.rope_table(Sx, rot, pos0=7, device=dev)
+        for mode in (1, -1):
+            fused = ops.gemm(A2, B2, rope_tab=tab, rope_mode=mode, rope_S=Sx, rope_hd=hd, rope_rot=rot,
+                             rope_ncols=2 * H * hd, force_bn=512)
+            plain = ops.gemm(A2, B2, out_dtype=torch.float32)
+            qq = plain.view(Mx // Sx, Sx, 3, H, hd).clone()
+            cs = tab[None, :, None, None, :, 0]
+            sn = tab[None, :, None, None, :, 1] * mode
+            x1, x2 = qq[:, :, :2, :, 0:rot:2].clone(), qq[:, :, :2, :, 1:rot:2].clone()
+            qq[:, :, :2, :, 0:rot:2] = x1 * cs - x2 * sn
+            qq[:, :, :2, :, 1:rot:2] = x2 * cs + x1 * sn
+            ok &= report(f"pair fused rope epilogue mode={mode}", fused, qq.view(Mx, -1))
+        # strided-batch output (attention-style: heads interleaved in the row), forced pair
+        Bsz, S_, H_, hd_ = 2, 256, 2, 256
+        pb = torch.softmax(torch.randn(Bsz, H_, S_, S_, device=dev), -1).to(torch.bfloat16)
+        vb = (torch.randn(Bsz, S_, H_, hd_, device=dev) * 0.3).to(torch.bfloat16)
+        ob = torch.empty(Bsz, S_, H_, hd_, device=dev, dtype=torch.bfloat16)
+        ops.gemm(pb, vb.permute(0, 2, 1, 3), out=ob.permute(0, 2, 1, 3), b_mn=True, force_bn=512)
+        ok &= report("pair batched PV into [B,S,H,hd]", ob.permute(0, 2, 1, 3), pb.float() @ vb.permute(0, 2, 1, 3).float())
         # perf vs 1-CTA
         for (M, N, K, bmn) in ((1024, 4096, 4096, False), (1024, 16384, 4096, False), (1024, 4096, 16384, True), (8192, 8192, 8192, False)):
             A, B = mk((M, K), False, dev), mk((N, K), bmn, dev)
