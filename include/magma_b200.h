@@ -396,6 +396,25 @@ int mb200_gptj_sched_infer(const mb200_gptj_model_ex* m, const void* x, void* lo
                            void* hidden, void* kcache, void* vcache, int32_t S_kv_max, int32_t pos0, int32_t B, int32_t S,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* Device-resident decode loop (magma/sampling.py:78-109 issues one LM call per generated token from the host and syncs
+ * on `.all()` every step). Here the cache position of the step lives in DEVICE memory (pos_dev, int32[1]): no argument
+ * of a decode step changes from token to token, so the caller captures ONE step in a CUDA graph — mb200_decode_embed
+ * (input embedding of the token emitted last) -> mb200_gptj_sched_decode_step (= mb200_gptj_sched_infer with S = 1,
+ * last_only, position read on the device) -> mb200_argmax -> mb200_decode_advance (store the new ids at column pos + 1 of
+ * the [B, ld_tok] id buffer, record whether every row emitted EOS, pos += 1) — and replays it per token. Token ids are
+ * the same as the host-driven loop's (same kernels, same order). */
+int mb200_gptj_sched_decode_step(const mb200_gptj_model_ex* m, const void* x, void* logits, int64_t ldv, void* kcache,
+                                 void* vcache, int32_t S_kv_max, const int32_t* pos_dev, int32_t B, void* ws,
+                                 size_t ws_bytes, void* stream);
+int mb200_decode_embed(const int64_t* tokens, int64_t ld_tok, const int32_t* pos_dev, const void* wte, void* x, int32_t B,
+                       int32_t d, int32_t vocab, void* stream);
+int mb200_decode_advance(const int64_t* next, int64_t* tokens, int64_t ld_tok, int32_t* pos_dev, int64_t eos,
+                         uint8_t* flags, int32_t s0, int32_t n_flags, int32_t B, void* stream);
+/* mb200_rope_table / mb200_attn_decode with the position read from device memory (shared memory sized for S_kv_max). */
+int mb200_rope_table_dev(float* tab, int32_t S, int32_t rot, const int32_t* pos0_dev, void* stream);
+int mb200_attn_decode_dev(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, void* out, int64_t ld_out,
+                          int32_t B, int32_t H, int32_t hd, int32_t S_kv_max, const int32_t* pos_dev, void* stream);
+
 /* out = s[0] * u + r1 + r2 over n bf16 elements (s: DEVICE fp32 scalar or NULL = 1; r1, r2 optional) — the
  * `* adapter_scale` of ParallelAdapter.forward (magma/adapters.py:63-66,85-92) with the residual sum folded in. */
 int mb200_scale_add(const void* u, const float* s, const void* r1, const void* r2, void* out, int64_t n, void* stream);

@@ -189,4 +189,6 @@ EXPORTED_SYMBOLS = [
     "mb200_col_moments", "mb200_channel_affine", "mb200_col2im3x3", "mb200_avgpool_nhwc_bwd",
     "mb200_kv_append", "mb200_gptj_sched_infer_workspace_bytes", "mb200_gptj_sched_infer",
     "mb200_gptj_sched_backward_range", "mb200_bn_finalize_fwd", "mb200_bn_bwd_coeffs",
+    "mb200_gptj_sched_decode_step", "mb200_decode_embed", "mb200_decode_advance", "mb200_rope_table_dev",
+    "mb200_attn_decode_dev",
 ]

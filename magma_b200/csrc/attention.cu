@@ -17,6 +17,8 @@
 //   dP = dO V^T ; dV = P^T dO (P, dO as MN-major operands: same smem bytes) ; dS = P*(dP - rowsum(dP*P))/sqrt(hd)
 //   dQ = dS K ; dK = dS^T Q, both with the inverse rotary rotation applied on the way out (they are gradients of the
 //   rotated q,k), written straight into the fused dqkv buffer.
+#include <stdlib.h>
+
 #include "gemm_common.cuh"
 
 namespace mb200 {
@@ -624,6 +626,173 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// short-key forward: the WHOLE key range (Sk <= 384 at head_dim 64, <= 256 at head_dim 128) resident on chip
+// ---------------------------------------------------------------------------------------------
+// The ViT case (T = 257 keys, head_dim 64, no mask; 24 layers x B x 16 heads per step). The two-sweep kernel above is a
+// chain of ~18 dependent TMA / MMA / softmax round trips per CTA for three key tiles (measured 94 us per launch at
+// B = 8: profiles/r02_launches_step_flash_v1_summary.txt — no faster than the GEMM + softmax + GEMM path it replaced).
+// Here Q, every K tile and every V tile are loaded at once, the NKT score tiles are issued back to back into NKT x 128
+// TMEM columns behind ONE commit, each thread (= query row) makes three passes over its row in TMEM — maximum;
+// e = exp(s - max) written back in place with tcgen05.st, and the sum; p = bf16(e / sum) into the P operand tiles — and
+// the NKT P V products accumulate behind one more commit: 3 synchronisation points per CTA. Same rounding points as the
+// materialised softmax (fp32 scores, fp32 exp / sum, probabilities rounded to bf16 before P V).
+template <int NKT>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nhb = p.hd >> 6;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + nhb * kTile;             // NKT tiles
+  uint8_t* sV = sK + NKT * nhb * kTile;       // NKT tiles
+  uint8_t* sP = sV + NKT * nhb * kTile;       // NKT x 2 k-blocks of 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NKT * 2 * kTile);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_o = bars + 3;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int qi = q0 + t;
+
+  pdl_trigger();
+  if (t == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_o = tmem + 384;
+  pdl_wait();
+
+  if (t == 0) {
+    mbar_expect_tx(bar_qk, (1 + NKT) * nhb * kTile);
+    for (int kb = 0; kb < nhb; ++kb) tma_load_4d(sQ + kb * kTile, &tmQ, bar_qk, kb * 64, q0, h, b);
+    for (int j = 0; j < NKT; ++j)
+      for (int kb = 0; kb < nhb; ++kb) tma_load_4d(sK + (j * nhb + kb) * kTile, &tmK, bar_qk, kb * 64, j * 128, h, b);
+    mbar_expect_tx(bar_v, NKT * nhb * kTile);
+    for (int j = 0; j < NKT; ++j)
+      for (int kb = 0; kb < nhb; ++kb) tma_load_4d(sV + (j * nhb + kb) * kTile, &tmV, bar_v, kb * 64, j * 128, h, b);
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < NKT; ++j)
+      issue_mma<false, false>(tmem + (uint32_t)(j * 128), smem_u32(sQ), smem_u32(sK + j * nhb * kTile), nhb, 128);
+    umma_commit(bar_s);
+  }
+  const int row_lim = !p.causal ? p.Sk : min(p.Sk, qi + p.kv_off + 1);  // keys [0, row_lim) are visible to this row
+  const bool row_ok = qi < p.Sq;
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+  // (tcgen05.ld / .st are warp-collective: every loop bound and branch around them below is warp-uniform; what differs
+  // per row — the causal limit — only masks values)
+  const int nch = min(NKT * 4, (p.Sk + 31) >> 5);  // 32-column chunks that contain keys
+  // pass 1: row maximum
+  float m = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    uint32_t rr[32];
+    tmem_ld_32x32(lane_addr + (uint32_t)(c * 32), rr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (c * 32 + e < row_lim) m = fmaxf(m, __uint_as_float(rr[e]) * p.scale);
+  }
+  if (m == -INFINITY) m = 0.f;
+  // pass 2: e = exp(s - max) written back in place, and the sum
+  float l = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < NKT * 4; ++c) {
+    uint32_t rr[32];
+    if (c < nch) {
+      tmem_ld_32x32(lane_addr + (uint32_t)(c * 32), rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float ev = c * 32 + e < row_lim ? __expf(__uint_as_float(rr[e]) * p.scale - m) : 0.f;
+        l += ev;
+        rr[e] = __float_as_uint(ev);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) rr[e] = 0u;
+    }
+    tmem_st_32x32(lane_addr + (uint32_t)(c * 32), rr);
+  }
+  tmem_st_wait();
+  const float inv = (row_ok && l > 0.f) ? 1.f / l : 0.f;
+  if (p.stats != nullptr && row_ok) p.stats[((long long)b * p.H + h) * p.Sq + qi] = make_float2(m, inv);
+  // pass 3: probabilities -> bf16 -> P operand tiles (and global P when asked for)
+  bf16* prow = p.P ? p.P + (((long long)b * p.H + h) * p.Sq + qi) * p.ldP : nullptr;
+  const uint32_t sP_s = smem_u32(sP);
+#pragma unroll 1
+  for (int c = 0; c < NKT * 4; ++c) {
+    uint32_t rr[32];
+    tmem_ld_32x32(lane_addr + (uint32_t)(c * 32), rr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(rr[g8 * 8 + e]) * inv;
+      const uint4 u = pack8f(f);
+      const int col = c * 32 + g8 * 8;  // key index
+      st_operand_chunk(sP_s + (uint32_t)((col >> 7) * 2 * kTile), t, (col & 127) >> 6, (col & 63) >> 3, u);
+      if (prow != nullptr && row_ok && col < p.ldP) *reinterpret_cast<uint4*>(prow + col) = u;
+    }
+  }
+  if (prow != nullptr && row_ok)
+    for (int col = NKT * 128; col < p.ldP; col += 8) *reinterpret_cast<uint4*>(prow + col) = make_uint4(0, 0, 0, 0);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0) {
+    tc_fence_after();
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < NKT; ++j)
+      issue_mma<false, true>(tmem_o, sP_s + (uint32_t)(j * 2 * kTile), smem_u32(sV + j * nhb * kTile), 2, p.hd,
+                             j > 0 ? 1u : 0u);
+    umma_commit(bar_o);
+  }
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  bf16* orow = p.O + ((long long)b * p.Sq + qi) * p.ldo + (long long)h * p.hd;
+  for (int c = 0; c < p.hd / 32; ++c) {
+    uint32_t rr[32];
+    tmem_ld_32x32(lane_addr + (uint32_t)(384 + c * 32), rr);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 8) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(rr[e + k]);
+        *reinterpret_cast<uint4*>(orow + c * 32 + e) = pack8f(f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
 static int tile_map(CUtensorMap* m, const void* ptr, long long ld, long long bs0, long long bs1, int rows, int cols,
@@ -742,6 +911,29 @@ int attn_fwd_flash(const bf16* q, long long ldq, long long q_bsh, long long q_bs
   p.stats = reinterpret_cast<float2*>(stats);
   const int nhb = hd / 64;
   const dim3 grid((Sq + 127) / 128, H, B);
+  // short key ranges (the ViT: 257 keys, head_dim 64) stay entirely on chip: one pass, three synchronisation points
+  const int nkt = (Sk + 127) / 128;
+  static int use_short = -1;
+  if (use_short < 0) {
+    const char* e = getenv("MB200_ATTN_SHORT");
+    use_short = e ? atoi(e) : 1;
+  }
+  if (use_short && ((hd == 64 && nkt <= 3) || (hd == 128 && nkt <= 2))) {
+    const int smem = ((1 + 2 * nkt) * nhb + 2 * nkt) * kTile + 1024 + 128;
+#define MB_SHORT(NK)                                                                                                 \
+  {                                                                                                                  \
+    static bool set = false;                                                                                         \
+    if (!set) {                                                                                                      \
+      MB_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); \
+      set = true;                                                                                                    \
+    }                                                                                                                \
+    MB_CUDA(launch_pdl(attn_fwd_short_kernel<NK>, grid, dim3(kAttThreads), (size_t)smem, st, tq, tk, tv, p));        \
+  }
+    if (nkt == 1) MB_SHORT(1) else if (nkt == 2) MB_SHORT(2) else MB_SHORT(3)
+#undef MB_SHORT
+    count_launch();
+    return 0;
+  }
   if (hd <= 128) {
     const int smem = (5 * nhb + 2) * kTile + 1024 + 128;
     static bool set = false;

@@ -427,3 +427,80 @@ extern "C" int mb200_cast_bf16_to_f32(const void* src, float* dst, int64_t n, vo
   MB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident decode loop (magma/sampling.py:78-109 runs one host-driven LM call per token with an `.all()` sync
+// each step): the step's cache position lives in DEVICE memory, so one CUDA graph of the whole decode step is replayed
+// per token with no host-side argument changing. These are the three small kernels around the LM call that read /
+// advance that position; the LM schedule itself takes it through mb200_gptj_sched_decode_step.
+// ---------------------------------------------------------------------------------------------
+namespace mb200 {
+__global__ void rope_table_dev_kernel(float2* __restrict__ tab, int S, int half, int rot, const int* __restrict__ pos0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * half) return;
+  const int p = i % half, s = i / half;
+  const float inv_freq = 1.0f / powf(10000.0f, (float)(2 * p) / (float)rot);
+  float sn, cs;
+  sincosf((float)(*pos0 + s) * inv_freq, &sn, &cs);
+  tab[i] = make_float2(cs, sn);
+}
+
+// x[b] = wte[tokens[b][pos]] : the input embedding of the decode step at cache position `pos` (the token emitted last)
+__global__ void decode_embed_kernel(const long long* __restrict__ tokens, long long ld_tok, const int* __restrict__ pos,
+                                    const bf16* __restrict__ wte, bf16* __restrict__ out, int d, int vocab) {
+  long long tok = tokens[(long long)blockIdx.x * ld_tok + *pos];
+  if (tok < 0 || tok >= vocab) tok = 0;
+  const uint4* src = reinterpret_cast<const uint4*>(wte + tok * (long long)d);
+  uint4* dst = reinterpret_cast<uint4*>(out + (long long)blockIdx.x * d);
+  for (int c = threadIdx.x; c < (d >> 3); c += blockDim.x) dst[c] = __ldg(src + c);
+}
+
+// tokens[b][pos + 1] = next[b]; flags[pos + 1 - s0] = every row emitted EOS (sampling.py:109); pos += 1. One CTA.
+__global__ void decode_advance_kernel(const long long* __restrict__ next, long long* __restrict__ tokens, long long ld_tok,
+                                      int* __restrict__ pos, long long eos, unsigned char* __restrict__ flags, int s0,
+                                      int n_flags, int B) {
+  const int p = *pos;
+  int is_eos = 1;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const long long t = next[b];
+    if (p + 1 < ld_tok) tokens[(long long)b * ld_tok + p + 1] = t;
+    is_eos &= (t == eos);
+  }
+  const int all = __syncthreads_and(is_eos);
+  if (threadIdx.x == 0) {
+    const int i = p + 1 - s0;
+    if (flags != nullptr && i >= 0 && i < n_flags) flags[i] = (unsigned char)all;
+    *pos = p + 1;
+  }
+}
+}  // namespace mb200
+
+extern "C" int mb200_rope_table_dev(float* tab, int32_t S, int32_t rot, const int32_t* pos0_dev, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(S > 0 && rot > 0 && rot % 2 == 0 && pos0_dev != nullptr, MB200_E_SHAPE, "rope_table_dev: bad S=%d rot=%d", S, rot);
+  const int n = S * (rot / 2);
+  mb200::rope_table_dev_kernel<<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<float2*>(tab), S, rot / 2, rot,
+                                                                          pos0_dev);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_decode_embed(const int64_t* tokens, int64_t ld_tok, const int32_t* pos_dev, const void* wte, void* x,
+                                  int32_t B, int32_t d, int32_t vocab, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(d % 8 == 0 && B > 0 && tokens && pos_dev, MB200_E_SHAPE, "decode_embed: bad B=%d d=%d", B, d);
+  mb200::decode_embed_kernel<<<B, 256, 0, ST(stream)>>>((const long long*)tokens, ld_tok, pos_dev, (const bf16*)wte,
+                                                         (bf16*)x, d, vocab);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_decode_advance(const int64_t* next, int64_t* tokens, int64_t ld_tok, int32_t* pos_dev, int64_t eos,
+                                    uint8_t* flags, int32_t s0, int32_t n_flags, int32_t B, void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(B > 0 && next && tokens && pos_dev, MB200_E_ARG, "decode_advance: null argument");
+  mb200::decode_advance_kernel<<<1, 256, 0, ST(stream)>>>((const long long*)next, (long long*)tokens, ld_tok, pos_dev,
+                                                          (long long)eos, flags, s0, n_flags, B);
+  MB_LAUNCH_CHECK();
+  return 0;
+}

@@ -362,7 +362,10 @@ int make_store_map(CUtensorMap* out, const void* ptr, bool f32, int N, int M, in
   MB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0 &&
                  (nb0 == 1 || (bs0 * esz) % 16 == 0) && (nb1 == 1 || (bs1 * esz) % 16 == 0),
              MB200_E_ALIGN, "gemm output must be 16B aligned in pointer, row stride and batch strides");
-  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)nb0, (cuuint64_t)nb1};
+  // TMA stores clip at 16-byte granules: the map ends at N rounded DOWN to 16 bytes; the epilogue's threads write the
+  // remaining N % 8 (bf16) / N % 4 (fp32) columns themselves (epi_tile_v3). At least one granule so the map stays legal.
+  const int n16 = f32 ? (N & ~3) : (N & ~7);
+  cuuint64_t dims[4] = {(cuuint64_t)(n16 > 0 ? n16 : (f32 ? 4 : 8)), (cuuint64_t)M, (cuuint64_t)nb0, (cuuint64_t)nb1};
   cuuint64_t strides[3] = {(cuuint64_t)(ld * esz), (cuuint64_t)((nb0 > 1 ? bs0 : ld) * esz),
                            (cuuint64_t)((nb1 > 1 ? bs1 : ld) * esz)};
   cuuint32_t box[4] = {(cuuint32_t)(f32 ? 32 : 64), 128, 1, 1};

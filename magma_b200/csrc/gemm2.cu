@@ -253,9 +253,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
 #undef MB_EPI
     }
-    // the staging slots must outlive the bulk stores that read them, and the stores must have landed before the grid
-    // counts as complete for its dependents
-    if (q == 0 && lane == 0) tma_store_wait_all();
+    // the staging slots must outlive the bulk stores that read them (the writes themselves are complete, like every
+    // memory operation of the grid, before a dependent grid's griddepcontrol.wait returns)
+    if (q == 0 && lane == 0) tma_store_wait_read0();
   }
 
   // neither CTA may exit (or free TMEM) while the pair still reads its shared memory / TMEM

@@ -499,7 +499,9 @@ __device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi
   int rope_pos = 0;
   if constexpr (ROPE) rope_pos = grow % p.rope_S;
 
-  uint4 cur[NIN > 0 ? NIN : 1][4], nxt[NIN > 0 ? NIN : 1][4];
+  // row-shaped inputs are fetched TWO chunks ahead (an L2 round trip under load is about two chunks of epilogue work;
+  // the first two fetches are issued before the accumulator wait and ride under the mainloop)
+  uint4 cur[NIN > 0 ? NIN : 1][4], nxt[NIN > 0 ? NIN : 1][4], nx2[NIN > 0 ? NIN : 1][4];
   auto load_inputs = [&](int ch, uint4 (&dst)[NIN > 0 ? NIN : 1][4]) {
     if constexpr (NIN > 0) {
       const int n0 = n_tile0 + ch * 32;
@@ -522,7 +524,8 @@ __device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi
       }
     }
   };
-  load_inputs(0, cur);  // overlaps the accumulator wait
+  load_inputs(0, cur);
+  if (NCH > 1) load_inputs(1, nxt);
   mbar_wait(c.tmem_full, c.full_phase);
   tc_fence_after();
   const int n_valid_ch = min(NCH, (p.N - n_tile0 + 31) / 32);  // chunks of this tile that start inside the matrix
@@ -530,7 +533,7 @@ __device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi
 #pragma unroll 1
   for (int ch = 0; ch < n_valid_ch; ++ch) {
     const int n0 = n_tile0 + ch * 32;
-    if (ch + 1 < n_valid_ch) load_inputs(ch + 1, nxt);
+    if (ch + 2 < n_valid_ch) load_inputs(ch + 2, nx2);
     uint32_t rr[32];
     tmem_ld_32x32(c.tmem_acc + (uint32_t)(ch * 32), rr);
     tmem_ld_wait();
@@ -578,7 +581,26 @@ __device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi
         }
       }
     }
+    // Columns [N16, N) — the last N % 8 bf16 (N % 4 fp32) columns of a ragged N such as the 50258-wide LM head: a TMA
+    // store clips at 16-byte granules, not at elements (measured: a [.., 1002]-wide bf16 store also wrote columns
+    // 1002..1007), so the output maps end at N16 = N rounded down to 16 bytes and the thread that owns the row writes
+    // those few elements itself. AUX stores its pre-activation tail below, before the activation is applied.
+    const int n16 = F32 ? (p.N & ~3) : (p.N & ~7);
+    const bool has_tail = n0 + 32 > n16 && n0 < p.N && row_ok;
+    if constexpr (AUX) {
+      if (has_tail) {  // (fully unrolled with static indices: a runtime index would move v[] to local memory)
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j >= n16 && n0 + j < p.N) p.aux_out[c.boff + (long long)grow * p.ldc + n0 + j] = __float2bfloat16(v[j]);
+      }
+    }
     if constexpr (F32) {
+      if (has_tail) {
+        float* crow = reinterpret_cast<float*>(p.C) + c.boff + (long long)grow * p.ldc + n0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j >= n16 && n0 + j < p.N) crow[j] = ACCUM ? crow[j] + v[j] : v[j];
+      }
       // one 32-column chunk = one [128 x 32] fp32 box
       const uint32_t slot_s = c.pool_s + (box & 1u) * 16384u;
 #pragma unroll
@@ -643,6 +665,12 @@ __device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
       }
+      if (has_tail) {
+        bf16* crow = reinterpret_cast<bf16*>(p.C) + c.boff + (long long)grow * p.ldc + n0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j >= n16 && n0 + j < p.N) crow[j] = __float2bfloat16(v[j]);
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         sts128u(slot_out + row_s + (((uint32_t)(half * 4 + k) ^ sw) << 4), f32x8_to_bf16(v + 8 * k));
@@ -666,7 +694,10 @@ __device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi
 #pragma unroll
       for (int i = 0; i < NIN; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cur[i][k] = nxt[i][k];
+        for (int k = 0; k < 4; ++k) {
+          cur[i][k] = nxt[i][k];
+          nxt[i][k] = nx2[i][k];
+        }
     }
   }
   if (n_valid_ch <= 0) {  // (cannot happen: tiles start inside the matrix) keep the TMEM protocol intact regardless

@@ -564,13 +564,19 @@ int make_infer_plan(InferPlan& P, const mb200_gptj_model_ex* m, int B, int S, in
   return 0;
 }
 
+// pos_dev != NULL: decode step (S == 1) whose cache position is read from DEVICE memory by the kernels that need it
+// (rotary table, fused cache attention) — nothing in the launch sequence depends on the position, so the whole step can
+// be captured once in a CUDA graph and replayed per token (pos0 is ignored).
 int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, long long ldv, int last_only, bf16s* hidden,
-                  bf16s* kcache, bf16s* vcache, int Smax, int pos0, int B, int S, void* ws, size_t ws_bytes, void* st) {
+                  bf16s* kcache, bf16s* vcache, int Smax, int pos0, int B, int S, void* ws, size_t ws_bytes, void* st,
+                  const int32_t* pos_dev = nullptr) {
   InferPlan P;
   MBS_TRY(make_infer_plan(P, m, B, S, kcache ? Smax : S, ws));
   MBS_REQUIRE(ws != nullptr && ws_bytes >= P.bytes, MB200_E_ARG, "gptj_sched_infer: workspace too small (%zu < %zu)",
               ws_bytes, P.bytes);
   MBS_REQUIRE((kcache == nullptr) == (vcache == nullptr), MB200_E_ARG, "gptj_sched_infer: kcache and vcache go together");
+  MBS_REQUIRE(!pos_dev || (kcache && S == 1), MB200_E_ARG, "gptj_sched_decode_step: needs a KV cache and S == 1");
+  if (pos_dev) pos0 = 0;
   MBS_REQUIRE(pos0 >= 0 && (kcache ? pos0 + S <= Smax : pos0 == 0), MB200_E_SHAPE,
               "gptj_sched_infer: pos0=%d S=%d does not fit the cache (%d) / needs a cache", pos0, S, Smax);
   for (int l = 1; l < m->n_layer; ++l)
@@ -587,7 +593,8 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
     SplitScope(void* w, size_t b) { t_splitk_ws = w; t_splitk_bytes = (long long)b; }
     ~SplitScope() { t_splitk_ws = nullptr; t_splitk_bytes = 0; }
   } split_scope(P.splitk, P.splitk_bytes);
-  MBS_TRY(mb200_rope_table(P.rope_tab, S, m->rotary_dim, pos0, st));
+  if (pos_dev) MBS_TRY(mb200_rope_table_dev(P.rope_tab, S, m->rotary_dim, pos_dev, st));
+  else MBS_TRY(mb200_rope_table(P.rope_tab, S, m->rotary_dim, pos0, st));
   const bf16s* xin = x;
   for (int l = 0; l < m->n_layer; ++l) {
     const mb200_gptj_layer_ex& L = m->layers[l];
@@ -605,7 +612,9 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
     }
     bf16s* kc = kcache ? kcache + (size_t)l * cache_layer : nullptr;
     bf16s* vc = vcache ? vcache + (size_t)l * cache_layer : nullptr;
-    if (kcache && S == 1) {
+    if (kcache && S == 1 && pos_dev) {
+      MBS_TRY(mb200_attn_decode_dev(P.qkv, 3 * d, kc, vc, P.attn_o, d, B, H, hd, Smax, pos_dev, st));
+    } else if (kcache && S == 1) {
       MBS_TRY(mb200_attn_decode(P.qkv, 3 * d, kc, vc, P.attn_o, d, B, H, hd, Smax, pos0, st));
     } else if (flash_ok(hd)) {  // prompts of any length and prefill continuations: fused forward over qkv or the cache
       const long long qb0 = hd, qb1 = (long long)S * 3 * d;
@@ -705,6 +714,16 @@ extern "C" int mb200_gptj_sched_infer(const mb200_gptj_model_ex* m, const void* 
   if (rc) return rc;
   return mb200::forward_infer(m, (const mb200::bf16s*)x, (mb200::bf16s*)logits, ldv, last_only, (mb200::bf16s*)hidden,
                               (mb200::bf16s*)kcache, (mb200::bf16s*)vcache, S_kv_max, pos0, B, S, ws, ws_bytes, stream);
+}
+
+extern "C" int mb200_gptj_sched_decode_step(const mb200_gptj_model_ex* m, const void* x, void* logits, int64_t ldv,
+                                            void* kcache, void* vcache, int32_t S_kv_max, const int32_t* pos_dev,
+                                            int32_t B, void* ws, size_t ws_bytes, void* stream) {
+  int rc = mb200::rt_check_arch();
+  if (rc) return rc;
+  MBS_REQUIRE(pos_dev != nullptr, MB200_E_ARG, "gptj_sched_decode_step: pos_dev is NULL");
+  return mb200::forward_infer(m, (const mb200::bf16s*)x, (mb200::bf16s*)logits, ldv, 1, nullptr, (mb200::bf16s*)kcache,
+                              (mb200::bf16s*)vcache, S_kv_max, 0, B, 1, ws, ws_bytes, stream, pos_dev);
 }
 
 extern "C" size_t mb200_gptj_sched_workspace_bytes(const mb200_gptj_model_ex* m, int32_t B, int32_t S) {

@@ -39,8 +39,13 @@ __global__ void kv_append_kernel(const bf16* __restrict__ qkv, long long ld, bf1
 static constexpr int kDecThreads = 256;
 __global__ void __launch_bounds__(kDecThreads)
 attn_decode_kernel(const bf16* __restrict__ qkv, long long ld_qkv, bf16* __restrict__ kc, bf16* __restrict__ vc,
-                   bf16* __restrict__ out, long long ld_out, int H, int hd, int Smax, int pos) {
+                   bf16* __restrict__ out, long long ld_out, int H, int hd, int Smax, int pos_host,
+                   const int* __restrict__ pos_dev) {
   extern __shared__ float sc[];  // [pos+1] scores, then [32] reduction scratch
+  // the cache position: a kernel argument, or — device-resident decode loop, one replayed CUDA graph per token — read
+  // from device memory (shared memory is then sized for Smax by the launch)
+  const int pos = pos_dev ? *pos_dev : pos_host;
+  if (pos < 0 || pos >= Smax) return;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = pos + 1;
@@ -119,7 +124,31 @@ extern "C" int mb200_attn_decode(const void* qkv, int64_t ld_qkv, void* kcache, 
   const size_t smem = (((size_t)(pos + 1) + 31) & ~(size_t)31) * 4 + 32 * 4;
   attn_decode_kernel<<<B * H, kDecThreads, smem, (cudaStream_t)stream>>>((const bf16*)qkv, ld_qkv, (bf16*)kcache,
                                                                          (bf16*)vcache, (bf16*)out, ld_out, H, hd,
-                                                                         S_kv_max, pos);
+                                                                         S_kv_max, pos, nullptr);
+  count_launch();
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// the same step with the cache position read from device memory (graph-replayed decode loop)
+extern "C" int mb200_attn_decode_dev(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, void* out,
+                                     int64_t ld_out, int32_t B, int32_t H, int32_t hd, int32_t S_kv_max,
+                                     const int32_t* pos_dev, void* stream) {
+  int rc = check_arch();
+  if (rc) return rc;
+  MB_REQUIRE(hd % 8 == 0 && S_kv_max > 0 && pos_dev != nullptr, MB200_E_SHAPE, "attn_decode_dev: bad hd=%d Smax=%d", hd,
+             S_kv_max);
+  const size_t smem = (((size_t)S_kv_max + 31) & ~(size_t)31) * 4 + 32 * 4;
+  MB_REQUIRE(smem <= 200 * 1024, MB200_E_SHAPE, "attn_decode_dev: cache length %d needs %zu bytes of shared memory", S_kv_max,
+             smem);
+  static bool set = false;
+  if (!set) {
+    MB_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    set = true;
+  }
+  attn_decode_kernel<<<B * H, kDecThreads, smem, (cudaStream_t)stream>>>((const bf16*)qkv, ld_qkv, (bf16*)kcache,
+                                                                         (bf16*)vcache, (bf16*)out, ld_out, H, hd,
+                                                                         S_kv_max, 0, pos_dev);
   count_launch();
   MB_CUDA(cudaGetLastError());
   return 0;

@@ -450,6 +450,28 @@ class B200GPTJForCausalLM(nn.Module):
         return out
 
     @torch.no_grad()
+    def decode_step_dev(self, x, cache, pos_dev, logits):
+        """One decode step (S = 1, last-position logits into the preallocated `logits` [B, ldv]) whose cache position is
+        read from DEVICE memory (`pos_dev`, int32 [1]): no host-side argument changes from token to token, so
+        sampling.generate captures the step once in a CUDA graph and replays it (mb200_gptj_sched_decode_step). The
+        caller advances `pos_dev` (ops.decode_advance) and keeps `cache.pos` in step."""
+        B, S, d = x.shape
+        assert S == 1 and x.dtype == torch.bfloat16 and x.is_contiguous()
+        m = self._cmodel_ex()[0]
+        nbytes = lib().mb200_gptj_sched_infer_workspace_bytes(ctypes.byref(m), B, 1, cache.S_max)
+        if nbytes == 0:
+            raise MB200Error(lib().mb200_last_error().decode())
+        ws = self._ws.get("infer")
+        if ws is None or ws.numel() < nbytes:
+            self._ws.pop("infer", None)
+            ws = self._ws["infer"] = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+        check(lib().mb200_gptj_sched_decode_step(ctypes.byref(m), ops._ptr(x), ops._ptr(logits),
+                                                 ctypes.c_int64(logits.stride(0)), ops._ptr(cache.k), ops._ptr(cache.v),
+                                                 cache.S_max, ops._ptr(pos_dev), B, ops._ptr(ws),
+                                                 ctypes.c_size_t(ws.numel()), ops._stream()))
+        return logits
+
+    @torch.no_grad()
     def decode_logits(self, inputs_embeds, cache):
         """Last-position logits only (what magma/sampling.py:92 consumes): the LM head runs on B rows, not B*S."""
         _, lg = self._run_forward(inputs_embeds, None, training=False, cache=cache, last_only=True)

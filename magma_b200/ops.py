@@ -277,12 +277,29 @@ def dropout_apply(x, mask, p):
     return y
 
 
-def argmax(x, V=None):
+def argmax(x, V=None, out=None):
     rows = x.shape[0]
     V = x.shape[1] if V is None else V
-    out = torch.empty(rows, dtype=torch.int64, device=x.device)
+    if out is None:
+        out = torch.empty(rows, dtype=torch.int64, device=x.device)
     check(lib().mb200_argmax(_ptr(x), ctypes.c_int64(x.stride(0)), rows, V, _ptr(out), _stream()))
     return out
+
+
+def decode_embed(tokens, pos_dev, wte, out):
+    """out[b] = wte[tokens[b, pos]] with the column `pos` read from DEVICE memory (int32 [1]) — the input embedding of
+    a graph-replayed decode step (mb200_decode_embed)."""
+    V, d = wte.shape
+    check(lib().mb200_decode_embed(_ptr(tokens), ctypes.c_int64(tokens.stride(0)), _ptr(pos_dev), _ptr(wte), _ptr(out),
+                                   tokens.shape[0], d, V, _stream()))
+    return out
+
+
+def decode_advance(next_tokens, tokens, pos_dev, eos, flags, s0):
+    """tokens[:, pos + 1] = next_tokens; flags[pos + 1 - s0] = all rows emitted `eos`; pos += 1 (all on the device)."""
+    check(lib().mb200_decode_advance(_ptr(next_tokens), _ptr(tokens), ctypes.c_int64(tokens.stride(0)), _ptr(pos_dev),
+                                     ctypes.c_int64(-1 if eos is None else int(eos)), _ptr(flags), int(s0),
+                                     flags.numel() if flags is not None else 0, tokens.shape[0], _stream()))
 
 
 def nchw_to_nhwc8(x):

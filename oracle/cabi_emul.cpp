@@ -1011,4 +1011,41 @@ int mb200_vit_assemble(void* x_, const void* pe_, const void* cls_, const void* 
   return 0;
 }
 
+// device-resident decode loop: on the CPU the "device" position is ordinary memory
+int mb200_rope_table_dev(float* tab, int32_t S, int32_t rot, const int32_t* pos0_dev, void* st) {
+  EM_REQUIRE(pos0_dev != nullptr, MB200_E_ARG, "rope_table_dev: null position");
+  return mb200_rope_table(tab, S, rot, *pos0_dev, st);
+}
+int mb200_attn_decode_dev(const void* qkv, int64_t ld_qkv, void* kc, void* vc, void* out, int64_t ld_out, int32_t B,
+                          int32_t H, int32_t hd, int32_t Smax, const int32_t* pos_dev, void* st) {
+  EM_REQUIRE(pos_dev != nullptr, MB200_E_ARG, "attn_decode_dev: null position");
+  return mb200_attn_decode(qkv, ld_qkv, kc, vc, out, ld_out, B, H, hd, Smax, *pos_dev, st);
+}
+int mb200_decode_embed(const int64_t* tokens, int64_t ld_tok, const int32_t* pos_dev, const void* wte_, void* x_, int32_t B,
+                       int32_t d, int32_t vocab, void*) {
+  EM_REQUIRE(d % 8 == 0 && B > 0 && tokens && pos_dev, MB200_E_SHAPE, "decode_embed: bad B / d");
+  const bf16_t* wte = (const bf16_t*)wte_;
+  bf16_t* x = (bf16_t*)x_;
+  for (long long b = 0; b < B; ++b) {
+    long long tok = tokens[b * ld_tok + *pos_dev];
+    if (tok < 0 || tok >= vocab) tok = 0;
+    memcpy(x + b * d, wte + tok * (long long)d, (size_t)d * 2);
+  }
+  return 0;
+}
+int mb200_decode_advance(const int64_t* next, int64_t* tokens, int64_t ld_tok, int32_t* pos_dev, int64_t eos,
+                         uint8_t* flags, int32_t s0, int32_t n_flags, int32_t B, void*) {
+  EM_REQUIRE(B > 0 && next && tokens && pos_dev, MB200_E_ARG, "decode_advance: null argument");
+  const int p = *pos_dev;
+  int all = 1;
+  for (long long b = 0; b < B; ++b) {
+    if (p + 1 < ld_tok) tokens[b * ld_tok + p + 1] = next[b];
+    all &= next[b] == eos;
+  }
+  const int i = p + 1 - s0;
+  if (flags && i >= 0 && i < n_flags) flags[i] = (uint8_t)all;
+  *pos_dev = p + 1;
+  return 0;
+}
+
 }  // extern "C"

@@ -102,7 +102,8 @@ def _ref_general(q, k, v, causal):
 
 @pytest.mark.parametrize("S,H,hd,causal", [(129, 2, 256, True), (257, 4, 64, False), (300, 2, 256, True),
                                             (128, 2, 128, True), (1, 1, 64, False), (640, 2, 128, True),
-                                            (2048, 2, 256, True), (70, 3, 192, False)])
+                                            (2048, 2, 256, True), (70, 3, 192, False), (384, 2, 64, True),
+                                            (256, 2, 128, False)])
 def test_attn_flash_forward_matches_materialised_softmax(S, H, hd, causal):
     import torch
 

@@ -245,3 +245,38 @@ def test_config2_full_size_matches_oracle():
     assert r["logits"] < 3e-2
     bad = {k: round(e, 4) for k, e in r["grads"].items() if e >= 3e-2}
     assert not bad, bad
+
+
+def test_graph_replayed_decode_emits_the_same_tokens_as_the_host_driven_loop(monkeypatch):
+    """magma/sampling.py:78-109 at temperature 0: the device-resident decode loop (one CUDA graph of the decode step
+    replayed per token, cache position in device memory) against the host-driven loop over the same kernels — every
+    emitted id identical, including the early exit when all rows hit EOS."""
+    import torch
+
+    from _gpu_util import build_magma_from_weights, gpu_device
+    from oracle import magma_oracle as O
+    from tools.model_check import small_cfg
+
+    dev = gpu_device()
+    cfg = small_cfg(n_layer=3)
+    w = O.init_weights(cfg, seed=9)
+    w["lm.lm_head.weight"] = w["lm.lm_head.weight"] * 8  # sharpen the head: greedy ids not decided by bf16 near-ties
+    w16 = {k: v.to(torch.bfloat16).float() for k, v in w.items()}
+    model = build_magma_from_weights(w16, cfg, {"mlp": {"adapter_type": "normal", "downsample_factor": 4}}, 32, dev)
+    model.eval()
+    g = torch.Generator().manual_seed(3)
+    emb = (torch.randn(4, 7, cfg.d, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+    monkeypatch.setenv("MB200_DECODE_GRAPH", "0")
+    host = model.generate(emb, max_steps=40, temperature=0.0, decode=False).cpu()
+    monkeypatch.setenv("MB200_DECODE_GRAPH", "1")
+    graph = model.generate(emb, max_steps=40, temperature=0.0, decode=False).cpu()
+    assert host.shape == graph.shape and torch.equal(host, graph)
+    # early exit: make EOS the argmax of every row from some step on (bias the EOS logit hard), both loops stop alike
+    model.lm.lm_head.bias.data[cfg.eos_token] = 1e4
+    model.lm.invalidate()
+    model.lm.attach_arena(model.arena)
+    monkeypatch.setenv("MB200_DECODE_GRAPH", "0")
+    host = model.generate(emb, max_steps=40, temperature=0.0, decode=False).cpu()
+    monkeypatch.setenv("MB200_DECODE_GRAPH", "1")
+    graph = model.generate(emb, max_steps=40, temperature=0.0, decode=False).cpu()
+    assert host.shape == graph.shape and torch.equal(host, graph) and host.shape[1] < 7 + 40
