@@ -32,11 +32,13 @@ class B200Engine:
         # experimental data-parallel knobs (both off by default): exchange gradients as bf16, and keep a
         # few SMs out of the persistent GEMM grids so NCCL's CTAs run beside the backward GEMMs
         self.comm_dtype = torch.bfloat16 if os.environ.get("MB200_DP_BF16", "0") == "1" else None
-        gemm_sms = int(os.environ.get("MB200_DP_GEMM_SMS", "0"))
-        if self.world > 1 and gemm_sms > 0:
-            from ._lib import lib
-
-            lib().mb200_set_gemm_sm_limit(gemm_sms)
+        # SM carve-out for the gradient exchange: while an all-reduce is in flight (from the first bucket issued in
+        # backward until the optimizer step has waited for the last one) the persistent GEMM grids leave 148 - n SMs
+        # alone, so NCCL's CTAs run BESIDE the backward GEMMs instead of queueing behind 148-CTA grids (each NCCL CTA
+        # otherwise takes an SM at a kernel boundary and the next GEMM's last CTAs start only when it leaves).
+        # Outside that window every kernel gets all SMs. MB200_DP_GEMM_SMS=0 disables it.
+        self.dp_gemm_sms = int(os.environ.get("MB200_DP_GEMM_SMS", "0")) if self.world > 1 else 0
+        self._carved = False
         self._pending = []
         self.chunks = dp.layer_chunks(len(model.lm.transformer.h), n_buckets)  # (hi, lo), last layers first
         self._segments = None  # optimizer parameter groups, built at the first step (utils.configure_param_groups)
@@ -68,6 +70,11 @@ class B200Engine:
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
             dp.allreduce_slice(arena.grad, lo, hi, comm_dtype=self.comm_dtype)
+        if self.dp_gemm_sms > 0 and not self._carved:  # GEMMs launched from here on leave room for NCCL
+            from ._lib import lib
+
+            lib().mb200_set_gemm_sm_limit(self.dp_gemm_sms)
+            self._carved = True
 
     def backward(self, loss):
         """engine.backward (train_loop.py:18): loss/grad_accum scaling, chunked backward with overlapped all-reduce
@@ -100,6 +107,11 @@ class B200Engine:
             return
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if self._carved:  # the exchange is ordered before everything launched from here on: all SMs again
+            from ._lib import lib
+
+            lib().mb200_set_gemm_sm_limit(0)
+            self._carved = False
         cfg = self.config
         lr = cfg.lr_at(self.global_step) if hasattr(cfg, "lr_at") else cfg.lr
         if self._segments is None:
