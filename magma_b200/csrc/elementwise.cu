@@ -395,7 +395,9 @@ extern "C" int mb200_add(const void* a, const void* b, const void* c, void* y, i
 
 extern "C" int mb200_sumsq(const float* x, int64_t n, float* out, void* stream) {
   MB_ENTER();
-  sumsq_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, n, out);
+  int grid = grid_for(n, 256);
+  if (grid > kSumsqMaxBlocks) grid = kSumsqMaxBlocks;
+  sumsq_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, out);
   MB_LAUNCH_CHECK();
   return 0;
 }

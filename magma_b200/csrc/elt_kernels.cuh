@@ -605,15 +605,38 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
 // through a device-side squared-norm, and the bf16 compute copy of the weights refreshed in the same pass.
 // HBM-bound: 16 B read + 14 B written per parameter.
 // ---------------------------------------------------------------------------------------------
+// Deterministic: per-block partial sums land in a fixed slot each and the LAST block to finish adds them in a fixed order
+// — every data-parallel rank holds bit-identical gradients after the all-reduce and must derive the bit-identical clipping
+// coefficient from them, or the replicas' parameters drift apart by an ulp per step (an atomicAdd of the block sums, the
+// previous version, is order-dependent in its last bits; tests/test_dp_gpu.py caught exactly that on 2 B200s).
+static constexpr int kSumsqMaxBlocks = 2048;
+__device__ float g_sumsq_part[kSumsqMaxBlocks];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
   __shared__ float red[32];
+  __shared__ int is_last;
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
     s += v * v;
   }
   const float t = block_sum<256>(s, red);
-  if (threadIdx.x == 0) atomicAdd(out, t);
+  if (threadIdx.x == 0) {
+    g_sumsq_part[blockIdx.x] = t;
+    __threadfence();
+    is_last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float a = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) a += *((volatile float*)&g_sumsq_part[i]);
+  const float total = block_sum<256>(a, red);
+  if (threadIdx.x == 0) {
+    out[0] += total;
+    g_sumsq_ticket = 0;
+  }
 }
 
 __global__ void adamw_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m1,

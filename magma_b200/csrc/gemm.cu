@@ -510,6 +510,17 @@ static SmallPlan plan_small_m(int N, int K, int M, size_t ws_bytes) {
   return best;
 }
 
+// Scratch lent by the caller (mb200_gemm_args.splitk_ws) serves two users that never meet in one launch but do follow each
+// other on a stream: split-K partial slices (front of the buffer) and stream-K flags + partial tiles (the LAST
+// kStreamKRegion bytes, when the buffer is large enough to keep kStreamKMinFront for split-K) — separate regions, so
+// split-K data never lands on stream-K's epoch flags.
+static constexpr size_t kStreamKRegion = (size_t)64 << 20;
+static constexpr size_t kStreamKMinFront = (size_t)32 << 20;
+static inline size_t splitk_budget(const mb200_gemm_args* a) {
+  const size_t b = a->splitk_ws ? (size_t)a->splitk_ws_bytes : 0;
+  return b >= kStreamKRegion + kStreamKMinFront ? b - kStreamKRegion : b;
+}
+
 int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   MB_REQUIRE(a != nullptr, MB200_E_ARG, "null gemm args");
   MB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->nb0 > 0 && a->nb1 > 0, MB200_E_SHAPE,
@@ -538,7 +549,7 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
                        a->force_bn != 512;
   int plan_split = 1;
   if (small_m && !a->force_bn) {
-    const SmallPlan pl = plan_small_m(a->N, a->K, a->M, a->splitk_ws ? (size_t)a->splitk_ws_bytes : 0);
+    const SmallPlan pl = plan_small_m(a->N, a->K, a->M, splitk_budget(a));
     bn = pl.bn;
     plan_split = pl.split;
   }
@@ -612,6 +623,9 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
     }
     kp.b_static = (a->B.static_data != 0 && preload) ? 1 : 0;
   }
+  kp.sk_on = 0;
+  kp.sk_ws = nullptr;
+  kp.sk_flags = nullptr;
   kp.split_k = 1;
   kp.kb_per_split = (a->K + BK - 1) / BK;
   kp.splitk_ws = nullptr;
@@ -638,7 +652,7 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
       if (split > num_kb / 4) split = num_kb / 4;
     }
     const long long ld_ws = (a->N + 3) / 4 * 4;
-    while (split > 1 && (size_t)split * a->M * ld_ws * sizeof(float) > (size_t)a->splitk_ws_bytes) --split;
+    while (split > 1 && (size_t)split * a->M * ld_ws * sizeof(float) > splitk_budget(a)) --split;
     if (split > 1) {
       const int kb_per = (num_kb + split - 1) / split;
       split = (num_kb + kb_per - 1) / kb_per;  // every split owns at least one k-block
@@ -689,16 +703,76 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
     // the rotary epilogue of the row-per-thread path works on whole 32-column chunks
     if (kp.epi_kind == EK_ROPE && (a->rope_hd % 32 != 0 || a->rope_rot % 32 != 0 || a->rope_ncols % 32 != 0))
       kp.epi_kind = EK_GENERIC;
+    // ---- stream-K of the last wave (see GemmKernelParams::sk_*): only when the caller lent scratch memory ----
+    kp.sk_on = 0;
+    CUtensorMap tmWs;
+    {
+      static int sk_env = -1;
+      if (sk_env < 0) {
+        const char* e = getenv("MB200_STREAMK");  // 0 = never split the last wave (A/B switch)
+        sk_env = e ? atoi(e) : 1;
+      }
+      const int ncl = gemm_sms() / 2;
+      const int T = kp.total_tiles, KBn = (a->K + BK - 1) / BK;
+      const int W = T / ncl, R = T - W * ncl;
+      if (sk_env && a->splitk_ws && a->nb0 * a->nb1 == 1 && kp.epi_kind != EK_GENERIC && R > 0 && R < ncl && KBn >= 16 &&
+          !a->force_bn) {
+        const int h = (int)(((long long)R * KBn + ncl - 1) / ncl);
+        const int tail = KBn - h, nh = ncl - R;
+        const long long U = (long long)R * tail;
+        // pieces per helper (slots) and per tile (the owner's partial list) must stay small: every partial is a
+        // 256 KB L2 round trip on the owner's critical path
+        int pmax = 0, per_tile = 0;
+        if (h >= 8 && tail >= 1 && h < KBn) {
+          for (int j = 0; j < nh; ++j) {
+            const long long lo = (long long)j * U / nh, hi = (long long)(j + 1) * U / nh;
+            const int np = hi > lo ? (int)((hi - 1) / tail - lo / tail) + 1 : 0;
+            if (np > pmax) pmax = np;
+          }
+          for (int ti = 0; ti < R; ++ti) {
+            const long long x0 = (long long)ti * tail, x1 = x0 + tail;
+            int n = 0;
+            for (int j = 0; j < nh; ++j) {
+              const long long lo = (long long)j * U / nh, hi = (long long)(j + 1) * U / nh;
+              if (hi > lo && lo < x1 && hi > x0) ++n;
+            }
+            if (n > per_tile) per_tile = n;
+          }
+        }
+        const size_t flag_bytes = 65536;
+        const size_t need = flag_bytes + (size_t)nh * (size_t)(pmax > 0 ? pmax : 1) * 256 * 256 * sizeof(float);
+        uint8_t* sk_base = reinterpret_cast<uint8_t*>(a->splitk_ws) + (a->splitk_ws_bytes - (long long)kStreamKRegion);
+        if (pmax >= 1 && pmax <= 4 && per_tile >= 1 && per_tile <= 3 && need <= kStreamKRegion &&
+            (size_t)a->splitk_ws_bytes >= kStreamKRegion + kStreamKMinFront &&
+            (size_t)nh * pmax * 2 * sizeof(unsigned int) <= flag_bytes) {
+          static unsigned int epoch = 0x5eed0000u;
+          kp.sk_on = 1;
+          kp.sk_W = W;
+          kp.sk_R = R;
+          kp.sk_h = h;
+          kp.sk_tail = tail;
+          kp.sk_nh = nh;
+          kp.sk_pmax = pmax;
+          kp.sk_U = U;
+          kp.sk_flags = reinterpret_cast<unsigned int*>(sk_base);
+          kp.sk_ws = reinterpret_cast<float*>(sk_base + flag_bytes);
+          kp.sk_epoch = ++epoch;
+          rc = make_store_map(&tmWs, kp.sk_ws, true, 256, nh * pmax * 256, 1, 1, 256, 0, 0);
+          if (rc) return rc;
+        }
+      }
+    }
     CUtensorMap tmC, tmAux;
     rc = make_store_map(&tmC, a->C, f32, a->N, a->M, a->nb0, a->nb1, a->ldc, a->c_bs0, a->c_bs1);
     if (rc) return rc;
+    if (!kp.sk_on) tmWs = tmC;
     if (a->aux_out) {
       rc = make_store_map(&tmAux, a->aux_out, false, a->N, a->M, a->nb0, a->nb1, a->ldc, a->c_bs0, a->c_bs1);
       if (rc) return rc;
     } else {
       tmAux = tmC;
     }
-    return launch_gemm2(tmA, tmB, tmC, tmAux, kp, amn, bmn, f32, stream);
+    return launch_gemm2(tmA, tmB, tmC, tmAux, tmWs, kp, amn, bmn, f32, stream);
   }
   if (small_m) {
     switch (bn) {

@@ -32,7 +32,7 @@ template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
-                     const __grid_constant__ GemmKernelParams p) {
+                     const __grid_constant__ CUtensorMap tmWs, const __grid_constant__ GemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -58,6 +58,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmC);
     if (p.aux_out) tma_prefetch_desc(&tmAux);
+    if (p.sk_on) tma_prefetch_desc(&tmWs);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) {
@@ -88,35 +89,40 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // NOW, while this launch still waits for its predecessor, so the first HBM round trip (~1.5 us of weights the L2
       // has never seen) is not added to the exposed start-up of every GEMM.
       int npre = 0;
-      if (p.b_static && cid < p.total_tiles) {
+      WorkItem w0;
+      const bool any = next_item(p, cid, ncl, num_kb, 0, w0);
+      if (p.b_static && any) {
         const int tpb = p.tiles_m * p.tiles_n;
-        const int z = cid / tpb;
-        const int r = cid - z * tpb;
+        const int z = w0.tile / tpb;
+        const int r = w0.tile - z * tpb;
         const int n_row = (r / p.tiles_m) * BN2 + (int)rank * HB;
         const int z0 = z % p.nb0, z1 = z / p.nb0;
-        npre = num_kb < kStages2 ? num_kb : kStages2;
-        for (int kb = 0; kb < npre; ++kb) {
-          if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * kStage2);
-          uint8_t* sb = smem_b + kb * kB2;
+        const int nk0 = w0.kb1 - w0.kb0;
+        npre = nk0 < kStages2 ? nk0 : kStages2;
+        for (int i = 0; i < npre; ++i) {
+          const int kb = w0.kb0 + i;
+          if (rank == 0) mbar_expect_tx(&full_bar[i], 2 * kStage2);
+          uint8_t* sb = smem_b + i * kB2;
           if constexpr (B_MN) {
 #pragma unroll
-            for (int i = 0; i < HB / 64; ++i)
-              tma_load_4d_2sm(sb + i * 8192, &tmB, &full_bar[kb], n_row + i * 64, kb * BK, z0, z1);
+            for (int c = 0; c < HB / 64; ++c)
+              tma_load_4d_2sm(sb + c * 8192, &tmB, &full_bar[i], n_row + c * 64, kb * BK, z0, z1);
           } else {
-            tma_load_4d_2sm(sb, &tmB, &full_bar[kb], kb * BK, n_row, z0, z1);
+            tma_load_4d_2sm(sb, &tmB, &full_bar[i], kb * BK, n_row, z0, z1);
           }
         }
       }
       pdl_wait();
-      for (int t = cid; t < p.total_tiles; t += ncl) {
+      WorkItem w;
+      for (int it = 0; next_item(p, cid, ncl, num_kb, it, w); ++it) {
         const int tpb = p.tiles_m * p.tiles_n;
-        const int z = t / tpb;
-        const int r = t - z * tpb;
+        const int z = w.tile / tpb;
+        const int r = w.tile - z * tpb;
         const int m_blk = (r % p.tiles_m) * 2 + (int)rank;  // in 128-row units
         const int n_row = (r / p.tiles_m) * BN2 + (int)rank * HB;
         const int z0 = z % p.nb0, z1 = z / p.nb0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const bool preloaded = t == cid && kb < npre;  // slot known free, expect_tx posted, B already in flight
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          const bool preloaded = it == 0 && kb - w.kb0 < npre;  // slot known free, expect_tx posted, B already in flight
           if (!preloaded) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStage2);
@@ -155,14 +161,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint32_t a_kadv = A_MN ? 2048u : 32u, b_kadv = B_MN ? 2048u : 32u;
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = cid; t < p.total_tiles; t += ncl, ++it) {
+      WorkItem w;
+      for (int it = 0; next_item(p, cid, ncl, num_kb, it, w); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_a + stage * kA2);
@@ -171,7 +177,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc(sa + k * a_kadv, a_lbo, 1024);
             const uint64_t db = make_smem_desc(sb + k * b_kadv, b_lbo, 1024);
-            umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, da, db, idesc, ((kb - w.kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[stage], 3);  // frees the slot in both CTAs
           if (++stage == kStages2) {
@@ -186,9 +192,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
     pdl_wait();
     const int q = warp & 3;
-    int it = 0;
     uint32_t box = 0;  // boxes published so far (staging slot = box & 1)
-    for (int t = cid; t < p.total_tiles; t += ncl, ++it) {
+    WorkItem w;
+    for (int it = 0; next_item(p, cid, ncl, num_kb, it, w); ++it) {
+      const int t = w.tile;
       const int tpb = p.tiles_m * p.tiles_n;
       const int z = t / tpb;
       const int r = t - z * tpb;
@@ -231,7 +238,59 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       c.z1 = z1;
       c.tmC = &tmC;
       c.tmAux = &tmAux;
-#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM) epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT>(p, c, box)
+      c.npart = 0;
+      if (w.kind == 2) {
+        // ---- stream-K helper: this piece's fp32 partial tile -> workspace slot (plain TMA stores), then the flag ----
+        GemmKernelParams pw = p;
+        pw.N = BN2;
+        pw.M = 0x7fffffff;
+        pw.alpha = 1.f;
+        pw.bias = nullptr;
+        c.boff = 0;
+        c.row_cta0 = w.slot * 256 + (int)rank * BM;
+        c.n_blk = 0;
+        c.z0 = c.z1 = 0;
+        c.tmC = &tmWs;
+        epi_tile_v3<BN2, 0, 0, 0, false, false, false, float>(pw, c, box);
+        if (q == 0 && lane == 0) {
+          tma_store_wait_all();  // the bulk stores have been performed ...
+          asm volatile("fence.proxy.async;" ::: "memory");  // ... (async proxy -> generic proxy)
+          __threadfence();       // ... and are ordered before the flag for any observer on the device
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + w.slot * 2 + (int)rank), "r"(p.sk_epoch)
+                       : "memory");
+        }
+        continue;
+      }
+      if (w.kind == 1) {
+        // ---- stream-K owner: the helpers' pieces of this tile's k-blocks [h, num_kb) ----
+        const int ti = w.tile - p.sk_W * ncl;
+        const long long x0 = (long long)ti * p.sk_tail, x1 = x0 + p.sk_tail;
+        int j = (int)(x0 * p.sk_nh / p.sk_U);
+        if (j > 0) --j;
+        while (j + 1 < p.sk_nh && (long long)(j + 1) * p.sk_U / p.sk_nh <= x0) ++j;  // last helper starting at or before x0
+        for (; j < p.sk_nh && c.npart < 6; ++j) {
+          const long long a = (long long)j * p.sk_U / p.sk_nh, b = (long long)(j + 1) * p.sk_U / p.sk_nh;
+          if (a >= x1) break;
+          if (b <= x0 || b <= a) continue;
+          const int slot = j * p.sk_pmax + (int)(ti - a / p.sk_tail);
+          if (lane == 0) {  // wait until that helper's half for this CTA has landed
+            const unsigned int* f = p.sk_flags + slot * 2 + (int)rank;
+            unsigned int v;
+            unsigned int spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              if (v != p.sk_epoch && ++spins > MB200_SPIN_LIMIT) __trap();
+            } while (v != p.sk_epoch);
+          }
+          c.part[c.npart++] = p.sk_ws + ((long long)slot * 256 + (long long)rank * BM) * 256;
+        }
+        __syncwarp();
+      }
+#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM)                                          \
+  do {                                                                                     \
+    if (w.kind == 1) epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT, true>(p, c, box);  \
+    else epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT, false>(p, c, box);      \
+  } while (0)
       if constexpr (sizeof(OutT) == 4) {
         switch (p.epi_kind) {
           case EK_ACCUM: MB_EPI(0, 0, 0, false, false, true); break;
@@ -269,7 +328,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 template <bool A_MN, bool B_MN, typename OutT>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
-                   const GemmKernelParams& kp, cudaStream_t stream) {
+                   const CUtensorMap& tmWs, const GemmKernelParams& kp, cudaStream_t stream) {
   auto kern = gemm2_tcgen05_kernel<A_MN, B_MN, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -277,13 +336,13 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     attr_set = true;
   }
   const int max_clusters = gemm_sms() / 2;
-  const int clusters = kp.total_tiles < max_clusters ? kp.total_tiles : max_clusters;
+  const int clusters = kp.sk_on ? kp.sk_R + kp.sk_nh : (kp.total_tiles < max_clusters ? kp.total_tiles : max_clusters);
   {
     const double nb = (double)kp.total_tiles / ((double)kp.tiles_m * kp.tiles_n);
     const double flops = 2.0 * kp.M * (double)kp.N * kp.K * nb;
     const double bytes = nb * (2.0 * ((double)kp.M * kp.K + (double)kp.N * kp.K) + (double)sizeof(OutT) * kp.M * kp.N);
     GemmProfScope prof(stream, flops, bytes);
-    MB_CUDA(launch_pdl(kern, dim3(clusters * 2), dim3(kThreads), kSmem2, stream, tmA, tmB, tmC, tmAux, kp));
+    MB_CUDA(launch_pdl(kern, dim3(clusters * 2), dim3(kThreads), kSmem2, stream, tmA, tmB, tmC, tmAux, tmWs, kp));
   }
   count_launch();
   MB_CUDA(cudaGetLastError());
@@ -291,17 +350,17 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 }
 
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
-                 const GemmKernelParams& kp, bool a_mn, bool b_mn, bool f32, cudaStream_t stream) {
+                 const CUtensorMap& tmWs, const GemmKernelParams& kp, bool a_mn, bool b_mn, bool f32, cudaStream_t stream) {
   if (f32) {
-    if (!a_mn && !b_mn) return launch2<false, false, float>(tmA, tmB, tmC, tmAux, kp, stream);
-    if (!a_mn && b_mn) return launch2<false, true, float>(tmA, tmB, tmC, tmAux, kp, stream);
-    if (a_mn && !b_mn) return launch2<true, false, float>(tmA, tmB, tmC, tmAux, kp, stream);
-    return launch2<true, true, float>(tmA, tmB, tmC, tmAux, kp, stream);
+    if (!a_mn && !b_mn) return launch2<false, false, float>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
+    if (!a_mn && b_mn) return launch2<false, true, float>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
+    if (a_mn && !b_mn) return launch2<true, false, float>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
+    return launch2<true, true, float>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
   }
-  if (!a_mn && !b_mn) return launch2<false, false, bf16>(tmA, tmB, tmC, tmAux, kp, stream);
-  if (!a_mn && b_mn) return launch2<false, true, bf16>(tmA, tmB, tmC, tmAux, kp, stream);
-  if (a_mn && !b_mn) return launch2<true, false, bf16>(tmA, tmB, tmC, tmAux, kp, stream);
-  return launch2<true, true, bf16>(tmA, tmB, tmC, tmAux, kp, stream);
+  if (!a_mn && !b_mn) return launch2<false, false, bf16>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
+  if (!a_mn && b_mn) return launch2<false, true, bf16>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
+  if (a_mn && !b_mn) return launch2<true, false, bf16>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
+  return launch2<true, true, bf16>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
 }
 
 }  // namespace mb200

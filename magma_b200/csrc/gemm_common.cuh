@@ -63,7 +63,64 @@ struct GemmKernelParams {
   float* splitk_ws;
   long long ld_ws;
   int b_static;  // B is never written by a kernel of this stream (frozen weights): its first tiles load before the PDL wait
+  // stream-K of the last (partial) wave — CTA-pair kernel only, see gemm2.cu. W full waves of whole tiles, then the R
+  // remaining tiles: cluster c < R accumulates k-blocks [0, h) of tile W*ncl + c ("owner"), the nh = ncl - R other
+  // clusters ("helpers") share the k-blocks [h, num_kb) of those R tiles in contiguous ranges of the tail space
+  // (tile-major, `tail` = num_kb - h positions per tile) and hand their fp32 partial tiles to the owners through sk_ws.
+  int sk_on, sk_W, sk_R, sk_h, sk_tail, sk_nh, sk_pmax;
+  long long sk_U;          // R * tail
+  float* sk_ws;            // [nh * pmax slots][256 rows][256 cols] fp32
+  unsigned int* sk_flags;  // [nh * pmax slots][2 CTAs]: == sk_epoch once the slot's half has landed
+  unsigned int sk_epoch;
 };
+
+struct WorkItem {
+  int tile, kb0, kb1;
+  int kind;   // 0 = a whole tile, 1 = head of a split tile (owner: adds the helpers' partials, then the fused epilogue),
+              // 2 = a tail piece (helper: fp32 partial tile -> sk_ws slot)
+  int slot;   // kind 2: workspace slot
+};
+
+// the i-th work item of cluster `cid` (same sequence for the producer, the MMA issuer and the epilogue warps)
+__device__ __forceinline__ bool next_item(const GemmKernelParams& p, int cid, int ncl, int num_kb, int i, WorkItem& w) {
+  w.kb0 = 0;
+  w.kb1 = num_kb;
+  w.kind = 0;
+  w.slot = 0;
+  if (!p.sk_on) {
+    w.tile = cid + i * ncl;
+    return w.tile < p.total_tiles;
+  }
+  if (cid < p.sk_R) {  // owner: whole tiles first, the head of its split tile last (partials are long there by then)
+    if (i < p.sk_W) {
+      w.tile = cid + i * ncl;
+      return true;
+    }
+    if (i > p.sk_W) return false;
+    w.tile = p.sk_W * ncl + cid;
+    w.kb1 = p.sk_h;
+    w.kind = 1;
+    return true;
+  }
+  // helper: its tail pieces first (so that no owner ever waits), then whole tiles
+  const int j = cid - p.sk_R;
+  const long long a = (long long)j * p.sk_U / p.sk_nh, b = (long long)(j + 1) * p.sk_U / p.sk_nh;
+  const int np = b > a ? (int)((b - 1) / p.sk_tail - a / p.sk_tail) + 1 : 0;
+  if (i < np) {
+    const long long ti = a / p.sk_tail + i;
+    const long long u0 = a > ti * p.sk_tail ? a : ti * p.sk_tail;
+    const long long u1 = b < (ti + 1) * p.sk_tail ? b : (ti + 1) * p.sk_tail;
+    w.tile = p.sk_W * ncl + (int)ti;
+    w.kb0 = p.sk_h + (int)(u0 - ti * p.sk_tail);
+    w.kb1 = p.sk_h + (int)(u1 - ti * p.sk_tail);
+    w.kind = 2;
+    w.slot = j * p.sk_pmax + i;
+    return true;
+  }
+  if (i - np >= p.sk_W) return false;
+  w.tile = cid + (i - np) * ncl;
+  return true;
+}
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, SWIZZLE_128B, version 1)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -456,7 +513,17 @@ struct Epi3Ctx {
   int n_blk, z0, z1;
   const CUtensorMap* tmC;
   const CUtensorMap* tmAux;
+  // stream-K owner: fp32 partial tiles of the same rows (row stride 256 floats, this CTA's 128 rows) to add to the
+  // accumulator before alpha / bias / ...; summed in this fixed order (deterministic)
+  int npart;
+  const float* part[6];
 };
+
+__device__ __forceinline__ float4 ldcg128f(const float* ptr) {  // L2-coherent: written by another SM during this kernel
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  return v;
+}
 
 // one [128 x 128-byte] box of the CTA's tile is complete in `slot`: make the generic-proxy writes visible to the TMA
 // unit, wait until the box stored TWO boxes ago has been read out (so that the other slot is free for the next writer),
@@ -475,7 +542,7 @@ __device__ __forceinline__ void epi3_publish(const Epi3Ctx& c, const CUtensorMap
 }
 
 // `box` counts the boxes this CTA has published so far (slot = box & 1); it lives across tiles.
-template <int BN, int ACT, int DACT, int NRES, bool AUX, bool ROPE, bool ACCUM, typename OutT>
+template <int BN, int ACT, int DACT, int NRES, bool AUX, bool ROPE, bool ACCUM, typename OutT, bool SK = false>
 __device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi3Ctx& c, uint32_t& box) {
   constexpr bool F32 = sizeof(OutT) == 4;
   static_assert(!F32 || (!AUX && !ROPE && ACT == 0 && DACT == 0 && NRES == 0), "fp32 output: plain / accumulate only");
@@ -547,8 +614,29 @@ __device__ __forceinline__ void epi_tile_v3(const GemmKernelParams& p, const Epi
       }
     }
     float v[32];
+    if constexpr (SK) {
+      // stream-K owner: accumulator + the helpers' partial tiles (fixed order), then alpha
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+      for (int k = 0; k < c.npart; ++k) {
+        const float* src = c.part[k] + (long long)r_cta * 256 + ch * 32;
+        float4 t4[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t4[e] = ldcg128f(src + 4 * e);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[4 * e] += t4[e].x;
+          v[4 * e + 1] += t4[e].y;
+          v[4 * e + 2] += t4[e].z;
+          v[4 * e + 3] += t4[e].w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+    }
     if (p.bias) {
       if (n0 + 32 <= p.N) {
 #pragma unroll
@@ -715,6 +803,6 @@ int make_operand_map(CUtensorMap* out, const mb200_operand& op, int rows, int K,
 int make_store_map(CUtensorMap* out, const void* ptr, bool f32, int N, int M, int nb0, int nb1, long long ld,
                    long long bs0, long long bs1);
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
-                 const GemmKernelParams& kp, bool a_mn, bool b_mn, bool f32, cudaStream_t stream);
+                 const CUtensorMap& tmWs, const GemmKernelParams& kp, bool a_mn, bool b_mn, bool f32, cudaStream_t stream);
 
 }  // namespace mb200

@@ -75,9 +75,18 @@ struct Epi {
   int rope_mode = 0, rope_S = 0, rope_hd = 0, rope_rot = 0, rope_ncols = 0;
 };
 
+// scratch the training / ViT passes lend to the GEMM core (mb200_gemm_args.splitk_ws): 64 MB of stream-K flags and partial
+// tiles at its end, split-K slices in front (gemm.cu: kStreamKRegion)
+const size_t kGemmScratchBytes = (size_t)128 << 20;
+
 // split-K scratch of the pass being issued (small-M decode GEMMs stream their weights; see gemm.cu::plan_small_m)
 thread_local void* t_splitk_ws = nullptr;
 thread_local long long t_splitk_bytes = 0;
+
+struct ScratchScope {  // the scratch is only valid while the pass that owns the workspace is being issued
+  ScratchScope(void* w, size_t b) { t_splitk_ws = w; t_splitk_bytes = (long long)b; }
+  ~ScratchScope() { t_splitk_ws = nullptr; t_splitk_bytes = 0; }
+};
 
 int gemm(void* st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, int c_f32, const Epi& e = Epi(),
          int nb0 = 1, int nb1 = 1, long long c_bs0 = 0, long long c_bs1 = 0) {
@@ -158,6 +167,8 @@ struct Plan {
   int* n_valid;
   // backward temporaries
   bf16s *g0, *g1, *gs, *dt, *dzn, *dm, *dhact, *dh_mlp, *dattn_o, *dqkv, *dS, *dh, *da, *dhp;
+  void* gemm_ws;  // scratch lent to the GEMM core: stream-K partial tiles of the last wave, split-K slices
+  size_t gemm_ws_bytes;
   size_t bytes;
 };
 
@@ -267,6 +278,8 @@ int make_plan(Plan& P, const mb200_gptj_model_ex* m, int B, int S, void* ws) {
   P.dh = c.take<bf16s>(M * d);
   P.da = c.take<bf16s>(M * d);
   P.dhp = c.take<bf16s>(M * d);
+  P.gemm_ws_bytes = M > 128 ? kGemmScratchBytes : 0;
+  P.gemm_ws = P.gemm_ws_bytes ? c.take<uint8_t>(P.gemm_ws_bytes) : nullptr;
   P.bytes = align_up(c.off, 256);
   return 0;
 }
@@ -339,6 +352,7 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
   const float scale = 1.0f / sqrtf((float)hd);
   const long long qb0 = hd, qb1 = (long long)S * 3 * d;
   const long long pb0 = (long long)S * P.ldP, pb1 = (long long)H * S * P.ldP;
+  ScratchScope scratch(P.gemm_ws, P.gemm_ws_bytes);
   MBS_TRY(mb200_rope_table(P.rope_tab, S, m->rotary_dim, 0, st));
   MBS_TRY(rt_copy(P.acts[0].x_in, x, (size_t)M * d * sizeof(bf16s), st));
   for (int l = 0; l < m->n_layer; ++l) {
@@ -441,6 +455,7 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int laye
   const float scale = 1.0f / sqrtf((float)hd);
   const long long qb0 = hd, qb1 = (long long)S * 3 * d;
   const long long pb0 = (long long)S * P.ldP, pb1 = (long long)H * S * P.ldP;
+  ScratchScope scratch(P.gemm_ws, P.gemm_ws_bytes);
   // gradient w.r.t. the residual stream entering layer l lives in g[(l) & 1]
   bf16s* gb[2] = {P.g0, P.g1};
   if (layer_hi == m->n_layer) {  // dxf = loss_scale * dlogits Wlm ; g = LN_f backward
@@ -558,7 +573,7 @@ int make_infer_plan(InferPlan& P, const mb200_gptj_model_ex* m, int B, int S, in
   P.am.mean = P.am.rstd = P.aa.mean = P.aa.rstd = nullptr;  // no backward: LayerNorm statistics are not kept
   P.scores = c.take<float>(nP);
   P.rope_tab = c.take<float>((size_t)S * m->rotary_dim);
-  P.splitk_bytes = M <= 128 ? (size_t)16 * M * d * sizeof(float) : 0;
+  P.splitk_bytes = M <= 128 ? (size_t)16 * M * d * sizeof(float) : kGemmScratchBytes;
   P.splitk = P.splitk_bytes ? c.take<float>(P.splitk_bytes / sizeof(float)) : nullptr;
   P.bytes = align_up(c.off, 256);
   return 0;

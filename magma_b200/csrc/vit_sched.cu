@@ -62,10 +62,22 @@ struct Epi {
   int accumulate = 0;
 };
 
+// scratch lent to the GEMM core while a pass is being issued (mb200_gemm_args.splitk_ws: stream-K partial tiles of the
+// last wave — the M = 2056 GEMMs of ViT-L/14 are 1.5 - 2.9 waves of 256 x 256 tiles — and split-K slices)
+const size_t kGemmScratchBytes = (size_t)128 << 20;
+thread_local void* t_gemm_ws = nullptr;
+thread_local long long t_gemm_ws_bytes = 0;
+struct ScratchScope {
+  ScratchScope(void* w, size_t b) { t_gemm_ws = w; t_gemm_ws_bytes = (long long)b; }
+  ~ScratchScope() { t_gemm_ws = nullptr; t_gemm_ws_bytes = 0; }
+};
+
 int gemm(void* st, int M, int N, int K, Mat A, Mat B, void* C, long long ldc, int c_f32, const Epi& e = Epi(),
          int nb0 = 1, int nb1 = 1, long long c_bs0 = 0, long long c_bs1 = 0) {
   mb200_gemm_args g;
   memset(&g, 0, sizeof(g));
+  g.splitk_ws = t_gemm_ws;
+  g.splitk_ws_bytes = t_gemm_ws_bytes;
   g.M = M;
   g.N = N;
   g.K = K;
@@ -126,6 +138,7 @@ struct Plan {
   float* scores;  // [B,H,T,ldS] fp32: scores in forward, dP in backward
   // backward temporaries
   bf16s *gA, *gB, *gmid, *dh, *dhact, *dattn_o, *dqkv, *dS, *dpooled, *dpe;
+  void* gemm_ws;
   size_t bytes;
 };
 
@@ -181,6 +194,7 @@ int make_plan(Plan& P, const mb200_vit_model* m, int B, void* ws) {
   P.dS = c.take<bf16s>(nP);
   P.dpooled = c.take<bf16s>((size_t)B * w);
   P.dpe = c.take<bf16s>(np * w);
+  P.gemm_ws = c.take<uint8_t>(kGemmScratchBytes);
   P.bytes = align_up(c.off, 256);
   return 0;
 }
@@ -206,6 +220,7 @@ struct InferPlan {
   int T, M, ldS, ldpatch;
   bf16s *x, *h, *qkv, *P, *attn_o, *hact, *patches, *pooled;
   float* scores;
+  void* gemm_ws;
   size_t bytes;
 };
 
@@ -231,6 +246,7 @@ int make_infer_plan(InferPlan& P, const mb200_vit_model* m, int B, void* ws) {
   P.hact = c.take<bf16s>(M * (size_t)m->mlp);
   P.patches = c.take<bf16s>((size_t)B * g * g * P.ldpatch);
   P.pooled = c.take<bf16s>((size_t)B * w);
+  P.gemm_ws = c.take<uint8_t>(kGemmScratchBytes);
   P.bytes = align_up(c.off, 256);
   return 0;
 }
@@ -243,6 +259,7 @@ int forward_infer(const mb200_vit_model* m, const bf16s* images, bf16s* feats, i
   const int w = m->width, H = m->n_head, hd = w / H, T = P.T, M = P.M, g = m->image / m->patch;
   const int Kp = 3 * m->patch * m->patch;
   const float scale = 1.0f / sqrtf((float)hd);
+  ScratchScope scratch(P.gemm_ws, kGemmScratchBytes);
   // conv1 as im2col + GEMM (patch embeddings staged in h), then [cls; patches] + positional embedding
   MBS_TRY(rt_zero(P.patches, (size_t)B * g * g * P.ldpatch * sizeof(bf16s), st));
   MBS_TRY(mb200_patchify(images, P.patches, P.ldpatch, B, m->image, m->patch, st));
@@ -302,6 +319,7 @@ int forward_train(const mb200_vit_model* m, const bf16s* images, bf16s* feats, i
   MBS_TRY(make_plan(P, m, B, ws));
   MBS_REQUIRE(ws != nullptr && ws_bytes >= P.bytes, MB200_E_ARG, "vit_forward_train: workspace too small (%zu < %zu)",
               ws_bytes, P.bytes);
+  ScratchScope scratch(P.gemm_ws, kGemmScratchBytes);
   MBS_REQUIRE(m->ld_conv % 8 == 0 && m->ld_conv >= P.Kp, MB200_E_ALIGN, "vit_forward_train: bad ld_conv");
   const int w = m->width, H = m->n_head, hd = w / H, T = P.T, M = P.M, np = B * P.g * P.g;
   const float scale = 1.0f / sqrtf((float)hd);
@@ -368,6 +386,7 @@ int backward(const mb200_vit_model* m, const mb200_vit_grads* G, const bf16s* df
   MBS_TRY(make_plan(P, m, B, ws));
   MBS_REQUIRE(ws != nullptr && ws_bytes >= P.bytes, MB200_E_ARG, "vit_backward: workspace too small");
   MBS_REQUIRE(G && G->layers && dfeats, MB200_E_ARG, "vit_backward: null gradient table / dfeats");
+  ScratchScope scratch(P.gemm_ws, kGemmScratchBytes);
   const int w = m->width, H = m->n_head, hd = w / H, T = P.T, M = P.M, np = B * P.g * P.g, mlp = m->mlp;
   const float scale = 1.0f / sqrtf((float)hd);
   const long long qb0 = hd, qb1 = (long long)T * 3 * w;

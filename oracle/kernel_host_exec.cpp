@@ -108,6 +108,13 @@ static inline float atomicAdd(float* p, float v) {
   *p = old + v;
   return old;
 }
+static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) {
+  std::lock_guard<std::mutex> lk(g_atomic);
+  const unsigned int old = *p;
+  *p = old + v;
+  return old;
+}
+static inline void __threadfence() {}  // blocks run one after another here, threads of a block meet at barriers
 template <typename T>
 static inline T min(T a, T b) {
   return a < b ? a : b;

@@ -12,7 +12,7 @@ import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
-GROUPS = ["basic", "majors", "tails", "epilogue", "batched", "pair", "splitk", "smallm", "perf"]
+GROUPS = ["basic", "majors", "tails", "epilogue", "batched", "pair", "streamk", "splitk", "smallm", "perf"]
 
 
 def ref_gemm(A, B, a_mn, b_mn):
@@ -311,6 +311,77 @@ def run_group(g):
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 20
                 print(f"[PERF] M={M} N={N} K={K} bmn={int(bmn)} {'pair' if bn == 512 else '1cta'}: {ms*1000:.1f} us {2.0*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    elif g == "streamk":
+        # stream-K of the last wave on the CTA-pair kernel (scratch lent through splitk_ws): the shapes of the GPT-J block
+        # and of the ViT at the benchmark sizes, every epilogue family, bit-reproducible (fixed summation order)
+        import torch.nn.functional as F
+
+        ws = torch.full(((128 << 20) // 4,), float("nan"), device=dev, dtype=torch.float32)  # scratch needs no init
+        for (M, N, K, bmn, what) in ((1024, 4096, 4096, False, "64 tiles / 74 clusters: every tile split in two"),
+                                     (1024, 12288, 4096, False, "2 full waves + 44 tiles"),
+                                     (1024, 16384, 4096, True, "3 full waves + 34 tiles (up to 3 partials per tile)"),
+                                     (1024, 4096, 16384, True, "long K"),
+                                     (2056, 3072, 1024, False, "ViT qkv: ragged M, K = 1024"),
+                                     (1024, 50258, 4096, False, "LM head: ragged N")):
+            A, B = mk((M, K), False, dev, 0.5), mk((N, K), bmn, dev, 0.05)
+            ldc = (N + 7) // 8 * 8
+            C = torch.full((M, ldc), 7.0, device=dev, dtype=torch.bfloat16)
+            ops.gemm(A, B, out=C[:, :N], b_mn=bmn, splitk_ws=ws)
+            want = ref_gemm(A, B, False, bmn)
+            ok &= report(f"streamk plain M={M} N={N} K={K} ({what})", C[:, :N], want)
+            if ldc > N:
+                ok &= untouched(f"streamk M={M} N={N} columns >= N", C[:, N:], 7.0)
+            C2 = torch.full((M, ldc), 7.0, device=dev, dtype=torch.bfloat16)
+            ops.gemm(A, B, out=C2[:, :N], b_mn=bmn, splitk_ws=ws)
+            same = bool(torch.equal(C, C2))
+            print(f"[{'OK' if same else 'FAIL'}] streamk M={M} N={N} K={K}: second run bit-identical", flush=True)
+            ok &= same
+        M, N, K = 1024, 4096, 4096
+        A, B = mk((M, K), False, dev, 0.5), mk((N, K), False, dev, 0.05)
+        bias = torch.randn(N, device=dev).to(torch.bfloat16)
+        base = ref_gemm(A, B, False, False)
+        pre = base + bias.float()
+        r1, r2 = mk((M, N), False, dev), mk((M, N), False, dev)
+        C = ops.gemm(A, B, bias=bias, res1=r1, res2=r2, alpha=0.5, splitk_ws=ws)
+        ok &= report("streamk alpha+bias+res1+res2", C, 0.5 * base + bias.float() + r1.float() + r2.float())
+        aux = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        C = ops.gemm(A, B, bias=bias, act=ops.ACT_GELU_NEW, aux_out=aux, splitk_ws=ws)
+        ok &= report("streamk bias+gelu_new+aux: C", C, F.gelu(pre, approximate="tanh"))
+        ok &= report("streamk bias+gelu_new+aux: aux", aux, pre)
+        x = mk((M, N), False, dev)
+        C = ops.gemm(A, B, aux_in=x, dact=ops.DACT_RELU, splitk_ws=ws)
+        ok &= report("streamk dact relu", C, base * (x.float() > 0).float())
+        Cf = torch.ones(M, N, device=dev, dtype=torch.float32)
+        ops.gemm(A, B, out=Cf, accumulate=True, splitk_ws=ws)
+        ok &= report("streamk f32 accumulate", Cf, base + 1.0, tol=5e-3)
+        Sx, H, hd, rot = 128, 16, 256, 64
+        A2, B2 = mk((8 * Sx, 4096), False, dev, 0.5), mk((3 * H * hd, 4096), False, dev, 0.05)
+        tab = ops.rope_table(Sx, rot, pos0=0, device=dev)
+        fused = ops.gemm(A2, B2, rope_tab=tab, rope_mode=1, rope_S=Sx, rope_hd=hd, rope_rot=rot, rope_ncols=2 * H * hd,
+                         splitk_ws=ws)
+        plain = ops.gemm(A2, B2, out_dtype=torch.float32)
+        qq = plain.view(8, Sx, 3, H, hd).clone()
+        cs, sn = tab[None, :, None, None, :, 0], tab[None, :, None, None, :, 1]
+        x1, x2 = qq[:, :, :2, :, 0:rot:2].clone(), qq[:, :, :2, :, 1:rot:2].clone()
+        qq[:, :, :2, :, 0:rot:2] = x1 * cs - x2 * sn
+        qq[:, :, :2, :, 1:rot:2] = x2 * cs + x1 * sn
+        ok &= report("streamk qkv + fused rope (2 full waves + 44 tiles)", fused, qq.view(8 * Sx, -1))
+        for (M, N, K, bmn) in ((1024, 4096, 4096, False), (1024, 12288, 4096, False), (1024, 16384, 4096, False),
+                               (1024, 4096, 16384, True)):
+            A, B = mk((M, K), False, dev), mk((N, K), bmn, dev)
+            C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            for tag, w in (("stream-K", ws), ("whole tiles", None)):
+                for _ in range(3):
+                    ops.gemm(A, B, out=C, b_mn=bmn, splitk_ws=w)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    ops.gemm(A, B, out=C, b_mn=bmn, splitk_ws=w)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 20
+                print(f"[PERF] M={M} N={N} K={K} bmn={int(bmn)} {tag}: {ms*1000:.1f} us {2.0*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
     elif g == "splitk":
         import torch.nn.functional as F
 
