@@ -358,7 +358,8 @@ typedef struct {
   int32_t attn_adapter;
   int32_t attn_adapter_r;
   float ln_eps;
-  int32_t _pad;
+  int32_t adapter_act; /* bottleneck activation of every adapter (magma/adapters.py:11): 0 = ReLU (the reference default),
+                        * 1 = GeLU in the tanh form of the GPT-J MLP (hf:activations.py:59-66), pre-activation kept */
   const mb200_gptj_layer_ex* layers;
   const void* lnf_g;
   const void* lnf_b;

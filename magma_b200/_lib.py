@@ -145,7 +145,7 @@ class GptjModelExC(ctypes.Structure):
         ("attn_adapter", ctypes.c_int32),
         ("attn_adapter_r", ctypes.c_int32),
         ("ln_eps", ctypes.c_float),
-        ("_pad", ctypes.c_int32),
+        ("adapter_act", ctypes.c_int32),
         ("layers", ctypes.POINTER(GptjLayerExC)),
         ("lnf_g", ctypes.c_void_p),
         ("lnf_b", ctypes.c_void_p),

@@ -16,15 +16,40 @@ def _bf16(t):
     return t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
 
 
+def activation_kind(activation) -> int:
+    """The bottleneck activation as the kernels know it: 0 = ReLU (the reference default, adapters.py:11), 1 = GeLU in
+    the tanh form the GPT-J MLP itself uses (nn.GELU(approximate="tanh") / transformers' NewGELUActivation) — both are
+    fused into the down-projection's GEMM epilogue (the GeLU one also saves its pre-activation for the backward pass).
+    `activation` is what the reference passes: a module CLASS (or any zero-argument factory) instantiated once."""
+    if activation is nn.ReLU:
+        return 0
+    probe = activation() if callable(activation) and not isinstance(activation, nn.Module) else activation
+    if isinstance(probe, nn.ReLU):
+        return 0
+    if isinstance(probe, nn.GELU) and getattr(probe, "approximate", "none") == "tanh":
+        return 1
+    if type(probe).__name__ in ("NewGELUActivation", "GELUTanh"):
+        return 1
+    raise NotImplementedError(
+        f"adapter activation {activation!r}: magma_b200 fuses ReLU (the reference default, adapters.py:11) or the tanh "
+        "GeLU (nn.GELU(approximate='tanh')) into the bottleneck GEMMs; exact-erf GELU and others are not re-backed")
+
+
 class _AdapterFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wd, bd, wu, bu, residual):
+    def forward(ctx, x, wd, bd, wu, bu, residual, act=0):
         shp = x.shape
         x2 = _bf16(x).reshape(-1, shp[-1]).contiguous()
         wd16, bd16, wu16, bu16 = _bf16(wd), _bf16(bd), _bf16(wu), _bf16(bu)
-        t = ops.gemm(x2, wd16, bias=bd16, act=ops.ACT_RELU)
+        if act == 0:
+            t = ops.gemm(x2, wd16, bias=bd16, act=ops.ACT_RELU)
+            pre = t  # the ReLU mask is read off the output
+        else:
+            pre = torch.empty(x2.shape[0], wd16.shape[0], dtype=torch.bfloat16, device=x2.device)
+            t = ops.gemm(x2, wd16, bias=bd16, act=ops.ACT_GELU_NEW, aux_out=pre)
         y = ops.gemm(t, wu16, bias=bu16, res1=x2 if residual else None)
-        ctx.save_for_backward(x2, t, wd16, wu16)
+        ctx.save_for_backward(x2, t, wd16, wu16, pre)
+        ctx.act = act
         ctx.residual = residual
         ctx.shape = shp
         ctx.dtypes = (x.dtype, wd.dtype)
@@ -32,16 +57,17 @@ class _AdapterFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        x2, t, wd16, wu16 = ctx.saved_tensors
+        x2, t, wd16, wu16, pre = ctx.saved_tensors
         g = _bf16(gy).reshape(-1, ctx.shape[-1]).contiguous()
-        dt = ops.gemm(g, wu16, b_mn=True, aux_in=t, dact=ops.DACT_RELU)          # (g Wu) * 1[t>0]
+        dt = ops.gemm(g, wu16, b_mn=True, aux_in=pre,                            # (g Wu) * act'(pre)   (ReLU: 1[t>0])
+                      dact=ops.DACT_RELU if ctx.act == 0 else ops.DACT_GELU_NEW)
         dwu = ops.gemm(g, t, a_mn=True, b_mn=True, out_dtype=torch.float32)       # g^T t
         dbu = ops.colsum(g)
         dwd = ops.gemm(dt, x2, a_mn=True, b_mn=True, out_dtype=torch.float32)     # dt^T x
         dbd = ops.colsum(dt)
         dx = ops.gemm(dt, wd16, b_mn=True, res1=g if ctx.residual else None)      # dt Wd (+ g)
         xd, wdt = ctx.dtypes
-        return dx.reshape(ctx.shape).to(xd), dwd.to(wdt), dbd.to(wdt), dwu.to(wdt), dbu.to(wdt), None
+        return dx.reshape(ctx.shape).to(xd), dwd.to(wdt), dbd.to(wdt), dwu.to(wdt), dbu.to(wdt), None, None
 
 
 class Adapter(nn.Module):
@@ -50,8 +76,7 @@ class Adapter(nn.Module):
     def __init__(self, dim: int, downsample_factor: int = 4, activation: nn.Module = nn.ReLU,
                  add_layernorm: bool = False):
         super().__init__()
-        if activation is not nn.ReLU:
-            raise NotImplementedError("magma_b200 adapters fuse ReLU (the reference default, adapters.py:11)")
+        self.act_kind = activation_kind(activation)  # raises for activations the kernels do not fuse
         layers = []
         if add_layernorm:
             layers.append(nn.LayerNorm(dim))
@@ -84,7 +109,7 @@ class Adapter(nn.Module):
     def bottleneck_fn(self, x, residual):
         if self.add_layernorm:
             raise NotImplementedError("add_layernorm adapters are not re-backed yet")
-        return _AdapterFn.apply(x, self.down.weight, self.down.bias, self.up.weight, self.up.bias, residual)
+        return _AdapterFn.apply(x, self.down.weight, self.down.bias, self.up.weight, self.up.bias, residual, self.act_kind)
 
     def forward(self, x):
         return self.bottleneck_fn(x, True)  # self.adapter(x) + x

@@ -139,7 +139,8 @@ struct AdapterActs {
   bf16s* zn;    // [M,d] LN(z) when the adapter has a leading LayerNorm
   float* mean;  // [M]
   float* rstd;  // [M]
-  bf16s* t;     // [M,r] hidden (post ReLU)
+  bf16s* t;     // [M,r] hidden (post activation)
+  bf16s* pre;   // [M,r] pre-activation (GeLU adapters only: ReLU's mask is read off t)
   bf16s* u;     // [M,d] up-projection output before scaling (scaled_parallel only)
 };
 
@@ -196,11 +197,13 @@ inline bool flash_ok(int hd) {
 inline bool has_ln(const mb200_adapter_ex& a) { return a.ln_g != nullptr; }
 inline bool has_scale(const mb200_adapter_ex& a) { return a.scale != nullptr; }
 
-void carve_adapter(Carver& c, AdapterActs& a, const mb200_adapter_ex& ad, int kind, size_t M, size_t d, int r) {
+void carve_adapter(Carver& c, AdapterActs& a, const mb200_adapter_ex& ad, int kind, size_t M, size_t d, int r,
+                   int act = 0, bool training = true) {
   a.zn = nullptr;
   a.mean = a.rstd = nullptr;
-  a.t = a.u = nullptr;
+  a.t = a.u = a.pre = nullptr;
   if (kind == MB200_ADAPTER_NONE) return;
+  if (act != 0 && training) a.pre = c.take<bf16s>(M * (size_t)r);
   if (has_ln(ad)) {
     a.zn = c.take<bf16s>(M * d);
     a.mean = c.take<float>(M);
@@ -214,6 +217,7 @@ int make_plan(Plan& P, const mb200_gptj_model_ex* m, int B, int S, void* ws) {
   MBS_REQUIRE(m && m->layers && m->n_layer > 0 && m->n_layer <= 64, MB200_E_SHAPE, "gptj_sched: n_layer out of range");
   MBS_REQUIRE(B > 0 && S > 0 && m->n_head > 0 && m->d % m->n_head == 0 && m->d % 8 == 0 && m->d_ff % 8 == 0,
               MB200_E_SHAPE, "gptj_sched: bad d / n_head / d_ff");
+  MBS_REQUIRE(m->adapter_act == 0 || m->adapter_act == 1, MB200_E_ARG, "gptj_sched: adapter_act must be 0 (ReLU) or 1 (GeLU)");
   MBS_REQUIRE((m->d / m->n_head) % 8 == 0 && m->rotary_dim % 4 == 0 && m->rotary_dim <= m->d / m->n_head, MB200_E_SHAPE,
               "gptj_sched: head_dim must be a multiple of 8 and rotary_dim a multiple of 4 within it");
   for (int l = 0; l < m->n_layer; ++l) {
@@ -249,8 +253,8 @@ int make_plan(Plan& P, const mb200_gptj_model_ex* m, int B, int S, void* ws) {
     a.pre = c.take<bf16s>(M * dff);
     a.mlp_out = c.take<bf16s>(M * d);
     a.a_out = c.take<bf16s>(M * d);
-    carve_adapter(c, a.am, m->layers[l].mlp_ad, m->mlp_adapter, M, d, m->mlp_adapter_r);
-    carve_adapter(c, a.aa, m->layers[l].attn_ad, m->attn_adapter, M, d, m->attn_adapter_r);
+    carve_adapter(c, a.am, m->layers[l].mlp_ad, m->mlp_adapter, M, d, m->mlp_adapter_r, m->adapter_act);
+    carve_adapter(c, a.aa, m->layers[l].attn_ad, m->attn_adapter, M, d, m->attn_adapter_r, m->adapter_act);
   }
   P.scores = c.take<float>(nP);
   P.hact = c.take<bf16s>(M * dff);
@@ -284,9 +288,10 @@ int make_plan(Plan& P, const mb200_gptj_model_ex* m, int B, int S, void* ws) {
   return 0;
 }
 
-// out = s * A(z) + res1 + res2, A(z) = Wu relu(Wd LN?(z) + bd) + bu   (s = 1 without adapter_scale)
+// out = s * A(z) + res1 + res2, A(z) = Wu act(Wd LN?(z) + bd) + bu   (s = 1 without adapter_scale; act = ReLU, or the
+// tanh GeLU with its pre-activation kept for the backward pass when a.pre is carved)
 int adapter_fwd(void* st, const mb200_adapter_ex& ad, AdapterActs& a, int M, int d, int r, float eps, const bf16s* z,
-                bf16s* out, const bf16s* res1, const bf16s* res2) {
+                bf16s* out, const bf16s* res1, const bf16s* res2, int act) {
   const bf16s* zin = z;
   if (has_ln(ad)) {
     MBS_TRY(mb200_layernorm_fwd(z, d, ad.ln_g, ad.ln_b, a.zn, d, a.mean, a.rstd, M, d, eps, st));
@@ -294,7 +299,8 @@ int adapter_fwd(void* st, const mb200_adapter_ex& ad, AdapterActs& a, int M, int
   }
   Epi e1;
   e1.bias = ad.bd;
-  e1.act = MB200_ACT_RELU;
+  e1.act = act ? MB200_ACT_GELU_NEW : MB200_ACT_RELU;
+  e1.aux_out = act ? a.pre : nullptr;  // (inference plans carve no pre buffer)
   MBS_TRY(gemm(st, M, r, d, mat(zin, d), mat(ad.wd, d), a.t, r, 0, e1));
   Epi e2;
   e2.bias = ad.bu;
@@ -310,7 +316,7 @@ int adapter_fwd(void* st, const mb200_adapter_ex& ad, AdapterActs& a, int M, int
 
 // g = dL/d(out) of adapter_fwd. dz_out = res + dL/dz through the adapter; parameter gradients accumulate or overwrite.
 int adapter_bwd(void* st, const mb200_adapter_ex& ad, const AdapterActs& a, const Plan& P, int M, int d, int r,
-                const bf16s* g, const bf16s* z, bf16s* dz_out, const bf16s* res, int acc) {
+                const bf16s* g, const bf16s* z, bf16s* dz_out, const bf16s* res, int acc, int act) {
   const bf16s* gu = g;  // gradient w.r.t. the up-projection output
   if (has_scale(ad)) {
     if (ad.g_scale) MBS_TRY(mb200_dot(g, a.u, (int64_t)M * d, ad.g_scale, acc, st));  // d s = <g, u>
@@ -319,9 +325,9 @@ int adapter_bwd(void* st, const mb200_adapter_ex& ad, const AdapterActs& a, cons
   }
   const bf16s* zin = has_ln(ad) ? a.zn : z;
   Epi e1;
-  e1.dact = MB200_DACT_RELU;
-  e1.aux_in = a.t;
-  MBS_TRY(gemm(st, M, r, d, mat(gu, d), mat(ad.wu, r, 1), P.dt, r, 0, e1));  // dt = (gu Wu) * 1[t > 0]
+  e1.dact = act ? MB200_DACT_GELU_NEW : MB200_DACT_RELU;
+  e1.aux_in = act ? a.pre : a.t;
+  MBS_TRY(gemm(st, M, r, d, mat(gu, d), mat(ad.wu, r, 1), P.dt, r, 0, e1));  // dt = (gu Wu) * act'(pre)   (ReLU: 1[t > 0])
   if (ad.g_wd) {
     Epi ew;
     ew.accumulate = acc;
@@ -392,13 +398,13 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
       MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), wmat(L.w_out, d), P.ax, d, 0, e));
     } else if (m->attn_adapter == MB200_ADAPTER_NORMAL) {  // AdapterWrapper: A(attn_out) + attn_out
       MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), wmat(L.w_out, d), a.a_out, d, 0));
-      MBS_TRY(adapter_fwd(st, L.attn_ad, a.aa, M, d, m->attn_adapter_r, m->ln_eps, a.a_out, P.ax, a.a_out, xin));
+      MBS_TRY(adapter_fwd(st, L.attn_ad, a.aa, M, d, m->attn_adapter_r, m->ln_eps, a.a_out, P.ax, a.a_out, xin, m->adapter_act));
     } else {  // ParallelAdapterWrapper: attn(h) + s * A(h)
       Epi e;
       e.res1 = xin;
       e.ld_res = d;
       MBS_TRY(gemm(st, M, d, d, mat(a.attn_o, d), wmat(L.w_out, d), a.a_out, d, 0, e));
-      MBS_TRY(adapter_fwd(st, L.attn_ad, a.aa, M, d, m->attn_adapter_r, m->ln_eps, a.h, P.ax, a.a_out, nullptr));
+      MBS_TRY(adapter_fwd(st, L.attn_ad, a.aa, M, d, m->attn_adapter_r, m->ln_eps, a.h, P.ax, a.a_out, nullptr, m->adapter_act));
     }
     {  // fc_in + bias + gelu_new, pre-activation kept
       Epi e;
@@ -415,12 +421,12 @@ int forward(const mb200_gptj_model_ex* m, const bf16s* x, const int64_t* labels,
       MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), xout, d, 0, eo));
     } else if (m->mlp_adapter == MB200_ADAPTER_NORMAL) {  // Sequential(mlp, Adapter): A(mlp(h)) + mlp(h)
       MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), a.mlp_out, d, 0, eo));
-      MBS_TRY(adapter_fwd(st, L.mlp_ad, a.am, M, d, m->mlp_adapter_r, m->ln_eps, a.mlp_out, xout, a.mlp_out, P.ax));
+      MBS_TRY(adapter_fwd(st, L.mlp_ad, a.am, M, d, m->mlp_adapter_r, m->ln_eps, a.mlp_out, xout, a.mlp_out, P.ax, m->adapter_act));
     } else {  // ParallelAdapter: mlp(h) + s * A(h)
       eo.res1 = P.ax;
       eo.ld_res = d;
       MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), a.mlp_out, d, 0, eo));
-      MBS_TRY(adapter_fwd(st, L.mlp_ad, a.am, M, d, m->mlp_adapter_r, m->ln_eps, a.h, xout, a.mlp_out, nullptr));
+      MBS_TRY(adapter_fwd(st, L.mlp_ad, a.am, M, d, m->mlp_adapter_r, m->ln_eps, a.h, xout, a.mlp_out, nullptr, m->adapter_act));
     }
   }
   // ln_f + LM head (+ shifted cross-entropy; the logits' gradient is written now, scaled in backward)
@@ -474,10 +480,10 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int laye
     // ---- MLP branch ----
     const bf16s* dm = g;
     if (m->mlp_adapter == MB200_ADAPTER_NORMAL) {
-      MBS_TRY(adapter_bwd(st, L.mlp_ad, a.am, P, M, d, m->mlp_adapter_r, g, a.mlp_out, P.dm, g, acc));
+      MBS_TRY(adapter_bwd(st, L.mlp_ad, a.am, P, M, d, m->mlp_adapter_r, g, a.mlp_out, P.dm, g, acc, m->adapter_act));
       dm = P.dm;
     } else if (m->mlp_adapter == MB200_ADAPTER_PARALLEL) {
-      MBS_TRY(adapter_bwd(st, L.mlp_ad, a.am, P, M, d, m->mlp_adapter_r, g, a.h, P.dm, nullptr, acc));
+      MBS_TRY(adapter_bwd(st, L.mlp_ad, a.am, P, M, d, m->mlp_adapter_r, g, a.h, P.dm, nullptr, acc, m->adapter_act));
       dh_acc = P.dm;
     }
     {
@@ -494,10 +500,10 @@ int backward(const mb200_gptj_model_ex* m, bf16s* dx, float loss_scale, int laye
     // ---- attention branch ----
     const bf16s* da = g;
     if (m->attn_adapter == MB200_ADAPTER_NORMAL) {
-      MBS_TRY(adapter_bwd(st, L.attn_ad, a.aa, P, M, d, m->attn_adapter_r, g, a.a_out, P.da, g, acc));
+      MBS_TRY(adapter_bwd(st, L.attn_ad, a.aa, P, M, d, m->attn_adapter_r, g, a.a_out, P.da, g, acc, m->adapter_act));
       da = P.da;
     } else if (m->attn_adapter == MB200_ADAPTER_PARALLEL) {
-      MBS_TRY(adapter_bwd(st, L.attn_ad, a.aa, P, M, d, m->attn_adapter_r, g, a.h, P.dhp, dh_acc, acc));
+      MBS_TRY(adapter_bwd(st, L.attn_ad, a.aa, P, M, d, m->attn_adapter_r, g, a.h, P.dhp, dh_acc, acc, m->adapter_act));
       dh_acc = P.dhp;
     }
     MBS_TRY(gemm(st, M, d, d, mat(da, d), wmat(L.w_out, d, 1), P.dattn_o, d, 0));  // d(attn_o) = da Wo
@@ -568,8 +574,8 @@ int make_infer_plan(InferPlan& P, const mb200_gptj_model_ex* m, int B, int S, in
   P.a_out = c.take<bf16s>(M * d);
   P.mlp_out = c.take<bf16s>(M * d);
   P.xf_ln = c.take<bf16s>(M * d);
-  carve_adapter(c, P.am, m->layers[0].mlp_ad, m->mlp_adapter, M, d, m->mlp_adapter_r);
-  carve_adapter(c, P.aa, m->layers[0].attn_ad, m->attn_adapter, M, d, m->attn_adapter_r);
+  carve_adapter(c, P.am, m->layers[0].mlp_ad, m->mlp_adapter, M, d, m->mlp_adapter_r, m->adapter_act, false);
+  carve_adapter(c, P.aa, m->layers[0].attn_ad, m->attn_adapter, M, d, m->attn_adapter_r, m->adapter_act, false);
   P.am.mean = P.am.rstd = P.aa.mean = P.aa.rstd = nullptr;  // no backward: LayerNorm statistics are not kept
   P.scores = c.take<float>(nP);
   P.rope_tab = c.take<float>((size_t)S * m->rotary_dim);
@@ -664,13 +670,13 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
       MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), wmat(L.w_out, d), P.ax, d, 0, e));
     } else if (m->attn_adapter == MB200_ADAPTER_NORMAL) {
       MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), wmat(L.w_out, d), P.a_out, d, 0));
-      MBS_TRY(adapter_fwd(st, L.attn_ad, P.aa, M, d, m->attn_adapter_r, m->ln_eps, P.a_out, P.ax, P.a_out, xin));
+      MBS_TRY(adapter_fwd(st, L.attn_ad, P.aa, M, d, m->attn_adapter_r, m->ln_eps, P.a_out, P.ax, P.a_out, xin, m->adapter_act));
     } else {
       Epi e;
       e.res1 = xin;
       e.ld_res = d;
       MBS_TRY(gemm(st, M, d, d, mat(P.attn_o, d), wmat(L.w_out, d), P.a_out, d, 0, e));
-      MBS_TRY(adapter_fwd(st, L.attn_ad, P.aa, M, d, m->attn_adapter_r, m->ln_eps, P.h, P.ax, P.a_out, nullptr));
+      MBS_TRY(adapter_fwd(st, L.attn_ad, P.aa, M, d, m->attn_adapter_r, m->ln_eps, P.h, P.ax, P.a_out, nullptr, m->adapter_act));
     }
     {
       Epi e;
@@ -686,12 +692,12 @@ int forward_infer(const mb200_gptj_model_ex* m, const bf16s* x, bf16s* logits, l
       MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), xout, d, 0, eo));
     } else if (m->mlp_adapter == MB200_ADAPTER_NORMAL) {
       MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), P.mlp_out, d, 0, eo));
-      MBS_TRY(adapter_fwd(st, L.mlp_ad, P.am, M, d, m->mlp_adapter_r, m->ln_eps, P.mlp_out, xout, P.mlp_out, P.ax));
+      MBS_TRY(adapter_fwd(st, L.mlp_ad, P.am, M, d, m->mlp_adapter_r, m->ln_eps, P.mlp_out, xout, P.mlp_out, P.ax, m->adapter_act));
     } else {
       eo.res1 = P.ax;
       eo.ld_res = d;
       MBS_TRY(gemm(st, M, d, dff, mat(P.hact, dff), wmat(L.w_fc_out, dff), P.mlp_out, d, 0, eo));
-      MBS_TRY(adapter_fwd(st, L.mlp_ad, P.am, M, d, m->mlp_adapter_r, m->ln_eps, P.h, xout, P.mlp_out, nullptr));
+      MBS_TRY(adapter_fwd(st, L.mlp_ad, P.am, M, d, m->mlp_adapter_r, m->ln_eps, P.h, xout, P.mlp_out, nullptr, m->adapter_act));
     }
     xin = xout;
   }

@@ -317,6 +317,10 @@ class B200GPTJForCausalLM(nn.Module):
         if len(kinds) != 1:
             raise MB200Error("all blocks must carry the same adapter configuration")
         mk, ak = kinds.pop()
+        acts = {getattr(ad, "act_kind", 0) for blk in self.transformer.h
+                for ad in (_split_mlp(blk.mlp)[2], _split_attn(blk.attn)[2]) if ad is not None}
+        if len(acts) > 1:
+            raise MB200Error("all adapters must use the same activation")
         for name, p in self.named_parameters():
             if "adapter" not in name and (p.dtype != torch.bfloat16 or p.device.type != self._device.type):
                 raise MB200Error(f"frozen LM parameter {name} must be bf16 on {self._device} (got {p.dtype}, {p.device})")
@@ -325,6 +329,7 @@ class B200GPTJForCausalLM(nn.Module):
         m.vocab, m.d_ff = self.lm_head.weight.shape[0], cfg.intermediate_size
         m.mlp_adapter, m.mlp_adapter_r, m.attn_adapter, m.attn_adapter_r = mk, rm, ak, ra
         m.ln_eps = cfg.layer_norm_epsilon
+        m.adapter_act = acts.pop() if acts else 0
         m.layers = ctypes.cast(layers, ctypes.POINTER(GptjLayerExC))
         m.lnf_g, m.lnf_b = self.transformer.ln_f.weight.data_ptr(), self.transformer.ln_f.bias.data_ptr()
         m.w_lm, m.b_lm = self.lm_head.weight.data_ptr(), self.lm_head.bias.data_ptr()

@@ -42,6 +42,9 @@ class OracleConfig:
     rotary_dim: int = 64
     vocab: int = 50258  # len(tokenizer) after resize (magma/magma.py:50)
     ln_eps: float = 1e-5
+    # adapter activation (magma/adapters.py:11: `activation: nn.Module = nn.ReLU`): "relu" (every shipped config) or
+    # "gelu" = the tanh GeLU of the GPT-J MLP (NewGELUActivation / nn.GELU(approximate="tanh")) — north_star's variant
+    adapter_act: str = "relu"
     # adapters (magma/magma.py:73-90): None | dict(adapter_type=..., downsample_factor=...)
     mlp_adapter: Optional[dict] = field(default_factory=lambda: {"adapter_type": "normal", "downsample_factor": 4})
     attn_adapter: Optional[dict] = None
@@ -186,10 +189,10 @@ def gptj_block(x, w, l, cfg: OracleConfig, positions, past_kv=None):
         inner = f"{p}.attn.attn_block" if kind == "normal" else f"{p}.attn.module"
         a, kv = gptj_attention(h, w, inner, cfg, positions, past_kv)
         if kind == "normal":  # AdapterWrapper.forward, adapters.py:109-116
-            a = adapter_mlp(a, w, f"{p}.attn") + a
+            a = adapter_mlp(a, w, f"{p}.attn", cfg.adapter_act) + a
         else:  # ParallelAdapterWrapper.forward, adapters.py:85-92
             scale = w.get(f"{p}.attn.adapter_scale", torch.ones(1))
-            a = a + adapter_mlp(h, w, f"{p}.attn") * scale
+            a = a + adapter_mlp(h, w, f"{p}.attn", cfg.adapter_act) * scale
     else:
         a, kv = gptj_attention(h, w, f"{p}.attn", cfg, positions, past_kv)
     # mlp branch
@@ -197,10 +200,10 @@ def gptj_block(x, w, l, cfg: OracleConfig, positions, past_kv=None):
         kind = cfg.mlp_adapter.get("adapter_type", "normal")
         if kind == "normal":  # nn.Sequential(mlp, Adapter), magma.py:143-148
             m = gptj_mlp(h, w, f"{p}.mlp.0")
-            m = adapter_forward(m, w, f"{p}.mlp.1")
+            m = adapter_forward(m, w, f"{p}.mlp.1", cfg.adapter_act)
         else:  # ParallelAdapter.forward, adapters.py:63-66
             scale = w.get(f"{p}.mlp.adapter_scale", torch.ones(1))
-            m = gptj_mlp(h, w, f"{p}.mlp.module") + adapter_mlp(h, w, f"{p}.mlp") * scale
+            m = gptj_mlp(h, w, f"{p}.mlp.module") + adapter_mlp(h, w, f"{p}.mlp", cfg.adapter_act) * scale
     else:
         m = gptj_mlp(h, w, f"{p}.mlp")
     return a + m + x, kv  # :411

@@ -42,19 +42,23 @@ def build_lm(cfg, w, dev):
     gc = GPTJConfig(vocab_size=cfg.vocab, max_position_embeddings=2048, hidden_size=cfg.d, num_layers=cfg.n_layer,
                     num_heads=cfg.n_head, rotary_dim=cfg.rotary_dim)
     lm = B200GPTJForCausalLM(gc, device=dev)
+    import functools
+
+    # the reference passes the activation as a module class (adapters.py:11); "gelu" = the tanh GeLU variant
+    act = nn.ReLU if getattr(cfg, "adapter_act", "relu") == "relu" else functools.partial(nn.GELU, approximate="tanh")
     for blk in lm.transformer.h:
         if cfg.mlp_adapter:
             f = cfg.mlp_adapter.get("downsample_factor", 4)
             if cfg.mlp_adapter.get("adapter_type", "normal") == "normal":
-                blk.mlp = nn.Sequential(blk.mlp, Adapter(cfg.d, f).to(dev))
+                blk.mlp = nn.Sequential(blk.mlp, Adapter(cfg.d, f, activation=act).to(dev))
             else:
-                blk.mlp = ParallelAdapter(blk.mlp, cfg.d, f)
+                blk.mlp = ParallelAdapter(blk.mlp, cfg.d, f, activation=act)
         if cfg.attn_adapter:
             f = cfg.attn_adapter.get("downsample_factor", 4)
             if cfg.attn_adapter.get("adapter_type", "normal") == "normal":
-                blk.attn = AdapterWrapper(blk.attn, cfg.d, f)
+                blk.attn = AdapterWrapper(blk.attn, cfg.d, f, activation=act)
             else:
-                blk.attn = ParallelAdapterWrapper(blk.attn, cfg.d, f)
+                blk.attn = ParallelAdapterWrapper(blk.attn, cfg.d, f, activation=act)
     for n, p in lm.named_parameters():
         if "adapter" in n:
             p.data = p.data.to(dev)
@@ -256,6 +260,11 @@ def group_lm_variants(dev):
                                  attn_adapter={"adapter_type": "parallel", "downsample_factor": 4}),
                   "lm[parallel mlp+attn]")
     ok &= lm_case(dev, small_cfg(d=1024, n_head=4), "lm[hd=256, S=70]", B=3, S=70)
+    # adapter activation as a parameter (adapters.py:11): the tanh-GeLU variant north_star names, normal and parallel wiring
+    ok &= lm_case(dev, small_cfg(adapter_act="gelu"), "lm[mlp normal f=4, GeLU adapters]")
+    ok &= lm_case(dev, small_cfg(adapter_act="gelu", mlp_adapter={"adapter_type": "parallel", "downsample_factor": 4},
+                                 attn_adapter={"adapter_type": "normal", "downsample_factor": 8}),
+                  "lm[GeLU adapters: parallel mlp + normal attn]")
     return ok
 
 
