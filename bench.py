@@ -146,16 +146,17 @@ class ClockSampler:
         return out
 
 
-def synthetic_host_batches(n, seed):
+def synthetic_host_batches(n, seed, batch=B_PER_GPU, seq=S, res=RES, max_caption=None):
     import torch
 
     g = torch.Generator().manual_seed(seed)
     out = []
+    hi = (max_caption if max_caption is not None else seq - 2) + 1
     for _ in range(n):
-        images = torch.randn(B_PER_GPU, 3, RES, RES, generator=g)
-        caps = torch.randint(0, 50256, (B_PER_GPU, S), generator=g)
-        lens = torch.randint(S // 4, S - 2 + 1, (B_PER_GPU,), generator=g)
-        caps = torch.where(torch.arange(S)[None, :] >= lens[:, None], torch.full_like(caps, 50256), caps)
+        images = torch.randn(batch, 3, res, res, generator=g)
+        caps = torch.randint(0, 50256, (batch, seq), generator=g)
+        lens = torch.randint(min(seq // 4, hi - 1), hi, (batch,), generator=g)
+        caps = torch.where(torch.arange(seq)[None, :] >= lens[:, None], torch.full_like(caps, 50256), caps)
         out.append((images.pin_memory(), caps.pin_memory()))
     return out
 
@@ -253,7 +254,23 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n, note=""):
+# BASELINE.json config 4 asks for an NFNet-F6 encoder, which the reference does not have (its conv
+# encoders are timm nf_resnet50 and the CLIP ResNets) and this repo has not built; the conv-trunk hot path that IS built is
+# the encoder MAGMA_v1.yml actually ships, CLIP RN50x16 (`clip_resnet_large`) at its native 384 px. Its prefix is 144 tokens
+# (one per 12 x 12 position), which must fit inside seq_len (fact 3): 144 + 128 caption positions = 272.
+CONV = {"batch": 16, "res": 384, "seq": 272, "encoder": "clip_resnet_large"}
+
+
+def workload_config(n, note="", conv=False):
+    if conv:
+        return {"workload": "BASELINE.json config 4, conv-trunk variant that exists: CLIP RN50x16 (clip_resnet_large, the "
+                            "encoder of MAGMA_v1.yml; NFNet-F6 is in neither the reference nor this repo) at 384x384 -> "
+                            "144-token prefix + GPT-J-6B + MLP adapters (normal, f=4), batch 16 per GPU, seq_len 272 "
+                            "(= 144 prefix + 128 caption positions), fwd+bwd+AdamW, LM and image encoder frozen (eval-mode "
+                            "BatchNorm folded), random-init weights",
+                "global_batch": CONV["batch"] * n, "seq_len": CONV["seq"], "image": CONV["res"], "parallelism": f"dp{n}",
+                "l2": "working set per step (12.2 GB of bf16 weights streamed) exceeds the 126 MB L2; no explicit flush",
+                "note": note}
     return {"workload": "BASELINE.json config 2: CLIP ViT-L/14 (clip_vit_large, pooled -> image_seq_len 2) + GPT-J-6B "
                         "+ MLP adapters (normal, f=4), batch 8 per GPU, 224x224 images, seq_len 128, fwd+bwd+AdamW, "
                         "LM and image encoder frozen, random-init weights",
@@ -277,14 +294,17 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     L = _lib.lib()
-    mc = MultimodalConfig(batch_size=B_PER_GPU * world, train_steps=args.steps, encoder_name="clip_vit_large",
+    conv = args.workload == "conv"
+    Bw, Sw, Rw = (CONV["batch"], CONV["seq"], CONV["res"]) if conv else (B_PER_GPU, S, RES)
+    mc = MultimodalConfig(batch_size=Bw * world, train_steps=args.steps,
+                          encoder_name=CONV["encoder"] if conv else "clip_vit_large",
                           adapter_config={"mlp": {"adapter_type": "normal", "downsample_factor": 4}}, image_seq_len=2,
-                          image_embed_dropout_prob=0.1, use_image_embed_layernorm=True, image_size=RES, seq_len=S,
+                          image_embed_dropout_prob=0.1, use_image_embed_layernorm=True, image_size=Rw, seq_len=Sw,
                           gradient_accumulation_steps=1, freeze_img_encoder=True, lr=8e-4, lr_decay_iters=300000)
     model = Magma(mc, device=dev, init_seed=0)
     model.train()
     engine = B200Engine(model, mc)
-    host = synthetic_host_batches(4, 1234 + rank)
+    host = synthetic_host_batches(4, 1234 + rank, Bw, Sw, Rw, max_caption=(Sw - 144 - 2) if conv else None)
     dev_batches = [(i.to(dev, non_blocking=True).to(torch.bfloat16), c.to(dev, non_blocking=True)) for i, c in host]
     torch.cuda.synchronize()
 
@@ -326,7 +346,7 @@ def run_b200(args):
     clocks = sampler.stop() if sampler else None
     last_loss = float(loss.detach())
     ms_step = ms_total / args.steps
-    value = B_PER_GPU * world / (ms_step / 1e3)
+    value = Bw * world / (ms_step / 1e3)
 
     # ---- end-to-end through train_step with pinned host batches (e2e) ----
     def loader():
@@ -345,7 +365,7 @@ def run_b200(args):
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    e2e = {"value": B_PER_GPU * world / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
+    e2e = {"value": Bw * world / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": host[0][0].numel() * 4 + host[0][1].numel() * 8, "d2h_bytes_per_step": 4,
            "api": "magma_b200.train_loop.train_step(config, loader, engine) with pinned fp32 images + int64 captions"}
 
@@ -380,8 +400,10 @@ def run_b200(args):
                 "gemm_ms_per_step_profiled": ms.value / n_prof, "profiled_step_ms": prof_step_ms,
                 "gemm_share_of_profiled_step": (ms.value / n_prof) / prof_step_ms,
                 "gemm_share_of_step": min(1.0, (ms.value / n_prof) / ms_step),
-                "step_algorithmic_tflops": FLOPS_PER_SAMPLE * B_PER_GPU / (ms_step / 1e3) / 1e12,
-                "step_frac_of_peak": FLOPS_PER_SAMPLE * B_PER_GPU / (ms_step / 1e3) / 1e12 / peak_tf}
+                # whole-step figure: closed-form FLOPs of config 2; for the conv workload the GEMM launches' own counted
+                # FLOPs (every conv is a GEMM here) over the timed step
+                "step_algorithmic_tflops": (fl.value / n_prof if conv else FLOPS_PER_SAMPLE * Bw) / (ms_step / 1e3) / 1e12,
+                "step_frac_of_peak": (fl.value / n_prof if conv else FLOPS_PER_SAMPLE * Bw) / (ms_step / 1e3) / 1e12 / peak_tf}
         tr = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")
         if os.path.exists(tr):
             try:
@@ -421,14 +443,14 @@ def run_b200(args):
             allreduce = {"error": repr(exc)[:200]}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not conv:
         r = cpu_reference_run(steps=1, warmup=1, budget_s=60.0)
         cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     # ---- the reference's PyTorch-eager path on the SAME GPU in the same run (north_star's ">= 6x over eager" target):
     # HF GPT-J eager + the reference's adapter wiring, bf16, LM frozen (tools/eager_baseline.py: no magma_b200 code)
     gpu_eager = None
-    if rank == 0 and world == 1 and not args.no_gpu_eager:
+    if rank == 0 and world == 1 and not args.no_gpu_eager and not conv:
         try:
             torch.cuda.empty_cache()
             from tools import eager_baseline
@@ -444,7 +466,7 @@ def run_b200(args):
         line = {"metric": "image-caption samples/sec (fwd+bwd)", "value": value, "unit": "samples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic", "config": workload_config(world), "e2e": e2e, "gpu_launches": int(launches),
+                "data": "synthetic", "config": workload_config(world, conv=conv), "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager": gpu_eager, "allreduce": allreduce,
                 "loss": last_loss,
                 "trainable_params": int(model.arena.numel)}
@@ -575,9 +597,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
-    ap.add_argument("--workload", default="train", choices=["train", "decode"],
+    ap.add_argument("--workload", default="train", choices=["train", "decode", "conv"],
                     help="train = BASELINE.json config 2 (the metric's configuration, default); decode = config 5 "
-                         "(Magma.generate: batch 32, 224x224 image prefix, 256 greedy steps, KV cache)")
+                         "(Magma.generate: batch 32, 224x224 image prefix, 256 greedy steps, KV cache); conv = config 4's "
+                         "conv-trunk hot path with the encoder that exists (CLIP RN50x16 @ 384, batch 16, seq_len 272)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -114,7 +114,8 @@ typedef struct {
   const void* res1;   /* bf16 [M,N], row stride ld_res, batch strides as C, or NULL */
   const void* res2;   /* bf16 [M,N], row stride ld_res, or NULL */
   int64_t ld_res;
-  int32_t force_bn;   /* 0 = auto tile width, else 64/128/256, or 512 = CTA-pair 256x256 kernel (testing / tuning) */
+  int32_t force_bn;   /* 0 = auto tile width, else 64/128/256, 512 = CTA-pair 256x256 kernel, 768 = CTA-pair kernel with
+                       * stream-K of the last wave (needs splitk_ws) — testing / tuning */
   /* fused rotary embedding (rotate_every_two, hf:gptj/modeling_gptj.py:57-67) applied to adjacent column pairs after
    * the bias: for columns c < rope_ncols with (c % rope_hd) < rope_rot, using (cos, sin) = rope_tab[row % rope_S]
    * [(c % rope_hd)/2] (fp32 pairs, mb200_rope_table). rope_mode +1 = forward, -1 = inverse; rope_tab NULL = off. */

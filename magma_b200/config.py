@@ -59,7 +59,7 @@ class MultimodalConfig:
     seq_len: int = None  # present but never read by the reference; magma_b200 uses it to set Magma.seq_len
     # freezing
     freeze_lm: bool = True  # must stay true: the LM is frozen on this path
-    freeze_img_encoder: bool = True  # false trains the encoder (ViT: vit_train.cu; conv trunks: train-mode BN)
+    freeze_img_encoder: bool = True  # false trains the encoder (ViT: vit_sched.cu; conv trunks: train-mode BN)
     image_embed_dropout_prob: float = 0.0  # nn.Dropout on the prefix (image_prefix.py:104)
     use_image_embed_layernorm: bool = False  # LayerNorm on the prefix (image_prefix.py:106-107)
     # adapters

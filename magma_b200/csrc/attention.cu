@@ -1,7 +1,7 @@
 // magma_b200 — fused causal self-attention for one (batch, head) per CTA when the whole sequence fits one tile
 // (S <= 128 — BASELINE.json config 2 has S = 128), head_dim a multiple of 64 up to 256.
 //
-// Replaces, per layer, the 3 (forward) / 6 (backward) launches of the GEMM-based path in engine.cu — QK^T GEMM,
+// Replaces, per layer, the 3 (forward) / 6 (backward) launches of the GEMM-based path of the schedules — QK^T GEMM,
 // softmax kernel, PV GEMM; dP, dV, softmax-bwd, dQ, dK GEMMs — which spend most of their ~12-18 us each on fixed
 // launch / prologue / epilogue cost for 0.5 % of the step's FLOPs. Numerics are those of the reference
 // (GPTJAttention._attn, hf:gptj/modeling_gptj.py:136-149): fp32 scores from bf16 q,k, / sqrt(hd), causal mask,

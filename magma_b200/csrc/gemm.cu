@@ -539,9 +539,9 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
   int rc = check_arch();
   if (rc) return rc;
 
-  const bool force2 = a->force_bn == 512;  // testing: force the CTA-pair kernel
+  const bool force2 = a->force_bn == 512 || a->force_bn == 768;  // testing: force the CTA-pair kernel (768: + stream-K)
   int bn = force2 ? 256 : (a->force_bn ? a->force_bn : pick_bn(a->M, a->N, a->K, a->nb0 * a->nb1));
-  MB_REQUIRE(bn == 64 || bn == 128 || bn == 256, MB200_E_ARG, "gemm: force_bn must be 64/128/256 (or 512 = 2-CTA)");
+  MB_REQUIRE(bn == 64 || bn == 128 || bn == 256, MB200_E_ARG, "gemm: force_bn must be 64/128/256 (or 512 / 768 = 2-CTA)");
 
   CUtensorMap tmA, tmB;
   // small-M problems (decode: M = batch <= 32) stage only a 32-row A box per k-block (see Cfg<BN, AROWS>)
@@ -707,16 +707,23 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
     kp.sk_on = 0;
     CUtensorMap tmWs;
     {
+      // OFF by default. Measured on a B200 (profiles/r02_streamk_ab.log): correct and bit-reproducible, but no faster —
+      // 28.9 vs 28.0 us at N = K = 4096, 96.5 vs 97.1 us at K = 16384, and slower on the multi-wave shapes (96 vs 75 us
+      // for qkv, 132 vs 100 us for fc_in) where the owners' partial-tile reads sit on the critical path. The long-K
+      // GEMMs already run at the POWER-limited rate (1.42 - 1.47 PFLOP/s = cuBLAS's sustained figure, sw_power_cap
+      // active): filling the 20 idle SMs lowers the clock of the other 128. MB200_STREAMK=1 (or force_bn = 768 for one
+      // call) turns it on; the parity group `streamk` of tools/gemm_check.py keeps it honest.
       static int sk_env = -1;
       if (sk_env < 0) {
-        const char* e = getenv("MB200_STREAMK");  // 0 = never split the last wave (A/B switch)
-        sk_env = e ? atoi(e) : 1;
+        const char* e = getenv("MB200_STREAMK");
+        sk_env = e ? atoi(e) : 0;
       }
+      const bool sk_forced = a->force_bn == 768;
       const int ncl = gemm_sms() / 2;
       const int T = kp.total_tiles, KBn = (a->K + BK - 1) / BK;
       const int W = T / ncl, R = T - W * ncl;
-      if (sk_env && a->splitk_ws && a->nb0 * a->nb1 == 1 && kp.epi_kind != EK_GENERIC && R > 0 && R < ncl && KBn >= 16 &&
-          !a->force_bn) {
+      if ((sk_env || sk_forced) && a->splitk_ws && a->nb0 * a->nb1 == 1 && kp.epi_kind != EK_GENERIC && R > 0 && R < ncl &&
+          KBn >= 16 && (!a->force_bn || sk_forced)) {
         const int h = (int)(((long long)R * KBn + ncl - 1) / ncl);
         const int tail = KBn - h, nh = ncl - R;
         const long long U = (long long)R * tail;

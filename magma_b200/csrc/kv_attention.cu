@@ -155,7 +155,7 @@ extern "C" int mb200_attn_decode_dev(const void* qkv, int64_t ld_qkv, void* kcac
 }
 
 // K/V rows of a prefill (or any S > 1 continuation) into the static cache — the launch gptj_forward issues, exposed for
-// the host-only general schedule (csrc/gptj_sched.cu).
+// the host-only LM schedule (csrc/gptj_sched.cu).
 extern "C" int mb200_kv_append(const void* qkv, int64_t ld_qkv, void* kcache, void* vcache, int32_t B, int32_t S,
                                int32_t H, int32_t hd, int32_t S_kv_max, int32_t pos0, void* stream) {
   int rc = check_arch();

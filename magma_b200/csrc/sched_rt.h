@@ -1,4 +1,4 @@
-// magma_b200 — the small runtime interface that HOST-ONLY schedule files (vit_train.cu) are written against.
+// magma_b200 — the small runtime interface that HOST-ONLY schedule files (gptj_sched.cu, vit_sched.cu) are written against.
 //
 // A schedule file contains no kernels and no CUDA runtime calls: it carves a workspace and issues the primitive
 // operators of the C ABI (include/magma_b200.h: mb200_gemm, mb200_layernorm_*, mb200_softmax_*, ...) plus the three

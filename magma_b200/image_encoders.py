@@ -97,7 +97,7 @@ _VIT_TOP_FIELDS = (("cls", "class_embedding"), ("pos", "positional_embedding"), 
 
 
 class _VitTrainFn(torch.autograd.Function):
-    """feats = ViT(images) with the hand-written backward of csrc/vit_train.cu (`freeze_img_encoder: false`): every
+    """feats = ViT(images) with the hand-written backward of csrc/vit_sched.cu (`freeze_img_encoder: false`): every
     parameter gradient is written as fp32 straight into the trainable-parameter arena. `anchor` is one trainable
     parameter: it makes autograd call backward although the pixels carry no gradient."""
 

@@ -9,7 +9,7 @@ object with `.loss`, `.logits`, `.past_key_values`.
 
 All frozen weights are bf16 tensors on the GPU; parameter names follow HF GPT-J (`attn.q_proj.weight`, `mlp.fc_in.*`,
 `ln_1`, `ln_f`, `lm_head`) — the executable stand-in for the reference's fork. The whole
-28-block forward and backward run inside libmagma_b200.so (engine.cu); this file only owns tensors and plumbing.
+28-block forward and backward run inside libmagma_b200.so (csrc/gptj_sched.cu); this file only owns tensors and plumbing.
 """
 import ctypes
 import os
@@ -294,7 +294,7 @@ class B200GPTJForCausalLM(nn.Module):
         return c
 
     def _cmodel_ex(self):
-        """mb200_gptj_model_ex for the general schedule (same frozen-weight pointers, extended adapter tables)."""
+        """mb200_gptj_model_ex: frozen-weight pointers and the adapter tables (every adapter form of the reference)."""
         self._ensure_arena()
         if self._cmodel_ex_cache is not None:
             return self._cmodel_ex_cache

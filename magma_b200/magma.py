@@ -111,7 +111,7 @@ class Magma(nn.Module):
         else:
             raise NotImplementedError("freeze_lm: false (full LM fine-tuning) is outside the re-backed hot path")
         # magma.py:98-100 freezes the encoder only when asked to (MAGMA_v1.yml trains it). The ViT family has a backward
-        # pass (csrc/vit_train.cu); the conv trunks do not (eval-mode BatchNorm folded into their weights).
+        # pass (csrc/vit_sched.cu); the conv trunks do not (eval-mode BatchNorm folded into their weights).
         enc_trains = (not config.freeze_img_encoder) and getattr(self.image_prefix.enc, "supports_training", False)
         for param in self.image_prefix.enc.parameters():
             param.requires_grad = enc_trains

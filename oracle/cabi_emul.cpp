@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE — CPU emulation of the PRIMITIVE operators of the magma_b200 C ABI.
 //
-// Purpose: the model-level schedules of the product (csrc/vit_train.cu, written against csrc/sched_rt.h) are host
+// Purpose: the model-level schedules of the product (csrc/vit_sched.cu, csrc/gptj_sched.cu, written against csrc/sched_rt.h) are host
 // code that only carves a workspace and issues primitive operators. tests/ compile such a schedule file as plain C++
 // together with this file and run it on CPU tensors, so that every pointer offset, leading dimension, operand major,
 // batch stride and accumulate flag of the schedule is checked against the oracle (torch autograd of
@@ -806,7 +806,7 @@ int mb200_attn_bwd_tile(const void* qkv_, int64_t ld, const void* dO_, int64_t l
   return 0;
 }
 
-// KV cache   (engine.cu: kv_append_kernel / attn_decode_kernel)
+// KV cache   (kv_attention.cu: kv_append_kernel / attn_decode_kernel)
 int mb200_kv_append(const void* qkv_, int64_t ld, void* kc_, void* vc_, int32_t B, int32_t S, int32_t H, int32_t hd,
                     int32_t Smax, int32_t pos0, void*) {
   EM_TRACE(0, (double)B * S * H * hd * 8, "kv_append\tB=%d S=%d H=%d hd=%d", B, S, H, hd);

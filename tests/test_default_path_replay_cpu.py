@@ -65,7 +65,7 @@ def test_generate_harness_and_reference_greedy_golden_replay(replay, monkeypatch
     """KV-cache decoding on the CPU: the generate group of the GPU harness (greedy tokens identical to the oracle's, a
     decode step equal to the full forward) and the reference's own greedy-token golden
     (tests/test_model_gpu.py::test_vit_embed_generate_match_reference_golden), through sampling.generate ->
-    decode_logits -> the emulated entry points (prefill + per-token decode of the general schedule)."""
+    decode_logits -> the emulated entry points (prefill + per-token decode of csrc/gptj_sched.cu)."""
     import test_model_gpu as G
     from tools import model_check
 
@@ -83,7 +83,7 @@ def test_full_smoke_replays_with_decode(replay, capsys):
 
 
 def test_generate_works_for_layernorm_and_scaled_adapters(replay, monkeypatch):
-    """language_model routes adapters with add_layernorm / adapter_scale through the general schedule for decoding too:
+    """language_model routes adapters with add_layernorm / adapter_scale through the same schedule for decoding too:
     greedy tokens of the KV-cache loop equal an argmax over full re-forwards of the growing sequence."""
     import test_e2e_dryrun_cpu as E
     from oracle import magma_oracle as O

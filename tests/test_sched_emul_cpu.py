@@ -1,6 +1,6 @@
 """Dry run of the product's host-only schedule files on the CPU.
 
-magma_b200/csrc/vit_train.cu (ViT training forward + backward) contains no kernels: it carves a workspace and issues
+magma_b200/csrc/vit_sched.cu (ViT inference forward, training forward + backward) contains no kernels: it carves a workspace and issues
 primitive C-ABI operators. Here the SAME source file is compiled as plain C++ against oracle/cabi_emul.cpp (a scalar
 CPU emulation of those primitives with bf16 storage, test infrastructure only) and run on CPU tensors, so every
 pointer offset, leading dimension, operand major, batch stride and accumulate flag of the schedule is held to torch

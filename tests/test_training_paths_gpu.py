@@ -1,5 +1,5 @@
 """GPU tests of the training paths beyond the frozen-encoder benchmark configuration: the ViT training schedule
-(csrc/vit_train.cu), the general GPT-J + adapters schedule (csrc/gptj_sched.cu: add_layernorm / scaled_parallel forms),
+(csrc/vit_sched.cu), the add_layernorm / scaled_parallel adapter forms of the LM schedule (csrc/gptj_sched.cu),
 conv-trunk training (BatchNorm in training mode), the optimizer parameter groups, engine checkpoint resume, and the
 elementwise kernels written for them. All of them run on a B200 (first hardware run: round 2, gpurun call 1 —
 profiles/r02_training_paths_first_hw_run.log); nothing here is expected to fail.

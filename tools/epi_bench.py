@@ -49,7 +49,7 @@ def main():
         return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
 
     def case(tag, M, N, K, *, bias=False, act=0, res=0, aux=False, a_mn=False, b_mn=False, f32=False, force_bn=0,
-             dact=0, check=True):
+             dact=0, check=True, use_ws=True):
         nbuf = max(1, min(8, int(200e6 // (N * K * 2)) + 1)) if N * K * 2 > 30e6 else 1
         Bs = [rnd(K, N) if b_mn else rnd(N, K) for _ in range(nbuf)]
         A = rnd(K, M, scale=1.0) if a_mn else rnd(M, K, scale=1.0)
@@ -68,8 +68,8 @@ def main():
             kw["res1"] = rnd(M, N, scale=1.0)
         if res >= 2:
             kw["res2"] = rnd(M, N, scale=1.0)
-        ws = torch.empty(64 << 20, device=dev, dtype=torch.float32)
-        kw["splitk_ws"] = ws
+        if use_ws:  # scratch lent to the GEMM core (split-K of few-tile long-K shapes), as the schedules do
+            kw["splitk_ws"] = torch.empty(32 << 20, device=dev, dtype=torch.float32)
         us = timed(lambda i: ops.gemm(A, Bs[i % nbuf], out=C, **kw), max(8, 2 * nbuf), s)
         tf = 2.0 * M * N * K / us / 1e6
         err = float("nan")
@@ -122,7 +122,9 @@ def main():
     if "adapter" in only:
         M, d, r = 1024, 4096, 1024
         case("adapter down (bias+relu)", M, r, d, bias=True, act=ops.ACT_RELU)
+        case("adapter down (no scratch: bn=64)", M, r, d, bias=True, act=ops.ACT_RELU, use_ws=False)
         case("adapter down pair-forced", M, r, d, bias=True, act=ops.ACT_RELU, force_bn=512)
+        case("adapter dgrad-up (no scratch)", M, r, d, b_mn=True, dact=ops.DACT_RELU, use_ws=False)
         case("adapter up (bias+res2)", M, d, r, bias=True, res=2)
         case("adapter dgrad-up (drelu)", M, r, d, b_mn=True, dact=ops.DACT_RELU)
         case("adapter dgrad-down (+res1)", M, d, r, b_mn=True, res=1)

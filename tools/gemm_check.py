@@ -326,13 +326,13 @@ def run_group(g):
             A, B = mk((M, K), False, dev, 0.5), mk((N, K), bmn, dev, 0.05)
             ldc = (N + 7) // 8 * 8
             C = torch.full((M, ldc), 7.0, device=dev, dtype=torch.bfloat16)
-            ops.gemm(A, B, out=C[:, :N], b_mn=bmn, splitk_ws=ws)
+            ops.gemm(A, B, out=C[:, :N], b_mn=bmn, splitk_ws=ws, force_bn=768)
             want = ref_gemm(A, B, False, bmn)
             ok &= report(f"streamk plain M={M} N={N} K={K} ({what})", C[:, :N], want)
             if ldc > N:
                 ok &= untouched(f"streamk M={M} N={N} columns >= N", C[:, N:], 7.0)
             C2 = torch.full((M, ldc), 7.0, device=dev, dtype=torch.bfloat16)
-            ops.gemm(A, B, out=C2[:, :N], b_mn=bmn, splitk_ws=ws)
+            ops.gemm(A, B, out=C2[:, :N], b_mn=bmn, splitk_ws=ws, force_bn=768)
             same = bool(torch.equal(C, C2))
             print(f"[{'OK' if same else 'FAIL'}] streamk M={M} N={N} K={K}: second run bit-identical", flush=True)
             ok &= same
@@ -342,23 +342,23 @@ def run_group(g):
         base = ref_gemm(A, B, False, False)
         pre = base + bias.float()
         r1, r2 = mk((M, N), False, dev), mk((M, N), False, dev)
-        C = ops.gemm(A, B, bias=bias, res1=r1, res2=r2, alpha=0.5, splitk_ws=ws)
+        C = ops.gemm(A, B, bias=bias, res1=r1, res2=r2, alpha=0.5, splitk_ws=ws, force_bn=768)
         ok &= report("streamk alpha+bias+res1+res2", C, 0.5 * base + bias.float() + r1.float() + r2.float())
         aux = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        C = ops.gemm(A, B, bias=bias, act=ops.ACT_GELU_NEW, aux_out=aux, splitk_ws=ws)
+        C = ops.gemm(A, B, bias=bias, act=ops.ACT_GELU_NEW, aux_out=aux, splitk_ws=ws, force_bn=768)
         ok &= report("streamk bias+gelu_new+aux: C", C, F.gelu(pre, approximate="tanh"))
         ok &= report("streamk bias+gelu_new+aux: aux", aux, pre)
         x = mk((M, N), False, dev)
-        C = ops.gemm(A, B, aux_in=x, dact=ops.DACT_RELU, splitk_ws=ws)
+        C = ops.gemm(A, B, aux_in=x, dact=ops.DACT_RELU, splitk_ws=ws, force_bn=768)
         ok &= report("streamk dact relu", C, base * (x.float() > 0).float())
         Cf = torch.ones(M, N, device=dev, dtype=torch.float32)
-        ops.gemm(A, B, out=Cf, accumulate=True, splitk_ws=ws)
+        ops.gemm(A, B, out=Cf, accumulate=True, splitk_ws=ws, force_bn=768)
         ok &= report("streamk f32 accumulate", Cf, base + 1.0, tol=5e-3)
         Sx, H, hd, rot = 128, 16, 256, 64
         A2, B2 = mk((8 * Sx, 4096), False, dev, 0.5), mk((3 * H * hd, 4096), False, dev, 0.05)
         tab = ops.rope_table(Sx, rot, pos0=0, device=dev)
         fused = ops.gemm(A2, B2, rope_tab=tab, rope_mode=1, rope_S=Sx, rope_hd=hd, rope_rot=rot, rope_ncols=2 * H * hd,
-                         splitk_ws=ws)
+                         splitk_ws=ws, force_bn=768)
         plain = ops.gemm(A2, B2, out_dtype=torch.float32)
         qq = plain.view(8, Sx, 3, H, hd).clone()
         cs, sn = tab[None, :, None, None, :, 0], tab[None, :, None, None, :, 1]
@@ -371,13 +371,14 @@ def run_group(g):
             A, B = mk((M, K), False, dev), mk((N, K), bmn, dev)
             C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
             for tag, w in (("stream-K", ws), ("whole tiles", None)):
+                fb = 768 if w is not None else 0
                 for _ in range(3):
-                    ops.gemm(A, B, out=C, b_mn=bmn, splitk_ws=w)
+                    ops.gemm(A, B, out=C, b_mn=bmn, splitk_ws=w, force_bn=fb)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(20):
-                    ops.gemm(A, B, out=C, b_mn=bmn, splitk_ws=w)
+                    ops.gemm(A, B, out=C, b_mn=bmn, splitk_ws=w, force_bn=fb)
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 20
