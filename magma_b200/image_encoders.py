@@ -159,6 +159,14 @@ class B200VisionTransformer(nn.Module):
         self._cache = None
         self._gcache = None
 
+    def load_state_dict(self, *a, **kw):  # the packed conv1 / proj^T copies the kernels read are derived from the weights
+        self.invalidate()
+        return super().load_state_dict(*a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):  # reached when a parent module loads a checkpoint
+        self.invalidate()
+        return super()._load_from_state_dict(*a, **kw)
+
     def attach_arena(self, arena):
         """Trainable encoder (freeze_img_encoder: false): parameters are fp32 master views of the arena and the
         kernels read the arena's bf16 compute copy."""
@@ -607,7 +615,8 @@ class B200ModifiedResNet(nn.Module):
                 return self._train_forward(x)[0]                          # reference-literal frozen trunk under train()
         # frozen, or a trainable trunk in eval mode: running statistics folded into the weights (re-packed from the
         # current fp32 parameters after every training forward, which resets self._packed)
-        if os.environ.get("MB200_RESNET_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing():
+        if x.is_cuda and os.environ.get("MB200_RESNET_GRAPH", "1") != "0" and \
+                not torch.cuda.is_current_stream_capturing():
             return self._forward_graphed(x)
         return self._forward_eager(x)
 

@@ -90,8 +90,8 @@ class Magma(nn.Module):
 
             self.transforms = get_transforms(config.image_size, config.encoder_name,
                                              input_resolution=self.image_prefix.enc.input_resolution)
-        except Exception:  # torchvision / PIL preprocessing is host-side and optional
-            self.transforms = None
+        except Exception as e:  # torchvision / PIL preprocessing is host-side and optional
+            self.transforms, self._transforms_error = None, e
 
         if config.adapter_config:
             mlp_config = deepcopy(config.adapter_config.get("mlp", None))
@@ -198,6 +198,10 @@ class Magma(nn.Module):
             if isinstance(inp, str):
                 input_list[i] = self.tokenizer.encode(inp, return_tensors="pt")
             elif isinstance(inp, ImageInput):
+                if self.transforms is None:
+                    raise RuntimeError("image preprocessing is unavailable: magma_b200.transforms.get_transforms failed "
+                                       f"at construction ({getattr(self, '_transforms_error', None)!r}); pass an "
+                                       "already-transformed image tensor instead of an ImageInput")
                 input_list[i] = inp.get_transformed_image(transform_fn=self.transforms)
             else:
                 raise Exception(f"Invalid input type:{type(inp)}")
@@ -257,7 +261,9 @@ class Magma(nn.Module):
         if not os.path.exists(checkpoint_path):
             raise FileNotFoundError(f"checkpoint {checkpoint_path} does not exist (no network: cannot download)")
         model = cls(config=config_path, device=device, init_seed=None)
-        sd = torch.load(checkpoint_path, map_location=torch.device("cpu"))
+        # weights_only=False: DeepSpeed payloads hold non-tensor client state (as checkpoint.read_training_checkpoint)
+        sd = torch.load(checkpoint_path, map_location=torch.device("cpu"), weights_only=False)
+        partial = bool(sd.get("trainable_only", False)) if isinstance(sd, dict) else False
         if "module" in sd.keys():
             sd = sd["module"]
         print_main(f"loading magma checkpoint from: {checkpoint_path}")
@@ -267,6 +273,18 @@ class Magma(nn.Module):
         missing, unexpected = model.load_state_dict(sd, strict=False)
         missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer.")) and
                    not k.endswith("num_batches_tracked")]
+        if partial:
+            # a B200Engine.save_checkpoint(trainable_only=True) file: only what trains is in it. Loaded on top of the
+            # frozen weights this constructor initialised (config paths / random init) — say so, loudly.
+            frozen = {n for n, p in model.named_parameters() if not p.requires_grad}
+            still = [k for k in missing if k not in frozen and k in dict(model.named_parameters())]
+            if still or unexpected:
+                raise RuntimeError(f"trainable-only checkpoint lacks trainable keys {still[:4]} / has unexpected keys "
+                                   f"{list(unexpected)[:4]}")
+            print_main(f"NOTE: {checkpoint_path} is a trainable-only checkpoint ({len(sd)} tensors); the "
+                       f"{len(missing)} frozen LM / encoder tensors keep the values the config initialised. Save with "
+                       "save_model(..., full=True) for a self-contained file.")
+            missing = []
         if missing or unexpected:
             raise RuntimeError(f"checkpoint does not match the model: {len(missing)} missing (e.g. {missing[:4]}), "
                                f"{len(unexpected)} unexpected (e.g. {list(unexpected)[:4]}); "

@@ -139,8 +139,17 @@ class B200Engine:
             return True
         model = self.module
         trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+        # buffers of every module that owns a trainable parameter travel with it: a training conv trunk updates its
+        # BatchNorm running_mean / running_var / num_batches_tracked each forward (image_encoders.py), and the folded
+        # eval path reads them
+        stateful = set()
+        for mname, mod in model.named_modules():
+            if any(p is not None and p.requires_grad for p in mod._parameters.values()):
+                stateful.update(f"{mname}.{b}" if mname else b for b, t in mod._buffers.items()
+                                if t is not None and b not in mod._non_persistent_buffers_set)
         sd = {k: v for k, v in model.state_dict().items()
-              if not k.startswith(("word_embedding.", "transformer.")) and (not trainable_only or k in trainable)}
+              if not k.startswith(("word_embedding.", "transformer.")) and
+              (not trainable_only or k in trainable or k in stateful)}
         state = dict(client_state or {})
         state.update({"global_step_engine": self.global_step, "micro_step": self.micro_step,
                       "trainable_only": bool(trainable_only)})
@@ -162,10 +171,16 @@ class B200Engine:
         missing, unexpected = model.load_state_dict(sd, strict=False)
         if unexpected:
             raise RuntimeError(f"checkpoint has {len(unexpected)} keys the model does not (e.g. {list(unexpected)[:4]})")
-        if not payload.get("trainable_only", False):
-            missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
-            if missing:
-                raise RuntimeError(f"checkpoint lacks {len(missing)} model keys (e.g. {missing[:4]})")
+        missing = [k for k in missing if not k.startswith(("word_embedding.", "transformer."))]
+        if payload.get("trainable_only", False):  # frozen weights are not in the file; everything that trains must be
+            need = {n for n, p in model.named_parameters() if p.requires_grad}
+            for mname, mod in model.named_modules():
+                if any(p is not None and p.requires_grad for p in mod._parameters.values()):
+                    need.update(f"{mname}.{b}" if mname else b for b, t in mod._buffers.items()
+                                if t is not None and b not in mod._non_persistent_buffers_set)
+            missing = [k for k in missing if k in need]
+        if missing:
+            raise RuntimeError(f"checkpoint lacks {len(missing)} model keys (e.g. {missing[:4]})")
         if optim is not None:
             ck.load_arena_optimizer_state(model.arena, optim, load_optimizer_states)
         else:

@@ -50,8 +50,12 @@ def get_world_info():
     return int(os.environ["LOCAL_RANK"]), int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 
 
-def save_model(model_engine, save_dir, global_step, config=None):
-    """magma/utils.py:89-96 — config.yml next to the engine checkpoint, client state {global_step, config}."""
+def save_model(model_engine, save_dir, global_step, config=None, full=None):
+    """magma/utils.py:89-96 — config.yml next to the engine checkpoint, client state {global_step, config}.
+    `full=True` (or MB200_SAVE_FULL=1; not a config field, so config.yml stays readable by the reference's schema) also
+    writes the frozen LM / encoder weights, which makes <tag>/mp_rank_00_model_states.pt loadable by
+    `Magma.from_checkpoint` on its own as in the reference; the default keeps the 12 GB of weights that never change out
+    of every periodic save (from_checkpoint then loads it on top of the initialised frozen weights and says so)."""
     import yaml
 
     os.makedirs(save_dir, exist_ok=True)
@@ -59,7 +63,10 @@ def save_model(model_engine, save_dir, global_step, config=None):
     if cfg is not None and is_main():
         with open(os.path.join(str(save_dir), "config.yml"), "w") as f:
             yaml.dump(cfg, f, default_flow_style=False)
-    model_engine.save_checkpoint(save_dir, client_state={"global_step": global_step, "config": cfg})
+    if full is None:
+        full = os.environ.get("MB200_SAVE_FULL", "0") == "1"
+    model_engine.save_checkpoint(save_dir, client_state={"global_step": global_step, "config": cfg},
+                                 trainable_only=not full)
 
 
 def load_model(model_engine, load_dir, load_optimizer_states=True, load_lr_scheduler_states=True):

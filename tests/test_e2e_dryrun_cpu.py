@@ -132,10 +132,12 @@ def test_magma_with_a_trainable_vit_end_to_end(emul_ops, monkeypatch, tmp_path):
     assert got == pytest.approx(want, abs=1e-5)
 
 
-def test_magma_with_a_trainable_conv_trunk_trains(emul_ops, monkeypatch):
-    """MAGMA_v1.yml's encoder type (a CLIP conv trunk, freeze_img_encoder: false): the whole step runs and learns."""
+def test_magma_with_a_trainable_conv_trunk_trains(emul_ops, monkeypatch, tmp_path):
+    """MAGMA_v1.yml's encoder type (a CLIP conv trunk, freeze_img_encoder: false): the whole step runs and learns, and a
+    (trainable-only) checkpoint carries the BatchNorm running statistics the folded eval path reads."""
     from magma_b200.image_encoders import register_resnet
     from magma_b200.train_loop import B200Engine
+    from magma_b200.utils import load_model, save_model
 
     cfg = tiny_cfg(vit_image=64)
     register_resnet("clip_resnet_dry", (1, 1, 1, 1), 16, 64)          # 4 prefix tokens of width 512
@@ -159,6 +161,32 @@ def test_magma_with_a_trainable_conv_trunk_trains(emul_ops, monkeypatch):
         losses.append(float(o.loss.detach()))
     assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.05, losses
     assert not torch.equal(rm0, model.image_prefix.enc.bn1.running_mean)   # BatchNorm ran in training mode
+    # resume: a fresh model + load_model must give the same EVAL features (running_mean / running_var travel with the
+    # trainable-only file) and a checkpoint stripped of them must be refused, not loaded with statistics of (0, 1)
+    save_model(eng, str(tmp_path), eng.global_step, config=mc)
+    payload = torch.load(tmp_path / f"global_step{eng.global_step}" / "mp_rank_00_model_states.pt", weights_only=False)
+    assert payload["trainable_only"] and "image_prefix.enc.bn1.running_var" in payload["module"]
+    assert not any(k.startswith("lm.transformer.h.0.attn") for k in payload["module"])       # frozen LM stays out
+    model.eval()
+    with torch.no_grad():
+        want = model.image_prefix(images.to(torch.bfloat16)).float()
+    model2, mc2 = build(monkeypatch, cfg, None, S, encoder="clip_resnet_dry", lr=5e-3, image_enc_lr=5e-4,
+                        warmup_num_steps=2)
+    model2.lm.init_weights(seed=0)
+    model2.image_prefix.enc.init_weights(seed=1)
+    model2.finalize()
+    eng2 = B200Engine(model2, mc2, n_buckets=2)
+    assert load_model(eng2, str(tmp_path)) == eng.global_step
+    assert torch.equal(model2.image_prefix.enc.bn1.running_mean, model.image_prefix.enc.bn1.running_mean)
+    model2.eval()
+    with torch.no_grad():
+        got = model2.image_prefix(images.to(torch.bfloat16)).float()
+    assert rel(got, want) < 1e-6
+    for k in [k for k in payload["module"] if k.endswith(("running_mean", "running_var"))]:
+        del payload["module"][k]
+    torch.save(payload, tmp_path / f"global_step{eng.global_step}" / "mp_rank_00_model_states.pt")
+    with pytest.raises(RuntimeError, match="lacks"):
+        eng2.load_checkpoint(str(tmp_path))
 
 
 def _dp_worker(rank, world, port, q):
@@ -366,3 +394,44 @@ def test_from_checkpoint_round_trip(emul_ops, monkeypatch, tmp_path, reference_n
     assert torch.equal(got, want)
     with pytest.raises(FileNotFoundError):
         Magma.from_checkpoint(mc, str(tmp_path / "nope.pt"), device="cpu")
+
+
+def test_save_model_then_from_checkpoint_as_in_the_reference(emul_ops, monkeypatch, tmp_path, capsys):
+    """The reference's workflow (train.py:120-140 -> README.md:74): save_model(...) then
+    Magma.from_checkpoint(<tag>/mp_rank_00_model_states.pt). `full=True` writes a self-contained file; the default
+    trainable-only file is loaded on top of the initialised frozen weights with a message, not an opaque key error."""
+    from magma_b200.magma import Magma
+    from magma_b200.train_loop import B200Engine
+    from magma_b200.utils import save_model
+
+    cfg = tiny_cfg()
+    S = 16
+    w16 = oracle_weights(cfg)
+    model, mc = build(monkeypatch, cfg, w16, S, freeze_enc=True, lr=1e-2, warmup_num_steps=2)
+    model.train()
+    images, captions = O.synthetic_batch(cfg, 2, S, seed=5)
+    images = images.to(torch.bfloat16)
+    eng = B200Engine(model, mc, n_buckets=2)
+    for _ in range(3):
+        o = eng(images, captions)
+        eng.backward(o.loss)
+        eng.step()
+    model.eval()
+    with torch.no_grad():
+        want = model(images, captions).logits.float().clone()
+    save_model(eng, str(tmp_path / "full"), eng.global_step, config=mc, full=True)
+    save_model(eng, str(tmp_path / "part"), eng.global_step, config=mc)
+    f_full = tmp_path / "full" / "global_step3" / "mp_rank_00_model_states.pt"
+    f_part = tmp_path / "part" / "global_step3" / "mp_rank_00_model_states.pt"
+    assert f_part.stat().st_size < 0.5 * f_full.stat().st_size
+    loaded = Magma.from_checkpoint(mc, str(f_full), device="cpu")
+    loaded.eos_token, loaded.image_token = cfg.eos_token, cfg.image_token
+    with torch.no_grad():
+        assert torch.equal(loaded(images, captions).logits.float(), want)
+    # trainable-only: frozen weights come from the constructor (random here), so only the trained tensors are checked
+    capsys.readouterr()
+    part = Magma.from_checkpoint(mc, str(f_part), device="cpu")
+    assert "trainable-only checkpoint" in capsys.readouterr().out
+    sd_m, sd_p = model.state_dict(), part.state_dict()
+    trained = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert trained and all(torch.equal(sd_m[n].float(), sd_p[n].float()) for n in trained)
