@@ -341,7 +341,14 @@ def run_b200(args):
         loss = device_step(i)
     e1.record()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_mine = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_mine)
+    rank_ms = None
+    if world > 1:  # evidence for the scaling number: every rank's own device time for the same K steps
+        t = torch.zeros(world, device=dev)
+        t[rank] = ms_mine / args.steps
+        dist.all_reduce(t)
+        rank_ms = [round(float(x), 3) for x in t]
     launches = L.mb200_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     last_loss = float(loss.detach())
@@ -468,8 +475,10 @@ def run_b200(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world, conv=conv), "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager": gpu_eager, "allreduce": allreduce,
-                "loss": last_loss,
+                "loss": last_loss, "rank_ms_per_step": rank_ms,
                 "trainable_params": int(model.arena.numel)}
+        if os.environ.get("MB200_DP_DIAG_NO_EXCHANGE", "0") == "1":
+            line["INVALID"] = "diagnostic run: gradient exchange skipped (MB200_DP_DIAG_NO_EXCHANGE=1)"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

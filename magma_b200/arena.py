@@ -30,6 +30,7 @@ class ParamArena:
             self._grad_views.append(self.grad[o : o + n].view(p.shape))
             self._shadow_views.append(self.shadow[o : o + n].view(p.shape))
         self._synced_version = None
+        self._ready_event = None  # set by B200Engine.step when the optimizer runs on its own stream (wait_ready)
         self.sync_shadow(force=True)
         self.exp_avg = None
         self.exp_avg_sq = None
@@ -39,8 +40,17 @@ class ParamArena:
     def _version(self):
         return sum(p._version for p in self.params)
 
+    def wait_ready(self):
+        """Order the current stream after the last optimizer step. B200Engine.step launches the fused AdamW on a side
+        stream so that it runs under the next step's frozen-encoder forward (HBM-bound beside tensor-bound work); every
+        consumer of the arena goes through sync_shadow() first, which calls this. Code that reads parameters directly
+        right after engine.step() calls engine.synchronize()."""
+        if self._ready_event is not None:
+            torch.cuda.current_stream().wait_event(self._ready_event)
+
     def sync_shadow(self, force=False):
         """Refresh the bf16 compute copy when any master parameter changed (load_state_dict, optimizer.step...)."""
+        self.wait_ready()
         v = self._version()
         if force or v != self._synced_version:
             for p, o in zip(self.params, self.offsets):  # guard against .data having been re-pointed by .to()/.half()

@@ -722,7 +722,7 @@ int gemm_impl(const mb200_gemm_args* a, cudaStream_t stream) {
       const int ncl = gemm_sms() / 2;
       const int T = kp.total_tiles, KBn = (a->K + BK - 1) / BK;
       const int W = T / ncl, R = T - W * ncl;
-      if ((sk_env || sk_forced) && a->splitk_ws && a->nb0 * a->nb1 == 1 && kp.epi_kind != EK_GENERIC && R > 0 && R < ncl &&
+      if ((sk_env || sk_forced) && !amn && !f32 && a->splitk_ws && a->nb0 * a->nb1 == 1 && kp.epi_kind != EK_GENERIC && R > 0 && R < ncl &&
           KBn >= 16 && (!a->force_bn || sk_forced)) {
         const int h = (int)(((long long)R * KBn + ncl - 1) / ncl);
         const int tail = KBn - h, nh = ncl - R;

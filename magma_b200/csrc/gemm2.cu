@@ -28,8 +28,19 @@ static constexpr int kStages2 = kSmemBudget / kStage2;  // 6
 static constexpr int kEpi2 = 4 * 32 * 64 * 4;
 static constexpr int kSmem2 = kStages2 * kStage2 + kEpi2 + 1024 + 256;
 
-template <bool A_MN, bool B_MN, typename OutT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// SK = true is the stream-K variant (opt-in, gemm.cu): kept in its own instantiation because its owner / helper epilogue
+// paths cost the default kernel registers (ptxas: 408 bytes of spills in the epilogue warps when both lived in one kernel,
+// +5-13 % on every short GEMM of the step).
+// Registers: the epilogue warps need ~230 registers (a 32-column fp32 row chunk + prefetched epilogue inputs), the
+// producer / MMA / TMEM-allocator warps < 72 (40 spills a little). Launched at kRegsLaunch per thread and redistributed with setmaxnreg
+// (warpgroup 0 shrinks to kRegsLean, warpgroup 1 grows to kRegsEpi: 128 * 72 + 128 * 232 = 256 * 152), the CTA holds
+// 38 912 of the SM's 65 536 registers instead of all of them, so blocks of OTHER kernels — the optimizer on its side
+// stream, the next launch's PDL prologue of a shared-memory-light kernel — can be resident beside a persistent GEMM CTA.
+static constexpr int kRegsLaunch = 152, kRegsLean = 72, kRegsEpi = 232;
+static_assert(128 * kRegsLean + 128 * kRegsEpi == kThreads * kRegsLaunch, "setmaxnreg budget");
+
+template <bool A_MN, bool B_MN, typename OutT, bool SK>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kRegsLaunch)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                      const __grid_constant__ CUtensorMap tmWs, const __grid_constant__ GemmKernelParams p) {
@@ -58,7 +69,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmC);
     if (p.aux_out) tma_prefetch_desc(&tmAux);
-    if (p.sk_on) tma_prefetch_desc(&tmWs);
+    if (SK && p.sk_on) tma_prefetch_desc(&tmWs);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) {
@@ -80,6 +91,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   // the producer before its first A load, the epilogue warps before their first residual load / store. The MMA
   // issuer only reads shared memory and TMEM.
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLean));
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
@@ -90,7 +103,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // has never seen) is not added to the exposed start-up of every GEMM.
       int npre = 0;
       WorkItem w0;
-      const bool any = next_item(p, cid, ncl, num_kb, 0, w0);
+      const bool any = next_item<SK>(p, cid, ncl, num_kb, 0, w0);
       if (p.b_static && any) {
         const int tpb = p.tiles_m * p.tiles_n;
         const int z = w0.tile / tpb;
@@ -114,7 +127,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       pdl_wait();
       WorkItem w;
-      for (int it = 0; next_item(p, cid, ncl, num_kb, it, w); ++it) {
+      for (int it = 0; next_item<SK>(p, cid, ncl, num_kb, it, w); ++it) {
         const int tpb = p.tiles_m * p.tiles_n;
         const int z = w.tile / tpb;
         const int r = w.tile - z * tpb;
@@ -162,7 +175,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       WorkItem w;
-      for (int it = 0; next_item(p, cid, ncl, num_kb, it, w); ++it) {
+      for (int it = 0; next_item<SK>(p, cid, ncl, num_kb, it, w); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -188,13 +201,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         umma_commit_2sm(&tmem_full[acc], 3);  // accumulator complete -> both epilogues
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     pdl_wait();
     const int q = warp & 3;
     uint32_t box = 0;  // boxes published so far (staging slot = box & 1)
     WorkItem w;
-    for (int it = 0; next_item(p, cid, ncl, num_kb, it, w); ++it) {
+    for (int it = 0; next_item<SK>(p, cid, ncl, num_kb, it, w); ++it) {
       const int t = w.tile;
       const int tpb = p.tiles_m * p.tiles_n;
       const int z = t / tpb;
@@ -239,6 +254,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       c.tmC = &tmC;
       c.tmAux = &tmAux;
       c.npart = 0;
+      if constexpr (SK) {
       if (w.kind == 2) {
         // ---- stream-K helper: this piece's fp32 partial tile -> workspace slot (plain TMA stores), then the flag ----
         GemmKernelParams pw = p;
@@ -286,10 +302,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __syncwarp();
       }
-#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM)                                          \
-  do {                                                                                     \
-    if (w.kind == 1) epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT, true>(p, c, box);  \
-    else epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT, false>(p, c, box);      \
+      }  // SK
+#define MB_EPI(ACT, DACT, NRES, AUX, ROPE, ACCUM)                                                   \
+  do {                                                                                              \
+    if constexpr (SK) {                                                                             \
+      if (w.kind == 1) epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT, true>(p, c, box);  \
+      else epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT, false>(p, c, box);             \
+    } else {                                                                                        \
+      epi_tile_v3<BN2, ACT, DACT, NRES, AUX, ROPE, ACCUM, OutT, false>(p, c, box);                  \
+    }                                                                                               \
   } while (0)
       if constexpr (sizeof(OutT) == 4) {
         switch (p.epi_kind) {
@@ -326,10 +347,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
-template <bool A_MN, bool B_MN, typename OutT>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
+template <bool A_MN, bool B_MN, typename OutT, bool SK>
+static int launch2_sk(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
                    const CUtensorMap& tmWs, const GemmKernelParams& kp, cudaStream_t stream) {
-  auto kern = gemm2_tcgen05_kernel<A_MN, B_MN, OutT>;
+  auto kern = gemm2_tcgen05_kernel<A_MN, B_MN, OutT, SK>;
   static bool attr_set = false;
   if (!attr_set) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
@@ -347,6 +368,21 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   count_launch();
   MB_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <bool A_MN, bool B_MN, typename OutT>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
+                   const CUtensorMap& tmWs, const GemmKernelParams& kp, cudaStream_t stream) {
+  // stream-K is planned for K-major frozen-weight GEMMs with bf16 output only (gemm.cu); everything else takes the
+  // default instantiation
+  if constexpr (!A_MN && sizeof(OutT) == 2) {
+    if (kp.sk_on) return launch2_sk<A_MN, B_MN, OutT, true>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
+  }
+  if (kp.sk_on) {
+    set_error("gemm: stream-K was planned for an operand combination it is not built for");
+    return MB200_E_ARG;
+  }
+  return launch2_sk<A_MN, B_MN, OutT, false>(tmA, tmB, tmC, tmAux, tmWs, kp, stream);
 }
 
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,

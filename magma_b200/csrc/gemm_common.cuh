@@ -82,12 +82,13 @@ struct WorkItem {
 };
 
 // the i-th work item of cluster `cid` (same sequence for the producer, the MMA issuer and the epilogue warps)
+template <bool SK = true>
 __device__ __forceinline__ bool next_item(const GemmKernelParams& p, int cid, int ncl, int num_kb, int i, WorkItem& w) {
   w.kb0 = 0;
   w.kb1 = num_kb;
   w.kind = 0;
   w.slot = 0;
-  if (!p.sk_on) {
+  if (!SK || !p.sk_on) {  // the default kernel is instantiated with SK = false: none of the split bookkeeping exists there
     w.tile = cid + i * ncl;
     return w.tile < p.total_tiles;
   }

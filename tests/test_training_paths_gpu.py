@@ -172,6 +172,7 @@ def test_encoder_learning_rate_group_and_weight_decay_exemptions():
         out = eng(images.to(dev).to(torch.bfloat16), captions.to(dev))
         eng.backward(out.loss)
         eng.step()
+    eng.synchronize()  # parameters are read directly below (the optimizer runs on its own stream)
     enc = [float((sd[k].detach() - before[k]).abs().max()) for k in sd if k.startswith("image_prefix.enc.")]
     oth = [float((sd[k].detach() - before[k]).abs().max()) for k in sd if not k.startswith("image_prefix.enc.")]
     # Adam's step is ~lr per element: the encoder's largest move is ~1e-3 of the others'
@@ -242,6 +243,40 @@ def test_engine_checkpoint_resume_continues_the_same_trajectory(tmp_path):
     got = steps(eng2, 3)
     assert max(abs(a - b) for a, b in zip(got, want)) < 2e-3, (got, want)
     assert load_model(eng2, str(tmp_path / "missing")) == 0
+
+
+def test_optimizer_on_its_own_stream_gives_the_same_trajectory(monkeypatch):
+    """B200Engine.step issues the fused AdamW on a side stream so it runs under the next step's frozen-encoder forward;
+    consumers are ordered by ParamArena.wait_ready(). Same data, dropout off: losses and the fp32 master parameters
+    after 5 steps are bit-identical to the in-stream optimizer (MB200_PIPELINE_OPT=0)."""
+    import torch
+
+    from magma_b200.train_loop import B200Engine
+    from oracle import magma_oracle as O
+
+    dev = _dev()
+
+    def run(pipelined):
+        monkeypatch.setenv("MB200_PIPELINE_OPT", "1" if pipelined else "0")
+        model, mc, cfg, _ = _build(dev, freeze_enc=True)
+        model.train()
+        images, captions = O.synthetic_batch(cfg, 2, 32, seed=4)
+        x, c = images.to(dev).to(torch.bfloat16), captions.to(dev)
+        eng = B200Engine(model, mc, n_buckets=2)
+        assert (eng.opt_stream is not None) == (pipelined and dev.type == "cuda")
+        losses = []
+        for _ in range(5):
+            o = eng(x, c)
+            eng.backward(o.loss)
+            eng.step()
+            losses.append(o.loss.detach())
+        eng.synchronize()
+        return [float(l) for l in losses], model.arena.master.clone()
+
+    l1, m1 = run(True)
+    l0, m0 = run(False)
+    assert l1 == l0 and torch.equal(m1, m0), (l1, l0)
+    assert l1[-1] < l1[0]
 
 
 def _variant_weights(cfg, mlp, attn, mlp_ln, attn_ln, seed=5):

@@ -479,6 +479,7 @@ def group_magma(dev):
         eng.backward(out.loss)
         eng.step()
         losses.append(float(out.loss.detach()))
+    eng.synchronize()
     moved = sum(float((sd[k].detach() - before[k]).abs().sum()) for k in trainable)
     good = moved > 0 and losses[-1] < losses[0] and abs(losses[1] - losses[0]) < 1e-6
     ok &= good
