@@ -355,6 +355,13 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = Bw * world / (ms_step / 1e3)
 
+    if os.environ.get("MB200_DP_TRACE", "0") == "1":  # diagnostic: event timeline of two consecutive steps, every rank
+        engine.trace_report()
+        for i in range(2):
+            device_step(i)
+        rep = engine.trace_report()
+        print(f"[trace rank {rank}]\n" + "\n".join(f"  {ms:9.3f} ms  {lab}" for lab, ms in rep), flush=True)
+
     # ---- end-to-end through train_step with pinned host batches (e2e) ----
     def loader():
         i = 0
@@ -412,7 +419,7 @@ def run_b200(args):
                 "step_algorithmic_tflops": (fl.value / n_prof if conv else FLOPS_PER_SAMPLE * Bw) / (ms_step / 1e3) / 1e12,
                 "step_frac_of_peak": (fl.value / n_prof if conv else FLOPS_PER_SAMPLE * Bw) / (ms_step / 1e3) / 1e12 / peak_tf}
         tr = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")
-        if os.path.exists(tr):
+        if os.path.exists(tr) and not conv:  # the capture is of the config-2 step; the conv workload has other shapes
             try:
                 tj = json.load(open(tr))
                 roof["traffic"] = tj.get("bytes_per_launch")
@@ -445,6 +452,18 @@ def run_b200(args):
                          "busbw_gbs": 2 * (world - 1) / world * nbytes / (ar_ms / 1e3) / 1e9,
                          "note": "fp32 gradient arena, one NCCL all-reduce, nothing else running; in the step it is issued in "
                                  "slices overlapped with backward"}
+            if engine.peer is not None:  # the peer-memory exchange of the whole arena, isolated, same way
+                for _ in range(2):
+                    engine.peer.allreduce_slice(g, 0, g.numel())
+                torch.cuda.synchronize()
+                a0.record()
+                for _ in range(5):
+                    engine.peer.allreduce_slice(g, 0, g.numel())
+                a1.record()
+                torch.cuda.synchronize()
+                pm = max_over_ranks(a0.elapsed_time(a1) / 5)
+                allreduce["peer_kernel_ms_isolated"] = pm
+                allreduce["peer_kernel_busbw_gbs"] = 2 * (world - 1) / world * nbytes / (pm / 1e3) / 1e9
             g.zero_()
         except Exception as exc:  # diagnostics only
             allreduce = {"error": repr(exc)[:200]}
@@ -475,7 +494,7 @@ def run_b200(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world, conv=conv), "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager": gpu_eager, "allreduce": allreduce,
-                "loss": last_loss, "rank_ms_per_step": rank_ms,
+                "loss": last_loss, "rank_ms_per_step": rank_ms, "gradient_exchange": engine.exchange_kind,
                 "trainable_params": int(model.arena.numel)}
         if os.environ.get("MB200_DP_DIAG_NO_EXCHANGE", "0") == "1":
             line["INVALID"] = "diagnostic run: gradient exchange skipped (MB200_DP_DIAG_NO_EXCHANGE=1)"

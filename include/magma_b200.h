@@ -60,6 +60,11 @@ int mb200_check_device(void);
  * may leave a few SMs free for NCCL's CTAs so the gradient all-reduce overlaps the backward GEMMs. Returns the limit in
  * effect. */
 int mb200_set_gemm_sm_limit(int n_sms);
+/* Cap the grids of the optimizer kernels (mb200_sumsq, mb200_adamw_step) at n_blocks blocks of 256 threads (0 = the
+ * default, 16 blocks per SM). With 2 blocks per SM they fit in the registers a persistent GEMM CTA leaves free, so an
+ * optimizer step issued on a side stream runs BESIDE the next step's frozen-encoder GEMMs instead of owning every SM
+ * until it is done (B200Engine). Returns the cap in effect. */
+int mb200_set_optimizer_grid(int n_blocks);
 /* number of kernels this library has launched since load (bench.py reports the delta as gpu_launches). */
 long long mb200_launch_count(void);
 /* optional per-launch CUDA-event timing of the GEMM core (used by bench.py for the roofline numbers):
@@ -231,6 +236,13 @@ int mb200_sample(const void* logits, int32_t dtype, int64_t ld, int32_t rows, in
                  int32_t top_k, float top_p, uint64_t seed, uint64_t offset, int64_t* tokens, uint8_t* keep_mask,
                  void* stream);
 int mb200_add(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
+/* Data-parallel gradient exchange over peer memory (stands where DeepSpeed's gradient all-reduce stood, train.py:103-111).
+ * bufs[r], r < world: rank r's fp32 exchange buffer as mapped into THIS process (peer memory for r != own rank; 16-byte
+ * aligned, same layout on every rank). Elements [offset, offset + n) — the calling rank's shard — are read from all
+ * `world` buffers, summed in rank order and written back into all of them. The caller brackets the launches of all ranks
+ * with a device-side barrier on each side. max_blocks caps the grid (0 = default). */
+int mb200_peer_reduce_bcast(void* const* bufs, int32_t world, int64_t offset, int64_t n, int32_t max_blocks,
+                            void* stream);
 
 /* Fused AdamW over a flat fp32 arena (torch.optim.AdamW(betas=(0.9,0.95)) of train.py:96-101) with global-norm
  * clipping (gradient_clipping, magma/config.py:126) and refresh of the bf16 compute copy. gnorm_sq: device fp32 [1]

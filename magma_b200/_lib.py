@@ -179,12 +179,12 @@ EXPORTED_SYMBOLS = [
     "mb200_softmax_fwd", "mb200_softmax_bwd", "mb200_build_labels", "mb200_embed_assemble", "mb200_embed_gather",
     "mb200_cross_entropy", "mb200_colsum", "mb200_dropout_fwd", "mb200_dropout_apply", "mb200_patchify",
     "mb200_nchw_to_nhwc8", "mb200_im2col3x3", "mb200_avgpool_nhwc",
-    "mb200_vit_assemble", "mb200_argmax", "mb200_sample", "mb200_add", "mb200_sumsq", "mb200_adamw_step",
+    "mb200_vit_assemble", "mb200_argmax", "mb200_sample", "mb200_add", "mb200_peer_reduce_bcast", "mb200_sumsq", "mb200_adamw_step",
     "mb200_cast_f32_to_bf16", "mb200_cast_bf16_to_f32",
     "mb200_vit_workspace_bytes", "mb200_vit_forward", "mb200_attn_decode", "mb200_attn_fwd_tile", "mb200_attn_fwd_flash",
     "mb200_attn_bwd_tile",
     "mb200_vit_train_workspace_bytes", "mb200_vit_forward_train", "mb200_vit_backward", "mb200_quick_gelu_bwd",
-    "mb200_layernorm_param_grad_rows", "mb200_set_gemm_sm_limit", "mb200_scale_add", "mb200_dot",
+    "mb200_layernorm_param_grad_rows", "mb200_set_gemm_sm_limit", "mb200_set_optimizer_grid", "mb200_scale_add", "mb200_dot",
     "mb200_gptj_sched_workspace_bytes", "mb200_gptj_sched_forward", "mb200_gptj_sched_backward",
     "mb200_col_moments", "mb200_channel_affine", "mb200_col2im3x3", "mb200_avgpool_nhwc_bwd",
     "mb200_kv_append", "mb200_gptj_sched_infer_workspace_bytes", "mb200_gptj_sched_infer",

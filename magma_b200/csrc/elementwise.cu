@@ -14,9 +14,35 @@ static inline int grid_for(long long n, int threads) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// Kernels meant to be resident BESIDE a persistent GEMM CTA (optimizer on its side stream, peer-memory gradient exchange)
+// ask for the same shared-memory / L1 split as the GEMM (maximum shared memory): an SM's carve-out is only reconfigured
+// when the SM is empty, so a resident block of a kernel that prefers a large L1 keeps a 209 KB GEMM CTA off that SM until
+// it leaves — co-residency then degenerates into time slicing. These kernels stream and have no use for L1.
+template <typename K>
+static void prefer_max_smem_carveout(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+static void co_resident_kernels_init() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  prefer_max_smem_carveout(adamw_kernel);
+  prefer_max_smem_carveout(sumsq_kernel);
+  prefer_max_smem_carveout(peer_reduce_bcast_kernel);
+  prefer_max_smem_carveout(cast_f32_bf16_kernel);
+}
+
+static int g_opt_grid = 0;  // mb200_set_optimizer_grid
+static inline int opt_grid(int grid) { return (g_opt_grid > 0 && grid > g_opt_grid) ? g_opt_grid : grid; }
+
 }  // namespace mb200
 
 using namespace mb200;
+
+extern "C" int mb200_set_optimizer_grid(int n_blocks) {
+  g_opt_grid = n_blocks > 0 ? n_blocks : 0;
+  return g_opt_grid;
+}
 
 // =============================================================================================
 // C ABI
@@ -397,7 +423,28 @@ extern "C" int mb200_sumsq(const float* x, int64_t n, float* out, void* stream) 
   MB_ENTER();
   int grid = grid_for(n, 256);
   if (grid > kSumsqMaxBlocks) grid = kSumsqMaxBlocks;
+  grid = opt_grid(grid);
+  co_resident_kernels_init();
   sumsq_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, out);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mb200_peer_reduce_bcast(void* const* bufs, int32_t world, int64_t offset, int64_t n, int32_t max_blocks,
+                                       void* stream) {
+  MB_ENTER();
+  MB_REQUIRE(world >= 1 && world <= 16, MB200_E_ARG, "peer_reduce_bcast: world must be in [1, 16]");
+  MB_REQUIRE(offset % 4 == 0 && n % 4 == 0, MB200_E_ALIGN, "peer_reduce_bcast: offset and n must be multiples of 4");
+  if (n == 0) return 0;
+  PeerBufs pb;
+  for (int r = 0; r < 16; ++r) pb.p[r] = r < world ? reinterpret_cast<float*>(bufs[r]) : nullptr;
+  for (int r = 0; r < world; ++r)
+    MB_REQUIRE(pb.p[r] != nullptr && (reinterpret_cast<uintptr_t>(pb.p[r]) & 15) == 0, MB200_E_ALIGN,
+               "peer_reduce_bcast: buffer %d is null or not 16-byte aligned", r);
+  int grid = grid_for(n / 4, 256);
+  if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;
+  co_resident_kernels_init();
+  peer_reduce_bcast_kernel<<<grid, 256, 0, ST(stream)>>>(pb, world, offset / 4, n / 4);
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -410,7 +457,8 @@ extern "C" int mb200_adamw_step(float* master, float* grad, float* exp_avg, floa
   MB_REQUIRE(step >= 1, MB200_E_ARG, "adamw: step must be >= 1");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   MB_REQUIRE(n % 4 == 0, MB200_E_ALIGN, "adamw: n must be a multiple of 4 (the arena pads every tensor to 64)");
-  adamw_kernel<<<grid_for(n / 4, 256), 256, 0, ST(stream)>>>(master, grad, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n / 4, lr,
+  co_resident_kernels_init();
+  adamw_kernel<<<opt_grid(grid_for(n / 4, 256)), 256, 0, ST(stream)>>>(master, grad, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n / 4, lr,
                                                          beta1, beta2, eps, weight_decay, grad_scale, gnorm_sq,
                                                          max_norm, bc1, bc2, zero_grad);
   MB_LAUNCH_CHECK();

@@ -600,6 +600,32 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gradient exchange over NVLink peer memory (data parallelism; replaces the NCCL all-reduce of DeepSpeed's engine,
+// train.py:103-111). Every rank owns one shard of the slice: it reads that shard from ALL ranks' exchange buffers
+// (peer-mapped pointers: plain loads over NVLink / NVSwitch), adds them in rank order, and stores the sum back into ALL
+// ranks' buffers — reduce-scatter and all-gather in one pass, one launch per rank and slice. The ranks touch disjoint
+// shards, so the exchange is race-free between a barrier before (every rank's slice is published) and one after (every
+// store has landed). Every rank ends with the owner's bits: replicas stay bit-identical. No shared memory and ~40
+// registers: its blocks are resident BESIDE the persistent GEMM CTAs of backward (NCCL's CTAs need an SM of their own).
+// ---------------------------------------------------------------------------------------------
+struct PeerBufs {
+  float* p[16];
+};
+__global__ void peer_reduce_bcast_kernel(PeerBufs bufs, int world, long long off4, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = __ldcs(reinterpret_cast<const float4*>(bufs.p[0]) + off4 + i);
+    for (int r = 1; r < world; ++r) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(bufs.p[r]) + off4 + i);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    for (int r = 0; r < world; ++r) __stcs(reinterpret_cast<float4*>(bufs.p[r]) + off4 + i, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Optimizer step for the (small) trainable set: fused AdamW over a flat fp32 arena (torch.optim.AdamW semantics,
 // train.py:96-101 betas=(0.9,0.95)), with global-norm gradient clipping (config.py:126 gradient_clipping) folded in
 // through a device-side squared-norm, and the bf16 compute copy of the weights refreshed in the same pass.
@@ -613,17 +639,46 @@ static constexpr int kSumsqMaxBlocks = 2048;
 __device__ float g_sumsq_part[kSumsqMaxBlocks];
 __device__ unsigned int g_sumsq_ticket = 0;
 
+// Deterministic AND grid-independent: the input is cut into kSumsqMaxBlocks logical parts (float4 index / 256 modulo
+// kSumsqMaxBlocks); a part is always summed in the same order (per thread over its chunks, then the fixed block tree), the
+// parts are added in index order by the last block to finish. A block takes parts blockIdx.x, blockIdx.x + gridDim.x, ...
+// so the launch may use any grid (B200Engine caps it at 2 blocks per SM when the optimizer runs beside GEMMs) without
+// changing a bit of the result — data-parallel replicas and pipelined / in-stream optimizers stay bit-identical.
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
   __shared__ float red[32];
   __shared__ int is_last;
-  float s = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = x[i];
-    s += v * v;
+  const bool vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0;  // unaligned views take the scalar loop below (same parts)
+  const long long n4 = vec ? (n >> 2) : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const long long stride = (long long)kSumsqMaxBlocks * 256;
+  for (int part = blockIdx.x; part < kSumsqMaxBlocks; part += gridDim.x) {
+    if ((long long)part * 256 >= n4 && (n4 << 2) + (long long)part * 256 >= n) {  // empty part (short inputs)
+      if (threadIdx.x == 0) g_sumsq_part[part] = 0.f;
+      continue;
+    }
+    float s = 0.f;
+    long long i = (long long)part * 256 + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // 4 independent 16-byte loads in flight per thread
+      const float4 a = __ldcs(x4 + i), b = __ldcs(x4 + i + stride), c = __ldcs(x4 + i + 2 * stride),
+                   d = __ldcs(x4 + i + 3 * stride);
+      s += a.x * a.x; s += a.y * a.y; s += a.z * a.z; s += a.w * a.w;
+      s += b.x * b.x; s += b.y * b.y; s += b.z * b.z; s += b.w * b.w;
+      s += c.x * c.x; s += c.y * c.y; s += c.z * c.z; s += c.w * c.w;
+      s += d.x * d.x; s += d.y * d.y; s += d.z * d.z; s += d.w * d.w;
+    }
+    for (; i < n4; i += stride) {
+      const float4 a = x4[i];
+      s += a.x * a.x; s += a.y * a.y; s += a.z * a.z; s += a.w * a.w;
+    }
+    for (long long j = (n4 << 2) + (long long)part * 256 + threadIdx.x; j < n; j += stride) {  // tail / unaligned input
+      const float v = x[j];
+      s += v * v;
+    }
+    const float t = block_sum<256>(s, red);
+    if (threadIdx.x == 0) g_sumsq_part[part] = t;
+    __syncthreads();  // red[] is reused by the next part
   }
-  const float t = block_sum<256>(s, red);
   if (threadIdx.x == 0) {
-    g_sumsq_part[blockIdx.x] = t;
     __threadfence();
     is_last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
   }
@@ -631,7 +686,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
   if (!is_last) return;
   __threadfence();
   float a = 0.f;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) a += *((volatile float*)&g_sumsq_part[i]);
+  for (int i = threadIdx.x; i < kSumsqMaxBlocks; i += 256) a += *((volatile float*)&g_sumsq_part[i]);
   const float total = block_sum<256>(a, red);
   if (threadIdx.x == 0) {
     out[0] += total;
@@ -654,7 +709,8 @@ __global__ void adamw_kernel(float* __restrict__ w, float* __restrict__ g, float
   float4* a4 = reinterpret_cast<float4*>(m1);
   float4* v4 = reinterpret_cast<float4*>(m2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 wv = w4[i], gv = g4[i], av = a4[i], vv = v4[i];
+    // streaming (evict-first) accesses: 7 GB pass once through the L2 beside GEMMs that live on L2-resident tiles
+    float4 wv = __ldcs(w4 + i), gv = __ldcs(g4 + i), av = __ldcs(a4 + i), vv = __ldcs(v4 + i);
     float* wp = &wv.x;
     float* gp = &gv.x;
     float* ap = &av.x;
@@ -670,9 +726,9 @@ __global__ void adamw_kernel(float* __restrict__ w, float* __restrict__ g, float
       wi -= step * (a / (sqrtf(v) * inv_sqrt_bc2 + eps));
       wp[e] = wi;
     }
-    w4[i] = wv;
-    a4[i] = av;
-    v4[i] = vv;
+    __stcs(w4 + i, wv);
+    __stcs(a4 + i, av);
+    __stcs(v4 + i, vv);
     if (shadow) {
       __nv_bfloat162 h0 = __floats2bfloat162_rn(wv.x, wv.y), h1 = __floats2bfloat162_rn(wv.z, wv.w);
       uint2 u;
@@ -680,7 +736,7 @@ __global__ void adamw_kernel(float* __restrict__ w, float* __restrict__ g, float
       u.y = *reinterpret_cast<uint32_t*>(&h1);
       reinterpret_cast<uint2*>(shadow)[i] = u;
     }
-    if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (zero_grad) __stcs(g4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
 

@@ -62,6 +62,60 @@ def allreduce_slice(flat_grad: torch.Tensor, lo, hi, group=None, comm_dtype=None
     return None
 
 
+def shard_bounds(lo: int, hi: int, world: int, align: int = ALIGN) -> List[Tuple[int, int]]:
+    """Cut the arena slice [lo, hi) into `world` contiguous shards (the last ones may be empty), each a multiple of
+    `align` elements except possibly the tail: shard r is what rank r reduces in the peer-memory exchange."""
+    n = hi - lo
+    per = ((n + world - 1) // world + align - 1) // align * align
+    out = []
+    for r in range(world):
+        s0 = min(hi, lo + r * per)
+        out.append((s0, min(hi, s0 + per)))
+    return out
+
+
+class PeerExchange:
+    """SUM all-reduce of arena slices over NVLink peer memory with this package's own kernel
+    (csrc/elt_kernels.cuh::peer_reduce_bcast_kernel) instead of NCCL.
+
+    Why: NCCL's all-reduce kernels need shared memory, so each of their CTAs needs an SM of its own; the persistent GEMM
+    grids of backward own every SM, the collective only gets SMs at kernel boundaries, and the GEMM whose CTAs it
+    displaces runs a second wave — measured on 2 x B200 the exchange cost the step its full isolated duration (1.8 ms of
+    31.2) whatever the NCCL channel count, bucket count, SM carve-out or wire dtype (profiles/r02_n2_dp_sweep.log,
+    r02_scaling_n2.log). The kernel here uses no shared memory and ~40 registers, so its blocks sit BESIDE the GEMM CTAs
+    (the pair GEMM leaves 26 k registers per SM free, csrc/gemm2.cu).
+
+    Layout: one symmetric fp32 exchange buffer E of the arena's size per rank (torch.distributed._symmetric_memory:
+    allocation, handle exchange and the device-side barrier are torch's; the data path is ours). Per slice, on the comm
+    stream: E[slice] <- grad[slice]; barrier; rank r sums shard r of the slice over all ranks' E in rank order and stores
+    it into all ranks' E (loads / stores over NVLink); barrier; grad[slice] <- E[slice]. All ranks end with identical bits.
+    """
+
+    def __init__(self, numel: int, device, group=None, max_blocks: int = 0):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.E = symm.empty(numel, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.E, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(self.ptrs) == self.world and self.ptrs[self.rank] == self.E.data_ptr()
+        self.max_blocks = max_blocks
+
+    def allreduce_slice(self, flat_grad: torch.Tensor, lo: int, hi: int):
+        from . import ops
+
+        if lo is None or hi <= lo:
+            return
+        self.E[lo:hi].copy_(flat_grad[lo:hi])
+        self.hdl.barrier(channel=0)                      # every rank's slice is published
+        s0, s1 = shard_bounds(lo, hi, self.world)[self.rank]
+        if s1 > s0:
+            ops.peer_reduce_bcast(self.ptrs, s0, s1 - s0, self.max_blocks)
+        self.hdl.barrier(channel=0)                      # every shard's sum has landed in every rank's E
+        flat_grad[lo:hi].copy_(self.E[lo:hi])
+
+
 def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     """Rank `rank` takes samples [lo, hi) of the global batch (rank i takes [8i, 8i+8))."""
     per = global_batch // world

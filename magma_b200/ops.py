@@ -417,6 +417,13 @@ def add(a, b, c=None):
     return y
 
 
+def peer_reduce_bcast(buffer_ptrs, offset, n, max_blocks=0):
+    """mb200_peer_reduce_bcast: `buffer_ptrs` = device addresses of every rank's exchange buffer as mapped here."""
+    arr = (ctypes.c_void_p * len(buffer_ptrs))(*[ctypes.c_void_p(int(p)) for p in buffer_ptrs])
+    check(lib().mb200_peer_reduce_bcast(arr, len(buffer_ptrs), ctypes.c_int64(offset), ctypes.c_int64(n), int(max_blocks),
+                                        _stream()))
+
+
 def cast_f32_to_bf16(src, dst):
     check(lib().mb200_cast_f32_to_bf16(_ptr(src), _ptr(dst), ctypes.c_int64(src.numel()), _stream()))
 

@@ -36,6 +36,13 @@ class B200Engine:
         # by ParamArena.wait_ready() (called from sync_shadow(), i.e. by every forward); MB200_PIPELINE_OPT=0 puts the
         # optimizer back on the caller's stream.
         self.opt_stream = torch.cuda.Stream() if (on_gpu and os.environ.get("MB200_PIPELINE_OPT", "1") != "0") else None
+        if self.opt_stream is not None:
+            # 2 optimizer blocks per SM fit in the registers a persistent GEMM CTA leaves free (csrc/gemm2.cu: 152 of 256
+            # per thread after setmaxnreg); the default 16 per SM would own every SM until the optimizer is done
+            from ._lib import lib
+
+            n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            lib().mb200_set_optimizer_grid(int(os.environ.get("MB200_OPT_BLOCKS_PER_SM", "2")) * n_sm)
         # experimental data-parallel knobs (both off by default): exchange gradients as bf16, and keep a
         # few SMs out of the persistent GEMM grids so NCCL's CTAs run beside the backward GEMMs
         self.comm_dtype = torch.bfloat16 if os.environ.get("MB200_DP_BF16", "0") == "1" else None
@@ -46,17 +53,37 @@ class B200Engine:
         # Outside that window every kernel gets all SMs. MB200_DP_GEMM_SMS=0 disables it.
         self.dp_gemm_sms = int(os.environ.get("MB200_DP_GEMM_SMS", "0")) if self.world > 1 else 0
         self._carved = False
+        # Gradient exchange: this package's peer-memory kernel (dp.PeerExchange) by default; MB200_DP_EXCHANGE=nccl, the
+        # bf16 wire format, or a box where peer memory cannot be set up take the NCCL all-reduce (said on stderr and in
+        # self.exchange_kind, which bench.py prints).
+        self.peer = None
+        self.exchange_kind = "none" if self.world == 1 else "nccl"
+        if self.world > 1 and on_gpu and self.comm_dtype is None and os.environ.get("MB200_DP_EXCHANGE", "peer") == "peer":
+            try:
+                n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+                self.peer = dp.PeerExchange(model.arena.numel, model.arena.grad.device,
+                                            max_blocks=int(os.environ.get("MB200_DP_PEER_BLOCKS", str(n_sm))))
+                self.exchange_kind = "peer-memory kernel"
+            except Exception as exc:  # no peer access / IPC refused in this container: NCCL carries the exchange
+                import sys
+
+                print(f"[magma_b200] peer-memory gradient exchange unavailable ({exc!r}); using NCCL", file=sys.stderr)
         # measurement only: MB200_DP_DIAG_NO_EXCHANGE=1 skips the gradient all-reduce (the ranks then train on their own
         # shards — NOT data parallelism), to separate what the exchange costs from what N GPUs of one box cost each
         # other in clocks (bench.py prints the per-rank step times)
         self._diag_no_exchange = os.environ.get("MB200_DP_DIAG_NO_EXCHANGE", "0") == "1"
         self._pending = []
+        # MB200_DP_TRACE=1: CUDA-event timeline of one step (main / comm / optimizer streams), printed by trace_report()
+        self._trace = [] if os.environ.get("MB200_DP_TRACE", "0") == "1" and on_gpu else None
         self.chunks = dp.layer_chunks(len(model.lm.transformer.h), n_buckets)  # (hi, lo), last layers first
         self._segments = None  # optimizer parameter groups, built at the first step (utils.configure_param_groups)
 
     # DeepSpeed-engine surface used by the reference -------------------------------------------------
     def __call__(self, images, captions):
-        return self.module(images, captions)
+        self._mark("forward: enqueue start (main)")
+        out = self.module(images, captions)
+        self._mark("forward: end (main)")
+        return out
 
     def train(self, mode=True):
         self.module.train(mode)
@@ -65,6 +92,23 @@ class B200Engine:
     def eval(self):
         self.module.eval()
         return self
+
+    def _mark(self, label, stream=None):
+        if self._trace is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        self._trace.append((label, ev))
+
+    def trace_report(self):
+        """[(label, ms since the first mark)] of everything marked since the last report (synchronizes)."""
+        if not self._trace:
+            return []
+        torch.cuda.synchronize()
+        t0 = self._trace[0][1]
+        out = [(lab, t0.elapsed_time(ev)) for lab, ev in self._trace]
+        self._trace = []
+        return out
 
     def _is_boundary(self):
         return (self.micro_step + 1) % self.grad_accum == 0
@@ -78,9 +122,15 @@ class B200Engine:
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
+        self._mark(f"backward: slice [{lo}, {hi}) ready (main)")
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            dp.allreduce_slice(arena.grad, lo, hi, comm_dtype=self.comm_dtype)
+            self._mark(f"exchange [{lo}, {hi}) start (comm)", self.comm_stream)
+            if self.peer is not None:
+                self.peer.allreduce_slice(arena.grad, lo, hi)
+            else:
+                dp.allreduce_slice(arena.grad, lo, hi, comm_dtype=self.comm_dtype)
+            self._mark(f"exchange [{lo}, {hi}) end (comm)", self.comm_stream)
         if self.dp_gemm_sms > 0 and not self._carved:  # GEMMs launched from here on leave room for NCCL
             from ._lib import lib
 
@@ -102,11 +152,13 @@ class B200Engine:
             lm._after_chunk = after
         else:
             lm._after_chunk = None
+        self._mark("backward: enqueue start (main)")
         try:
             loss.backward()
         finally:
             lm._loss_scale_hint = None
             lm._after_chunk = None
+        self._mark("backward: end (main)")
         if boundary and self.world > 1:
             self._allreduce_slice(*arena.slice_for(["image_prefix."]))
 
@@ -139,7 +191,9 @@ class B200Engine:
                   segments=segs)
         if self.opt_stream is not None:
             with torch.cuda.stream(self.opt_stream):
+                self._mark("optimizer start (opt)", self.opt_stream)
                 arena.adamw_step(**kw)
+                self._mark("optimizer end (opt)", self.opt_stream)
                 ev = torch.cuda.Event()
                 ev.record(self.opt_stream)
             arena._ready_event = ev

@@ -439,6 +439,7 @@ int mb200_prof_read(double* a, double* b, double* c, long long* n) {
   return 0;
 }
 int mb200_set_gemm_sm_limit(int) { return 148; }
+int mb200_set_optimizer_grid(int n) { return n; }
 
 int mb200_rope(void* qkv_, int64_t ld, int32_t rows, int32_t S, int32_t H, int32_t hd, int32_t rot, int32_t pos0,
                int32_t inverse, void*) {  // rope_kernel: in place on q and k of a fused [rows][3][H][hd] buffer
@@ -555,6 +556,14 @@ int mb200_argmax(const void* x_, int64_t ldx, int32_t rows, int32_t V, int64_t* 
   return 0;
 }
 
+int mb200_peer_reduce_bcast(void* const* bufs, int32_t world, int64_t offset, int64_t n, int32_t, void*) {
+  for (int64_t i = offset; i < offset + n; ++i) {
+    float acc = reinterpret_cast<float*>(bufs[0])[i];
+    for (int r = 1; r < world; ++r) acc += reinterpret_cast<float*>(bufs[r])[i];
+    for (int r = 0; r < world; ++r) reinterpret_cast<float*>(bufs[r])[i] = acc;
+  }
+  return 0;
+}
 int mb200_add(const void* a_, const void* b_, const void* c_, void* y_, int64_t n, void*) {
   EM_REQUIRE(n % 8 == 0, MB200_E_SHAPE, "add: n must be a multiple of 8");
   const bf16_t *a = (const bf16_t*)a_, *b = (const bf16_t*)b_, *c = (const bf16_t*)c_;

@@ -100,6 +100,8 @@ static inline int __shfl_xor_sync(unsigned, int v, int o) {
   return r;
 }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+template <typename T> static inline T __ldcs(const T* p) { return *p; }             // cache-streaming hints: plain accesses
+template <typename T> static inline void __stcs(T* p, const T& v) { *p = v; }
 static inline void pdl_trigger() {}
 static inline void pdl_wait() {}
 static inline float atomicAdd(float* p, float v) {

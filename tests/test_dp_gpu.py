@@ -1,5 +1,6 @@
-"""Hardware data-parallel parity ("Distributed"): on 2 B200s over NCCL, the gradients the engine
-holds after its overlapped all-reduce — divided by the world size, as the fused optimizer kernel does — equal the
+"""Hardware data-parallel parity ("Distributed"): on 2 B200s, with the gradient exchange carried by
+this package's peer-memory kernel (default), by NCCL, and by NCCL with a bf16 wire format, the gradients the engine
+holds after its overlapped exchange — divided by the world size, as the fused optimizer kernel does — equal the
 single-GPU gradients of the CONCATENATED batch, and one optimizer step leaves every rank with identical parameters
 that equal the single-GPU step. Reference semantics: DeepSpeed data parallelism averages the per-rank mean losses'
 gradients (train.py:103-111, magma/utils.py:26-34), which equals the gradient of the mean over the concatenated batch
@@ -14,14 +15,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out_dir, comm_bf16):
+def _worker(rank, world, port, out_dir, mode):
     import torch
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
+    comm_bf16 = mode == "nccl-bf16"
     if comm_bf16:
         os.environ["MB200_DP_BF16"] = "1"
+    os.environ["MB200_DP_EXCHANGE"] = "peer" if mode == "peer" else "nccl"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world)
     from _gpu_util import build_magma_from_weights
@@ -43,6 +46,8 @@ def _worker(rank, world, port, out_dir, comm_bf16):
     model.train()
     model.config.image_embed_dropout_prob = 0.0
     eng = B200Engine(model, model.config, n_buckets=2)
+    if mode == "peer":  # no silent NCCL fallback in the test of the peer-memory kernel
+        assert eng.exchange_kind == "peer-memory kernel", eng.exchange_kind
     lo, hi = rank * (B // world), (rank + 1) * (B // world)
     out = eng(images[lo:hi].to(dev).to(torch.bfloat16), captions[lo:hi].to(dev))
     eng.backward(out.loss)
@@ -84,16 +89,17 @@ def _single(out_dir):
     return model.arena.grad.float().cpu(), float(out.loss.detach()), model.arena.names
 
 
-@pytest.mark.parametrize("comm_bf16", [False, True])
-def test_allreduced_gradients_equal_the_concatenated_batch(tmp_path, comm_bf16):
+@pytest.mark.parametrize("mode", ["peer", "nccl", "nccl-bf16"])
+def test_allreduced_gradients_equal_the_concatenated_batch(tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     world = 2
-    port = 29500 + (os.getpid() % 1000) + (7 if comm_bf16 else 0)
-    mp.spawn(_worker, args=(world, port, str(tmp_path), comm_bf16), nprocs=world, join=True)
+    comm_bf16 = mode == "nccl-bf16"
+    port = 29500 + (os.getpid() % 1000) + {"peer": 0, "nccl": 7, "nccl-bf16": 14}[mode]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), mode), nprocs=world, join=True)
     r0 = torch.load(tmp_path / "rank0.pt")
     r1 = torch.load(tmp_path / "rank1.pt")
     g_ref, loss_ref, _ = _single(str(tmp_path))
@@ -108,6 +114,6 @@ def test_allreduced_gradients_equal_the_concatenated_batch(tmp_path, comm_bf16):
     # bf16 exchange rounds each rank's gradient once (2^-9 relative).
     tol = 1.5e-2 if comm_bf16 else 2e-3
     e = rel(r0["grads"], g_ref)
-    print(f"DP parity (N = 2, {'bf16' if comm_bf16 else 'fp32'} exchange): rel-Frobenius {e:.2e} over {g_ref.numel()} "
+    print(f"DP parity (N = 2, {mode} exchange): rel-Frobenius {e:.2e} over {g_ref.numel()} "
           f"gradient elements; loss {loss_ref:.4f}")
     assert e < tol, e

@@ -1,0 +1,33 @@
+"""Host logic of the peer-memory gradient exchange (magma_b200/dp.py::PeerExchange): the shard partition, and the
+reduce + broadcast primitive's contract on the emulated C ABI — "ranks" are plain host buffers here; the kernel itself
+runs on 2 B200s in tests/test_dp_gpu.py."""
+import torch
+
+from magma_b200 import dp
+
+
+def test_shard_bounds_cover_the_slice_in_aligned_contiguous_pieces():
+    for lo, hi, w in [(0, 1024, 2), (64, 64 + 64 * 25, 8), (0, 64, 8), (128, 128, 2), (0, 241_332_224, 8)]:
+        b = dp.shard_bounds(lo, hi, w)
+        assert len(b) == w and b[0][0] == lo and b[-1][1] == hi
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert all((s0 - lo) % dp.ALIGN == 0 and (s1 - s0) % 4 == 0 for s0, s1 in b)
+        sizes = [s1 - s0 for s0, s1 in b]
+        assert sizes == sorted(sizes, reverse=True) and sum(sizes) == hi - lo   # equal shards, ragged / empty tail only
+
+
+def test_every_rank_ends_with_the_same_sum(emul_ops):
+    from magma_b200 import ops
+
+    world, n = 4, 64 * 9
+    g = torch.Generator().manual_seed(0)
+    grads = [torch.randn(n, generator=g) for _ in range(world)]
+    want = torch.stack(grads).sum(0)
+    E = [x.clone() for x in grads]                       # each rank's exchange buffer after "E <- grad"
+    ptrs = [e.data_ptr() for e in E]
+    for rank in range(world):                            # every rank reduces + broadcasts its own shard
+        s0, s1 = dp.shard_bounds(0, n, world)[rank]
+        if s1 > s0:
+            ops.peer_reduce_bcast(ptrs, s0, s1 - s0)
+    for e in E:
+        assert torch.equal(e, E[0]) and torch.allclose(e, want, atol=1e-6)

@@ -255,3 +255,17 @@ def test_batchnorm_bookkeeping_kernel_source(kx):
     assert torch.allclose(dg, 2.0 + bn.weight.grad, rtol=1e-3, atol=1e-3) and torch.allclose(db, 2.0 + bn.bias.grad, rtol=1e-4, atol=1e-4)
     dz = dy * co[0] + z * co[1] + co[2]
     assert torch.allclose(dz, zz.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_sumsq_kernel_source_parts_cover_every_element(kx):
+    """The grid-independent squared norm (elt_kernels.cuh::sumsq_kernel): 2048 logical parts over float4 chunks, a scalar
+    tail, and the scalar path for a view that is not 16-byte aligned. (The CPU executor runs it on a 4-block grid; the GPU
+    test checks that any grid gives the same bits.)"""
+    g = torch.Generator().manual_seed(3)
+    for n in (150 * 256 * 4 + 4 * 77 + 3, 1000, 5):   # (inputs long enough for several chunks per part: GPU test)
+        x = torch.randn(n + 1, generator=g)
+        for view in ((x[:n], x[1:]) if n <= 1000 else (x[:n],)):   # aligned / 4-byte-offset view
+            out = torch.full((1,), 2.0)
+            assert kx.mb200_sumsq(P(view), LL(n), P(out), None) == 0
+            want = 2.0 + float((view.double() ** 2).sum())
+            assert abs(float(out) - want) < 2e-5 * want, (n, float(out), want)

@@ -70,3 +70,30 @@ def test_adapter_standalone_matches_golden(golden_dir):
     assert ((x.grad.cpu() - xo.grad).norm() / xo.grad.norm()).item() < 1e-1  # relu mask decided near 0
     gup = ad.adapter[2].weight.grad.cpu()
     assert ((gup - w["a.adapter.2.weight"].grad).norm() / w["a.adapter.2.weight"].grad.norm()).item() < 3e-2
+
+
+def test_sumsq_is_bit_identical_for_any_grid():
+    """mb200_sumsq (the clipping norm): B200Engine caps the optimizer kernels' grids when the optimizer runs beside the
+    next step's GEMMs; the result must not depend on the grid (data-parallel replicas / pipelined vs in-stream optimizer
+    stay bit-identical) and must equal the fp64 sum to fp32 accuracy."""
+    import torch
+
+    from magma_b200 import ops
+    from magma_b200._lib import lib
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(241_332_224 // 8 + 4 * 3 + 1, generator=g).to(dev)
+    outs = []
+    try:
+        for cap in (0, 296, 148, 7):
+            lib().mb200_set_optimizer_grid(cap)
+            for view in (x[:-1], x[1:]):       # 16-byte aligned / not
+                o = torch.zeros(1, device=dev)
+                ops.sumsq(view, o)
+                outs.append((cap, float(o), float((view.double() ** 2).sum())))
+    finally:
+        lib().mb200_set_optimizer_grid(0)
+    for cap, got, want in outs:
+        assert abs(got - want) < 2e-5 * want, (cap, got, want)
+    assert len({o[1] for o in outs[0::2]}) == 1 and len({o[1] for o in outs[1::2]}) == 1, outs
