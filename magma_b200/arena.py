@@ -19,7 +19,9 @@ class ParamArena:
         self.numel = off
         self.master = torch.zeros(off, dtype=torch.float32, device=device)
         self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=device)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        # In a data-parallel job on GPUs the gradient buffer is symmetric (peer-mappable) memory, so that the gradient
+        # exchange kernel reads and writes the ranks' gradients in place over NVLink (dp.PeerExchange); elsewhere plain.
+        self.grad, self.grad_is_symmetric = dp.alloc_gradient_buffer(off, device)
         self._grad_views = []
         self._shadow_views = []
         for p, o in zip(self.params, self.offsets):

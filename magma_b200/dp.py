@@ -62,6 +62,35 @@ def allreduce_slice(flat_grad: torch.Tensor, lo, hi, group=None, comm_dtype=None
     return None
 
 
+def exchange_mode() -> str:
+    """'nccl' (default) or 'peer' (MB200_DP_EXCHANGE): which mechanism carries the gradient exchange. Both are built,
+    parity-tested on 2 GPUs and measured."""
+    import os
+
+    m = os.environ.get("MB200_DP_EXCHANGE", "nccl").lower()
+    return "peer" if m == "peer" else "nccl"
+
+
+def alloc_gradient_buffer(numel: int, device):
+    """(zeroed fp32 buffer, is_symmetric). Symmetric memory (torch.distributed._symmetric_memory) when a multi-rank
+    process group exists, the device is a GPU and the peer-memory exchange is selected (the default); a failure to
+    allocate it is not an error — the exchange then stages through its own buffer or uses NCCL."""
+    import os
+
+    device = torch.device(device)
+    if (device.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            and exchange_mode() == "peer" and os.environ.get("MB200_DP_BF16", "0") != "1"):
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            t = symm.empty(numel, dtype=torch.float32, device=device)
+            t.zero_()
+            return t, True
+        except Exception:
+            pass
+    return torch.zeros(numel, dtype=torch.float32, device=device), False
+
+
 def shard_bounds(lo: int, hi: int, world: int, align: int = ALIGN) -> List[Tuple[int, int]]:
     """Cut the arena slice [lo, hi) into `world` contiguous shards (the last ones may be empty), each a multiple of
     `align` elements except possibly the tail: shard r is what rank r reduces in the peer-memory exchange."""
@@ -85,18 +114,26 @@ class PeerExchange:
     r02_scaling_n2.log). The kernel here uses no shared memory and ~40 registers, so its blocks sit BESIDE the GEMM CTAs
     (the pair GEMM leaves 26 k registers per SM free, csrc/gemm2.cu).
 
-    Layout: one symmetric fp32 exchange buffer E of the arena's size per rank (torch.distributed._symmetric_memory:
-    allocation, handle exchange and the device-side barrier are torch's; the data path is ours). Per slice, on the comm
-    stream: E[slice] <- grad[slice]; barrier; rank r sums shard r of the slice over all ranks' E in rank order and stores
-    it into all ranks' E (loads / stores over NVLink); barrier; grad[slice] <- E[slice]. All ranks end with identical bits.
+    Layout: the arena's fp32 gradient buffer is symmetric memory (torch.distributed._symmetric_memory: allocation, handle
+    exchange and the device-side barrier are torch's; the data path is ours), so the exchange works IN PLACE. Per slice,
+    on the comm stream: barrier (every rank's slice is final); rank r sums shard r of the slice over all ranks' gradient
+    buffers in rank order and stores the sum into all of them (loads / stores over NVLink); barrier. All ranks end with
+    identical bits. If a rank's arena predates the process group, a symmetric staging copy E is used instead
+    (E <- grad before, grad <- E after).
     """
 
-    def __init__(self, numel: int, device, group=None, max_blocks: int = 0):
+    def __init__(self, flat_grad: torch.Tensor, grad_is_symmetric: bool, group=None, max_blocks: int = 0):
         import torch.distributed._symmetric_memory as symm
 
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        self.E = symm.empty(numel, dtype=torch.float32, device=device)
+        # in place when the arena's gradient buffer is itself symmetric on EVERY rank (the usual case: ParamArena
+        # allocates it that way once the process group exists); else through a symmetric staging copy E of it
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(grad_is_symmetric), group=self.group)
+        self.in_place = all(flags)
+        self.E = flat_grad if self.in_place else symm.empty(flat_grad.numel(), dtype=torch.float32,
+                                                            device=flat_grad.device)
         self.hdl = symm.rendezvous(self.E, self.group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(self.ptrs) == self.world and self.ptrs[self.rank] == self.E.data_ptr()
@@ -107,13 +144,15 @@ class PeerExchange:
 
         if lo is None or hi <= lo:
             return
-        self.E[lo:hi].copy_(flat_grad[lo:hi])
-        self.hdl.barrier(channel=0)                      # every rank's slice is published
+        if not self.in_place:
+            self.E[lo:hi].copy_(flat_grad[lo:hi])
+        self.hdl.barrier(channel=0)                      # every rank's slice is final / published
         s0, s1 = shard_bounds(lo, hi, self.world)[self.rank]
         if s1 > s0:
             ops.peer_reduce_bcast(self.ptrs, s0, s1 - s0, self.max_blocks)
-        self.hdl.barrier(channel=0)                      # every shard's sum has landed in every rank's E
-        flat_grad[lo:hi].copy_(self.E[lo:hi])
+        self.hdl.barrier(channel=0)                      # every shard's sum has landed on every rank
+        if not self.in_place:
+            flat_grad[lo:hi].copy_(self.E[lo:hi])
 
 
 def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:

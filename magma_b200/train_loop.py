@@ -28,7 +28,9 @@ class B200Engine:
         self.global_step = 0
         self.betas, self.eps = betas, eps
         on_gpu = getattr(getattr(model, "device", None), "type", "cuda") == "cuda"
-        self.comm_stream = torch.cuda.Stream() if (self.world > 1 and on_gpu) else None
+        # high priority: the exchange's blocks are placed first when SM resources free up, so a slice — and above all the
+        # last one, which the optimizer waits for while the next step's encoder forward already runs — finishes sooner
+        self.comm_stream = torch.cuda.Stream(priority=-1) if (self.world > 1 and on_gpu) else None
         # The optimizer (global-norm reduction + fused AdamW: 7.2 GB of HBM traffic, ~1.4 ms at 6 B scale) is issued on
         # its own stream, ordered after backward and the gradient exchange. Nothing in the next step reads a trainable
         # parameter before the image prefix projection, so with a frozen encoder it runs UNDER the next step's encoder
@@ -53,17 +55,17 @@ class B200Engine:
         # Outside that window every kernel gets all SMs. MB200_DP_GEMM_SMS=0 disables it.
         self.dp_gemm_sms = int(os.environ.get("MB200_DP_GEMM_SMS", "0")) if self.world > 1 else 0
         self._carved = False
-        # Gradient exchange: this package's peer-memory kernel (dp.PeerExchange) by default; MB200_DP_EXCHANGE=nccl, the
-        # bf16 wire format, or a box where peer memory cannot be set up take the NCCL all-reduce (said on stderr and in
-        # self.exchange_kind, which bench.py prints).
+        # Gradient exchange: NCCL all-reduce per slice, or (MB200_DP_EXCHANGE=peer) this package's peer-memory kernel
+        # (dp.PeerExchange); which one ran is in self.exchange_kind (bench.py prints it). dp.exchange_mode() has the
+        # default and DESIGN.md section 6 the measurements behind it.
         self.peer = None
         self.exchange_kind = "none" if self.world == 1 else "nccl"
-        if self.world > 1 and on_gpu and self.comm_dtype is None and os.environ.get("MB200_DP_EXCHANGE", "peer") == "peer":
+        if self.world > 1 and on_gpu and self.comm_dtype is None and dp.exchange_mode() == "peer":
             try:
                 n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-                self.peer = dp.PeerExchange(model.arena.numel, model.arena.grad.device,
+                self.peer = dp.PeerExchange(model.arena.grad, getattr(model.arena, "grad_is_symmetric", False),
                                             max_blocks=int(os.environ.get("MB200_DP_PEER_BLOCKS", str(n_sm))))
-                self.exchange_kind = "peer-memory kernel"
+                self.exchange_kind = "peer-memory kernel" + (" (in place)" if self.peer.in_place else " (staged)")
             except Exception as exc:  # no peer access / IPC refused in this container: NCCL carries the exchange
                 import sys
 

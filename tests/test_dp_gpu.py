@@ -47,7 +47,7 @@ def _worker(rank, world, port, out_dir, mode):
     model.config.image_embed_dropout_prob = 0.0
     eng = B200Engine(model, model.config, n_buckets=2)
     if mode == "peer":  # no silent NCCL fallback in the test of the peer-memory kernel
-        assert eng.exchange_kind == "peer-memory kernel", eng.exchange_kind
+        assert eng.exchange_kind == "peer-memory kernel (in place)", eng.exchange_kind
     lo, hi = rank * (B // world), (rank + 1) * (B // world)
     out = eng(images[lo:hi].to(dev).to(torch.bfloat16), captions[lo:hi].to(dev))
     eng.backward(out.loss)
