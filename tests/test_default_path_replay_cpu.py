@@ -54,6 +54,18 @@ def test_shared_layer_parity_case_replays_at_small_size(replay):
     assert len(r["grads"]) == 3 * 4 + 4
 
 
+def test_kv_decode_parity_case_replays_at_small_size(replay):
+    """The body of tests/test_model_gpu.py::test_config5_full_size_kv_decode_matches_oracle (cache prefill, then greedy
+    single-token steps, teacher-forced against one cache-less oracle forward) on a small geometry with emulated kernels."""
+    import test_model_gpu as G
+    from tools.model_check import small_cfg
+
+    r = G._kv_decode_case(replay, small_cfg(n_layer=3, vit_layers=2), B=3, n_prompt=5, n_steps=4,
+                          vit_name="clip_vit_shared_decode_small")
+    assert max(r["logits"]) < 3e-2, r["logits"]
+    assert all(r["picks"]), r
+
+
 def test_reference_assertion_behaviour_replays(replay, monkeypatch):
     import test_model_gpu as G
 

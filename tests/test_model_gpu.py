@@ -164,20 +164,15 @@ def test_full_size_step_properties():
     assert torch.equal(frozen_before, model.lm.transformer.h[5].attn.out_proj.weight)
 
 
-def _shared_layer_case(dev, cfg, B, S, seed=0, vit_name="clip_vit_shared_case"):
-    """Magma.forward + backward against the oracle on a model whose FROZEN per-layer weights are one set of random
-    tensors shared by every GPT-J / ViT layer (the host-memory trick of bench.py's CPU arm: identical shapes, FLOPs
-    and kernels per layer, 1/28 of the fp32 host weights), while every layer keeps its OWN adapter parameters, so the
-    per-layer trainable gradients are compared one by one. Adapter weights are O(0.05) with down-projection biases of
-    +-3 (tools/model_check.py::boost_adapters): every bottleneck ReLU is decided away from zero and bf16 / fp32 agree
-    on the mask. Returns the measured errors."""
+def _shared_layer_weights(cfg, seed=0):
+    """Oracle-named weights of a model whose frozen per-layer tensors are shared by all layers and whose adapters are
+    per-layer, O(0.05), with decided ReLU masks (see _shared_layer_case)."""
+    import dataclasses
+
     import torch
 
-    from _gpu_util import build_magma_from_weights, rel
     from oracle import magma_oracle as O
     from tools.model_check import boost_adapters
-
-    import dataclasses
 
     one = dataclasses.replace(cfg, n_layer=1, vit_layers=1)
     w1 = O.init_weights(one, seed=seed)
@@ -201,7 +196,22 @@ def _shared_layer_case(dev, cfg, B, S, seed=0, vit_name="clip_vit_shared_case"):
     for k in w:
         if k.endswith("adapter.0.weight"):
             w[k] = w[k] * min(1.0, (512.0 / cfg.d) ** 0.5) * 0.5
-    w = {k: (v.to(torch.bfloat16).float() if ".adapter." in k else v) for k, v in w.items()}
+    return {k: (v.to(torch.bfloat16).float() if ".adapter." in k else v) for k, v in w.items()}
+
+
+def _shared_layer_case(dev, cfg, B, S, seed=0, vit_name="clip_vit_shared_case"):
+    """Magma.forward + backward against the oracle on a model whose FROZEN per-layer weights are one set of random
+    tensors shared by every GPT-J / ViT layer (the host-memory trick of bench.py's CPU arm: identical shapes, FLOPs
+    and kernels per layer, 1/28 of the fp32 host weights), while every layer keeps its OWN adapter parameters, so the
+    per-layer trainable gradients are compared one by one. Adapter weights are O(0.05) with down-projection biases of
+    +-3 (tools/model_check.py::boost_adapters): every bottleneck ReLU is decided away from zero and bf16 / fp32 agree
+    on the mask. Returns the measured errors."""
+    import torch
+
+    from _gpu_util import build_magma_from_weights, rel
+    from oracle import magma_oracle as O
+
+    w = _shared_layer_weights(cfg, seed)
     model = build_magma_from_weights(w, cfg, {"mlp": cfg.mlp_adapter}, S, dev, vit_name=vit_name)
     model.eval()
     images, captions = O.synthetic_batch(cfg, B, S, seed=seed + 3)
@@ -245,6 +255,73 @@ def test_config2_full_size_matches_oracle():
     assert r["logits"] < 3e-2
     bad = {k: round(e, 4) for k, e in r["grads"].items() if e >= 3e-2}
     assert not bad, bad
+
+
+def _kv_decode_case(dev, cfg, B, n_prompt, n_steps, seed=0, vit_name="clip_vit_shared_decode_case"):
+    """KV-cache decoding against the oracle, teacher-forced: image prefix + n_prompt prompt ids are prefilled into a static
+    cache (`decode_logits`: multi-position attention over the cache, small-M weight-streaming GEMMs, last-position LM
+    head), then n_steps single-token steps (fused cache-append + decode attention) each fed the DEVICE's own greedy token.
+    The oracle has no cache: one full causal forward over the final sequence gives the logits of every position. Returns
+    per-position logits errors and, per emitted token, whether it is the oracle's argmax or inside an oracle near-tie."""
+    import torch
+
+    from _gpu_util import build_magma_from_weights, rel
+    from magma_b200 import ops
+    from magma_b200.language_model import KVCache
+    from oracle import magma_oracle as O
+
+    w = _shared_layer_weights(cfg, seed)
+    L = cfg.image_seq_len
+    S = L + n_prompt + n_steps
+    model = build_magma_from_weights(w, cfg, {"mlp": cfg.mlp_adapter}, S, dev, vit_name=vit_name)
+    model.eval()
+    images, captions = O.synthetic_batch(cfg, B, S, seed=seed + 3)
+    images = images.to(torch.bfloat16).float()
+    prompt = captions[:, :n_prompt].clamp(max=cfg.eos_token - 1)
+    lm, lc = model.lm, model.lm.config
+    with torch.no_grad():
+        emb = model.embed([images.to(dev), prompt.to(dev)])
+        assert emb.shape[1] == L + n_prompt
+        cache = KVCache(lc.num_layers, B, lc.num_heads, S, lc.hidden_size // lc.num_heads, dev)
+        got, toks = [], []
+        logits = lm.decode_logits(emb, cache)
+        for i in range(n_steps):
+            got.append(logits.float().cpu()[:, : cfg.vocab])
+            nxt = ops.argmax(logits.contiguous(), logits.shape[-1])
+            toks.append(nxt.cpu())
+            if i + 1 < n_steps:
+                logits = lm.decode_logits(lm.transformer.wte(nxt[:, None]), cache)
+    toks = torch.stack(toks, 1)                                      # [B, n_steps] device-chosen greedy tokens
+    full = torch.cat([prompt, toks, torch.full((B, S - n_prompt - n_steps), cfg.eos_token)], 1)[:, : S]
+    _, logits_o, _ = O.magma_forward(images, full, w, cfg)            # [B, S, V]; position p sees tokens <= p
+    errs, picks = [], []
+    for i in range(n_steps):
+        ref = logits_o[:, L + n_prompt - 1 + i].detach().float()
+        errs.append(rel(got[i], ref))
+        top2 = ref.topk(2, dim=-1)
+        is_argmax = toks[:, i] == top2.indices[:, 0]
+        near_tie = (top2.values[:, 0] - ref.gather(1, toks[:, i:i + 1])[:, 0]) < 0.05 * ref.abs().max(dim=-1).values
+        picks.append(bool((is_argmax | near_tie).all()))
+    return {"logits": errs, "picks": picks, "toks": toks}
+
+
+def test_config5_full_size_kv_decode_matches_oracle():
+    """BASELINE.json config 5's path at FULL SIZE against the oracle: GPT-J-6B (28 layers, d = 4096, 16 heads of 256,
+    V = 50258) + ViT-L/14 prefix + MLP adapters, an 8-position prompt (2 prefix + 6 ids) prefilled into the static KV
+    cache, then greedy single-token steps — the small-M weight-streaming GEMMs with their split-K plans at K = 4096 /
+    16384, cache attention at head_dim 256 and the ragged LM head that `bench.py --workload decode` times. Batch 4 keeps
+    the oracle's fp32 forward to seconds; the kernels and split plans are those of every M <= 32.
+    Bars: logits rel-Frobenius < 3e-2 at every position; every emitted token is the oracle's argmax or inside a near-tie."""
+    import torch
+
+    from oracle import magma_oracle as O
+
+    r = _kv_decode_case(torch.device(os.environ.get("MB200_TEST_DEVICE", "cuda:0")), O.OracleConfig(), B=4, n_prompt=6,
+                        n_steps=4, vit_name="clip_vit_large_fullsize_decode_case")
+    print(f"full-size KV decode vs oracle: logits rel per position {[round(e, 4) for e in r['logits']]}, tokens "
+          f"{r['toks'][0].tolist()} ...")
+    assert max(r["logits"]) < 3e-2, r["logits"]
+    assert all(r["picks"]), r["picks"]
 
 
 def test_graph_replayed_decode_emits_the_same_tokens_as_the_host_driven_loop(monkeypatch):
