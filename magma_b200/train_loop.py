@@ -3,10 +3,11 @@ stands where the DeepSpeed engine stood (train.py:103-111): `engine(images, capt
 `engine.step()`.
 
 Data parallelism is the reference's only strategy. With the LM frozen the only exchange is the
-gradient of the ~0.24 B trainable parameters, which live in one flat fp32 arena: the engine all-reduces contiguous
-arena slices over NCCL on a side stream as soon as the backward pass has finished the layers they belong to
-(backward is issued in layer chunks), so the exchange overlaps the remaining backward; the fused AdamW kernel then
-applies 1/world averaging, global-norm clipping and the bf16 weight refresh in one pass."""
+gradient of the ~0.24 B trainable parameters, which live in one flat fp32 arena: the engine sums contiguous arena
+slices across ranks (NCCL all-reduce, or this package's peer-memory kernel: dp.PeerExchange) on a side stream as soon as
+the backward pass has finished the layers they belong to (backward is issued in layer chunks), so the exchange overlaps
+the remaining backward; the fused AdamW kernel, on a stream of its own, then applies 1/world averaging, global-norm
+clipping and the bf16 weight refresh in one pass."""
 import os
 
 import torch
@@ -33,10 +34,11 @@ class B200Engine:
         self.comm_stream = torch.cuda.Stream(priority=-1) if (self.world > 1 and on_gpu) else None
         # The optimizer (global-norm reduction + fused AdamW: 7.2 GB of HBM traffic, ~1.4 ms at 6 B scale) is issued on
         # its own stream, ordered after backward and the gradient exchange. Nothing in the next step reads a trainable
-        # parameter before the image prefix projection, so with a frozen encoder it runs UNDER the next step's encoder
-        # forward (tensor-bound), and at N > 1 the tail of the gradient exchange hides there too. Consumers are ordered
-        # by ParamArena.wait_ready() (called from sync_shadow(), i.e. by every forward); MB200_PIPELINE_OPT=0 puts the
-        # optimizer back on the caller's stream.
+        # parameter before the image prefix projection, so with a frozen encoder it runs beside the next step's encoder
+        # forward, and at N > 1 the tail of the gradient exchange hides there too. Measured: the
+        # overlap happens, the power-capped step itself moves by < 0.1 ms, end to end it is worth 0.3-0.5 ms. Consumers
+        # are ordered by ParamArena.wait_ready() (called from sync_shadow(), i.e. by every forward);
+        # MB200_PIPELINE_OPT=0 puts the optimizer back on the caller's stream.
         self.opt_stream = torch.cuda.Stream() if (on_gpu and os.environ.get("MB200_PIPELINE_OPT", "1") != "0") else None
         if self.opt_stream is not None:
             # 2 optimizer blocks per SM fit in the registers a persistent GEMM CTA leaves free (csrc/gemm2.cu: 152 of 256
@@ -45,8 +47,9 @@ class B200Engine:
 
             n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
             lib().mb200_set_optimizer_grid(int(os.environ.get("MB200_OPT_BLOCKS_PER_SM", "2")) * n_sm)
-        # experimental data-parallel knobs (both off by default): exchange gradients as bf16, and keep a
-        # few SMs out of the persistent GEMM grids so NCCL's CTAs run beside the backward GEMMs
+        # data-parallel knobs, both off by default and both measured without effect at N = 2 (DESIGN.md section 4,
+        # profiles/r02_n2_dp_sweep.log): exchange gradients as bf16, and keep a few SMs out of the persistent GEMM grids
+        # so NCCL's CTAs run beside the backward GEMMs
         self.comm_dtype = torch.bfloat16 if os.environ.get("MB200_DP_BF16", "0") == "1" else None
         # SM carve-out for the gradient exchange: while an all-reduce is in flight (from the first bucket issued in
         # backward until the optimizer step has waited for the last one) the persistent GEMM grids leave 148 - n SMs
