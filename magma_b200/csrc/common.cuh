@@ -278,7 +278,10 @@ __device__ __forceinline__ float gelu_new_grad_f(float x) {
   float s = __fdividef(1.f, 1.f + __expf(-2.f * u));  // sigmoid(2u) = 0.5 (1 + tanh u);  1 - tanh^2 u = 4 s (1 - s)
   return s + 2.f * x * s * (1.f - s) * k0 * (1.f + 3.f * k1 * x * x);
 }
-__device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.f + __expf(-1.702f * x)); }
+// x * sigmoid(1.702 x) with the approximate divide (rcp.approx + mul, 2 ulp): the IEEE '/' is a ~20-instruction dependent
+// chain with a slow-path branch, which at one epilogue warp per scheduler made the ViT c_fc epilogue cost more than its
+// mainloop (tools/epi_bench.py: vit fc 48 us against 19 us for the same GEMM with bias only).
+__device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.f + __expf(-1.702f * x)); }
 
 #include "warp_helpers.cuh"
 

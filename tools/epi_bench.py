@@ -49,7 +49,7 @@ def main():
         return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
 
     def case(tag, M, N, K, *, bias=False, act=0, res=0, aux=False, a_mn=False, b_mn=False, f32=False, force_bn=0,
-             dact=0, check=True, use_ws=True):
+             dact=0, check=True, use_ws=True, rope=0):
         nbuf = max(1, min(8, int(200e6 // (N * K * 2)) + 1)) if N * K * 2 > 30e6 else 1
         Bs = [rnd(K, N) if b_mn else rnd(N, K) for _ in range(nbuf)]
         A = rnd(K, M, scale=1.0) if a_mn else rnd(M, K, scale=1.0)
@@ -68,6 +68,10 @@ def main():
             kw["res1"] = rnd(M, N, scale=1.0)
         if res >= 2:
             kw["res2"] = rnd(M, N, scale=1.0)
+        if rope:  # GPT-J's rotary epilogue on the q,k thirds of a fused qkv output (S = 128, head_dim 256, 64 rotary dims)
+            kw.update(rope_tab=ops.rope_table(128, 64, device=dev), rope_mode=rope, rope_S=128, rope_hd=256, rope_rot=64,
+                      rope_ncols=(2 * N // 3) if rope > 0 else N)
+            check = False
         if use_ws:  # scratch lent to the GEMM core (split-K of few-tile long-K shapes), as the schedules do
             kw["splitk_ws"] = torch.empty(32 << 20, device=dev, dtype=torch.float32)
         us = timed(lambda i: ops.gemm(A, Bs[i % nbuf], out=C, **kw), max(8, 2 * nbuf), s)
@@ -112,6 +116,7 @@ def main():
     if "block" in only:
         M, d = 1024, 4096
         case("qkv fwd", M, 3 * d, d)
+        case("qkv fwd (+rope epilogue)", M, 3 * d, d, rope=1)
         case("out fwd (+res1)", M, d, d, res=1)
         case("fc_in fwd (bias+gelu+aux)", M, 4 * d, d, bias=True, act=ops.ACT_GELU_NEW, aux=True)
         case("fc_out fwd (+bias)", M, d, 4 * d, bias=True)
