@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: everything that was written after round 1's GPU budget was spent, in one gpurun.
-#   gpurun --timeout 1500 -- 'bash tools/r2_first_gpu_call.sh'
+#   gpurun --timeout 1500 -- 'bash tools/gpu_calls/r2_first_gpu_call.sh'
 # Writes gpurun_out/r2_*.log. Nothing here changes defaults; the knobs are environment variables.
 set -u
 mkdir -p gpurun_out
@@ -26,4 +26,4 @@ nvidia-smi > gpurun_out/r2_nvsmi.log 2>&1
 echo done
 
 # A second call, on 2 GPUs, for the data-parallel knobs (each line: samples/s at N = 2):
-#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/n2_sweep.sh'
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_calls/n2_sweep.sh'
