@@ -31,3 +31,17 @@ def test_every_rank_ends_with_the_same_sum(emul_ops):
             ops.peer_reduce_bcast(ptrs, s0, s1 - s0)
     for e in E:
         assert torch.equal(e, E[0]) and torch.allclose(e, want, atol=1e-6)
+
+
+def test_exchange_selection_and_plain_gradient_buffer_without_a_process_group(monkeypatch):
+    """NCCL is the default exchange; the symmetric gradient buffer is only asked for in a multi-rank
+    GPU job that selected the peer kernel — everywhere else (CPU, single process) the arena gets a plain zeroed buffer."""
+    monkeypatch.delenv("MB200_DP_EXCHANGE", raising=False)
+    assert dp.exchange_mode() == "nccl"
+    monkeypatch.setenv("MB200_DP_EXCHANGE", "PEER")
+    assert dp.exchange_mode() == "peer"
+    monkeypatch.setenv("MB200_DP_EXCHANGE", "something-else")
+    assert dp.exchange_mode() == "nccl"
+    monkeypatch.setenv("MB200_DP_EXCHANGE", "peer")
+    buf, symmetric = dp.alloc_gradient_buffer(192, "cpu")
+    assert not symmetric and buf.dtype == torch.float32 and buf.shape == (192,) and float(buf.abs().sum()) == 0.0
