@@ -45,3 +45,33 @@ def test_exchange_selection_and_plain_gradient_buffer_without_a_process_group(mo
     monkeypatch.setenv("MB200_DP_EXCHANGE", "peer")
     buf, symmetric = dp.alloc_gradient_buffer(192, "cpu")
     assert not symmetric and buf.dtype == torch.float32 and buf.shape == (192,) and float(buf.abs().sum()) == 0.0
+
+
+def test_partitions_hold_for_arbitrary_sizes():
+    """Property checks (hypothesis) of the two partitions the data-parallel path relies on: shard_bounds cuts any aligned
+    slice into `world` contiguous, aligned, non-increasing shards; layer_chunks covers [0, n_layer) exactly once from
+    the top down for any bucket count."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 1 << 16), st.integers(0, 1 << 14), st.integers(1, 16))
+    def shards(lo64, n64, world):
+        lo, hi = lo64 * dp.ALIGN, (lo64 + n64) * dp.ALIGN
+        b = dp.shard_bounds(lo, hi, world)
+        assert len(b) == world and b[0][0] == lo and b[-1][1] == hi
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all((s0 - lo) % dp.ALIGN == 0 and (s1 - s0) % 4 == 0 and s1 >= s0 for s0, s1 in b)
+        sizes = [s1 - s0 for s0, s1 in b]
+        assert sizes == sorted(sizes, reverse=True)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 96), st.integers(1, 128))
+    def chunks(n_layer, n_buckets):
+        c = dp.layer_chunks(n_layer, n_buckets)
+        assert c[0][0] == n_layer and c[-1][1] == 0 and all(hi > lo for hi, lo in c)
+        assert all(c[i][1] == c[i + 1][0] for i in range(len(c) - 1))
+        assert len(c) == min(n_buckets, n_layer)
+
+    shards()
+    chunks()
