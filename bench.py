@@ -428,6 +428,15 @@ def run_b200(args):
                                           f"algorithmic bytes per launch in this run: {by.value / max(n.value, 1):.0f}")
             except Exception:
                 pass
+        tc = os.path.join(ROOT, "profiles", "gemm_tc_util.json")
+        if roof is not None and os.path.exists(tc) and not conv:
+            try:  # BASELINE.json's second figure ("GPT-J block TC util %"): an ncu capture, not measurable inside a timed run
+                tj = json.load(open(tc))
+                roof["tc_util_ncu"] = {"gptj_block_tensor_pipe_pct_of_active_cycles": tj["gptj_block_tensor_pipe_pct_of_active_cycles"],
+                                       "gptj_block_tensor_pipe_pct_of_elapsed_cycles": tj["gptj_block_tensor_pipe_pct_of_elapsed_cycles"],
+                                       "source": tj["source"]}
+            except Exception:
+                pass
     if world > 1:
         dist.barrier()
 
